@@ -1,0 +1,205 @@
+/*
+ * rorl_b200 -- C ABI of the B200-native kernels behind the recurrent off-policy update hot path
+ * of FanmingL/Recurrent-Offpolicy-RL.
+ *
+ * The reference has no C ABI of its own: at this boundary it binds third-party pybind modules
+ * (selective_scan_cuda, causal_conv1d_cuda, flash_attn_2_cuda), in-tree Triton kernels and ATen.
+ * Every entry point below names the reference interface it replaces (file:line under
+ * /root/reference).  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - fp32, contiguous innermost dimension, 16-byte aligned bases; "ld_x" = row stride in floats;
+ *   - the caller owns every buffer (inputs, outputs, partial/workspace buffers) and keeps it alive
+ *     until `stream` has passed the call; the library allocates nothing, never synchronises and
+ *     never touches the host: every call is CUDA-graph capturable;
+ *   - return 0 on success; negative = argument error (-1 shape, -2 alignment, -3 null/inconsistent
+ *     argument, -4 workspace too small); 1000 + cudaError_t = launch error;
+ *   - re-entrant; all work is enqueued on `stream`;
+ *   - sm_100a only. There is no CPU implementation behind this ABI.
+ */
+#ifndef RORL_B200_H
+#define RORL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+/* ABI version, bumped on any signature change. */
+int rorl_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GILR real gated linear recurrence: h_t = f_t h_{t-1} + (1 - f_t) v_t, h_{-1} = 0.  [B, L, C].
+ * Replaces TritonSequentialScan.forward/backward = real_scan_tie_input_gate(v, f)
+ * (ref: offpolicy_rnn/models/gilr/scan_triton/real_rnn_tie_input_gate.py:170-214,264; kernels :9-33,
+ * :67-116).  Unlike the reference, v/f are NOT overwritten by the backward; C % 4 == 0 (the
+ * reference requires C % 256 == 0).
+ * The fused variants take the raw in_proj outputs and the reset flag start[B, L] (may be NULL) and
+ * apply v = tanh(u_v), f = sigmoid(u_f) * (1 - start) in-kernel (ref: gilr/gilr.py:52-56).
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_gilr_scan_fwd(const float* v, const float* f, float* h, int64_t B, int64_t L, int64_t C,
+                       cudaStream_t stream);
+int rorl_gilr_scan_bwd(const float* dh, const float* v, const float* f, const float* h, float* dv, float* df,
+                       int64_t B, int64_t L, int64_t C, cudaStream_t stream);
+int rorl_gilr_fused_fwd(const float* u_v, const float* u_f, const float* start, float* h, int64_t B, int64_t L,
+                        int64_t C, cudaStream_t stream);
+int rorl_gilr_fused_bwd(const float* dh, const float* u_v, const float* u_f, const float* h, const float* start,
+                        float* du_v, float* du_f, int64_t B, int64_t L, int64_t C, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LRU complex linear recurrence: h_t = f_t h_{t-1} + v_t (complex, per-step decay), h_{-1} = h0
+ * ([B, C], may be NULL = 0).  Replaces TritonSequentialScan_Complex = complex_scan(v_re, v_im,
+ * f_re, f_im, h0_re, h0_im, grad_detach) (ref: offpolicy_rnn/models/lru/scan_triton/
+ * complex_rnn.py:174-244; kernels :43-87, :90-170).  grad_detach is [B, L] (may be NULL = 0).
+ * No gradient is produced for h0 (ref :242).
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_lru_scan_fwd(const float* v_re, const float* v_im, const float* f_re, const float* f_im,
+                      const float* h0_re, const float* h0_im, float* h_re, float* h_im, int64_t B, int64_t L,
+                      int64_t C, cudaStream_t stream);
+int rorl_lru_scan_bwd(const float* g_re, const float* g_im, const float* f_re, const float* f_im,
+                      const float* h_re, const float* h_im, const float* h0_re, const float* h0_im,
+                      const float* grad_detach, float* dv_re, float* dv_im, float* df_re, float* df_im,
+                      int64_t B, int64_t L, int64_t C, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mamba selective scan with reset flag.  Replaces selective_scan_cuda.fwd / .bwd as called by
+ * SelectiveScanFn (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/selective_scan_interface_new.py:
+ * 19-84; semantics = selective_scan_ref :96-166) and the s6 Triton pair fwd_recurrence /
+ * bwd_recurrence (ref: offpolicy_rnn/models/s6/selective_scan/triton_scan.py:19-72,75-182).
+ *
+ * Token-major layout: u, delta, z, y: [B, L, D] with row strides ld_*; Bm, Cm: [B, L, N] with row
+ * strides ld_B, ld_C; A: [D, N] (already -exp(A_log)); Dskip, delta_bias: [D] or NULL; z may be NULL;
+ * start: [B, L] (1 = reset the state before this step) or NULL.  N in {16, 32, 64}; D % 4 == 0.
+ * ckpt (may be NULL when no backward follows): [B, L / rorl_selscan_ckpt_every(), D, N] state
+ * checkpoints the backward consumes; last_state (may be NULL): [B, D, N].
+ *
+ * Backward outputs: du, ddelta (w.r.t. the raw delta), dz: [B, L, D]; plus partial sums the caller
+ * reduces (deterministic; no atomics):
+ *   dBC_part  [ceil(D / rorl_selscan_dtile(N)), B, L, 2N]  sum over axis 0 -> dB = [..., :N], dC = [..., N:]
+ *   dA_part   [B, D, N]   sum over axis 0 -> dA
+ *   dD_part   [B, D], dbias_part [B, D]   sum over axis 0 -> dD, d(delta_bias)
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_selscan_dtile(int64_t N);
+int rorl_selscan_ckpt_every(void);
+int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start, float* y,
+                     float* ckpt, float* last_state, int64_t B, int64_t L, int64_t D, int64_t N, int64_t ld_u,
+                     int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_y, int delta_softplus,
+                     cudaStream_t stream);
+int rorl_selscan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start,
+                     const float* dy, const float* ckpt, float* du, float* ddelta, float* dz, float* dBC_part,
+                     float* dA_part, float* dD_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t N,
+                     int64_t ld_u, int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_dy,
+                     int64_t ld_du, int64_t ld_ddelta, int64_t ld_dz, int delta_softplus, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d over time + SiLU, with the valid-step mask applied to the conv INPUT.
+ * Replaces `x = mask * x; x = act(conv1d(x)[..., :L])` on the d_conv > 4 path
+ * (ref: offpolicy_rnn/models/smamba/mamba.py:207-212; nn.Conv1d construction :75-83).
+ * x, y: [B, L, D] token-major with row strides; w: [D, K] (= conv1d.weight[:, 0, :]); bias: [D] or
+ * NULL; mask: [B, L] or NULL.  K in {2, 3, 4, 8, 16}.  Backward: dx [B, L, D]; dw_part [P, D, K],
+ * dbias_part [P, D] with P = B * rorl_conv1d_nseg(L) are per-segment partial sums the caller reduces
+ * over axis 0.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_conv1d_nseg(int64_t L);
+int rorl_conv1d_silu_fwd(const float* x, const float* w, const float* bias, const float* mask, float* y,
+                         int64_t B, int64_t L, int64_t D, int64_t K, int64_t ld_x, int64_t ld_y,
+                         cudaStream_t stream);
+int rorl_conv1d_silu_bwd(const float* x, const float* w, const float* bias, const float* mask, const float* dy,
+                         float* dx, float* dw_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t K,
+                         int64_t ld_x, int64_t ld_dy, int64_t ld_dx, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused residual-add + LayerNorm / RMSNorm over the last dimension (rows = B*L tokens).
+ * Replaces layer_norm_fn / rms_norm_fn (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/triton/
+ * layernorm.py:464-478, kernels :65-120,196-290; semantics layernorm_cpu.py:6-35):
+ *   r = x + residual (residual may be NULL); y = norm(r) * w + b; residual_out = r (may be NULL).
+ * rstd/mean: [rows] saved for the backward (mean unused for RMS).
+ * Backward: dy [rows, C] and dres_out [rows, C] (gradient arriving at residual_out, may be NULL)
+ * -> dx [rows, C] (= gradient w.r.t. both x and residual); dw_part/db_part [nparts, C] with
+ * nparts = rorl_addnorm_nparts(rows), reduced over axis 0 by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_addnorm_nparts(int64_t rows);
+int rorl_addnorm_fwd(const float* x, const float* residual, const float* w, const float* b, float* y,
+                     float* residual_out, float* mean, float* rstd, int64_t rows, int64_t C, float eps, int is_rms,
+                     cudaStream_t stream);
+int rorl_addnorm_bwd(const float* dy, const float* dres_out, const float* r, const float* w, const float* mean,
+                     const float* rstd, float* dx, float* dw_part, float* db_part, int64_t rows, int64_t C,
+                     int is_rms, int has_bias, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused target-Q / masked-TD / actor / entropy reductions over the valid-step mask.
+ * Replaces the ATen chains in _target_Q, QValueGuard.clamp/update, _Q_loss, _policy_loss,
+ * _alpha_loss, _mask_mean (ref: offpolicy_rnn/algorithm/sac_full_length_rnn_ensembleQ.py:80-132,
+ * sac_full_length_rnn_redq.py:16-47, td3_full_length_rnn_ensembleQ.py:23-71,
+ * offpolicy_rnn/utility/q_value_guard.py:22-38).
+ *
+ * guard: device double[4] = {min, max, initialised(0/1), decay} (the reference keeps these as Python
+ * floats, i.e. doubles); work: device scratch of rorl_loss_work_floats() floats, zero-initialised
+ * once by the caller.  All kernels are single-launch, deterministic two-level reductions.
+ * ---------------------------------------------------------------------------------------------- */
+/* m[i] = min over the selected ensemble members of q[e, i] - alpha * logp[i] (logp may be NULL);
+ * on the first call (guard[2] == 0) also initialises guard min/max from m (ref q_value_guard.py:22-27). */
+int rorl_target_minq(const float* q, const int32_t* sel, int64_t nsel, int64_t E, int64_t M, const float* logp,
+                     const float* log_alpha, float* m, double* guard, float* work, cudaStream_t stream);
+/* y[i] = reward + (1 - done') * gamma * clamp(m, guard.min, guard.max) with done' = done zeroed where
+ * timeout > 0; then guard.update(y * mask) with EMA decay (ref q_value_guard.py:29-38);
+ * stats[0] = max |y|, stats[1] = sum(mask). */
+int rorl_target_finish(const float* m, const float* reward, const float* done, const float* timeout,
+                       const float* mask, float gamma, float* y, double* guard, float* stats, float* work,
+                       int64_t M, cudaStream_t stream);
+int64_t rorl_loss_work_floats(int64_t M);
+/* loss = sum_i mask_i sum_e (q[e,i] - y[i])^2 / nvalid; dq[e,i] = 2 mask_i (q - y) / nvalid. */
+int rorl_q_loss_fwd_bwd(const float* q, const float* y, const float* mask, const float* nvalid, float* loss,
+                        float* dq, float* work, int64_t E, int64_t M, cudaStream_t stream);
+/* actor: loss = sum_i mask_i (alpha logp_i - agg_e q[e,i]) / nvalid, agg = min (mode 0) or mean (mode 1);
+ * logp may be NULL (TD3).  Outputs dq [E, M], dlogp [M] (if logp), and the entropy side results
+ * out[0] = actor loss, out[1] = masked mean logp, out[2] = alpha loss = -log_alpha * mean(logp + H),
+ * out[3] = d alpha_loss / d log_alpha. */
+int rorl_actor_loss_fwd_bwd(const float* q, const float* logp, const float* mask, const float* nvalid,
+                            const float* log_alpha, float target_entropy, int mode, float* out, float* dq,
+                            float* dlogp, float* work, int64_t E, int64_t M, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-tensor AdamW step (+ optional Polyak target update) over a flat parameter arena.
+ * Replaces torch.optim.AdamW over param groups (ref: offpolicy_rnn/algorithm/sac.py:61,81-90;
+ * group construction sac_full_length_rnn_redq_sep_optim.py:37-102) and the per-parameter
+ * soft-update loop (ref: offpolicy_rnn/models/rnn_base.py:475-491).
+ * p, g, m, v (and target, may be NULL): flat fp32 arrays of n elements; seg_end[nseg] (int64, device)
+ * and seg_lr / seg_wd [nseg] (double, device) describe contiguous LR / weight-decay groups (nseg <= 64);
+ * step_ptr: device int32 count of completed steps (incremented on the stream after the update);
+ * grad_clip_value: clamp every gradient to +-value first (clip_grad_value_; <= 0 = off).
+ * target <- tau * target + (1 - tau) * p_new when target != NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_adamw_polyak(float* p, const float* g, float* m, float* v, float* target, const int64_t* seg_end,
+                      const double* seg_lr, const double* seg_wd, int64_t nseg, int64_t n, float beta1, float beta2,
+                      float eps, float tau, int32_t* step_ptr, float grad_clip_value, cudaStream_t stream);
+/* out[0] = sum(p^2) (l2_norm_square, ref rnn_base.py:531-532) */
+int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Trajectory gather: builds the padded, nest-stacked [rows, Lmax, F] fp32 batch of
+ * NestedMemoryArray.sample_trajs directly from a device-resident fp32 ring buffer, following a
+ * host-computed plan (ref: offpolicy_rnn/buffers/transition_buffer/nested_replay_memory.py:103-185;
+ * layout SURVEY.md App. A).  plan: device int64[4*ntraj + rows] = (src_start, row, ptr, len) per placed
+ * trajectory (src_start = first ring row, ptr = first step of its blank prefix in the batch row, len =
+ * stored steps), followed by row_end[rows] (first step of each row's tail).  colmap: device
+ * int32[3 + 2*npairs] = {start_col, mask_col, npairs, (dst_col, src_col)...} (pre-step target <- first
+ * transition's source columns); start_col is passed again by value.  batch [rows, Lmax, F] and valid
+ * [rows, Lmax] are fully written (zero-filled first).  max_len = longest `len` in the plan.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_traj_gather(const float* ring, int64_t F, const int64_t* plan, int64_t ntraj, const int32_t* colmap,
+                     int64_t start_col, float* batch, float* valid, int64_t rows, int64_t Lmax, int64_t skip,
+                     int64_t max_len, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RORL_B200_H */

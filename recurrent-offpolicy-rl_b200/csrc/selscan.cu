@@ -1,0 +1,621 @@
+// Mamba selective scan with reset flag (smamba / s6 encoders), forward and backward, sm_100a.
+//
+//   delta = softplus(delta_raw + delta_bias)
+//   h_t[n] = (1 - start_t) * exp(delta_t * A[d,n]) * h_{t-1}[n] + delta_t * u_t * B_t[n],  h_{-1} = 0
+//   y_t    = (sum_n h_t[n] * C_t[n] + D[d] * u_t) * silu(z_t)
+//
+// Semantics pinned by the reference's selective_scan_ref
+// (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/selective_scan_interface_new.py:96-166, reset at
+// :133-135); replaces the binary-only selective_scan_cuda.fwd/.bwd it calls at :47 and :72-75.
+//
+// Layout is token-major: u/delta/z/y are [B, L, D] with a row stride (so they may be column slices
+// of a wider projection output), B/C are [B, L, N].  That is what the projections on either side of
+// the scan produce/consume as GEMM operands, and it is also the s6 layer's native layout
+// (ref: offpolicy_rnn/models/s6/selective_scan/triton_scan.py:19-72).
+//
+// Work decomposition (N = d_state, S = 8 states per lane, LPD = N/8 lanes per channel):
+//   thread = (channel d, 8 of the N states); a warp holds 32/LPD channels; a CTA of 8 warps holds
+//   DT = 8*32/LPD channels of one batch row and walks the sequence serially in time, with h in
+//   registers.  The sum over n for y is an LPD-lane shuffle; there is no parallel-scan combine cost,
+//   no recomputation in the forward and exactly one exp per (t, d, n).  The kernel is bound by the
+//   MUFU (ex2) and FMA pipes, not by HBM; operands are staged per tile of steps
+//   in shared memory with cp.async double buffering, so HBM traffic is the algorithmic minimum.
+//
+// Backward: the forward (when asked) checkpoints h every 16 steps.  The backward walks 16-step
+// chunks in reverse: recompute h inside the chunk from the checkpoint into registers, then run the
+// adjoint recurrence  lambda_t = g_t C_t + a_{t+1} lambda_{t+1}.  dB/dC need a sum over channels:
+// a shuffle reduce-scatter across the warp's channels, a shared-memory sum across the 8 warps and
+// one partial tile per CTA in global memory, summed by the caller.  No atomics anywhere, so the
+// result is deterministic (the reference's CUDA backward is not, ref: results.md:4).
+#include "common.cuh"
+
+namespace rorl {
+
+constexpr int kSelThreads = 256;
+constexpr int kCkptEvery = 16;
+
+template <int N>
+struct SelCfg {
+    static_assert(N == 16 || N == 32 || N == 64, "d_state must be 16, 32 or 64");
+    static constexpr int S = 8;
+    static constexpr int LPD = N / S;         // lanes per channel
+    static constexpr int DPW = 32 / LPD;      // channels per warp
+    static constexpr int DT = 8 * DPW;        // channels per CTA
+    static constexpr int QPR = DT / 4;        // float4 quads per tile row
+};
+
+struct SelFwdParams {
+    const float *u, *delta, *z, *Bm, *Cm, *A, *Dskip, *dbias, *start;
+    float *y, *ckpt, *last_state;
+    int L, D;
+    int ld_u, ld_delta, ld_z, ld_B, ld_C, ld_y;
+    int nckpt;
+};
+
+template <int N, bool HAS_Z, bool SOFTPLUS>
+__global__ void __launch_bounds__(kSelThreads) selscan_fwd_kernel(const SelFwdParams p) {
+    using Cfg = SelCfg<N>;
+    constexpr int S = Cfg::S, LPD = Cfg::LPD, DPW = Cfg::DPW, DT = Cfg::DT, QPR = Cfg::QPR;
+    constexpr int TC = 32;                                  // steps per staged tile
+    constexpr int STAGE = TC * (3 * DT + 2 * N) + TC;       // u, delta, z, B, C, start
+    constexpr int NQ = TC * QPR / kSelThreads;              // float4 per thread per [TC x DT] tile
+    constexpr int NQB = (TC * N / 4 + kSelThreads - 1) / kSelThreads;
+    extern __shared__ __align__(16) float smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dl = lane / LPD, ng = lane % LPD;
+    const int dloc = warp * DPW + dl;
+    const int b = blockIdx.y, d0 = blockIdx.x * DT;
+    const int d = d0 + dloc;
+    const bool dvalid = d < p.D;
+    const int L = p.L;
+    const size_t row0 = (size_t)b * L;
+    const int ntiles = (L + TC - 1) / TC;
+    const int myq = tid % QPR;                               // this thread's quad column (fixed)
+    const bool qvalid = (d0 + myq * 4) < p.D;
+
+    float A2[S], h[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        A2[j] = dvalid ? p.A[(size_t)d * N + ng * S + j] * kLog2e : 0.f;
+        h[j] = 0.f;
+    }
+    const float Dd = (dvalid && p.Dskip) ? p.Dskip[d] : 0.f;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dbias && qvalid) bias4 = *reinterpret_cast<const float4*>(p.dbias + d0 + myq * 4);
+
+    auto issue = [&](int tile) {
+        if (tile < ntiles) {
+            float* st = smem + (tile & 1) * STAGE;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                int idx = tid + i * kSelThreads, r = idx / QPR, t = tile * TC + r;
+                bool ok = qvalid && t < L;
+                size_t row = row0 + (ok ? t : 0);
+                int col = d0 + myq * 4;
+                cp_async16(st + r * DT + myq * 4, p.u + row * p.ld_u + col, ok);
+                cp_async16(st + TC * DT + r * DT + myq * 4, p.delta + row * p.ld_delta + col, ok);
+                if (HAS_Z) cp_async16(st + 2 * TC * DT + r * DT + myq * 4, p.z + row * p.ld_z + col, ok);
+            }
+#pragma unroll
+            for (int i = 0; i < NQB; ++i) {
+                int idx = tid + i * kSelThreads;
+                if (idx < TC * N / 4) {
+                    int r = idx / (N / 4), q = idx % (N / 4), t = tile * TC + r;
+                    bool ok = t < L;
+                    size_t row = row0 + (ok ? t : 0);
+                    cp_async16(st + 3 * TC * DT + r * N + q * 4, p.Bm + row * p.ld_B + q * 4, ok);
+                    cp_async16(st + 3 * TC * DT + TC * N + r * N + q * 4, p.Cm + row * p.ld_C + q * 4, ok);
+                }
+            }
+            if (tid < TC) {
+                int t = tile * TC + tid;
+                bool ok = p.start != nullptr && t < L;
+                cp_async4(st + 3 * TC * DT + 2 * TC * N + tid, p.start + (ok ? row0 + t : 0), ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    issue(0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        float* st = smem + (tile & 1) * STAGE;
+        float* s_u = st;
+        float* s_dt = st + TC * DT;
+        float* s_z = st + 2 * TC * DT;
+        float* s_B = st + 3 * TC * DT;
+        float* s_C = s_B + TC * N;
+        float* s_start = s_C + TC * N;
+        cp_async_wait<0>();
+        // transform the elements this thread staged itself (visible to it without a barrier)
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            int idx = tid + i * kSelThreads, r = idx / QPR;
+            float4* pd = reinterpret_cast<float4*>(s_dt + r * DT + myq * 4);
+            float4 x = *pd;
+            x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+            if (SOFTPLUS) {
+                x.x = softplusf_fast(x.x); x.y = softplusf_fast(x.y);
+                x.z = softplusf_fast(x.z); x.w = softplusf_fast(x.w);
+            }
+            *pd = x;
+            if (HAS_Z) {
+                float4* pz = reinterpret_cast<float4*>(s_z + r * DT + myq * 4);
+                float4 zz = *pz;
+                zz.x *= sigmoidf_fast(zz.x); zz.y *= sigmoidf_fast(zz.y);
+                zz.z *= sigmoidf_fast(zz.z); zz.w *= sigmoidf_fast(zz.w);
+                *pz = zz;
+            }
+        }
+        __syncthreads();
+        issue(tile + 1);
+
+        const int tbase = tile * TC;
+        const int tcount = min(TC, L - tbase);
+#pragma unroll 2
+        for (int i = 0; i < tcount; ++i) {
+            const float dt = s_dt[i * DT + dloc];
+            const float uu = s_u[i * DT + dloc];
+            const float du = dt * uu;
+            if (s_start[i] != 0.f) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) h[j] = 0.f;
+            }
+            float Bv[S], Cv[S];
+            *reinterpret_cast<float4*>(Bv) = *reinterpret_cast<const float4*>(s_B + i * N + ng * S);
+            *reinterpret_cast<float4*>(Bv + 4) = *reinterpret_cast<const float4*>(s_B + i * N + ng * S + 4);
+            *reinterpret_cast<float4*>(Cv) = *reinterpret_cast<const float4*>(s_C + i * N + ng * S);
+            *reinterpret_cast<float4*>(Cv + 4) = *reinterpret_cast<const float4*>(s_C + i * N + ng * S + 4);
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                float a = ex2f(dt * A2[j]);
+                h[j] = fmaf(a, h[j], du * Bv[j]);
+                acc = fmaf(h[j], Cv[j], acc);
+            }
+#pragma unroll
+            for (int o = 1; o < LPD; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (ng == 0) {
+                float yv = fmaf(Dd, uu, acc);
+                if (HAS_Z) yv *= s_z[i * DT + dloc];
+                s_z[i * DT + dloc] = yv;
+            }
+            const int t = tbase + i;
+            if (p.ckpt != nullptr && (t % kCkptEvery) == kCkptEvery - 1 && dvalid) {
+                float* c = p.ckpt + (((size_t)b * p.nckpt + t / kCkptEvery) * p.D + d) * N + ng * S;
+                *reinterpret_cast<float4*>(c) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(c + 4) = make_float4(h[4], h[5], h[6], h[7]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            int idx = tid + i * kSelThreads, r = idx / QPR, t = tbase + r;
+            if (qvalid && t < L) {
+                float4 v = *reinterpret_cast<const float4*>(s_z + r * DT + myq * 4);
+                *reinterpret_cast<float4*>(p.y + (row0 + t) * p.ld_y + d0 + myq * 4) = v;
+            }
+        }
+    }
+    if (p.last_state != nullptr && dvalid) {
+        float* c = p.last_state + ((size_t)b * p.D + d) * N + ng * S;
+        *reinterpret_cast<float4*>(c) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(c + 4) = make_float4(h[4], h[5], h[6], h[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct SelBwdParams {
+    const float *u, *delta, *z, *Bm, *Cm, *A, *Dskip, *dbias, *start, *dy, *ckpt;
+    float *du, *ddelta, *dz, *dBC_part, *dA_part, *dD_part, *dbias_part;
+    int L, D, Bsz;
+    int ld_u, ld_delta, ld_z, ld_B, ld_C, ld_dy, ld_du, ld_ddelta, ld_dz;
+    int nckpt;
+};
+
+// Reduce-scatter 8 per-lane values across the DPW channel-lanes of a warp (lane bits above the
+// LPD state-group bits).  On return v[0..KEEP) hold sums over all channels of the warp for the
+// state indices [first, first + KEEP).
+template <int LPD>
+__device__ __forceinline__ void channel_reduce_scatter(float (&v)[8], int dl) {
+    constexpr int DPW = 32 / LPD;
+    int cnt = 8;
+#pragma unroll
+    for (int m = DPW / 2; m >= 1; m >>= 1) {
+        const bool up = (dl & m) != 0;
+        if (cnt > 1) {
+            const int half = cnt / 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < half) {
+                    float send = up ? v[i] : v[i + half];
+                    float keep = up ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m * LPD);
+                }
+            }
+            cnt = half;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], m * LPD);
+        }
+    }
+}
+
+template <int N, bool HAS_Z, bool SOFTPLUS>
+__global__ void __launch_bounds__(kSelThreads, 1) selscan_bwd_kernel(const SelBwdParams p) {
+    using Cfg = SelCfg<N>;
+    constexpr int S = Cfg::S, LPD = Cfg::LPD, DPW = Cfg::DPW, DT = Cfg::DT, QPR = Cfg::QPR;
+    constexpr int TC = kCkptEvery;
+    constexpr int STAGE = TC * (4 * DT + 2 * N) + TC;          // u, delta, z, dy, B, C, start
+    constexpr int NQ = (TC * QPR + kSelThreads - 1) / kSelThreads;
+    constexpr int NQB = (TC * N / 4 + kSelThreads - 1) / kSelThreads;
+    // number of state values each lane keeps after the channel reduce-scatter, and its first index
+    constexpr int KEEP = (DPW >= 8) ? 1 : (8 / DPW);
+    extern __shared__ __align__(16) float smem[];
+    float* s_sigdt = smem + 2 * STAGE;          // [TC][DT] d softplus / d raw
+    float* s_sigz = s_sigdt + TC * DT;          // [TC][DT] sigmoid(z)
+    float* s_ypre = s_sigz + TC * DT;           // [TC][DT] y before the gate
+    float* s_red = s_ypre + TC * DT;            // [8 warps][TC][2N]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dl = lane / LPD, ng = lane % LPD;
+    const int dloc = warp * DPW + dl;
+    const int b = blockIdx.y, d0 = blockIdx.x * DT;
+    const int d = d0 + dloc;
+    const bool dvalid = d < p.D;
+    const int L = p.L;
+    const size_t row0 = (size_t)b * L;
+    const int nchunks = (L + TC - 1) / TC;
+    const int myq = tid % QPR;
+    const bool qvalid = (d0 + myq * 4) < p.D;
+    // state index this lane owns after the reduce-scatter
+    const int jfirst = (DPW >= 8) ? (dl >> (DPW == 16 ? 1 : 0)) : dl * KEEP;
+    const bool red_writer = (DPW == 16) ? ((dl & 1) == 0) : true;
+
+    float A2[S], dA[S], lam[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        A2[j] = dvalid ? p.A[(size_t)d * N + ng * S + j] * kLog2e : 0.f;
+        dA[j] = 0.f;
+        lam[j] = 0.f;   // a_{t+1} * lambda_{t+1}
+    }
+    const float Dd = (dvalid && p.Dskip) ? p.Dskip[d] : 0.f;
+    float dD_acc = 0.f, dbias_acc = 0.f;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dbias && qvalid) bias4 = *reinterpret_cast<const float4*>(p.dbias + d0 + myq * 4);
+
+    auto issue = [&](int k) {
+        if (k >= 0) {
+            float* st = smem + (k & 1) * STAGE;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                int idx = tid + i * kSelThreads;
+                if (idx < TC * QPR) {
+                    int r = idx / QPR, t = k * TC + r;
+                    bool ok = qvalid && t < L;
+                    size_t row = row0 + (ok ? t : 0);
+                    int col = d0 + myq * 4;
+                    cp_async16(st + r * DT + myq * 4, p.u + row * p.ld_u + col, ok);
+                    cp_async16(st + TC * DT + r * DT + myq * 4, p.delta + row * p.ld_delta + col, ok);
+                    if (HAS_Z) cp_async16(st + 2 * TC * DT + r * DT + myq * 4, p.z + row * p.ld_z + col, ok);
+                    cp_async16(st + 3 * TC * DT + r * DT + myq * 4, p.dy + row * p.ld_dy + col, ok);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NQB; ++i) {
+                int idx = tid + i * kSelThreads;
+                if (idx < TC * N / 4) {
+                    int r = idx / (N / 4), q = idx % (N / 4), t = k * TC + r;
+                    bool ok = t < L;
+                    size_t row = row0 + (ok ? t : 0);
+                    cp_async16(st + 4 * TC * DT + r * N + q * 4, p.Bm + row * p.ld_B + q * 4, ok);
+                    cp_async16(st + 4 * TC * DT + TC * N + r * N + q * 4, p.Cm + row * p.ld_C + q * 4, ok);
+                }
+            }
+            if (tid < TC) {
+                int t = k * TC + tid;
+                bool ok = p.start != nullptr && t < L;
+                cp_async4(st + 4 * TC * DT + 2 * TC * N + tid, p.start + (ok ? row0 + t : 0), ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    issue(nchunks - 1);
+    for (int k = nchunks - 1; k >= 0; --k) {
+        float* st = smem + (k & 1) * STAGE;
+        float* s_u = st;
+        float* s_dt = st + TC * DT;
+        float* s_z = st + 2 * TC * DT;
+        float* s_dy = st + 3 * TC * DT;
+        float* s_B = st + 4 * TC * DT;
+        float* s_C = s_B + TC * N;
+        float* s_start = s_C + TC * N;
+
+        // state entering the chunk (h at t = 16k - 1)
+        float h[S];
+        if (k > 0 && dvalid) {
+            const float* c = p.ckpt + (((size_t)b * p.nckpt + (k - 1)) * p.D + d) * N + ng * S;
+            float4 c0 = *reinterpret_cast<const float4*>(c), c1 = *reinterpret_cast<const float4*>(c + 4);
+            h[0] = c0.x; h[1] = c0.y; h[2] = c0.z; h[3] = c0.w;
+            h[4] = c1.x; h[5] = c1.y; h[6] = c1.z; h[7] = c1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) h[j] = 0.f;
+        }
+
+        cp_async_wait<0>();
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            int idx = tid + i * kSelThreads;
+            if (idx < TC * QPR) {
+                int r = idx / QPR;
+                float4* pd = reinterpret_cast<float4*>(s_dt + r * DT + myq * 4);
+                float4 x = *pd, sg;
+                x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+                if (SOFTPLUS) {
+                    sg = make_float4(sigmoidf_fast(x.x), sigmoidf_fast(x.y), sigmoidf_fast(x.z), sigmoidf_fast(x.w));
+                    x.x = softplusf_fast(x.x); x.y = softplusf_fast(x.y);
+                    x.z = softplusf_fast(x.z); x.w = softplusf_fast(x.w);
+                } else {
+                    sg = make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+                *pd = x;
+                *reinterpret_cast<float4*>(s_sigdt + r * DT + myq * 4) = sg;
+                if (HAS_Z) {
+                    float4 zz = *reinterpret_cast<const float4*>(s_z + r * DT + myq * 4);
+                    *reinterpret_cast<float4*>(s_sigz + r * DT + myq * 4) =
+                        make_float4(sigmoidf_fast(zz.x), sigmoidf_fast(zz.y), sigmoidf_fast(zz.z), sigmoidf_fast(zz.w));
+                }
+            }
+        }
+        __syncthreads();
+        issue(k - 1);
+
+        const int tbase = k * TC;
+        // ---- phase F: recompute h_t inside the chunk ----
+        float hb[TC][S];
+#pragma unroll
+        for (int i = 0; i < TC; ++i) {
+            if (tbase + i < L) {
+                const float dt = s_dt[i * DT + dloc];
+                const float uu = s_u[i * DT + dloc];
+                const float du = dt * uu;
+                const bool rst = s_start[i] != 0.f;
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    float a = rst ? 0.f : ex2f(dt * A2[j]);
+                    h[j] = fmaf(a, h[j], du * s_B[i * N + ng * S + j]);
+                    hb[i][j] = h[j];
+                    acc = fmaf(h[j], s_C[i * N + ng * S + j], acc);
+                }
+                if (HAS_Z) {
+#pragma unroll
+                    for (int o = 1; o < LPD; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (ng == 0) s_ypre[i * DT + dloc] = fmaf(Dd, uu, acc);
+                }
+            }
+        }
+        // ---- phase R: adjoint recurrence, latest step first ----
+#pragma unroll
+        for (int i = TC - 1; i >= 0; --i) {
+            if (tbase + i < L) {
+                const float dt = s_dt[i * DT + dloc];
+                const float uu = s_u[i * DT + dloc];
+                const float du = dt * uu;
+                const float dyv = s_dy[i * DT + dloc];
+                const bool rst = s_start[i] != 0.f;
+                float g = dyv;
+                float dzv = 0.f;
+                if (HAS_Z) {
+                    const float zr = s_z[i * DT + dloc], sg = s_sigz[i * DT + dloc];
+                    g = dyv * zr * sg;
+                    dzv = dyv * s_ypre[i * DT + dloc] * sg * (1.0f + zr * (1.0f - sg));
+                }
+                float dC[S], dB[S];
+                float sB = 0.f, sA = 0.f;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const float Bj = s_B[i * N + ng * S + j], Cj = s_C[i * N + ng * S + j];
+                    const float l = fmaf(g, Cj, lam[j]);
+                    dC[j] = g * hb[i][j];
+                    dB[j] = l * du;
+                    sB = fmaf(l, Bj, sB);
+                    const float ahp = fmaf(-du, Bj, hb[i][j]);   // a_t * h_{t-1}
+                    const float t1 = l * ahp;
+                    dA[j] = fmaf(t1, dt, dA[j]);
+                    sA = fmaf(t1, A2[j], sA);
+                    const float a = rst ? 0.f : ex2f(dt * A2[j]);
+                    lam[j] = a * l;
+                }
+#pragma unroll
+                for (int o = 1; o < LPD; o <<= 1) {
+                    sB += __shfl_xor_sync(0xffffffffu, sB, o);
+                    sA += __shfl_xor_sync(0xffffffffu, sA, o);
+                }
+                if (ng == 0) {
+                    const float ddt = fmaf(sA, kLn2, uu * sB) * s_sigdt[i * DT + dloc];
+                    dbias_acc += ddt;
+                    dD_acc = fmaf(g, uu, dD_acc);
+                    s_u[i * DT + dloc] = fmaf(g, Dd, dt * sB);
+                    s_dt[i * DT + dloc] = ddt;
+                    if (HAS_Z) s_z[i * DT + dloc] = dzv;
+                }
+                channel_reduce_scatter<LPD>(dC, dl);
+                channel_reduce_scatter<LPD>(dB, dl);
+                if (red_writer) {
+                    float* r = s_red + ((size_t)warp * TC + i) * (2 * N) + ng * S + jfirst;
+#pragma unroll
+                    for (int q = 0; q < KEEP; ++q) {
+                        r[q] = dB[q];
+                        r[N + q] = dC[q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- copy out du / ddelta / dz and the per-CTA dB|dC partial ----
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            int idx = tid + i * kSelThreads;
+            if (idx < TC * QPR) {
+                int r = idx / QPR, t = tbase + r;
+                if (qvalid && t < L) {
+                    size_t row = row0 + t;
+                    int col = d0 + myq * 4;
+                    *reinterpret_cast<float4*>(p.du + row * p.ld_du + col) =
+                        *reinterpret_cast<const float4*>(s_u + r * DT + myq * 4);
+                    *reinterpret_cast<float4*>(p.ddelta + row * p.ld_ddelta + col) =
+                        *reinterpret_cast<const float4*>(s_dt + r * DT + myq * 4);
+                    if (HAS_Z)
+                        *reinterpret_cast<float4*>(p.dz + row * p.ld_dz + col) =
+                            *reinterpret_cast<const float4*>(s_z + r * DT + myq * 4);
+                }
+            }
+        }
+        for (int idx = tid; idx < TC * 2 * N; idx += kSelThreads) {
+            int r = idx / (2 * N), t = tbase + r;
+            if (t < L) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += s_red[(size_t)w * TC * 2 * N + idx];
+                p.dBC_part[(((size_t)blockIdx.x * p.Bsz + b) * L + t) * (2 * N) + (idx % (2 * N))] = s;
+            }
+        }
+        // the next iteration's pre-barrier writes touch s_sigdt/s_sigz only; s_red and the stage
+        // are protected by that barrier.
+    }
+    if (dvalid) {
+        float* a = p.dA_part + ((size_t)b * p.D + d) * N + ng * S;
+        // dA accumulates t1 * delta with t1 = lambda * a_t h_{t-1}
+        *reinterpret_cast<float4*>(a) = make_float4(dA[0], dA[1], dA[2], dA[3]);
+        *reinterpret_cast<float4*>(a + 4) = make_float4(dA[4], dA[5], dA[6], dA[7]);
+        if (ng == 0) {
+            p.dD_part[(size_t)b * p.D + d] = dD_acc;
+            p.dbias_part[(size_t)b * p.D + d] = dbias_acc;
+        }
+    }
+}
+
+template <int N>
+constexpr size_t sel_fwd_smem() {
+    return sizeof(float) * 2 * (32 * (3 * SelCfg<N>::DT + 2 * N) + 32);
+}
+template <int N>
+constexpr size_t sel_bwd_smem() {
+    return sizeof(float) * (2 * (kCkptEvery * (4 * SelCfg<N>::DT + 2 * N) + kCkptEvery) +
+                            3 * kCkptEvery * SelCfg<N>::DT + 8 * kCkptEvery * 2 * N);
+}
+
+}  // namespace rorl
+
+using namespace rorl;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int N, bool HAS_Z, bool SP>
+static int launch_fwd(const SelFwdParams& p, int64_t B, cudaStream_t stream) {
+    auto kern = selscan_fwd_kernel<N, HAS_Z, SP>;
+    constexpr size_t smem = sel_fwd_smem<N>();
+    static bool once = (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
+    (void)once;
+    dim3 grid((unsigned)((p.D + SelCfg<N>::DT - 1) / SelCfg<N>::DT), (unsigned)B);
+    kern<<<grid, kSelThreads, smem, stream>>>(p);
+    RORL_RETURN_LAUNCH();
+}
+template <int N, bool HAS_Z, bool SP>
+static int launch_bwd(const SelBwdParams& p, int64_t B, cudaStream_t stream) {
+    auto kern = selscan_bwd_kernel<N, HAS_Z, SP>;
+    constexpr size_t smem = sel_bwd_smem<N>();
+    static bool once = (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
+    (void)once;
+    dim3 grid((unsigned)((p.D + SelCfg<N>::DT - 1) / SelCfg<N>::DT), (unsigned)B);
+    kern<<<grid, kSelThreads, smem, stream>>>(p);
+    RORL_RETURN_LAUNCH();
+}
+
+#define SEL_DISPATCH(FN, P, B, STREAM)                                         \
+    do {                                                                       \
+        if (N == 16) {                                                         \
+            if (has_z) return sp ? FN<16, true, true>(P, B, STREAM) : FN<16, true, false>(P, B, STREAM);   \
+            return sp ? FN<16, false, true>(P, B, STREAM) : FN<16, false, false>(P, B, STREAM);            \
+        } else if (N == 32) {                                                  \
+            if (has_z) return sp ? FN<32, true, true>(P, B, STREAM) : FN<32, true, false>(P, B, STREAM);   \
+            return sp ? FN<32, false, true>(P, B, STREAM) : FN<32, false, false>(P, B, STREAM);            \
+        } else {                                                               \
+            if (has_z) return sp ? FN<64, true, true>(P, B, STREAM) : FN<64, true, false>(P, B, STREAM);   \
+            return sp ? FN<64, false, true>(P, B, STREAM) : FN<64, false, false>(P, B, STREAM);            \
+        }                                                                      \
+    } while (0)
+
+extern "C" {
+
+int rorl_selscan_dtile(int64_t N) {
+    if (N == 16) return SelCfg<16>::DT;
+    if (N == 32) return SelCfg<32>::DT;
+    if (N == 64) return SelCfg<64>::DT;
+    return RORL_ERR_SHAPE;
+}
+
+int rorl_selscan_ckpt_every(void) { return kCkptEvery; }
+
+int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start, float* y,
+                     float* ckpt, float* last_state, int64_t B, int64_t L, int64_t D, int64_t N, int64_t ld_u,
+                     int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_y, int delta_softplus,
+                     cudaStream_t stream) {
+    if (!u || !delta || !A || !Bm || !Cm || !y) return RORL_ERR_ARG;
+    if (B <= 0 || L <= 0 || D <= 0 || B > 65535) return RORL_ERR_SHAPE;
+    if (N != 16 && N != 32 && N != 64) return RORL_ERR_SHAPE;
+    if (D % 4 || ld_u % 4 || ld_delta % 4 || ld_B % 4 || ld_C % 4 || ld_y % 4 || (z && ld_z % 4)) return RORL_ERR_ALIGN;
+    if (!aligned16(u) || !aligned16(delta) || !aligned16(Bm) || !aligned16(Cm) || !aligned16(y) ||
+        (z && !aligned16(z)) || (delta_bias && !aligned16(delta_bias)) || (ckpt && !aligned16(ckpt)) ||
+        (last_state && !aligned16(last_state)))
+        return RORL_ERR_ALIGN;
+    SelFwdParams p;
+    p.u = u; p.delta = delta; p.z = z; p.Bm = Bm; p.Cm = Cm; p.A = A; p.Dskip = Dskip; p.dbias = delta_bias;
+    p.start = start; p.y = y; p.ckpt = ckpt; p.last_state = last_state;
+    p.L = (int)L; p.D = (int)D;
+    p.ld_u = (int)ld_u; p.ld_delta = (int)ld_delta; p.ld_z = (int)ld_z; p.ld_B = (int)ld_B; p.ld_C = (int)ld_C;
+    p.ld_y = (int)ld_y;
+    p.nckpt = (int)(L / kCkptEvery);
+    const bool has_z = z != nullptr, sp = delta_softplus != 0;
+    SEL_DISPATCH(launch_fwd, p, B, stream);
+}
+
+int rorl_selscan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start,
+                     const float* dy, const float* ckpt, float* du, float* ddelta, float* dz, float* dBC_part,
+                     float* dA_part, float* dD_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t N,
+                     int64_t ld_u, int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_dy,
+                     int64_t ld_du, int64_t ld_ddelta, int64_t ld_dz, int delta_softplus, cudaStream_t stream) {
+    if (!u || !delta || !A || !Bm || !Cm || !dy || !du || !ddelta || !dBC_part || !dA_part || !dD_part ||
+        !dbias_part)
+        return RORL_ERR_ARG;
+    if ((z != nullptr) != (dz != nullptr)) return RORL_ERR_ARG;
+    if (L > kCkptEvery && !ckpt) return RORL_ERR_ARG;
+    if (B <= 0 || L <= 0 || D <= 0 || B > 65535) return RORL_ERR_SHAPE;
+    if (N != 16 && N != 32 && N != 64) return RORL_ERR_SHAPE;
+    if (D % 4 || ld_u % 4 || ld_delta % 4 || ld_B % 4 || ld_C % 4 || ld_dy % 4 || ld_du % 4 || ld_ddelta % 4 ||
+        (z && (ld_z % 4 || ld_dz % 4)))
+        return RORL_ERR_ALIGN;
+    if (!aligned16(u) || !aligned16(delta) || !aligned16(Bm) || !aligned16(Cm) || !aligned16(dy) || !aligned16(du) ||
+        !aligned16(ddelta) || (z && (!aligned16(z) || !aligned16(dz))) || (delta_bias && !aligned16(delta_bias)) ||
+        (ckpt && !aligned16(ckpt)) || !aligned16(dA_part))
+        return RORL_ERR_ALIGN;
+    SelBwdParams p;
+    p.u = u; p.delta = delta; p.z = z; p.Bm = Bm; p.Cm = Cm; p.A = A; p.Dskip = Dskip; p.dbias = delta_bias;
+    p.start = start; p.dy = dy; p.ckpt = ckpt;
+    p.du = du; p.ddelta = ddelta; p.dz = dz; p.dBC_part = dBC_part; p.dA_part = dA_part; p.dD_part = dD_part;
+    p.dbias_part = dbias_part;
+    p.L = (int)L; p.D = (int)D; p.Bsz = (int)B;
+    p.ld_u = (int)ld_u; p.ld_delta = (int)ld_delta; p.ld_z = (int)ld_z; p.ld_B = (int)ld_B; p.ld_C = (int)ld_C;
+    p.ld_dy = (int)ld_dy; p.ld_du = (int)ld_du; p.ld_ddelta = (int)ld_ddelta; p.ld_dz = (int)ld_dz;
+    p.nckpt = (int)(L / kCkptEvery);
+    const bool has_z = z != nullptr, sp = delta_softplus != 0;
+    SEL_DISPATCH(launch_bwd, p, B, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""torch.autograd bindings of the C-ABI kernels, with the reference's op-level signatures.
+
+Each Function is the B200 counterpart of one autograd Function / fused op of the reference:
+
+  GILRScan / real_scan_tie_input_gate   <- TritonSequentialScan (ref: offpolicy_rnn/models/gilr/scan_triton/real_rnn_tie_input_gate.py:170-214,264)
+  LRUScan / complex_scan                <- TritonSequentialScan_Complex (ref: offpolicy_rnn/models/lru/scan_triton/complex_rnn.py:174-244)
+  SelectiveScan / selective_scan_fn     <- SelectiveScanFn (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/selective_scan_interface_new.py:19-93)
+  AddNorm / layer_norm_fn, rms_norm_fn  <- LayerNormFn (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/triton/layernorm.py:464-478)
+  CausalConv1dSiLU                      <- mask * x -> nn.Conv1d -> SiLU (ref: offpolicy_rnn/models/smamba/mamba.py:207-212)
+
+All of them require CUDA tensors: there is no CPU implementation (the oracle under oracle/ is test
+infrastructure and is never imported from here).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import _native as N
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """[B, L, D] tensor usable with a row stride: unit inner stride, uniform row stride, 16-B aligned."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    ok = (t.stride(-1) == 1 and t.stride(0) == t.shape[1] * t.stride(1) and t.stride(1) % 4 == 0
+          and t.data_ptr() % 16 == 0)
+    return t if ok else t.contiguous()
+
+
+def _flag(t, B, L):
+    """[B, L, 1] / [B, L] side-band flag -> contiguous fp32 [B, L] (or None)."""
+    if t is None:
+        return None
+    t = t.reshape(B, L)
+    return _f32c(t)
+
+
+# ------------------------------------------------------------------------------------------------
+# GILR
+# ------------------------------------------------------------------------------------------------
+class GILRScan(Function):
+    @staticmethod
+    def forward(ctx, v, f):
+        v, f = _f32c(v), _f32c(f)
+        B, L, C = v.shape
+        h = torch.empty_like(v)
+        N.call("rorl_gilr_scan_fwd", N.ptr(v), N.ptr(f), N.ptr(h), B, L, C, N.stream())
+        ctx.save_for_backward(v, f, h)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        v, f, h = ctx.saved_tensors
+        dh = _f32c(dh)
+        B, L, C = v.shape
+        dv, df = torch.empty_like(v), torch.empty_like(f)
+        N.call("rorl_gilr_scan_bwd", N.ptr(dh), N.ptr(v), N.ptr(f), N.ptr(h), N.ptr(dv), N.ptr(df), B, L, C, N.stream())
+        return dv, df
+
+
+class GILRFusedScan(Function):
+    """h = scan(tanh(u_v), sigmoid(u_f) * (1 - start)) with the activations fused into the scan."""
+
+    @staticmethod
+    def forward(ctx, u_v, u_f, start):
+        u_v, u_f = _f32c(u_v), _f32c(u_f)
+        B, L, C = u_v.shape
+        start = _flag(start, B, L)
+        h = torch.empty_like(u_v)
+        N.call("rorl_gilr_fused_fwd", N.ptr(u_v), N.ptr(u_f), N.ptr(start), N.ptr(h), B, L, C, N.stream())
+        ctx.save_for_backward(u_v, u_f, h, start)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        u_v, u_f, h, start = ctx.saved_tensors
+        dh = _f32c(dh)
+        B, L, C = u_v.shape
+        du_v, du_f = torch.empty_like(u_v), torch.empty_like(u_f)
+        N.call("rorl_gilr_fused_bwd", N.ptr(dh), N.ptr(u_v), N.ptr(u_f), N.ptr(h), N.ptr(start), N.ptr(du_v),
+               N.ptr(du_f), B, L, C, N.stream())
+        return du_v, du_f, None
+
+
+def real_scan_tie_input_gate(v, f):
+    return GILRScan.apply(v, f)
+
+
+def gilr_fused_scan(u_v, u_f, start=None):
+    return GILRFusedScan.apply(u_v, u_f, start)
+
+
+# ------------------------------------------------------------------------------------------------
+# LRU
+# ------------------------------------------------------------------------------------------------
+class LRUScan(Function):
+    @staticmethod
+    def forward(ctx, v_re, v_im, f_re, f_im, h0_re, h0_im, grad_detach):
+        v_re, v_im, f_re, f_im = map(_f32c, (v_re, v_im, f_re, f_im))
+        B, L, C = v_re.shape
+        h0_re = None if h0_re is None else _f32c(h0_re.reshape(B, C))
+        h0_im = None if h0_im is None else _f32c(h0_im.reshape(B, C))
+        gd = _flag(grad_detach, B, L)
+        h_re, h_im = torch.empty_like(v_re), torch.empty_like(v_im)
+        N.call("rorl_lru_scan_fwd", N.ptr(v_re), N.ptr(v_im), N.ptr(f_re), N.ptr(f_im), N.ptr(h0_re), N.ptr(h0_im),
+               N.ptr(h_re), N.ptr(h_im), B, L, C, N.stream())
+        ctx.save_for_backward(f_re, f_im, h_re, h_im, h0_re, h0_im, gd)
+        return h_re, h_im
+
+    @staticmethod
+    def backward(ctx, g_re, g_im):
+        f_re, f_im, h_re, h_im, h0_re, h0_im, gd = ctx.saved_tensors
+        g_re, g_im = _f32c(g_re), _f32c(g_im)
+        B, L, C = f_re.shape
+        dv_re, dv_im, df_re, df_im = (torch.empty_like(f_re) for _ in range(4))
+        N.call("rorl_lru_scan_bwd", N.ptr(g_re), N.ptr(g_im), N.ptr(f_re), N.ptr(f_im), N.ptr(h_re), N.ptr(h_im),
+               N.ptr(h0_re), N.ptr(h0_im), N.ptr(gd), N.ptr(dv_re), N.ptr(dv_im), N.ptr(df_re), N.ptr(df_im),
+               B, L, C, N.stream())
+        return dv_re, dv_im, df_re, df_im, None, None, None
+
+
+def complex_scan(v_re, v_im, f_re, f_im, h0_re=None, h0_im=None, grad_detach=None):
+    return LRUScan.apply(v_re, v_im, f_re, f_im, h0_re, h0_im, grad_detach)
+
+
+# ------------------------------------------------------------------------------------------------
+# selective scan (token-major core + reference-layout wrapper)
+# ------------------------------------------------------------------------------------------------
+class SelectiveScan(Function):
+    """Token-major selective scan: u, delta, z [B, L, D] (row-strided ok), Bm, Cm [B, L, N], A [D, N],
+    D / delta_bias [D], start [B, L].  Returns y [B, L, D] (and last_state [B, D, N])."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state):
+        u, delta, Bm, Cm = _rows(u), _rows(delta), _rows(Bm), _rows(Cm)
+        z = None if z is None else _rows(z)
+        A = _f32c(A)
+        Dskip = None if Dskip is None else _f32c(Dskip)
+        delta_bias = None if delta_bias is None else _f32c(delta_bias)
+        B, L, D = u.shape
+        Ns = A.shape[1]
+        start = _flag(start, B, L)
+        y = torch.empty((B, L, D), device=u.device, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad)
+        every = N.lib().rorl_selscan_ckpt_every()
+        nck = L // every
+        ckpt = torch.empty((B, nck, D, Ns), device=u.device, dtype=torch.float32) if (need_grad and nck > 0) else None
+        last = torch.empty((B, D, Ns), device=u.device, dtype=torch.float32) if return_last_state else None
+        N.call("rorl_selscan_fwd", N.ptr(u), N.ptr(delta), N.ptr(A), N.ptr(Bm), N.ptr(Cm), N.ptr(Dskip), N.ptr(z),
+               N.ptr(delta_bias), N.ptr(start), N.ptr(y), N.ptr(ckpt), N.ptr(last), B, L, D, Ns,
+               u.stride(1), delta.stride(1), 0 if z is None else z.stride(1), Bm.stride(1), Cm.stride(1), D,
+               int(bool(delta_softplus)), N.stream())
+        ctx.delta_softplus = bool(delta_softplus)
+        ctx.return_last_state = return_last_state
+        ctx.save_for_backward(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, ckpt)
+        if return_last_state:
+            ctx.mark_non_differentiable(last)
+            return y, last
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, ckpt = ctx.saved_tensors
+        dy = _rows(dy)
+        B, L, D = u.shape
+        Ns = A.shape[1]
+        dev = u.device
+        ntile = (D + N.lib().rorl_selscan_dtile(Ns) - 1) // N.lib().rorl_selscan_dtile(Ns)
+        du = torch.empty((B, L, D), device=dev, dtype=torch.float32)
+        ddelta = torch.empty_like(du)
+        dz = torch.empty_like(du) if z is not None else None
+        dBC = torch.empty((ntile, B, L, 2 * Ns), device=dev, dtype=torch.float32)
+        dA = torch.empty((B, D, Ns), device=dev, dtype=torch.float32)
+        dD = torch.empty((B, D), device=dev, dtype=torch.float32)
+        dbias = torch.empty((B, D), device=dev, dtype=torch.float32)
+        N.call("rorl_selscan_bwd", N.ptr(u), N.ptr(delta), N.ptr(A), N.ptr(Bm), N.ptr(Cm), N.ptr(Dskip), N.ptr(z),
+               N.ptr(delta_bias), N.ptr(start), N.ptr(dy), N.ptr(ckpt), N.ptr(du), N.ptr(ddelta), N.ptr(dz),
+               N.ptr(dBC), N.ptr(dA), N.ptr(dD), N.ptr(dbias), B, L, D, Ns,
+               u.stride(1), delta.stride(1), 0 if z is None else z.stride(1), Bm.stride(1), Cm.stride(1),
+               dy.stride(1), D, D, D, int(ctx.delta_softplus), N.stream())
+        dBC = dBC.sum(0) if ntile > 1 else dBC[0]
+        return (du, ddelta, dA.sum(0), dBC[..., :Ns], dBC[..., Ns:],
+                None if Dskip is None else dD.sum(0), dz,
+                None if delta_bias is None else dbias.sum(0), None, None, None)
+
+
+def selective_scan_tm(u, delta, A, Bm, Cm, Dskip=None, z=None, delta_bias=None, start=None, delta_softplus=False,
+                      return_last_state=False):
+    return SelectiveScan.apply(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state)
+
+
+def selective_scan_fn(u, delta, A, B, C, start, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """Reference-layout entry point: u, delta, z, start [B, D, L]; B, C [B, N, L]
+    (ref: selective_scan_interface_new.py:87-93).  `start` must be identical across channels, which is
+    how the reference builds it (repeat_interleave of a [B, L, 1] flag, ref: smamba/mamba.py:182-183)."""
+    tm = lambda t: None if t is None else t.transpose(1, 2)
+    st = None if start is None else start[:, 0, :]
+    out = selective_scan_tm(tm(u), tm(delta), A, tm(B), tm(C), D, tm(z), delta_bias, st, delta_softplus,
+                            return_last_state)
+    if return_last_state:
+        return out[0].transpose(1, 2), out[1]
+    return out.transpose(1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise causal conv + SiLU
+# ------------------------------------------------------------------------------------------------
+class CausalConv1dSiLU(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask):
+        x = _rows(x)
+        B, L, D = x.shape
+        w = _f32c(weight.reshape(D, -1))
+        K = w.shape[1]
+        bias = None if bias is None else _f32c(bias)
+        mask = _flag(mask, B, L)
+        y = torch.empty((B, L, D), device=x.device, dtype=torch.float32)
+        N.call("rorl_conv1d_silu_fwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(mask), N.ptr(y), B, L, D, K,
+               x.stride(1), D, N.stream())
+        ctx.save_for_backward(x, w, bias, mask)
+        ctx.wshape = weight.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, bias, mask = ctx.saved_tensors
+        dy = _rows(dy)
+        B, L, D = x.shape
+        K = w.shape[1]
+        P = B * N.lib().rorl_conv1d_nseg(L)
+        dx = torch.empty((B, L, D), device=x.device, dtype=torch.float32)
+        dw = torch.empty((P, D, K), device=x.device, dtype=torch.float32)
+        db = torch.empty((P, D), device=x.device, dtype=torch.float32)
+        N.call("rorl_conv1d_silu_bwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(mask), N.ptr(dy), N.ptr(dx), N.ptr(dw),
+               N.ptr(db), B, L, D, K, x.stride(1), dy.stride(1), D, N.stream())
+        return dx, dw.sum(0).reshape(ctx.wshape), (None if bias is None else db.sum(0)), None
+
+
+def causal_conv1d_silu(x, weight, bias=None, mask=None):
+    """x [B, L, D] token-major; weight [D, 1, K] (nn.Conv1d depthwise layout) or [D, K]; mask [B, L(,1)]."""
+    return CausalConv1dSiLU.apply(x, weight, bias, mask)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused residual add + LayerNorm / RMSNorm
+# ------------------------------------------------------------------------------------------------
+class AddNorm(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, eps, prenorm, is_rms):
+        shape = x.shape
+        C = shape[-1]
+        x2 = _f32c(x.reshape(-1, C))
+        r2 = None if residual is None else _f32c(residual.reshape(-1, C))
+        rows = x2.shape[0]
+        w = _f32c(weight)
+        b = None if bias is None else _f32c(bias)
+        y = torch.empty_like(x2)
+        need_res = prenorm or residual is not None
+        res_out = torch.empty_like(x2) if need_res else None
+        mean = None if is_rms else torch.empty((rows,), device=x.device, dtype=torch.float32)
+        rstd = torch.empty((rows,), device=x.device, dtype=torch.float32)
+        N.call("rorl_addnorm_fwd", N.ptr(x2), N.ptr(r2), N.ptr(w), N.ptr(b), N.ptr(y), N.ptr(res_out), N.ptr(mean),
+               N.ptr(rstd), rows, C, float(eps), int(is_rms), N.stream())
+        ctx.save_for_backward(res_out if need_res else x2, w, mean, rstd)
+        ctx.is_rms, ctx.has_bias, ctx.prenorm, ctx.has_res, ctx.shape = is_rms, b is not None, prenorm, residual is not None, shape
+        y = y.reshape(shape)
+        if prenorm:
+            return y, res_out.reshape(shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *args):
+        r, w, mean, rstd = ctx.saved_tensors
+        C = r.shape[-1]
+        rows = r.shape[0]
+        dy = _f32c(dy.reshape(-1, C))
+        dres = None
+        if ctx.prenorm and args and args[0] is not None:
+            dres = _f32c(args[0].reshape(-1, C))
+        nparts = N.lib().rorl_addnorm_nparts(rows)
+        dx = torch.empty_like(r)
+        dw = torch.empty((nparts, C), device=r.device, dtype=torch.float32)
+        db = torch.empty((nparts, C), device=r.device, dtype=torch.float32) if ctx.has_bias else None
+        N.call("rorl_addnorm_bwd", N.ptr(dy), N.ptr(dres), N.ptr(r), N.ptr(w), N.ptr(mean), N.ptr(rstd), N.ptr(dx),
+               N.ptr(dw), N.ptr(db), rows, C, int(ctx.is_rms), int(ctx.has_bias), N.stream())
+        dx = dx.reshape(ctx.shape)
+        return dx, dw.sum(0), (db.sum(0) if ctx.has_bias else None), (dx if ctx.has_res else None), None, None, None
+
+
+def layer_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False, is_rms_norm=False):
+    """Same contract as the reference's layer_norm_fn (ref: layernorm.py:464-478): the residual is added
+    first; with prenorm=True the (fp32) sum is returned next to the normalised output."""
+    return AddNorm.apply(x, weight, bias, residual, eps, prenorm, is_rms_norm)
+
+
+def rms_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False):
+    return AddNorm.apply(x, weight, bias, residual, eps, prenorm, True)

@@ -1,0 +1,374 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run here (the container that has /root/reference):   python tests/golden/make_golden.py
+Nothing on the GPU box runs this; tests read the .npz files it writes next to itself.
+
+Fixtures:
+  ops_*.npz      op-level in/out/grad of the reference's own restatements (scan_cpu, complex_scan_cpu,
+                 selective_scan_ref, layernorm_cpu)
+  layer_*.npz    RNNBase(['fc', <ID>, 'fc']) forward + input/parameter gradients for each encoder ID
+  sampler_*.npz  NestedMemoryArray.sample_trajs outputs for seeded buffers
+  update_*.npz   one or two full train_one_batch() calls of the reference algorithm classes (App. D harness)
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _refload import load_reference, REF_ROOT  # noqa: E402
+
+load_reference()
+torch.set_num_threads(4)
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name, sum(np.asarray(v).nbytes for v in out.values()) // 1024, "KiB")
+
+
+def flat_sd(sd, prefix=""):
+    return {f"{prefix}{k}/{n}": t.detach().clone().numpy() for k, m in sd.items() for n, t in m.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# op-level
+# ------------------------------------------------------------------------------------------------
+def gen_ops():
+    from offpolicy_rnn.models.gilr.scan_triton.real_rnn_tie_input_gate_cpu import scan_cpu
+    from offpolicy_rnn.models.lru.scan_triton.complex_rnn_cpu import complex_scan_cpu
+    from offpolicy_rnn.models.smamba.mamba_ssm.ops.selective_scan_interface_new import selective_scan_ref
+    from offpolicy_rnn.models.smamba.mamba_ssm.ops.triton.layernorm_cpu import layer_norm_fn, rms_norm_fn
+
+    g = torch.Generator().manual_seed(1)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    # gilr
+    B, L, C = 3, 37, 8
+    v = rn(B, L, C).requires_grad_()
+    f = torch.sigmoid(rn(B, L, C))
+    f[:, [0, 5, 6, 20]] = 0.0
+    f.requires_grad_()
+    h, _ = scan_cpu(v, f, torch.zeros(B, 1, C))
+    dh = rn(B, L, C)
+    dv, df = torch.autograd.grad(h, (v, f), dh)
+    save("ops_gilr.npz", v=v, f=f, h=h, dh=dh, dv=dv, df=df)
+    # lru
+    B, L, C = 2, 29, 8
+    vr, vi = rn(B, L, C).requires_grad_(), rn(B, L, C).requires_grad_()
+    fr = (0.9 * torch.cos(rn(B, L, C))).requires_grad_()
+    fi = (0.9 * torch.sin(rn(B, L, C))).requires_grad_()
+    h0r, h0i = rn(B, 1, C), rn(B, 1, C)
+    hr, hi, _, _ = complex_scan_cpu(vr, vi, fr, fi, h0r, h0i)
+    gr, gi = rn(B, L, C), rn(B, L, C)
+    grads = torch.autograd.grad((hr, hi), (vr, vi, fr, fi), (gr, gi))
+    save("ops_lru.npz", vr=vr, vi=vi, fr=fr, fi=fi, h0r=h0r, h0i=h0i, hr=hr, hi=hi, gr=gr, gi=gi,
+         dvr=grads[0], dvi=grads[1], dfr=grads[2], dfi=grads[3])
+    # selective scan (reference layout)
+    for tag, (B, D, L, N) in {"a": (2, 8, 45, 16), "b": (1, 4, 70, 32)}.items():
+        u, delta, z = rn(B, D, L).requires_grad_(), (0.5 * rn(B, D, L)).requires_grad_(), rn(B, D, L).requires_grad_()
+        A = (-torch.exp(0.3 * rn(D, N))).requires_grad_()
+        Bm, Cm = rn(B, N, L).requires_grad_(), rn(B, N, L).requires_grad_()
+        Dk, bias = rn(D).requires_grad_(), rn(D).requires_grad_()
+        st = torch.zeros(B, 1, L)
+        st[:, :, 0] = 1
+        st[0, :, 17] = 1
+        st[0, :, 18] = 1
+        st[-1, :, 33] = 1
+        start = st.expand(B, D, L).contiguous()
+        out, last = selective_scan_ref(u, delta, A, Bm, Cm, start, Dk, z=z, delta_bias=bias, delta_softplus=True,
+                                       return_last_state=True)
+        dout = rn(B, D, L)
+        gs = torch.autograd.grad(out, (u, delta, A, Bm, Cm, Dk, z, bias), dout)
+        save(f"ops_selscan_{tag}.npz", u=u, delta=delta, A=A, B=Bm, C=Cm, D=Dk, z=z, bias=bias, start=start, out=out,
+             last=last, dout=dout, du=gs[0], ddelta=gs[1], dA=gs[2], dB=gs[3], dC=gs[4], dD=gs[5], dz=gs[6], dbias=gs[7])
+    # add + norm
+    x, r = rn(10, 24).requires_grad_(), rn(10, 24).requires_grad_()
+    w, b = rn(24).requires_grad_(), rn(24).requires_grad_()
+    y, res = layer_norm_fn(x, w, b, residual=r, eps=1e-8, prenorm=True, residual_in_fp32=True)
+    dy, dres = rn(10, 24), rn(10, 24)
+    gs = torch.autograd.grad((y, res), (x, r, w, b), (dy, dres))
+    y2 = rms_norm_fn(x, w, None, residual=r, eps=1e-8, prenorm=False, residual_in_fp32=True)
+    gs2 = torch.autograd.grad(y2, (x, r, w), dy)
+    save("ops_addnorm.npz", x=x, r=r, w=w, b=b, y=y, res=res, dy=dy, dres=dres, dx=gs[0], dr=gs[1], dw=gs[2], db=gs[3],
+         y_rms=y2, dx_rms=gs2[0], dr_rms=gs2[1], dw_rms=gs2[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# layer-level
+# ------------------------------------------------------------------------------------------------
+LAYER_IDS = {"gilr": "gilr", "lru": "lru", "gru": "gru", "smamba_rms": "smamba_s16_c4_b2",
+             "smamba_ln": "smamba_s32_c8_b1_nln", "smamba_ff": "smamba_s16_c8_b1_ff"}
+
+
+def gen_layers():
+    from offpolicy_rnn.models.rnn_base import RNNBase
+    for tag, lid in LAYER_IDS.items():
+        torch.manual_seed(7)
+        net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
+        with torch.no_grad():   # make every parameter non-trivial (zero biases hide bugs)
+            for p in net.parameters():
+                if p.dim() == 1 or p.abs().max() == 0:
+                    p.add_(0.1 * torch.randn_like(p))
+        B, L = 3, 41
+        x = torch.randn(B, L, 12, requires_grad=True)
+        start = torch.zeros(B, L, 1)
+        start[:, 0] = 1
+        start[1, 15] = 1
+        start[2, 30:33] = 1
+        mask = torch.ones(B, L, 1)
+        mask[2, 28:33] = 0
+        hid = net.make_init_state(B)
+        if 'gru' not in lid:
+            hid.set_rnn_start(start)
+            hid.set_mask(mask)
+        y, _, _ = net.meta_forward(x, hid)
+        dy = torch.randn_like(y)
+        params = dict(net.named_parameters())
+        grads = torch.autograd.grad(y, [x] + list(params.values()), dy, allow_unused=True)
+        arrs = {"x": x, "start": start, "mask": mask, "y": y, "dy": dy, "dx": grads[0]}
+        for (n, p), gr in zip(params.items(), grads[1:]):
+            arrs["p/" + n] = p
+            if gr is not None:   # e.g. GILRLayer.layer_norm is constructed but never used
+                arrs["g/" + n] = gr
+        save(f"layer_{tag}.npz", layer_id=np.array(lid), **arrs)
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------------
+def fill_buffer(buf, Transition, rng, lens, S, A):
+    """Synthetic trajectories in the shape SAC.train() pushes them (ref: algorithm/sac.py:337-351)."""
+    for T in lens:
+        last_s, last_a, last_r = np.zeros((1, S)), np.zeros((1, A)), np.zeros((1, 1))
+        s = rng.standard_normal((1, S))
+        for t in range(T):
+            a = np.tanh(rng.standard_normal((1, A)))
+            ns = rng.standard_normal((1, S))
+            r = float(rng.standard_normal())
+            done = t == T - 1
+            buf.mem_push(Transition(state=s, last_state=last_s, last_action=last_a, action=a, next_state=ns, reward=r,
+                                    logp=None, mask=1, done=done, timeout=done, start=(t == 0), reward_input=last_r))
+            last_s, last_a, last_r, s = s, a, np.array([[r]]), ns
+
+
+def gen_sampler():
+    from offpolicy_rnn.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
+    from offpolicy_rnn.buffers.transition_buffer.replay_memory import Transition
+    cases = {
+        "a": dict(skip_extra=0, max_step=20, lens=[5, 3, 6, 4, 20, 9, 1, 12], batch=30, nest=True, S=3, A=2),
+        "b": dict(skip_extra=4, max_step=20, lens=[5, 3, 6, 4, 20, 9, 2, 12, 7], batch=40, nest=True, S=2, A=1),
+        "c": dict(skip_extra=0, max_step=12, lens=[12, 12, 5, 12, 7], batch=35, nest=False, S=2, A=2),
+        "d": dict(skip_extra=16, max_step=50, lens=[50] * 6, batch=6 * 50 - 1, nest=True, S=3, A=2),
+    }
+    for tag, c in cases.items():
+        buf = NestedMemoryArray(500, c["max_step"], additional_history_len=c["skip_extra"])
+        fill_buffer(buf, Transition, np.random.RandomState(3), c["lens"], c["S"], c["A"])
+        np.random.seed(11)
+        arrs = {}
+        for call in range(2):   # second call exercises the cached-array reuse path
+            tr, total, valid, lens = buf.sample_trajs(c["batch"], None, equalize_data_of_each_traj=True,
+                                                      nest_stack_trajs=c["nest"])
+            for n in tr._fields:
+                v = getattr(tr, n)
+                if v is not None:
+                    arrs[f"c{call}/{n}"] = np.array(v, copy=True)
+            arrs[f"c{call}/valid"] = np.array(valid, copy=True)
+            arrs[f"c{call}/lens"] = lens
+            arrs[f"c{call}/total"] = np.array(total)
+            arrs[f"c{call}/rng_next"] = np.array(np.random.get_state()[1][:4], dtype=np.int64)
+            arrs[f"c{call}/rng_pos"] = np.array(np.random.get_state()[2])
+        save(f"sampler_{tag}.npz", cfg=np.array(json.dumps(c)), **arrs)
+
+
+# ------------------------------------------------------------------------------------------------
+# full update (App. D harness)
+# ------------------------------------------------------------------------------------------------
+def install_algo_stubs():
+    gym = types.ModuleType("gym")
+    gym.Env = object
+    gym.Space = object
+    gym.Wrapper = object
+    spaces = types.ModuleType("gym.spaces")
+    spaces.Box = type("Box", (), {})
+    spaces.Discrete = type("Discrete", (), {})
+    gym.spaces = spaces
+    wr = types.ModuleType("gym.wrappers")
+    wr.RescaleAction = object
+    gym.wrappers = wr
+    sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.wrappers": wr})
+    sl = sys.modules["smart_logger"]
+    sl.Logger = object
+    sl.experiment_config = types.SimpleNamespace()
+    sl.init_config = lambda *a, **k: None
+    pt = types.ModuleType("smart_logger.parameter")
+    ptt = types.ModuleType("smart_logger.parameter.ParameterTemplate")
+    ptt.ParameterTemplate = object
+    pt.ParameterTemplate = ptt
+    sys.modules.update({"smart_logger.parameter": pt, "smart_logger.parameter.ParameterTemplate": ptt})
+    envs = types.ModuleType("envs")
+    mpe = types.ModuleType("envs.make_pomdp_env")
+    mpe.make_pomdp_env = lambda *a, **k: None
+    pc = types.ModuleType("envs.pomdp_config")
+    pc.env_config = {}
+    sys.modules.update({"envs": envs, "envs.make_pomdp_env": mpe, "envs.pomdp_config": pc})
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+
+
+UPDATE_CASES = {
+    "sac_smamba": dict(algo="sac", enc="smamba_s16_c4_b2_nln", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2),
+    "sac_gru": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2),
+    "td3_gilr": dict(algo="td3", enc="gilr", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1),
+    "td3_lru": dict(algo="td3", enc="lru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1),
+}
+
+
+def model_kwargs(c, value):
+    H = c["hidden"]
+    return dict(state_dim=c["S"], action_dim=c["A"], embedding_size=8, embedding_hidden=[H, H],
+                embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', c["enc"], 'fc'],
+                uni_model_hidden=[H, H], uni_model_activations=['elu', 'elu', 'linear'],
+                uni_model_layer_type=(['efc-8'] * 3 if value else ['fc'] * 3), fix_rnn_length=0,
+                uni_model_input_mapping_dim=8, reward_input=False, last_action_input=True, last_state_input=True,
+                separate_encoder=True)
+
+
+HP = dict(utd=1, policy_utd=1, randomize_mask=False, valid_number_post_randomized=0, random_trunc_traj=False,
+          randomize_first_hidden=False, gamma=0.99, sac_tau=0.995, policy_update_per=1, no_alpha_auto_tune=False,
+          policy_max_gradnorm=None, policy_embedding_max_gradnorm=None, value_max_gradnorm=None,
+          value_embedding_max_gradnorm=None, redq_m=2, target_action_noise_std=0.04, target_action_noise_clip=0.12,
+          policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5, rnn_value_lr=1e-5, alpha_lr=1e-4, policy_l2_norm=0.0,
+          value_l2_norm=0.0, sample_std=0.1, target_entropy_ratio=1.0)
+
+
+def gen_updates():
+    install_algo_stubs()
+    from offpolicy_rnn.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM, prepare_param_list
+    from offpolicy_rnn.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
+    from offpolicy_rnn.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
+    from offpolicy_rnn.buffers.transition_buffer.replay_memory import Transition
+    from offpolicy_rnn.policy_value_models.make_models import make_policy_model, make_value_model
+    from offpolicy_rnn.utility.q_value_guard import QValueGuard
+    from offpolicy_rnn.utility.timer import Timer
+
+    for tag, c in UPDATE_CASES.items():
+        torch.manual_seed(5)
+        np.random.seed(5)
+        cls = SACFullLengthRNNREDQ_SEP_OPTIM if c["algo"] == "sac" else TD3FullLengthRNNREDQ_SEP_OPTIM
+        A = object.__new__(cls)
+        hp = dict(HP, sac_batch_size=sum(c["lens"]) - 1)
+        if c["algo"] == "td3":
+            hp["no_alpha_auto_tune"] = True
+        A.parameter = types.SimpleNamespace(**hp)
+        A.timer = Timer()
+        A.device = A.sample_device = torch.device("cpu")
+        A.discrete_env = False
+        A.base_algorithm = c["algo"]
+        A.logger = lambda *a, **k: None
+        pk, vk = model_kwargs(c, False), model_kwargs(c, True)
+        if c["algo"] == "td3":
+            pk = dict(pk, sample_std=hp["sample_std"])
+        A.policy = make_policy_model(pk, c["algo"], False)
+        A.values = [make_value_model(vk, c["algo"], False)]
+        A.target_values = [make_value_model(vk, c["algo"], False)]
+        for m in [A.policy] + A.values:
+            with torch.no_grad():
+                for p in m.parameters():
+                    if p.dim() == 1 or p.abs().max() == 0:
+                        p.add_(0.05 * torch.randn_like(p))
+        A._value_update(tau=0.0)
+        A.log_sac_alpha = torch.zeros(1, requires_grad=True)
+        A.target_entropy = -float(c["A"]) * hp["target_entropy_ratio"]
+        for net in (A.values[0].embedding_network.layer_list + A.target_values[0].embedding_network.layer_list
+                    + A.values[0].uni_network.layer_list + A.target_values[0].uni_network.layer_list):
+            if hasattr(net, 'desire_ndim'):
+                net.desire_ndim = 4
+            if hasattr(net, 'in_proj') and hasattr(net.in_proj, 'desire_ndim'):
+                net.in_proj.desire_ndim = 4
+        A.amp_scalar = A.amp_scalar_critic = None
+        A.Q_guard = QValueGuard(True, True, 1 - 1e-3)
+        A.target_policy = make_policy_model(pk, c["algo"], False)
+        A.target_policy.copy_weight_from(A.policy, tau=0.0)
+        A.optim_class = torch.optim.AdamW
+        A.optimizer_policy = torch.optim.AdamW(prepare_param_list(A.policy, hp["rnn_policy_lr"], 0.0), lr=hp["policy_lr"], weight_decay=0.0)
+        A.optimizer_value = torch.optim.AdamW(prepare_param_list(A.values[0], hp["rnn_value_lr"], 0.0), lr=hp["value_lr"], weight_decay=0.0)
+        A.value_parameters = [p for v in A.values for p in v.parameters(True)]
+        A.value_embedding_parameters = [p for v in A.values for p in v.embedding_network.parameters(True)]
+        A.optimizer_alpha = torch.optim.AdamW([A.log_sac_alpha], lr=hp["alpha_lr"])
+        A.grad_num = 0
+        A.allow_nest_stack = cls.allow_nest_stack_trajs(A)
+        skip = cls._get_skip_len(A)
+        A.replay_buffer = NestedMemoryArray(1000, max(c["lens"]), additional_history_len=skip - 1)
+        fill_buffer(A.replay_buffer, Transition, np.random.RandomState(9), c["lens"], c["S"], c["A"])
+
+        arrs = {}
+        arrs.update(flat_sd(A.policy.state_dict(), "init/policy/"))
+        arrs.update(flat_sd(A.values[0].state_dict(), "init/value/"))
+        noises = []
+        orig_randn_like = torch.randn_like
+
+        def rec_randn_like(t, *a, **k):
+            out = orig_randn_like(t, *a, **k)
+            noises.append(out.detach().clone())
+            return out
+
+        np.random.seed(21)
+        torch.manual_seed(22)
+        torch.randn_like = rec_randn_like
+        try:
+            for call in range(c["calls"]):
+                snap = {}
+                orig_step = A.optimizer_value.step
+
+                def step_and_snap(*a, _orig=orig_step, _snap=snap, **k):
+                    _snap.update({f"{k2}/{n}": (p.grad.detach().clone().numpy() if p.grad is not None else None)
+                                  for k2, m in A.values[0].contextual_modules.items() for n, p in m.named_parameters()})
+                    return _orig(*a, **k)
+
+                A.optimizer_value.step = step_and_snap
+                log = A.train_one_batch()
+                A.optimizer_value.step = orig_step
+                A.grad_num += 1
+                for k, v in log.items():
+                    if isinstance(v, tuple):
+                        v = v[0]
+                    arrs[f"c{call}/log/{k}"] = np.array(float(v))
+                for k, v in snap.items():
+                    if v is not None:
+                        arrs[f"c{call}/vgrad/{k}"] = v
+                for k2, m in A.policy.contextual_modules.items():
+                    for n, p in m.named_parameters():
+                        if p.grad is not None:
+                            arrs[f"c{call}/pgrad/{k2}/{n}"] = p.grad.detach().clone().numpy()
+                arrs.update(flat_sd(A.policy.state_dict(), f"c{call}/policy/"))
+                arrs.update(flat_sd(A.values[0].state_dict(), f"c{call}/value/"))
+                arrs.update(flat_sd(A.target_values[0].state_dict(), f"c{call}/target/"))
+                arrs[f"c{call}/log_alpha"] = A.log_sac_alpha.detach().clone().numpy()
+        finally:
+            torch.randn_like = orig_randn_like
+        for i, nz in enumerate(noises):
+            arrs[f"noise/{i}"] = nz.numpy()
+        cfg = dict(case=c, hp=hp, policy_kwargs=pk, value_kwargs=vk, skip=skip, allow_nest_stack=bool(A.allow_nest_stack),
+                   n_noise=len(noises), np_seed_fill=9, np_seed_run=21)
+        save(f"update_{tag}.npz", cfg=np.array(json.dumps(cfg)), **arrs)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["ops", "layers", "sampler", "updates"]
+    if "ops" in which:
+        gen_ops()
+    if "layers" in which:
+        gen_layers()
+    if "sampler" in which:
+        gen_sampler()
+    if "updates" in which:
+        gen_updates()
