@@ -18,14 +18,17 @@ template <int VPL>  // float4 per lane; C = 128 * VPL
 __global__ void __launch_bounds__(kNormThreads) addnorm_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ w,
     const float* __restrict__ b, float* __restrict__ y, float* __restrict__ res_out, float* __restrict__ mean_o,
-    float* __restrict__ rstd_o, int64_t rows, float eps, int is_rms) {
-    constexpr int C = 128 * VPL;
+    float* __restrict__ rstd_o, int64_t rows, int C, float eps, int is_rms) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float invC = 1.0f / (float)C;
     float4 wv[VPL], bv[VPL];
+    bool ok[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-        wv[i] = reinterpret_cast<const float4*>(w)[i * 32 + lane];
-        bv[i] = b ? reinterpret_cast<const float4*>(b)[i * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        ok[i] = (i * 32 + lane) * 4 < C;
+        wv[i] = ok[i] ? reinterpret_cast<const float4*>(w)[i * 32 + lane] : zero4;
+        bv[i] = (b && ok[i]) ? reinterpret_cast<const float4*>(b)[i * 32 + lane] : zero4;
     }
     for (int64_t row = (int64_t)blockIdx.x * kNormWarps + warp; row < rows; row += (int64_t)gridDim.x * kNormWarps) {
         const float4* xp = reinterpret_cast<const float4*>(x + row * C);
@@ -33,8 +36,8 @@ __global__ void __launch_bounds__(kNormThreads) addnorm_fwd_kernel(
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            r[i] = xp[i * 32 + lane];
-            if (res) {
+            r[i] = ok[i] ? xp[i * 32 + lane] : zero4;
+            if (res && ok[i]) {
                 float4 q = reinterpret_cast<const float4*>(res + row * C)[i * 32 + lane];
                 r[i].x += q.x; r[i].y += q.y; r[i].z += q.z; r[i].w += q.w;
             }
@@ -42,17 +45,18 @@ __global__ void __launch_bounds__(kNormThreads) addnorm_fwd_kernel(
         }
         if (res_out) {
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) reinterpret_cast<float4*>(res_out + row * C)[i * 32 + lane] = r[i];
+            for (int i = 0; i < VPL; ++i)
+                if (ok[i]) reinterpret_cast<float4*>(res_out + row * C)[i * 32 + lane] = r[i];
         }
         float mean = 0.f;
-        if (!is_rms) mean = warp_sum(s) * (1.0f / C);
+        if (!is_rms) mean = warp_sum(s) * invC;
         float v = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             float a = r[i].x - mean, bq = r[i].y - mean, c = r[i].z - mean, dd = r[i].w - mean;
-            v += (a * a + bq * bq) + (c * c + dd * dd);
+            if (ok[i]) v += (a * a + bq * bq) + (c * c + dd * dd);
         }
-        v = warp_sum(v) * (1.0f / C);
+        v = warp_sum(v) * invC;
         const float rstd = rsqrtf(v + eps);
         if (lane == 0) {
             if (mean_o) mean_o[row] = mean;
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(kNormThreads) addnorm_fwd_kernel(
             o.y = (r[i].y - mean) * rstd * wv[i].y + bv[i].y;
             o.z = (r[i].z - mean) * rstd * wv[i].z + bv[i].z;
             o.w = (r[i].w - mean) * rstd * wv[i].w + bv[i].w;
-            reinterpret_cast<float4*>(y + row * C)[i * 32 + lane] = o;
+            if (ok[i]) reinterpret_cast<float4*>(y + row * C)[i * 32 + lane] = o;
         }
     }
 }
@@ -74,15 +78,19 @@ template <int VPL>
 __global__ void __launch_bounds__(kNormThreads) addnorm_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ dres, const float* __restrict__ r,
     const float* __restrict__ w, const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
-    float* __restrict__ dx, float* __restrict__ dw_part, float* __restrict__ db_part, int64_t rows, int is_rms,
+    float* __restrict__ dx, float* __restrict__ dw_part, float* __restrict__ db_part, int64_t rows, int C, int is_rms,
     int has_bias) {
-    constexpr int C = 128 * VPL;
-    __shared__ float s_acc[kNormWarps][C];
+    constexpr int CMAX = 128 * VPL;
+    __shared__ float s_acc[kNormWarps][CMAX];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float invC = 1.0f / (float)C;
     float4 wv[VPL], dw[VPL], db[VPL];
+    bool ok[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-        wv[i] = reinterpret_cast<const float4*>(w)[i * 32 + lane];
+        ok[i] = (i * 32 + lane) * 4 < C;
+        wv[i] = ok[i] ? reinterpret_cast<const float4*>(w)[i * 32 + lane] : zero4;
         dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -93,9 +101,9 @@ __global__ void __launch_bounds__(kNormThreads) addnorm_bwd_kernel(
         float c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            float4 rv = reinterpret_cast<const float4*>(r + row * C)[i * 32 + lane];
-            float4 g = reinterpret_cast<const float4*>(dy + row * C)[i * 32 + lane];
-            xh[i] = make_float4((rv.x - mean) * rstd, (rv.y - mean) * rstd, (rv.z - mean) * rstd, (rv.w - mean) * rstd);
+            float4 rv = ok[i] ? reinterpret_cast<const float4*>(r + row * C)[i * 32 + lane] : zero4;
+            float4 g = ok[i] ? reinterpret_cast<const float4*>(dy + row * C)[i * 32 + lane] : zero4;
+            xh[i] = ok[i] ? make_float4((rv.x - mean) * rstd, (rv.y - mean) * rstd, (rv.z - mean) * rstd, (rv.w - mean) * rstd) : zero4;
             wdy[i] = make_float4(g.x * wv[i].x, g.y * wv[i].y, g.z * wv[i].z, g.w * wv[i].w);
             dw[i].x = fmaf(g.x, xh[i].x, dw[i].x); dw[i].y = fmaf(g.y, xh[i].y, dw[i].y);
             dw[i].z = fmaf(g.z, xh[i].z, dw[i].z); dw[i].w = fmaf(g.w, xh[i].w, dw[i].w);
@@ -103,8 +111,8 @@ __global__ void __launch_bounds__(kNormThreads) addnorm_bwd_kernel(
             c1 += (xh[i].x * wdy[i].x + xh[i].y * wdy[i].y) + (xh[i].z * wdy[i].z + xh[i].w * wdy[i].w);
             c2 += (wdy[i].x + wdy[i].y) + (wdy[i].z + wdy[i].w);
         }
-        c1 = warp_sum(c1) * (1.0f / C);
-        c2 = is_rms ? 0.f : warp_sum(c2) * (1.0f / C);
+        c1 = warp_sum(c1) * invC;
+        c2 = is_rms ? 0.f : warp_sum(c2) * invC;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             float4 o;
@@ -112,11 +120,11 @@ __global__ void __launch_bounds__(kNormThreads) addnorm_bwd_kernel(
             o.y = (wdy[i].y - xh[i].y * c1 - c2) * rstd;
             o.z = (wdy[i].z - xh[i].z * c1 - c2) * rstd;
             o.w = (wdy[i].w - xh[i].w * c1 - c2) * rstd;
-            if (dres) {
+            if (dres && ok[i]) {
                 float4 q = reinterpret_cast<const float4*>(dres + row * C)[i * 32 + lane];
                 o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
             }
-            reinterpret_cast<float4*>(dx + row * C)[i * 32 + lane] = o;
+            if (ok[i]) reinterpret_cast<float4*>(dx + row * C)[i * 32 + lane] = o;
         }
     }
     // CTA-level sum of the per-warp dw / db accumulators, one partial row per CTA
@@ -152,15 +160,16 @@ int rorl_addnorm_fwd(const float* x, const float* residual, const float* w, cons
                      float* residual_out, float* mean, float* rstd, int64_t rows, int64_t C, float eps, int is_rms,
                      cudaStream_t stream) {
     if (!x || !w || !y || !rstd) return RORL_ERR_ARG;
-    if (rows <= 0 || C <= 0 || C % 128 || C > 1024) return RORL_ERR_SHAPE;
+    if (rows <= 0 || C <= 0 || C % 4 || C > 1024) return RORL_ERR_SHAPE;
     int64_t nb = (rows + kNormWarps - 1) / kNormWarps;
     if (nb > 148 * 16) nb = 148 * 16;
     dim3 grid((unsigned)nb);
-    switch (C / 128) {
-        case 1: addnorm_fwd_kernel<1><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, eps, is_rms); break;
-        case 2: addnorm_fwd_kernel<2><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, eps, is_rms); break;
-        case 4: addnorm_fwd_kernel<4><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, eps, is_rms); break;
-        case 8: addnorm_fwd_kernel<8><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, eps, is_rms); break;
+    const int vpl = C <= 128 ? 1 : (C <= 256 ? 2 : (C <= 512 ? 4 : 8));
+    switch (vpl) {
+        case 1: addnorm_fwd_kernel<1><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, (int)C, eps, is_rms); break;
+        case 2: addnorm_fwd_kernel<2><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, (int)C, eps, is_rms); break;
+        case 4: addnorm_fwd_kernel<4><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, (int)C, eps, is_rms); break;
+        case 8: addnorm_fwd_kernel<8><<<grid, kNormThreads, 0, stream>>>(x, residual, w, b, y, residual_out, mean, rstd, rows, (int)C, eps, is_rms); break;
         default: return RORL_ERR_SHAPE;
     }
     RORL_RETURN_LAUNCH();
@@ -172,13 +181,14 @@ int rorl_addnorm_bwd(const float* dy, const float* dres_out, const float* r, con
     if (!dy || !r || !w || !rstd || !dx || !dw_part) return RORL_ERR_ARG;
     if (!is_rms && !mean) return RORL_ERR_ARG;
     if (has_bias && !db_part) return RORL_ERR_ARG;
-    if (rows <= 0 || C <= 0 || C % 128 || C > 1024) return RORL_ERR_SHAPE;
+    if (rows <= 0 || C <= 0 || C % 4 || C > 1024) return RORL_ERR_SHAPE;
     dim3 grid((unsigned)rorl_addnorm_nparts(rows));
-    switch (C / 128) {
-        case 1: addnorm_bwd_kernel<1><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, is_rms, has_bias); break;
-        case 2: addnorm_bwd_kernel<2><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, is_rms, has_bias); break;
-        case 4: addnorm_bwd_kernel<4><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, is_rms, has_bias); break;
-        case 8: addnorm_bwd_kernel<8><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, is_rms, has_bias); break;
+    const int vpl = C <= 128 ? 1 : (C <= 256 ? 2 : (C <= 512 ? 4 : 8));
+    switch (vpl) {
+        case 1: addnorm_bwd_kernel<1><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, (int)C, is_rms, has_bias); break;
+        case 2: addnorm_bwd_kernel<2><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, (int)C, is_rms, has_bias); break;
+        case 4: addnorm_bwd_kernel<4><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, (int)C, is_rms, has_bias); break;
+        case 8: addnorm_bwd_kernel<8><<<grid, kNormThreads, 0, stream>>>(dy, dres_out, r, w, mean, rstd, dx, dw_part, db_part, rows, (int)C, is_rms, has_bias); break;
         default: return RORL_ERR_SHAPE;
     }
     RORL_RETURN_LAUNCH();

@@ -1,0 +1,247 @@
+"""GPU parity of every C-ABI kernel (called through rorl_b200.kernels -> ctypes -> librorl_b200.so)
+against (1) the committed golden fixtures produced by the unmodified reference and (2) the pinned
+oracle on the same seeded inputs.  Tolerance: 1e-3 relative fp32 (BASELINE.json), in practice ~1e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import T, assert_close, load_npz
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def K():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import rorl_b200.kernels as K
+    return K
+
+
+def G(a, grad=False):
+    return T(a, "cuda", grad)
+
+
+# ------------------------------------------------------------------------------------------------ gilr
+def test_gilr_golden(K):
+    g = load_npz("ops_gilr.npz")
+    v, f = G(g["v"], True), G(g["f"], True)
+    h = K.real_scan_tie_input_gate(v, f)
+    assert_close(h, g["h"], TOL, "h")
+    dv, df = torch.autograd.grad(h, (v, f), G(g["dh"]))
+    assert_close(dv, g["dv"], TOL, "dv")
+    assert_close(df, g["df"], TOL, "df")
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 4), (2, 5, 36), (4, 257, 256), (3, 130, 100), (32, 1002, 256)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_gilr_vs_oracle(K, shape, fused):
+    from oracle import ops as O
+    B, L, C = shape
+    gen = torch.Generator().manual_seed(B * 1000 + L)
+    uv, uf = torch.randn(B, L, C, generator=gen), torch.randn(B, L, C, generator=gen) + 1.0
+    start = (torch.rand(B, L, 1, generator=gen) < 0.05).float()
+    start[:, 0] = 1
+    if L > 3:
+        start[0, 2:4] = 1      # consecutive resets
+    dh = torch.randn(B, L, C, generator=gen)
+    # oracle
+    a, b = uv.clone().requires_grad_(), uf.clone().requires_grad_()
+    if fused:
+        v, f = torch.tanh(a), torch.sigmoid(b) * (1 - start)
+    else:
+        v, f = a, torch.sigmoid(b).detach().requires_grad_()
+        b = f
+    h_ref, _ = O.gilr_scan(v, f)
+    ga_ref, gb_ref = torch.autograd.grad(h_ref, (a, b), dh)
+    # kernel
+    if fused:
+        x, y = uv.cuda().requires_grad_(), uf.cuda().requires_grad_()
+        h = K.gilr_fused_scan(x, y, start.cuda())
+    else:
+        x, y = uv.cuda().requires_grad_(), f.detach().cuda().requires_grad_()
+        h = K.real_scan_tie_input_gate(x, y)
+    assert_close(h, h_ref, TOL, "h")
+    gx, gy = torch.autograd.grad(h, (x, y), dh.cuda())
+    assert_close(gx, ga_ref, TOL, "d_v")
+    assert_close(gy, gb_ref, TOL, "d_f")
+
+
+# ------------------------------------------------------------------------------------------------ lru
+def test_lru_golden(K):
+    g = load_npz("ops_lru.npz")
+    vr, vi, fr, fi = (G(g[k], True) for k in ("vr", "vi", "fr", "fi"))
+    hr, hi = K.complex_scan(vr, vi, fr, fi, G(g["h0r"]), G(g["h0i"]), None)
+    assert_close(hr, g["hr"], TOL, "hr")
+    assert_close(hi, g["hi"], TOL, "hi")
+    gs = torch.autograd.grad((hr, hi), (vr, vi, fr, fi), (G(g["gr"]), G(g["gi"])))
+    for got, k in zip(gs, ("dvr", "dvi", "dfr", "dfi")):
+        assert_close(got, g[k], TOL, k)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 4), (2, 67, 40), (4, 257, 256), (8, 1002, 256)])
+@pytest.mark.parametrize("detach", [False, True])
+def test_lru_vs_oracle(K, shape, detach):
+    from oracle import ops as O
+    B, L, C = shape
+    gen = torch.Generator().manual_seed(L)
+    mag = 0.9 + 0.099 * torch.rand(C, generator=gen)
+    ph = 6.28 * torch.rand(C, generator=gen)
+    start = (torch.rand(B, L, 1, generator=gen) < 0.03).float()
+    fr = (mag * torch.cos(ph)).expand(B, L, C) * (1 - start)
+    fi = (mag * torch.sin(ph)).expand(B, L, C) * (1 - start)
+    vr, vi = torch.randn(B, L, C, generator=gen), torch.randn(B, L, C, generator=gen)
+    h0r, h0i = torch.randn(B, 1, C, generator=gen), torch.randn(B, 1, C, generator=gen)
+    gd = (torch.rand(B, L, 1, generator=gen) < 0.1).float() if detach else None
+    gr, gi = torch.randn(B, L, C, generator=gen), torch.randn(B, L, C, generator=gen)
+    cpu_in = [t.clone().contiguous().requires_grad_() for t in (vr, vi, fr, fi)]
+    hr_ref, hi_ref = O.lru_scan(*cpu_in, h0r, h0i, gd)
+    ref = torch.autograd.grad((hr_ref, hi_ref), cpu_in, (gr, gi))
+    gpu_in = [t.clone().contiguous().cuda().requires_grad_() for t in (vr, vi, fr, fi)]
+    hr, hi = K.complex_scan(*gpu_in, h0r.cuda(), h0i.cuda(), None if gd is None else gd.cuda())
+    assert_close(hr, hr_ref, TOL, "hr")
+    assert_close(hi, hi_ref, TOL, "hi")
+    got = torch.autograd.grad((hr, hi), gpu_in, (gr.cuda(), gi.cuda()))
+    for a, b, n in zip(got, ref, ("dvr", "dvi", "dfr", "dfi")):
+        assert_close(a, b, TOL, n)
+
+
+# ------------------------------------------------------------------------------------------------ selective scan
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_selscan_golden(K, tag):
+    g = load_npz(f"ops_selscan_{tag}.npz")
+    names = ("u", "delta", "A", "B", "C", "D", "z", "bias")
+    u, delta, A, Bm, Cm, Dk, z, bias = (G(g[k], True) for k in names)
+    out, last = K.selective_scan_fn(u, delta, A, Bm, Cm, G(g["start"]), Dk, z=z, delta_bias=bias, delta_softplus=True,
+                                    return_last_state=True)
+    assert_close(out, g["out"], TOL, "out")
+    assert_close(last, g["last"], TOL, "last")
+    gs = torch.autograd.grad(out, (u, delta, A, Bm, Cm, Dk, z, bias), G(g["dout"]))
+    for got, k in zip(gs, ("du", "ddelta", "dA", "dB", "dC", "dD", "dz", "dbias")):
+        assert_close(got, g[k], TOL, k)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, D=64, L=130, N=16, z=True, sp=True),
+    dict(B=1, D=36, L=33, N=32, z=False, sp=False),
+    dict(B=2, D=96, L=70, N=64, z=True, sp=True),
+    dict(B=3, D=128, L=16, N=32, z=True, sp=True),
+    dict(B=2, D=512, L=1018, N=32, z=True, sp=True),
+])
+def test_selscan_vs_oracle(K, cfg):
+    from oracle import ops as O
+    B, D, L, N = cfg["B"], cfg["D"], cfg["L"], cfg["N"]
+    gen = torch.Generator().manual_seed(L + N)
+    rn = lambda *s: torch.randn(*s, generator=gen)
+    u, delta = rn(B, D, L), 0.5 * rn(B, D, L) - 1.0
+    z = rn(B, D, L) if cfg["z"] else None
+    A = -torch.exp(0.5 * rn(D, N))
+    Bm, Cm = rn(B, N, L), rn(B, N, L)
+    Dk, bias = rn(D), 0.3 * rn(D)
+    if not cfg["sp"]:
+        delta = delta.abs() * 0.2
+    st = (torch.rand(B, 1, L, generator=gen) < 0.02).float()
+    st[:, :, 0] = 1
+    if L > 40:
+        st[0, :, 31:33] = 1       # reset across the 32-step tile / 16-step chunk boundaries
+        st[0, :, 15] = 1
+        st[0, :, 16] = 1
+    start = st.expand(B, D, L).contiguous()
+    dout = rn(B, D, L)
+    ins = [u, delta, A, Bm, Cm, Dk, bias] + ([z] if z is not None else [])
+    cpu = [t.clone().requires_grad_() for t in ins]
+    out_ref, last_ref = O.selective_scan(cpu[0], cpu[1], cpu[2], cpu[3], cpu[4], start, cpu[5],
+                                         z=cpu[7] if z is not None else None, delta_bias=cpu[6],
+                                         delta_softplus=cfg["sp"], return_last_state=True)
+    ref = torch.autograd.grad(out_ref, cpu, dout)
+    gpu = [t.clone().cuda().requires_grad_() for t in ins]
+    out, last = K.selective_scan_fn(gpu[0], gpu[1], gpu[2], gpu[3], gpu[4], start.cuda(), gpu[5],
+                                    z=gpu[7] if z is not None else None, delta_bias=gpu[6],
+                                    delta_softplus=cfg["sp"], return_last_state=True)
+    assert_close(out, out_ref, TOL, "out")
+    assert_close(last, last_ref, TOL, "last_state")
+    got = torch.autograd.grad(out, gpu, dout.cuda())
+    for a, b, n in zip(got, ref, ["du", "ddelta", "dA", "dB", "dC", "dD", "dbias", "dz"]):
+        assert_close(a, b, TOL, n)
+
+
+def test_selscan_strided_inputs(K):
+    """u / z as column slices of one wider projection output, B / C as slices of x_dbl (the layout the
+    smamba mixer feeds the kernel)."""
+    from oracle import ops as O
+    B, L, D, N, R = 2, 50, 64, 32, 16
+    gen = torch.Generator().manual_seed(3)
+    xz = torch.randn(B, L, 2 * D, generator=gen)
+    xdbl = torch.randn(B, L, R + 2 * N, generator=gen)
+    delta = torch.randn(B, L, D, generator=gen) * 0.3
+    A = -torch.exp(0.3 * torch.randn(D, N, generator=gen))
+    start = torch.zeros(B, L, 1)
+    start[:, 0] = 1
+    start[1, 20] = 1
+    ref = O.selective_scan(xz[..., :D].transpose(1, 2), delta.transpose(1, 2), A, xdbl[..., R:R + N].transpose(1, 2),
+                           xdbl[..., R + N:].transpose(1, 2), start.transpose(1, 2).expand(B, D, L), None,
+                           z=xz[..., D:].transpose(1, 2), delta_softplus=True).transpose(1, 2)
+    xzg, xdg = xz.cuda(), xdbl.cuda()
+    y = K.selective_scan_tm(xzg[..., :D], delta.cuda(), A.cuda(), xdg[..., R:R + N], xdg[..., R + N:], None,
+                            xzg[..., D:], None, start.cuda(), True)
+    assert_close(y, ref, TOL, "y")
+
+
+# ------------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("K_", [2, 4, 8, 16])
+def test_conv1d_silu_vs_oracle(K, K_):
+    from oracle import ops as O
+    B, L, D = 3, 300, 96
+    gen = torch.Generator().manual_seed(K_)
+    x = torch.randn(B, L, D, generator=gen)
+    w, b = 0.3 * torch.randn(D, 1, K_, generator=gen), 0.1 * torch.randn(D, generator=gen)
+    mask = (torch.rand(B, L, 1, generator=gen) > 0.1).float()
+    dy = torch.randn(B, L, D, generator=gen)
+    cx, cw, cb = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    ref = O.causal_conv1d_silu(cx.transpose(1, 2), cw, cb, mask.transpose(1, 2)).transpose(1, 2)
+    rg = torch.autograd.grad(ref, (cx, cw, cb), dy)
+    gx, gw, gb = x.cuda().requires_grad_(), w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y = K.causal_conv1d_silu(gx, gw, gb, mask.cuda())
+    assert_close(y, ref, TOL, "y")
+    gg = torch.autograd.grad(y, (gx, gw, gb), dy.cuda())
+    for a, r, n in zip(gg, rg, ("dx", "dw", "db")):
+        assert_close(a, r, TOL, n)
+
+
+# ------------------------------------------------------------------------------------------------ add + norm
+def test_addnorm_golden(K):
+    g = load_npz("ops_addnorm.npz")
+    x, r, w, b = (G(g[k], True) for k in ("x", "r", "w", "b"))
+    y, res = K.layer_norm_fn(x, w, b, residual=r, eps=1e-8, prenorm=True, residual_in_fp32=True)
+    assert_close(y, g["y"], TOL, "y")
+    assert torch.equal(res.cpu(), torch.from_numpy(g["res"])), "residual must be the exact fp32 sum"
+    gs = torch.autograd.grad((y, res), (x, r, w, b), (G(g["dy"]), G(g["dres"])))
+    for got, k in zip(gs, ("dx", "dr", "dw", "db")):
+        assert_close(got, g[k], TOL, k)
+    y2 = K.rms_norm_fn(x, w, None, residual=r, eps=1e-8, prenorm=False, residual_in_fp32=True)
+    assert_close(y2, g["y_rms"], TOL, "y_rms")
+    gs = torch.autograd.grad(y2, (x, r, w), G(g["dy"]))
+    for got, k in zip(gs, ("dx_rms", "dr_rms", "dw_rms")):
+        assert_close(got, g[k], TOL, k)
+
+
+@pytest.mark.parametrize("C", [16, 256, 512])
+@pytest.mark.parametrize("rms", [False, True])
+def test_addnorm_vs_oracle(K, C, rms):
+    from oracle import ops as O
+    rows = 5000
+    gen = torch.Generator().manual_seed(C)
+    x, r = torch.randn(rows, C, generator=gen), torch.randn(rows, C, generator=gen)
+    w, b = torch.randn(C, generator=gen), torch.randn(C, generator=gen)
+    dy, dres = torch.randn(rows, C, generator=gen), torch.randn(rows, C, generator=gen)
+    cin = [t.clone().requires_grad_() for t in (x, r, w, b)]
+    y_ref, res_ref = O.add_norm(cin[0], cin[2], None if rms else cin[3], cin[1], 1e-8, True, rms)
+    ref = torch.autograd.grad((y_ref, res_ref), cin[:3] + ([] if rms else [cin[3]]), (dy, dres))
+    gin = [t.clone().cuda().requires_grad_() for t in (x, r, w, b)]
+    y, res = K.layer_norm_fn(gin[0], gin[2], None if rms else gin[3], residual=gin[1], eps=1e-8, prenorm=True,
+                             is_rms_norm=rms)
+    assert_close(y, y_ref, TOL, "y")
+    got = torch.autograd.grad((y, res), gin[:3] + ([] if rms else [gin[3]]), (dy.cuda(), dres.cuda()))
+    for a, c, n in zip(got, ref, ("dx", "dr", "dw", "db")):
+        assert_close(a, c, TOL, n)
