@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the recurrent off-policy update hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one complete SAC update (`train_one_batch`: sample -> target Q -> critic step + Polyak ->
+actor step -> alpha step; 5 encoder forwards, 2 backwards) with the smamba_s32_c16_b2_nln encoder on a
+synthetic HalfCheetah-V-shaped replay (obs 9, act 6) of 32 full 1000-step trajectories PER GPU
+(weak scaling: N GPUs update on 32*N trajectories, trajectory-sharded, NCCL gradient all-reduce).
+Metric: trajectory-steps/s = valid transitions updated on per second, whole job.
+
+  value  : K updates with the replay resident in HBM (host plan + device gather inside the step), CUDA events,
+           max over ranks.
+  e2e    : same update through the public API fed from HOST memory, the way the reference feeds it: per step a
+           pinned host batch is copied H2D and the logged scalars are read back D2H, inside the timed region.
+  roofline: the selective-scan kernel (forward or backward, whichever takes the larger share), timed alone
+           with CUDA events on its launch stream at the workload's shape.
+  cpu_baseline: the oracle's CPU port of the reference update with the GRU encoder (the reference's own
+           CPU-runnable config) on the same 32x1000 shape, on this box's host cores.
+`--impl reference` times the oracle port (CPU, all host threads) on a bounded sample of the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_DIM, A_DIM, T_LEN, N_TRAJ = 9, 6, 1000, 32
+ENCODER = os.environ.get("RORL_BENCH_ENCODER", "smamba_s32_c16_b2_nln")
+ALGO = os.environ.get("RORL_BENCH_ALGO", "sac")
+METRIC = "sac_update_trajectory_steps_per_s"
+
+
+def model_kwargs(enc, value, hidden=256):
+    return dict(state_dim=S_DIM, action_dim=A_DIM, embedding_size=128, embedding_hidden=[hidden, hidden],
+                embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', enc, 'fc'],
+                uni_model_hidden=[256, 256], uni_model_activations=['elu', 'elu', 'linear'],
+                uni_model_layer_type=(['efc-8'] * 3 if value else ['fc'] * 3), fix_rnn_length=0,
+                uni_model_input_mapping_dim=128, reward_input=False, last_action_input=True, last_state_input=True,
+                separate_encoder=True)
+
+
+HP = dict(gamma=0.99, sac_tau=0.995, policy_update_per=1, redq_m=2, policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5,
+          rnn_value_lr=1e-5, alpha_lr=1e-4, target_entropy_ratio=1.0, sac_batch_size=N_TRAJ * T_LEN - 1,
+          max_buffer_transition_num=N_TRAJ * T_LEN + 8)
+
+
+def synth_trajectory(rng, T=T_LEN):
+    """One trajectory in replay column order: state|last_state|last_action|action|next_state|reward|mask|start|done|
+    reward_input|timeout  (SURVEY.md 8d 'Synthetic inputs')."""
+    s = rng.standard_normal((T + 1, S_DIM))
+    a = np.tanh(rng.standard_normal((T, A_DIM)))
+    r = rng.standard_normal((T, 1))
+    z = np.zeros
+    last_s = np.vstack((z((1, S_DIM)), s[:T - 1]))
+    last_a = np.vstack((z((1, A_DIM)), a[:T - 1]))
+    r_in = np.vstack((z((1, 1)), r[:T - 1]))
+    start = z((T, 1)); start[0] = 1
+    done = z((T, 1)); done[-1] = 1
+    return np.hstack((s[:T], last_s, last_a, a, s[1:], r, np.ones((T, 1)), start, done, r_in, done))
+
+
+def template_transition():
+    from rorl_b200.buffers.transition_buffer.replay_memory import Transition
+    z = np.zeros
+    return Transition(state=z((1, S_DIM)), last_state=z((1, S_DIM)), last_action=z((1, A_DIM)), action=z((1, A_DIM)),
+                      next_state=z((1, S_DIM)), reward=0.0, logp=None, mask=1, done=False, timeout=False, start=True,
+                      reward_input=z((1, 1)))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append([x.strip() for x in out])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def summary(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rorl_b200._native as NV
+    from rorl_b200.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run"
+    torch.manual_seed(0)            # identical replicas on every rank
+    np.random.seed(0)               # identical sampler / REDQ stream on every rank
+    cls = SACFullLengthRNNREDQ_SEP_OPTIM if ALGO == "sac" else TD3FullLengthRNNREDQ_SEP_OPTIM
+    alg = cls(dict(HP), model_kwargs(ENCODER, False), model_kwargs(ENCODER, True), T_LEN, device=dev, dist_group=group)
+    alg.replay_buffer._init_memory_buffer(template_transition())
+    rng = np.random.RandomState(1000 + rank)   # every rank owns different trajectories (trajectory sharding)
+    for _ in range(N_TRAJ):
+        alg.replay_buffer.push_trajectory_array(synth_trajectory(rng))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm -------------------------------------------------------------------------------------
+    step_dev = lambda: alg.train_one_batch(sync=False)
+    for _ in range(args.warmup):
+        out = step_dev()
+    valid_steps = out["real_batch_size"]
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    l0 = NV.launch_count()
+    ms_total = timed(step_dev, args.steps)
+    launches = NV.launch_count() - l0
+    clk = clocks.summary() if clocks else None
+    ms_per_step = ms_total / args.steps
+    value = valid_steps * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: host batch -> H2D -> update -> D2H scalars, every step -------------------------------------
+    plan = alg.replay_buffer.plan_trajs(HP["sac_batch_size"], None, nest_stack_trajs=alg.allow_nest_stack)
+    b_dev, v_dev = alg.replay_buffer.gather_device(plan)
+    host_batch = b_dev.contiguous().cpu().pin_memory()
+    host_valid = v_dev.contiguous().cpu().pin_memory()
+
+    def step_e2e():
+        res = alg.update_on_host_batch(host_batch, host_valid, plan.total_size, plan.lens, sync=True)
+        assert np.isfinite(res["critic_loss"])
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    e2e_steps = max(3, args.steps // 2)
+    ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e = {"value": valid_steps * world / (ms_e2e * 1e-3), "unit": "trajectory-steps/s",
+           "h2d_bytes_per_step": int(host_batch.numel() * 4 + host_valid.numel() * 4),
+           "d2h_bytes_per_step": int(alg._stats.numel() * 4 + alg.Q_guard.state.numel() * 8 + 4), "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {"metric": METRIC, "value": value, "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ALGO.upper()} update, {ENCODER} encoder, {N_TRAJ} trajectories x {T_LEN} steps per GPU "
+                                   f"(obs {S_DIM}, act {A_DIM}, efc-8 twin-Q head, REDQ m=2, RESeL lr split)",
+                       "global_trajectories": N_TRAJ * world, "valid_steps_per_update": valid_steps * world,
+                       "parallelism": f"dp{world} (trajectory-sharded, NCCL grad all-reduce)" if world > 1 else "single GPU",
+                       "l2": "working set per step (activations > 1 GB) exceeds the 126 MB L2; no flush needed"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches)}
+    line["roofline"] = scan_roofline(alg, dev, ms_per_step)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(encoder="gru", n_traj=N_TRAJ, updates=2, warm=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def scan_roofline(alg, dev, ms_per_step):
+    """Time the selective-scan kernels alone at the workload shape [B=32, L=1018, D=512, N=32] with CUDA events on
+    the launch stream.  Operands (4 x 66.7 MB) exceed L2, so consecutive launches do not hit in cache."""
+    import torch
+    import rorl_b200.kernels as K
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    B, L, D, Ns = N_TRAJ, T_LEN + 18, 512, 32
+    g = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    u, delta, z = rn(B, L, D).requires_grad_(), (0.5 * rn(B, L, D) - 1).requires_grad_(), rn(B, L, D).requires_grad_()
+    Bm, Cm = rn(B, L, Ns).requires_grad_(), rn(B, L, Ns).requires_grad_()
+    A = (-torch.exp(0.3 * rn(D, Ns))).requires_grad_()
+    Dk, bias = rn(D).requires_grad_(), rn(D).requires_grad_()
+    start = torch.zeros(B, L, device=dev); start[:, :18] = 1
+    dy = rn(B, L, D)
+
+    def t(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e-3
+
+    with torch.no_grad():
+        t_fwd = t(lambda: K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True))
+    y = K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True)
+    t_both = t(lambda: torch.autograd.grad(K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True), (u, delta, A, Bm, Cm, Dk, z, bias), dy), n=10)
+    t_fwd_ck = t(lambda: K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True), n=10)   # forward incl. checkpoints
+    t_bwd = max(t_both - t_fwd_ck, 1e-9)
+    bytes_fwd = 4 * (4 * B * D * L + 2 * B * Ns * L + B * L)
+    bytes_bwd = 4 * (7 * B * D * L + 4 * B * Ns * L)
+    # per update: 2 blocks x (5 forward, 2 backward) launches
+    share_fwd, share_bwd = 10 * t_fwd / (ms_per_step * 1e-3), 4 * t_bwd / (ms_per_step * 1e-3)
+    if share_bwd > share_fwd:
+        name, ach, traffic = "selscan_bwd_kernel<32>", bytes_bwd / t_bwd / 1e9, bytes_bwd
+    else:
+        name, ach, traffic = "selscan_fwd_kernel<32>", bytes_fwd / t_fwd / 1e9, bytes_fwd
+    return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "algorithmic_bytes_per_launch": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+            "fwd": {"us": t_fwd * 1e6, "GBps": bytes_fwd / t_fwd / 1e9, "share_of_step": share_fwd},
+            "bwd": {"us": t_bwd * 1e6, "GBps": bytes_bwd / t_bwd / 1e9, "share_of_step": share_bwd},
+            "note": "selective scan at d_state=32 is MUFU/FMA-pipe bound, not HBM bound (SURVEY.md App. F)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_update_runner(encoder, n_traj, algo="sac"):
+    """Build the oracle's CPU update (test infrastructure; allowed here as the cpu_baseline / reference leg)."""
+    import torch
+    from oracle import model as OM, sampler as OS, update as OU
+    from rorl_b200.policy_value_models.make_models import make_policy_model, make_value_model
+    torch.manual_seed(0)
+    np.random.seed(0)
+    pk, vk = model_kwargs(encoder, False), model_kwargs(encoder, True)
+    pol, val = make_policy_model(pk, algo, False), make_value_model(vk, algo, False)   # weights only (CPU tensors)
+    skip = 1 + max([l.d_conv for l in pol.embedding_network.layer_list if hasattr(l, 'd_conv')] + [0])
+    buf = OS.RefNestedReplay(n_traj * T_LEN + 8, T_LEN, additional_history_len=skip - 1)
+    rng = np.random.RandomState(1000)
+    for _ in range(n_traj):
+        rows = synth_trajectory(rng)
+        if buf.buf is None:
+            t = template_transition()
+            buf._init(t)
+        n = rows.shape[0]
+        buf.traj_start.append(buf.ptr)
+        buf.buf[buf.ptr:buf.ptr + n] = rows
+        buf.ptr += n
+        buf.traj_len.append(n)
+        buf.count += n
+    hp = dict(HP, sac_batch_size=n_traj * T_LEN - 1, sample_std=0.1, target_action_noise_std=0.04, target_action_noise_clip=0.12)
+    gen = torch.Generator().manual_seed(1)
+    upd = OU.RefUpdate(pol.state_dict(), val.state_dict(), OM.ModelSpec(**pk), OM.ModelSpec(**vk), hp, buf,
+                       lambda shape: torch.randn(shape, generator=gen), algo=algo, redq=True,
+                       allow_nest_stack=('gru' not in encoder))
+    return upd, n_traj * T_LEN
+
+
+def cpu_baseline(encoder, n_traj, updates, warm):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    upd, valid = oracle_update_runner(encoder, n_traj)
+    for _ in range(warm):
+        upd.train_one_batch()
+    t0 = time.perf_counter()
+    for _ in range(updates):
+        upd.train_one_batch()
+    dt = (time.perf_counter() - t0) / updates
+    return {"value": valid / dt, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{updates} timed SAC updates (after {warm} warm-up) of the oracle CPU port with the {encoder} encoder on "
+                      f"{n_traj} trajectories x {T_LEN} steps, torch CPU ops on {cores} threads", "s_per_update": dt}
+
+
+def run_reference(args):
+    """Reference arm: the oracle's CPU port of the same config (the Python reference itself cannot travel to this
+    box; its selective_scan_cuda binary does not exist anywhere).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_traj = int(os.environ.get("RORL_REF_TRAJ", "2"))
+    upd, valid = oracle_update_runner(ENCODER, n_traj, ALGO)
+    for _ in range(args.warmup):
+        upd.train_one_batch()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        upd.train_one_batch()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = valid / dt
+    sample = (f"each step = one full {ALGO.upper()} update of the oracle CPU port ({ENCODER}, GPU-path semantics via "
+              f"selective_scan_ref restated) on {n_traj} trajectories x {T_LEN} steps (bounded sample of the 32 x 1000 workload)")
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "trajectory-steps/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"{ALGO.upper()} update, {ENCODER} encoder, {N_TRAJ} trajectories x {T_LEN} steps per GPU "
+                                             f"(obs {S_DIM}, act {A_DIM}, efc-8 twin-Q head, REDQ m=2, RESeL lr split)"},
+                      "cpu_baseline": {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        a.steps = a.steps if a.steps is not None else 3
+        a.warmup = a.warmup if a.warmup is not None else 1
+        run_reference(a)
+    else:
+        a.steps = a.steps if a.steps is not None else 20
+        a.warmup = max(3, a.warmup if a.warmup is not None else 3)
+        run_ours(a)

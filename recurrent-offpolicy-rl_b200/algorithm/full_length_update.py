@@ -1,0 +1,416 @@
+"""The recurrent off-policy update hot path: `train_one_batch()` of the full-length-trajectory SAC / TD3
+algorithms with ensemble-Q / REDQ targets and the RESeL per-encoder learning-rate split.
+
+Mirrors, step for step, the reference's
+  SACFullLengthRNNEnsembleQ.train_one_batch   ref: offpolicy_rnn/algorithm/sac_full_length_rnn_ensembleQ.py:297-467
+  _target_Q / _Q_loss / _policy_loss / _alpha_loss                                   :83-132
+  REDQ subset + mean aggregate                ref: sac_full_length_rnn_redq.py:16-47
+  TD3 targets / actor                         ref: td3_full_length_rnn_ensembleQ.py:23-71, td3_full_length_rnn_redq.py:14-50
+  prepare_param_list (RESeL groups)           ref: sac_full_length_rnn_redq_sep_optim.py:37-102
+  optimizers / log_alpha / target entropy     ref: sac.py:61-95
+with the B200-native restructuring:
+  * the batch never visits the host: host integer plan -> device gather (buffers/...nested_replay_memory.py);
+  * parameters, gradients, Adam moments and target parameters of each model live in flat fp32 arenas, so the
+    AdamW step + Polyak target update is ONE kernel per model (csrc/optim.cu) and a data-parallel gradient
+    all-reduce is ONE NCCL call per model;
+  * target-Q / guard / masked-TD / actor / entropy reductions are fused kernels producing the loss AND the
+    gradient seeds (csrc/losses.cu); no `.item()` inside the update -- logged scalars are gathered in one
+    device vector and read back once (or not at all with `sync=False`);
+  * the value network's parameters are frozen during the actor pass (the reference computes and then discards
+    those gradients, ref :122-123,268).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
+from ..policy_value_models.make_models import make_policy_model, make_value_model
+from ..utility.q_value_guard import QValueGuard
+
+DEFAULTS = dict(utd=1, policy_utd=1, randomize_mask=False, valid_number_post_randomized=0, random_trunc_traj=False,
+                randomize_first_hidden=False, gamma=0.99, sac_tau=0.995, policy_update_per=1, no_alpha_auto_tune=False,
+                policy_max_gradnorm=None, policy_embedding_max_gradnorm=None, value_max_gradnorm=None,
+                value_embedding_max_gradnorm=None, redq_m=2, target_action_noise_std=0.04,
+                target_action_noise_clip=0.12, policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5, rnn_value_lr=1e-4,
+                alpha_lr=1e-2, policy_l2_norm=0.0, value_l2_norm=0.0, sample_std=0.1, target_entropy_ratio=1.5,
+                sac_alpha=1.0, value_net_num=1, max_buffer_transition_num=1000000, sac_batch_size=1000)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# RESeL parameter groups (API-compatible helper) and the flat arena built from them
+# ------------------------------------------------------------------------------------------------------------------
+def prepare_param_list(model, rnn_lr, l2_norm):
+    """Param groups exactly as the reference builds them: modules whose name ends with 'encoder' and everything
+    that is not `embedding_model` keep the optimizer's base lr; every layer of the embedding network (pre-fc,
+    RNN, post-fc, norms) gets `rnn_lr` (ref: sac_full_length_rnn_redq_sep_optim.py:49-79)."""
+    groups = []
+    for k, v in model.contextual_modules.items():
+        kind = type(v).__name__
+        if k == 'embedding_model':
+            mods = [v.layer_list[0]] + [v.layer_list[i] for i in range(1, len(model.embedding_network.layer_list) - 1)] \
+                   + [v.layer_list[-1], v.activation_list]
+            for m in mods:
+                groups.append({"params": list(m.parameters(True)), "lr": rnn_lr, "weight_decay": l2_norm, "name": f"rnn-{kind}"})
+        else:
+            groups.append({"params": list(v.parameters(True)), "name": f"mlp-{kind}"})
+    return groups
+
+
+class FlatArena:
+    """All parameters of one model re-homed as views of one flat fp32 buffer (plus flat grad / Adam moments)."""
+
+    def __init__(self, model, device):
+        params = [p for p in model.parameters(True)]
+        seen, uniq = set(), []
+        for p in params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        self.offsets, n = [], 0
+        for p in uniq:
+            self.offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned inside the arena
+        self.numel = n
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, off in zip(uniq, self.offsets):
+                self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + p.numel()].view(p.shape)
+                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+
+    def offset_of(self, p) -> int:
+        for q, off in zip(self.params, self.offsets):
+            if q is p:
+                return off
+        raise KeyError
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, off in zip(self.params, self.offsets):     # autograd may have swapped .grad out; put the view back
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+
+
+class FusedAdamW:
+    """AdamW(betas=(0.9, 0.999), eps=1e-8) over a FlatArena with contiguous lr / weight-decay segments, fused with
+    the Polyak target update when a target arena is given (csrc/optim.cu)."""
+
+    def __init__(self, arena: FlatArena, groups: List[dict], lr: float, weight_decay: float, target: Optional[FlatArena] = None):
+        self.arena, self.target = arena, target
+        dev = arena.flat.device
+        self.m = torch.zeros_like(arena.flat)
+        self.v = torch.zeros_like(arena.flat)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        per_param = {}
+        for g in groups:
+            for p in g["params"]:
+                per_param[id(p)] = (g.get("lr", lr), g.get("weight_decay", weight_decay))
+        ends, lrs, wds = [], [], []
+        for p, off in zip(arena.params, arena.offsets):
+            cfg = per_param[id(p)]
+            end = off + (p.numel() + 3) // 4 * 4
+            if lrs and (lrs[-1], wds[-1]) == cfg:
+                ends[-1] = end
+            else:
+                ends.append(end), lrs.append(cfg[0]), wds.append(cfg[1])
+        assert len(ends) <= 64, 'too many lr segments; order modules so that groups are contiguous'
+        self.param_groups = [{"lr": a, "weight_decay": b, "end": e} for a, b, e in zip(lrs, wds, ends)]
+        self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
+        self.seg_lr = torch.tensor(lrs, dtype=torch.float64, device=dev)
+        self.seg_wd = torch.tensor(wds, dtype=torch.float64, device=dev)
+
+    def zero_grad(self):
+        self.arena.zero_grad()
+
+    def step(self, tau: Optional[float] = None, clip_value: float = 0.0):
+        tgt = self.target.flat if (self.target is not None and tau is not None) else None
+        N.call("rorl_adamw_polyak", N.ptr(self.arena.flat), N.ptr(self.arena.grad), N.ptr(self.m), N.ptr(self.v),
+               N.ptr(tgt), N.ptr(self.seg_end), N.ptr(self.seg_lr), N.ptr(self.seg_wd), len(self.param_groups),
+               self.arena.numel, 0.9, 0.999, 1e-8, float(tau if tau is not None else 1.0), N.ptr(self.step_count),
+               float(clip_value), N.stream())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the update
+# ------------------------------------------------------------------------------------------------------------------
+class FullLengthRNNUpdate:
+    """Holds what `train_one_batch` of the reference algorithm object touches and runs it.
+
+    Environment construction, rollout, evaluation and logging (ref: algorithm/sac.py:34-127,274-401) are out of
+    scope, so instead of reading them from an env the constructor takes `obs_dim`, `act_dim`,
+    `max_trajectory_len` and the model kwargs the reference derives from its flags (ref: sac.py:199-239).
+    """
+    base_algorithm = 'sac'
+    use_redq = True
+
+    def __init__(self, parameter, policy_args: dict, value_args: dict, max_trajectory_len: int, device=None,
+                 dist_group=None):
+        hp = dict(DEFAULTS)
+        hp.update(parameter if isinstance(parameter, dict) else vars(parameter))
+        self.parameter = SimpleNamespace(**hp)
+        for opt in ('policy_max_gradnorm', 'policy_embedding_max_gradnorm', 'value_max_gradnorm', 'value_embedding_max_gradnorm'):
+            if hp.get(opt) is not None:
+                raise NotImplementedError(f'{opt}: gradient clipping is not wired into the fused optimizer yet (all published configs leave it None)')
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = self.sample_device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('the update hot path runs on sm_100a kernels only; no CPU path exists')
+        self.discrete_env = False
+        self.dist_group = dist_group
+        td3 = self.base_algorithm == 'td3'
+        if td3:
+            self.parameter.no_alpha_auto_tune = True
+            policy_args = dict(policy_args, sample_std=self.parameter.sample_std)
+        self.policy_args, self.value_args = policy_args, value_args
+        assert self.parameter.value_net_num == 1
+        for item in value_args['uni_model_layer_type']:
+            assert item.startswith('e')
+        # models (ref: sac.py:61-70) --------------------------------------------------------------------------
+        self.policy = make_policy_model(policy_args, self.base_algorithm, False)
+        self.values = [make_value_model(value_args, self.base_algorithm, False)]
+        self.target_values = [make_value_model(value_args, self.base_algorithm, False)]
+        self.target_policy = make_policy_model(policy_args, self.base_algorithm, False)
+        for m in [self.policy, self.target_policy] + self.values + self.target_values:
+            m.to(self.device)
+        for net in (self.values[0].embedding_network.layer_list + self.target_values[0].embedding_network.layer_list
+                    + self.values[0].uni_network.layer_list + self.target_values[0].uni_network.layer_list):
+            if hasattr(net, 'desire_ndim'):                      # ref: sac_full_length_rnn_ensembleQ.py:25-32
+                net.desire_ndim = 4
+            if hasattr(net, 'in_proj') and hasattr(net.in_proj, 'desire_ndim'):
+                net.in_proj.desire_ndim = 4
+        a0 = math.log(self.parameter.sac_alpha) if self.parameter.no_alpha_auto_tune else 0.0
+        self.log_sac_alpha = torch.tensor([a0], dtype=torch.float32, device=self.device, requires_grad=True)
+        self.target_entropy = -float(policy_args['action_dim']) * self.parameter.target_entropy_ratio
+        self.replay_buffer = NestedMemoryArray(self.parameter.max_buffer_transition_num, max_trajectory_len,
+                                               additional_history_len=self._get_skip_len() - 1, device=self.device)
+        self.Q_guard = QValueGuard(True, True, 1 - 1e-3, device=self.device)
+        self.allow_nest_stack = self.allow_nest_stack_trajs()
+        self.grad_num = 0
+        self._finalize_models()
+        # scratch for the fused reductions
+        self._work = torch.zeros(int(N.lib().rorl_loss_work_floats(0)), dtype=torch.float32, device=self.device)
+        self._stats = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self._sel_all = None
+
+    # ---- construction helpers ---------------------------------------------------------------------------------
+    def _finalize_models(self):
+        """(Re)build arenas + optimizers after weights are in place; call again after load_state_dict."""
+        self._value_update(tau=0.0)
+        self.target_policy.copy_weight_from(self.policy, tau=0.0)
+        self.policy_arena = FlatArena(self.policy, self.device)
+        self.value_arena = FlatArena(self.values[0], self.device)
+        self.target_arena = FlatArena(self.target_values[0], self.device)
+        self.alpha_arena = SimpleNamespace(flat=self.log_sac_alpha.data, grad=torch.zeros_like(self.log_sac_alpha.data),
+                                           params=[self.log_sac_alpha], offsets=[0], numel=1, zero_grad=lambda: None)
+        p = self.parameter
+        self.optimizer_policy = FusedAdamW(self.policy_arena, prepare_param_list(self.policy, p.rnn_policy_lr, p.policy_l2_norm),
+                                           p.policy_lr, p.policy_l2_norm)
+        self.optimizer_value = FusedAdamW(self.value_arena, prepare_param_list(self.values[0], p.rnn_value_lr, p.value_l2_norm),
+                                          p.value_lr, p.value_l2_norm, target=self.target_arena)
+        # torch.optim.AdamW's default weight_decay (1e-2) applies: the reference passes only lr (ref: sac.py:90)
+        self.optimizer_alpha = FusedAdamW(self.alpha_arena, [{"params": [self.log_sac_alpha]}], p.alpha_lr, 1e-2)
+        self.value_parameters = list(self.values[0].parameters(True))
+        for m in self.values:
+            m.train()
+        for m in self.target_values:
+            m.eval()
+        self.target_policy.eval()
+        self.policy.train()
+        for q in self.target_arena.params + list(self.target_policy.parameters(True)):
+            q.requires_grad_(False)
+
+    def load_models(self, policy_sd=None, value_sd=None):
+        if policy_sd is not None:
+            self.policy.load_state_dict(policy_sd)
+        if value_sd is not None:
+            self.values[0].load_state_dict(value_sd)
+        self._finalize_models()
+
+    def _get_skip_len(self):
+        """1 + widest causal-conv window of any encoder layer (ref: sac_full_length_rnn_ensembleQ.py:57-68)."""
+        skip = 0
+        for net in (self.values[0].uni_network, self.values[0].embedding_network, self.policy.uni_network,
+                    self.policy.embedding_network):
+            for lid, layer in zip(net.layer_type, net.layer_list):
+                if 'smamba' in lid:
+                    skip = max(skip, layer.d_conv)
+        return skip + 1
+
+    def allow_nest_stack_trajs(self):
+        """ref: sac.py:130-138"""
+        for net in (self.values[0].uni_network, self.values[0].embedding_network, self.policy.uni_network,
+                    self.policy.embedding_network):
+            for lid in net.layer_type:
+                if 'transformer' in lid or 'gru' in lid:
+                    return False
+        return True
+
+    def _value_update(self, tau):
+        for v, t in zip(self.values, self.target_values):
+            t.copy_weight_from(v, tau)
+
+    # ---- fused reductions -----------------------------------------------------------------------------------------
+    def _target_Q(self, q_next, sel_idx, logp_next, reward, done, timeout, mask):
+        """y = r + (1 - done') * gamma * clamp(min_{sel} Q' - alpha * logp') and the guard update; fills
+        stats[0] = max|y|, stats[1] = n_valid."""
+        E, M = q_next.shape[0], q_next[0].numel()
+        m = torch.empty(M, dtype=torch.float32, device=self.device)
+        sel = torch.as_tensor(np.asarray(sel_idx), dtype=torch.int32).to(self.device, non_blocking=True)
+        # every operand is bound to a local until both launches are enqueued: a temporary freed right after
+        # data_ptr() would hand its block to the next temporary and the pointers would alias.
+        qn = q_next.contiguous()
+        lp = None if logp_next is None else logp_next.contiguous()
+        r_c, d_c, t_c, m_c = reward.contiguous(), done.contiguous(), timeout.contiguous(), mask.contiguous()
+        y = torch.empty_like(r_c)
+        N.call("rorl_target_minq", N.ptr(qn), N.ptr(sel), int(sel.numel()), E, M, N.ptr(lp), N.ptr(self.log_sac_alpha.data),
+               N.ptr(m), N.ptr(self.Q_guard.state), N.ptr(self._work), N.stream())
+        N.call("rorl_target_finish", N.ptr(m), N.ptr(r_c), N.ptr(d_c), N.ptr(t_c), N.ptr(m_c), float(self.parameter.gamma),
+               N.ptr(y), N.ptr(self.Q_guard.state), N.ptr(self._stats), N.ptr(self._work), M, N.stream())
+        return y
+
+    def _allreduce(self, t, op=None):
+        if self.dist_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.dist_group)
+
+    # ---- the hot path -----------------------------------------------------------------------------------------------
+    def train_one_batch(self, sync: bool = True) -> Dict:
+        """Sample a trajectory batch from the device-resident replay and run one update on it."""
+        p = self.parameter
+        assert p.utd == 1, 'utd > 1: call train_one_batch repeatedly'
+        # 1. sample (host plan, device gather) ------------------------------------------------------- ref :313-332
+        batch, batch_size, valid_ind, traj_len_array = self.replay_buffer.sample_trajs_device(
+            p.sac_batch_size, None, equalize_data_of_each_traj=True, nest_stack_trajs=self.allow_nest_stack)
+        return self.update_on_batch(batch, batch_size, valid_ind, traj_len_array, sync=sync)
+
+    def update_on_host_batch(self, host_batch: torch.Tensor, host_valid: torch.Tensor, batch_size: int,
+                             traj_len_array: np.ndarray, sync: bool = True) -> Dict:
+        """End-to-end entry for callers that sample on the host, as the reference does (ref :313-332): the
+        [rows, W, F] fp32 batch and [rows, W, 1] valid indicator come from (pinned) host memory."""
+        batch = host_batch.to(self.device, non_blocking=True)
+        valid = host_valid.to(self.device, non_blocking=True)
+        return self.update_on_batch(self.replay_buffer.array_to_transition(batch), batch_size, valid, traj_len_array, sync=sync)
+
+    def update_on_batch(self, batch, batch_size, valid_ind, traj_len_array, sync: bool = True) -> Dict:
+        p = self.parameter
+        td3 = self.base_algorithm == 'td3'
+        dev = self.device
+        state, last_state, action, last_action, next_state = batch.state, batch.last_state, batch.action, batch.last_action, batch.next_state
+        done, mask, reward, reward_input, timeout, rnn_start = batch.done, batch.mask, batch.reward, batch.reward_input, batch.timeout, batch.start
+        B, L = state.shape[0], state.shape[1]
+        # 2. target-pass side-band ------------------------------------------------------------------------ ref :338-341
+        d_valid = valid_ind[:, 1:] - valid_ind[:, :-1]
+        total_valid = valid_ind.clone()
+        total_valid[:, :-1] = torch.where(d_valid == 1, torch.ones_like(d_valid), total_valid[:, :-1])
+        d_start = rnn_start[:, 1:] - rnn_start[:, :-1]
+        total_start = rnn_start.clone()
+        total_start[:, :-1] = torch.where(d_start == -1, torch.zeros_like(d_start), total_start[:, :-1])
+        att = torch.zeros((B, L), dtype=torch.int32)                                                      # ref :358-366
+        k = min(traj_len_array.shape[1], L)
+        att[:, :k] = torch.from_numpy(traj_len_array[:, :k]).to(torch.int32)
+        tgt_att = torch.cat((att[:, 1:], torch.zeros((B, 1), dtype=torch.int32)), dim=-1)
+        att, tgt_att = att.to(dev, non_blocking=True), tgt_att.to(dev, non_blocking=True)
+        mk = lambda model: model.make_init_state(B, device=dev)
+        policy_hidden, target_policy_hidden = mk(self.policy), mk(self.policy)
+        target_hidden, value_hidden = mk(self.target_values[0]), mk(self.values[0])
+        for h in (target_policy_hidden, target_hidden):
+            h.set_rnn_start(total_start), h.set_mask(total_valid), h.set_attention_concat_mask(tgt_att)
+        for h in (value_hidden, policy_hidden):
+            h.set_rnn_start(rnn_start), h.set_mask(valid_ind), h.set_attention_concat_mask(att)
+        # 3. target Q (no grad) ------------------------------------------------------------------------------- ref :83-103
+        self.policy.eval()
+        with torch.no_grad():
+            pol_t = self.target_policy if (td3 and not self.use_redq) else self.policy
+            a_mean, _, a_next, logp_next, _, _ = pol_t.forward(next_state, state, action, target_policy_hidden, reward)
+            if td3:
+                noise = pol_t.noise_fn(a_mean) * p.target_action_noise_std
+                a_next = torch.clamp(a_mean + torch.clamp(noise, -p.target_action_noise_clip, p.target_action_noise_clip), -1, 1)
+                logp_next = None
+            q_next = self.target_values[0].forward(next_state, state, action, a_next, target_hidden, reward)[0]
+            E = q_next.shape[0]
+            sel = np.random.permutation(E)[:p.redq_m] if self.use_redq else np.arange(E)
+            target_Q = self._target_Q(q_next, sel, logp_next, reward, done, timeout, mask)
+        n_valid = self._stats[1:2]
+        if self.dist_group is not None:
+            self._sync_guard_and_count()
+        # 4. critic ------------------------------------------------------------------------------------------------ ref :105-114,261-295
+        for v in self.values:
+            v.train()
+        q = self.values[0].forward(state, last_state, last_action, action, value_hidden, reward_input)[0]
+        E, M = q.shape[0], q[0].numel()
+        dq = torch.empty((E, M), dtype=torch.float32, device=dev)
+        qc, tq_c, mask_c = q.contiguous(), target_Q.contiguous(), mask.contiguous()
+        N.call("rorl_q_loss_fwd_bwd", N.ptr(qc), N.ptr(tq_c), N.ptr(mask_c), N.ptr(n_valid),
+               N.ptr(self._stats[2:3]), N.ptr(dq), N.ptr(self._work), E, M, N.stream())
+        self.optimizer_value.zero_grad()
+        qc.backward(dq.view_as(qc))
+        self._allreduce(self.value_arena.grad)
+        self.optimizer_value.step(tau=p.sac_tau)   # + Polyak (ref :395)
+        for v in self.values:
+            v.eval()
+        self.policy.train()
+        # 5. actor + alpha ---------------------------------------------------------------------------------------- ref :116-132,405-432
+        did_policy = self.grad_num % p.policy_update_per == 0
+        if did_policy:
+            for w in self.value_arena.params:
+                w.requires_grad_(False)
+            try:
+                a_mean, _, a_samp, logp, _, _ = self.policy.forward(state, last_state, last_action, policy_hidden, reward_input)
+                a_in = a_mean if td3 else a_samp
+                qp = self.values[0].forward(state, last_state, last_action, a_in, value_hidden, reward_input, detach_embedding=True)[0]
+            finally:
+                for w in self.value_arena.params:
+                    w.requires_grad_(True)
+            qpc = qp.contiguous()
+            dqp = torch.empty((E, M), dtype=torch.float32, device=dev)
+            logp_c = None if td3 else logp.contiguous()
+            dlogp = None if td3 else torch.empty(M, dtype=torch.float32, device=dev)
+            N.call("rorl_actor_loss_fwd_bwd", N.ptr(qpc), N.ptr(logp_c), N.ptr(mask_c), N.ptr(n_valid),
+                   N.ptr(self.log_sac_alpha.data), float(self.target_entropy), 1 if self.use_redq else 0,
+                   N.ptr(self._stats[4:8]), N.ptr(dqp), N.ptr(dlogp), N.ptr(self._work), E, M, N.stream())
+            self.optimizer_policy.zero_grad()
+            if td3:
+                qpc.backward(dqp.view_as(qpc))
+            else:
+                torch.autograd.backward([qpc, logp_c], [dqp.view_as(qpc), dlogp.view_as(logp_c)])
+            self._allreduce(self.policy_arena.grad)
+            self.optimizer_policy.step()
+            if not p.no_alpha_auto_tune:
+                self.alpha_arena.grad.copy_(self._stats[7:8])
+                self._allreduce(self.alpha_arena.grad)
+                self.optimizer_alpha.step()
+                self.log_sac_alpha.data.clamp_(max=1.0)
+        self.grad_num += 1
+        # 6. logged scalars: one device vector, one read-back ---------------------------------------------------- ref :435-467
+        out = {'real_batch_size': batch_size, 'real_batch_traj_num': B, 'policy_updated': did_policy}
+        self.last_target_Q = target_Q
+        if not sync:
+            out['stats_device'] = self._stats
+            return out
+        s = self._stats.tolist()
+        g = self.Q_guard.state.tolist()
+        out.update({'critic_loss': s[2], 'target_q_max': s[0], 'log_alpha': float(self.log_sac_alpha.item()),
+                    'clip_min': g[0], 'clip_max': g[1], 'value_grad_norm': 0.0,
+                    'average_traj_len': self.replay_buffer.size / max(len(self.replay_buffer), 1)})
+        if did_policy:
+            out.update({'actor_loss': s[4], 'log_prob': s[5], 'policy_grad_norm': 0})
+            if not p.no_alpha_auto_tune:
+                out['alpha_loss'] = s[6]
+        return out
+
+    def _sync_guard_and_count(self):
+        """Data-parallel: make n_valid and the guard state identical on every rank."""
+        import torch.distributed as dist
+        self._allreduce(self._stats[1:2])
+        lo, hi = self.Q_guard.state[0:1], self.Q_guard.state[1:2]
+        self._allreduce(lo, dist.ReduceOp.MIN)
+        self._allreduce(hi, dist.ReduceOp.MAX)

@@ -1,0 +1,117 @@
+"""GPU parity of the complete update (`train_one_batch`) against the golden fixtures recorded from the
+UNMODIFIED reference (tests/golden/update_*.npz): same initial weights, same replay contents, same numpy
+RNG stream, the reference's own Gaussian draws injected.  Tolerances (BASELINE.json): <= 1e-3 relative for
+losses, gradients and updated parameters (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import T, assert_close, cfg_of, load_npz, nested_sd
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def fill_buffer(buf, Transition, rng, lens, S, A):
+    for Tn in lens:
+        last_s, last_a, last_r = np.zeros((1, S)), np.zeros((1, A)), np.zeros((1, 1))
+        s = rng.standard_normal((1, S))
+        for t in range(Tn):
+            a = np.tanh(rng.standard_normal((1, A)))
+            ns = rng.standard_normal((1, S))
+            r = float(rng.standard_normal())
+            done = t == Tn - 1
+            buf.mem_push(Transition(state=s, last_state=last_s, last_action=last_a, action=a, next_state=ns, reward=r,
+                                    logp=None, mask=1, done=done, timeout=done, start=(t == 0), reward_input=last_r))
+            last_s, last_a, last_r, s = s, a, np.array([[r]]), ns
+
+
+def build(tag):
+    from rorl_b200.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.buffers.transition_buffer.replay_memory import Transition
+    g = load_npz(f"update_{tag}.npz")
+    cfg = cfg_of(g)
+    c, hp = cfg["case"], cfg["hp"]
+    cls = SACFullLengthRNNREDQ_SEP_OPTIM if c["algo"] == "sac" else TD3FullLengthRNNREDQ_SEP_OPTIM
+    pk = {k: v for k, v in cfg["policy_kwargs"].items() if k != "sample_std"}
+    alg = cls(dict(hp, max_buffer_transition_num=1000), pk, cfg["value_kwargs"], max(c["lens"]), device=torch.device("cuda:0"))
+    assert alg._get_skip_len() == cfg["skip"]
+    assert alg.allow_nest_stack == cfg["allow_nest_stack"]
+    alg.load_models(nested_sd(g, "init/policy/", "cuda"), nested_sd(g, "init/value/", "cuda"))
+    fill_buffer(alg.replay_buffer, Transition, np.random.RandomState(cfg["np_seed_fill"]), c["lens"], c["S"], c["A"])
+    noises = iter([T(g[f"noise/{i}"], "cuda") for i in range(cfg["n_noise"])])
+
+    def noise_fn(like):
+        n = next(noises)
+        assert n.shape == like.shape
+        return n
+
+    alg.policy.noise_fn = noise_fn
+    alg.target_policy.noise_fn = noise_fn
+    np.random.seed(cfg["np_seed_run"])
+    return g, cfg, alg
+
+
+def module_params(model):
+    return {k: dict(m.named_parameters()) for k, m in model.contextual_modules.items()}
+
+
+@pytest.mark.parametrize("tag", ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru"])
+def test_update_matches_reference(tag):
+    g, cfg, alg = build(tag)
+    for call in range(cfg["case"]["calls"]):
+        log = alg.train_one_batch()
+        # gradients left in the arenas: critic grads (value), actor grads (policy)
+        vg = {k: {n: p.grad for n, p in m.items()} for k, m in module_params(alg.values[0]).items()}
+        pg = {k: {n: p.grad for n, p in m.items()} for k, m in module_params(alg.policy).items()}
+        for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "log_alpha", "target_q_max", "clip_min", "clip_max"):
+            key = f"c{call}/log/{k}"
+            if key in g and k in log:
+                ref = float(g[key])
+                assert abs(log[k] - ref) <= TOL * max(1.0, abs(ref)), (k, log[k], ref)
+        assert log["real_batch_size"] == int(g[f"c{call}/log/real_batch_size"])
+        worst = 0.0
+        for k, v in g.items():
+            if k.startswith(f"c{call}/vgrad/"):
+                mod, name = k[len(f"c{call}/vgrad/"):].split("/", 1)
+                worst = max(worst, assert_close(vg[mod][name], v, TOL, k))
+            if k.startswith(f"c{call}/pgrad/"):
+                mod, name = k[len(f"c{call}/pgrad/"):].split("/", 1)
+                worst = max(worst, assert_close(pg[mod][name], v, TOL, k))
+        for which, model in (("policy", alg.policy), ("value", alg.values[0]), ("target", alg.target_values[0])):
+            sd = model.state_dict()
+            for k, v in g.items():
+                pre = f"c{call}/{which}/"
+                if k.startswith(pre):
+                    mod, name = k[len(pre):].split("/", 1)
+                    worst = max(worst, assert_close(sd[mod][name], v, TOL, k))
+        assert abs(alg.log_sac_alpha.item() - float(g[f"c{call}/log_alpha"][0])) < 1e-6
+        print(f"{tag} call {call}: worst relative error {worst:.2e}")
+
+
+def test_sampler_device_bit_exact():
+    """Device gather == reference sample_trajs bit for bit (after the fp32 cast n2t applies)."""
+    from rorl_b200.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
+    from rorl_b200.buffers.transition_buffer.replay_memory import Transition
+    for tag in ("a", "b", "c", "d"):
+        g = load_npz(f"sampler_{tag}.npz")
+        c = cfg_of(g)
+        buf = NestedMemoryArray(500, c["max_step"], additional_history_len=c["skip_extra"], device=torch.device("cuda:0"))
+        fill_buffer(buf, Transition, np.random.RandomState(3), c["lens"], c["S"], c["A"])
+        np.random.seed(11)
+        for call in range(2):
+            tr, total, valid, lens = buf.sample_trajs_device(c["batch"], None, equalize_data_of_each_traj=True,
+                                                            nest_stack_trajs=c["nest"])
+            for n in tr._fields:
+                v = getattr(tr, n)
+                key = f"c{call}/{n}"
+                if v is None:
+                    assert key not in g
+                    continue
+                assert np.array_equal(v.cpu().numpy(), g[key].astype(np.float32)), (tag, call, n)
+            assert np.array_equal(valid.cpu().numpy(), g[f"c{call}/valid"].astype(np.float32))
+            assert np.array_equal(lens, g[f"c{call}/lens"])
+            assert total == int(g[f"c{call}/total"])
+            st = np.random.get_state()
+            assert st[2] == int(g[f"c{call}/rng_pos"])
