@@ -185,6 +185,21 @@ int rorl_adamw_polyak(float* p, const float* g, float* m, float* v, float* targe
 int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * tcgen05 tensor-core GEMM with fp32 parity (3xTF32 split accumulation in the TMEM accumulator).
+ * Replaces the cuBLAS fp32 SGEMMs behind nn.Linear / EnsembleLinear (ref: offpolicy_rnn/models/
+ * ensemble_linear_model.py:36-49; smamba projections, ref: offpolicy_rnn/models/smamba/mamba.py:176,231-233,252).
+ *   D[g][M, N] = act(A[g][M, K] * B[g][N, K]^T + bias[g][N]),  g = 0..G-1
+ * Both operands K-major (reduction dimension contiguous).  strideA / strideB == 0: operand shared by all g.
+ * act: 0 none, 1 ELU (Dpre, may be NULL, receives the pre-activation in D's layout for an exact ELU backward).
+ * passes: 3 = 3xTF32 (fp32 parity), 1 = plain TF32.  reduce_g != 0: the G products are
+ * summed into one D[M, N] (data-gradient of an ensemble layer with shared input).
+ * K, N, ld*, stride* multiples of 4; bases 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
+                 int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
+                 int64_t strideBias, int act, int passes, int reduce_g, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Trajectory gather: builds the padded, nest-stacked [rows, Lmax, F] fp32 batch of
  * NestedMemoryArray.sample_trajs directly from a device-resident fp32 ring buffer, following a
  * host-computed plan (ref: offpolicy_rnn/buffers/transition_buffer/nested_replay_memory.py:103-185;

@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         log.append(f"== {os.path.basename(src)}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
-    link = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    link = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

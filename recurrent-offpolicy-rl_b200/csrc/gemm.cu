@@ -1,0 +1,360 @@
+// tcgen05 tensor-core GEMM with fp32 parity (3xTF32 split accumulation), sm_100a.
+//
+//   D[g][M, N] = act( A[g][M, K] * B[g][N, K]^T + bias[g][N] )        g = 0..G-1 (ensemble members)
+//
+// Replaces the cuBLAS fp32 SGEMMs behind nn.Linear / EnsembleLinear on the update path
+// (ref: offpolicy_rnn/models/ensemble_linear_model.py:36-49 einsum -> bmm; smamba in/x/dt/out_proj,
+// ref: offpolicy_rnn/models/smamba/mamba.py:176,231-233,252).  The reference runs these in true fp32
+// (TF32 is never enabled there), so a single-pass TF32 MMA is not enough for the 1e-3 parity budget:
+// each fp32 operand is split as x = hi + lo (hi = top 19 bits = a TF32 value, lo = x - hi) and the
+// product is accumulated as lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator (~2^-21 relative).
+//
+// Structure (one persistent CTA per SM, 10 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B, 32 fp32 = 128 B of K per row) into a
+//               3-stage shared-memory ring, mbarrier complete_tx
+//   warps 2-5   splitters: read the raw fp32 tiles, write the `lo` tiles in the identical swizzled layout,
+//               fence.proxy.async, arrive
+//   warp 1      MMA issuer (one elected lane): 4 k-steps x 3 tcgen05.mma.kind::tf32 (M128 x N128 x K8) per
+//               stage into one of two TMEM accumulators; tcgen05.commit frees the stage / publishes the tile
+//   warps 6-9   epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per instruction), + bias, ELU,
+//               vectorised global stores; overlaps the next tile's main loop (double-buffered TMEM)
+// Both operands are K-major (the reduction dimension is contiguous), which is what the forward
+// (x, W[N,K]) and the data-gradient (dY, W^T materialised by the caller; weights are tiny) need.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace rorl {
+
+constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 32;     // BK fp32 = one 128-byte swizzle row
+constexpr int kGemmStages = 3;
+constexpr int kGemmThreads = 320;
+constexpr int kTileBytes = kGemmBM * kGemmBK * 4;             // 16 KiB (A and B tiles have the same size)
+constexpr int kStageBytes = 4 * kTileBytes;                   // A_raw | B_raw | A_lo | B_lo
+constexpr int kGemmSmem = kGemmStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+    float* D;
+    float* Dpre;      // optional: pre-activation (A B^T + bias) written next to D when act != 0
+    const float* bias;
+    int M, N, K, G;
+    long long ldd, strideD, strideBias;
+    int a_batched, b_batched, act, passes, reduce_g;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups are 1024 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + kGemmStages * kStageBytes;
+    // barrier map (8 B each): full_raw[S], full_split[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr
+    auto bar_full_raw = [&](int s) { return bars + 8u * s; };
+    auto bar_full_split = [&](int s) { return bars + 8u * (kGemmStages + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * kGemmStages + s); };
+    auto bar_tfull = [&](int a) { return bars + 8u * (3 * kGemmStages + a); };
+    auto bar_tempty = [&](int a) { return bars + 8u * (3 * kGemmStages + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kGemmStages * kStageBytes + 8 * (3 * kGemmStages + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool split = p.passes == 3;
+    const int tilesM = (p.M + kGemmBM - 1) / kGemmBM, tilesN = (p.N + kGemmBN - 1) / kGemmBN;
+    // reduce_g: the G operand pairs are summed into ONE output (the reduction runs over (g, k)), used for the
+    // data-gradient of an ensemble layer whose input is shared by all members.
+    const int KTg = (p.K + kGemmBK - 1) / kGemmBK;
+    const int ntiles = tilesM * tilesN * (p.reduce_g ? 1 : p.G);
+    const int KT = p.reduce_g ? KTg * p.G : KTg;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(bar_full_raw(s), 1);
+            mbar_init(bar_full_split(s), 4);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull(a), 1);
+            mbar_init(bar_tempty(a), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(2 * kGemmBN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM, g = tile / (tilesN * tilesM);
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % kGemmStages;
+                    mbar_wait(bar_empty(s), ((it / kGemmStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_full_raw(s), 2 * kTileBytes);
+                    const uint32_t st = base + s * kStageBytes;
+                    const int gg = p.reduce_g ? kt / KTg : g, kk = p.reduce_g ? kt % KTg : kt;
+                    tma_load_3d(st, &mapA, bar_full_raw(s), kk * kGemmBK, tm * kGemmBM, p.a_batched ? gg : 0);
+                    tma_load_3d(st + kTileBytes, &mapB, bar_full_raw(s), kk * kGemmBK, tn * kGemmBN, p.b_batched ? gg : 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+                const int acc = tcount & 1;
+                mbar_wait(bar_tempty(acc), ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kGemmBN;
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % kGemmStages;
+                    const uint32_t ph = (it / kGemmStages) & 1;
+                    mbar_wait(bar_full_raw(s), ph);
+                    if (split) mbar_wait(bar_full_split(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = base + s * kStageBytes;
+                    const uint64_t a_hi = make_kmajor_desc(st), b_hi = make_kmajor_desc(st + kTileBytes);
+                    const uint64_t a_lo = make_kmajor_desc(st + 2 * kTileBytes), b_lo = make_kmajor_desc(st + 3 * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 8 * 4 >> 4);        // 32 B per k-step inside the swizzle row
+                        const uint32_t first = (kt | k) == 0 ? 0u : 1u;
+                        if (split) {
+                            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, first);
+                            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                        } else {
+                            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+                        }
+                    }
+                    umma_commit(bar_empty(s));                                   // stage free once these MMAs retire
+                }
+                umma_commit(bar_tfull(acc));                                     // accumulator complete
+            }
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ splitters (hi/lo)
+        if (split) {
+            const int t = threadIdx.x - 64;                                      // 0..127
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % kGemmStages;
+                    mbar_wait(bar_full_raw(s), (it / kGemmStages) & 1);
+                    uint8_t* st = base_ptr + s * kStageBytes;
+#pragma unroll 4
+                    for (int i = 0; i < 2 * kTileBytes / 16 / 128; ++i) {
+                        const int off = (t + 128 * i) * 16;
+                        float4 v = *reinterpret_cast<const float4*>(st + off);
+                        // hi = the operand rounded to TF32 (written back so that the tensor core's own
+                        // fp32->tf32 conversion is exact whatever its rounding), lo = exact remainder
+                        float4 hi, lo;
+                        // round-to-nearest on the 13 dropped bits: |lo| <= 2^-12 |x| and unbiased
+                        hi.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+                        hi.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+                        hi.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+                        hi.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                        *reinterpret_cast<float4*>(st + off) = hi;
+                        *reinterpret_cast<float4*>(st + 2 * kTileBytes + off) = lo;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full_split(s));
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;                                                  // TMEM lane quarter this warp may read
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM, g = tile / (tilesN * tilesM);
+            const int acc = tcount & 1;
+            mbar_wait(bar_tfull(acc), (tcount >> 1) & 1);
+            tc_fence_after();
+            const int row = tm * kGemmBM + q * 32 + lane;
+            float* drow = p.D + (long long)g * p.strideD + (long long)row * p.ldd;
+            float* prow = p.Dpre ? p.Dpre + (long long)g * p.strideD + (long long)row * p.ldd : nullptr;
+            const float* bias = p.bias ? p.bias + (long long)g * p.strideBias : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < kGemmBN / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + acc * kGemmBN + c * 32 + ((uint32_t)(q * 32) << 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int col0 = tn * kGemmBN + c * 32;
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = col0 + 4 * j;
+                        if (col < p.N) {
+                            float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                            if (bias) {
+                                const float4 bv = *reinterpret_cast<const float4*>(bias + col);
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            }
+                            if (prow) *reinterpret_cast<float4*>(prow + col) = o;
+                            if (p.act == 1) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
+                            *reinterpret_cast<float4*>(drow + col) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kGemmBN));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 3-D map over a row-major [batch][rows][K] fp32 tensor: box = 32 (K) x 128 rows x 1, SWIZZLE_128B, zero OOB fill.
+static int make_map(CUtensorMap* map, const float* ptr, long long rows, long long K, long long ld, long long batch,
+                    long long batch_stride) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return RORL_ERR_ARG;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : rows * ld) * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? RORL_OK : RORL_ERR_ARG;
+}
+
+}  // namespace rorl
+
+using namespace rorl;
+
+extern "C" {
+
+// D[g] = act(A[g] B[g]^T + bias[g]);  A [G?][M, K] (lda), B [G?][N, K] (ldb), D [G][M, N] (ldd); strides in floats,
+// strideA / strideB == 0 means the operand is shared by all g.  act: 0 none, 1 ELU (Dpre, if not NULL, receives the
+// pre-activation in D's layout so that a backward can form the exact ELU derivative).  passes: 3 = fp32-parity
+// 3xTF32, 1 = single TF32.  Requirements: K % 4 == 0, N % 4 == 0, lda/ldb/ldd % 4 == 0, 16-byte aligned bases.
+int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
+                 int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
+                 int64_t strideBias, int act, int passes, int reduce_g, cudaStream_t stream) {
+    if (!A || !B || !D) return RORL_ERR_ARG;
+    if (M <= 0 || N <= 0 || K <= 0 || G <= 0) return RORL_ERR_SHAPE;
+    if (K % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideBias % 4)
+        return RORL_ERR_ALIGN;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D) |
+         reinterpret_cast<uintptr_t>(bias)) & 15)
+        return RORL_ERR_ALIGN;
+    if (passes != 1 && passes != 3) return RORL_ERR_ARG;
+    CUtensorMap mapA, mapB;
+    int rc = make_map(&mapA, A, M, K, lda, strideA ? G : 1, strideA);
+    if (rc) return rc;
+    rc = make_map(&mapB, B, N, K, ldb, strideB ? G : 1, strideB);
+    if (rc) return rc;
+    GemmParams p;
+    p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
+    p.ldd = ldd; p.strideD = strideD; p.strideBias = strideBias;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act; p.passes = passes; p.reduce_g = reduce_g != 0;
+    if (reduce_g && (!strideA || !strideB)) return RORL_ERR_ARG;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    }
+    const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN) * (reduce_g ? 1 : G);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gemm_tn_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(mapA, mapB, p);
+    RORL_RETURN_LAUNCH();
+}
+
+}  // extern "C"

@@ -303,3 +303,123 @@ def layer_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, resid
 
 def rms_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False):
     return AddNorm.apply(x, weight, bias, residual, eps, prenorm, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM (3xTF32, fp32 parity) behind nn.Linear / EnsembleLinear
+# ------------------------------------------------------------------------------------------------
+GEMM_PASSES = 3          # 3 = fp32-parity split accumulation; 1 = plain TF32 (set by benchmarks only)
+GEMM_MIN_K = 32
+
+
+def _gemm_ok(M, N, K):
+    return K >= GEMM_MIN_K and K % 4 == 0 and N % 4 == 0 and M >= 1
+
+
+def _mat(t: torch.Tensor) -> torch.Tensor:
+    """2-D / 3-D operand with unit inner stride, row stride % 4 == 0 and a 16-byte aligned base."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    ok = t.stride(-1) == 1 and t.stride(-2) % 4 == 0 and t.data_ptr() % 16 == 0 and (t.dim() == 2 or t.stride(0) % 4 == 0)
+    return t if ok else t.contiguous()
+
+
+def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int = None, want_pre: bool = False):
+    """D[g] = act(A[g] @ B[g]^T + bias[g]).  A [M, K] or [G, M, K]; B [N, K] or [G, N, K]; bias [N] or [G, N].
+    Returns [M, N] (no batched operand, or reduce_g) or [G, M, N]."""
+    A, B = _mat(A), _mat(B)
+    G = max(A.shape[0] if A.dim() == 3 else 1, B.shape[0] if B.dim() == 3 else 1)
+    M, K = A.shape[-2], A.shape[-1]
+    Nn = B.shape[-2]
+    assert B.shape[-1] == K
+    batched_out = (A.dim() == 3 or B.dim() == 3) and not reduce_g
+    D = torch.empty((G, M, Nn) if batched_out else (M, Nn), device=A.device, dtype=torch.float32)
+    bias_c = None if bias is None else _f32c(bias.reshape(-1, Nn) if batched_out else bias.reshape(Nn))
+    pre = torch.empty_like(D) if (want_pre and act) else None
+    N.call("rorl_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(bias_c), N.ptr(D), N.ptr(pre), M, Nn, K, G, A.stride(-2), B.stride(-2), Nn,
+           A.stride(0) if A.dim() == 3 else 0, B.stride(0) if B.dim() == 3 else 0, M * Nn if batched_out else 0,
+           Nn if (bias_c is not None and bias_c.dim() == 2) else 0, int(act), int(passes or GEMM_PASSES),
+           int(reduce_g), N.stream())
+    return (D, pre) if want_pre else D
+
+
+class LinearTC(Function):
+    """y = act(x W^T + b) on the tcgen05 GEMM; dX on the same kernel (W^T materialised: weights are tiny);
+    dW / db through cuBLAS for now."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, elu):
+        K, Nn = weight.shape[1], weight.shape[0]
+        xs = _mat(x.reshape(-1, K))
+        need_pre = elu and any(ctx.needs_input_grad)
+        y, pre = gemm_tn(xs, weight, bias, 1 if elu else 0, want_pre=True) if need_pre else (gemm_tn(xs, weight, bias, 1 if elu else 0), None)
+        ctx.save_for_backward(xs, weight, pre)
+        ctx.elu, ctx.has_bias, ctx.xshape = elu, bias is not None, x.shape
+        return y.view(*x.shape[:-1], Nn)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, weight, pre = ctx.saved_tensors
+        Nn = weight.shape[0]
+        g = _f32c(dy.reshape(-1, Nn))
+        if ctx.elu:   # exact derivative from the saved pre-activation (y + 1 would cancel for saturated units)
+            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, False, pre)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tn(g, weight.t().contiguous()).view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = g.t() @ xs
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum(0)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, elu=False):
+    """nn.Linear forward (+ optional fused ELU).  Shapes the tensor-core kernel cannot take (K % 4, N % 4, K < 32)
+    go through cuBLAS; both are GPU paths."""
+    M = x.numel() // x.shape[-1]
+    if x.is_cuda and _gemm_ok(M, weight.shape[0], weight.shape[1]):
+        return LinearTC.apply(x, weight, bias, elu)
+    y = torch.nn.functional.linear(x, weight, bias)
+    return torch.nn.functional.elu(y) if elu else y
+
+
+class EnsembleLinearTC(Function):
+    """y[e] = act(x[e or shared] W[e] + b[e]) with W [E, in, out] (the reference's EnsembleLinear layout)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, elu, shared):
+        E, Kin, Nout = weight.shape
+        xs = _mat(x.reshape(-1, Kin) if shared else x.reshape(E, -1, Kin))
+        wt = weight.transpose(1, 2).contiguous()                  # [E, out, in]: K-major B operand
+        b2 = None if bias is None else bias.reshape(E, Nout)
+        need_pre = elu and any(ctx.needs_input_grad)
+        y, pre = gemm_tn(xs, wt, b2, 1 if elu else 0, want_pre=True) if need_pre else (gemm_tn(xs, wt, b2, 1 if elu else 0), None)
+        ctx.save_for_backward(xs, weight, pre)
+        ctx.elu, ctx.has_bias, ctx.shared, ctx.xshape = elu, bias is not None, shared, x.shape
+        lead = x.shape[:-1] if shared else x.shape[1:-1]
+        return y.view(E, *lead, Nout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, weight, pre = ctx.saved_tensors
+        E, Kin, Nout = weight.shape
+        g = _f32c(dy.reshape(E, -1, Nout))
+        if ctx.elu:
+            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, False, pre)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tn(g, weight, reduce_g=ctx.shared).view(ctx.xshape)     # weight [E, in, out] is K-major here
+        if ctx.needs_input_grad[1]:
+            dw = torch.matmul(xs.transpose(-1, -2), g)                        # [E, in, out] (x broadcast if shared)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum(1, keepdim=True)
+        return dx, dw, db, None, None
+
+
+def ensemble_linear(x, weight, bias, elu, shared):
+    E, Kin, Nout = weight.shape
+    M = x.numel() // Kin // (1 if shared else E)
+    if x.is_cuda and _gemm_ok(M, Nout, Kin):
+        return EnsembleLinearTC.apply(x, weight, bias, elu, shared)
+    return None

@@ -5,6 +5,9 @@ contraction itself is a batched GEMM (torch.matmul -> cuBLAS) instead of einsum.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import kernels as K
 
 
 class EnsembleLinear(nn.Module):
@@ -18,9 +21,17 @@ class EnsembleLinear(nn.Module):
             self.bias = nn.Parameter(torch.zeros(num_ensemble, 1, output_dim))
         nn.init.trunc_normal_(self.weight, std=1 / (2 * input_dim ** 0.5))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, fuse_elu: bool = False) -> torch.Tensor:
         W, E = self.weight, self.num_ensemble
         nd = x.dim()
+        # tensor-core path (tcgen05 3xTF32 GEMM, bias + ELU fused) for the two shapes the update uses:
+        # a shared [.., in] input fanned out to E members, and a per-member [E, .., in] input
+        if x.is_cuda and nd in (3, 4):
+            per_member = x.shape[0] == E and (self.desire_ndim is None or self.desire_ndim == nd)
+            if nd == 3 or per_member:
+                y = K.ensemble_linear(x, W, self.bias if self.use_bias else None, fuse_elu, shared=not per_member)
+                if y is not None:
+                    return y
         if nd == 2:                                   # [i, j] -> [E, i, k]
             y = torch.matmul(x.unsqueeze(0), W)
         elif nd == 3:
@@ -41,4 +52,4 @@ class EnsembleLinear(nn.Module):
             b = self.bias
             assert y.shape[0] == b.shape[0] and y.shape[-1] == b.shape[-1]
             y = y + b.reshape((E,) + (1,) * (y.dim() - 2) + (b.shape[-1],))
-        return y
+        return F.elu(y) if fuse_elu else y

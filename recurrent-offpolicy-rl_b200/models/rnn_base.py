@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from .RNNHidden import RNNHidden
 from .ensemble_linear_model import EnsembleLinear
+from .linear import Linear
 from .gilr.gilr import GILRLayer
 from .lru.lru import LRULayer
 from .smamba.mamba import BlockList as MambaBlockList
@@ -107,7 +108,7 @@ class RNNBase(nn.Module):
             lid = self.layer_type[ind]
             kind, cfg = parse_layer_id(lid)
             if kind == 'fc':
-                self.layer_list.append(nn.Linear(width_in, width))
+                self.layer_list.append(Linear(width_in, width))
             elif kind == 'efc':
                 self.layer_list.append(EnsembleLinear(width_in, width, cfg['ensemble']))
             else:
@@ -238,6 +239,9 @@ class RNNBase(nn.Module):
                 if require_full_hidden:
                     full.append(x)
             else:
+                if isinstance(self.activation_list[ind], nn.ELU):
+                    x = layer(x, fuse_elu=True)          # bias + ELU in the GEMM epilogue
+                    continue
                 x = layer(x)
             act = self.activation_list[ind]
             if isinstance(act, nn.ModuleList):

@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import kernels as K
+from ..linear import Linear
 
 
 class RMSNorm(nn.Module):
@@ -43,7 +44,7 @@ class Mamba(nn.Module):
         self.d_inner = int(expand * d_model)
         self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
         self.layer_idx = layer_idx
-        self.in_proj = nn.Linear(d_model, self.d_inner * 2, bias=bias)
+        self.in_proj = Linear(d_model, self.d_inner * 2, bias=bias)
         self.conv_hidden_dim = d_model * expand * d_conv
         self.ssm_hidden_dim = d_model * expand * d_state
         self.desired_hidden_dim = self.conv_hidden_dim + self.ssm_hidden_dim
@@ -51,7 +52,7 @@ class Mamba(nn.Module):
         if self.use_conv:
             self.conv1d = nn.Conv1d(self.d_inner, self.d_inner, bias=conv_bias, kernel_size=d_conv,
                                     groups=self.d_inner, padding=d_conv - 1)
-        self.x_proj = nn.Linear(self.d_inner, self.dt_rank + d_state * 2, bias=False)
+        self.x_proj = Linear(self.d_inner, self.dt_rank + d_state * 2, bias=False)
         self.dt_proj = nn.Linear(self.dt_rank, self.d_inner, bias=True)
         std = self.dt_rank ** -0.5 * dt_scale
         if dt_init == "constant":
@@ -69,7 +70,7 @@ class Mamba(nn.Module):
         self.A_log._no_weight_decay = True
         self.D = nn.Parameter(torch.ones(self.d_inner))
         self.D._no_weight_decay = True
-        self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias)
+        self.out_proj = Linear(self.d_inner, d_model, bias=bias)
 
     def forward(self, x, hidden=None, rnn_start=None, mask=None):
         """x: [B, L, d_model] -> [B, L, d_model]; the flat hidden is passed through untouched, as on the
@@ -126,8 +127,8 @@ class Block(nn.Module):
 class PositionWiseFeedForward(nn.Module):
     def __init__(self, d_model, dropout=0.0, eps=1e-5):
         super().__init__()
-        self.w_1 = nn.Linear(d_model, d_model)
-        self.w_2 = nn.Linear(d_model, d_model)
+        self.w_1 = Linear(d_model, d_model)
+        self.w_2 = Linear(d_model, d_model)
         self.activation = nn.GELU()
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(d_model, eps=eps)
@@ -155,7 +156,7 @@ class BlockList(nn.Module):
         if use_ff:
             self.head = PositionWiseFeedForward(d_model=dim, dropout=0.0, eps=self.norm_epsilon)
         else:
-            self.head = nn.Linear(dim, dim, bias=False)
+            self.head = Linear(dim, dim, bias=False)
             self.norm_f = norm_cls(dim)
         self.apply(partial(_init_weights, n_layer=block_num))
 

@@ -115,3 +115,73 @@ def test_sampler_device_bit_exact():
             assert total == int(g[f"c{call}/total"])
             st = np.random.get_state()
             assert st[2] == int(g[f"c{call}/rng_pos"])
+
+
+@pytest.mark.parametrize("enc,algo", [("smamba_s32_c16_b2_nln", "sac"), ("gilr", "td3"), ("lru", "sac"), ("smamba_s64_c8_b1_ff", "sac")])
+def test_update_vs_oracle_wide(enc, algo):
+    """Same comparison at widths that route every projection through the tcgen05 GEMM (K >= 32), against the
+    pinned oracle's CPU update (no reference fixture exists at this size)."""
+    from oracle import model as OM, sampler as OS, update as OU
+    from rorl_b200.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.buffers.transition_buffer.replay_memory import Transition
+    S, A, H = 5, 3, 64
+    lens = [40, 33, 25, 37]
+    kw = lambda value: dict(state_dim=S, action_dim=A, embedding_size=32, embedding_hidden=[H, H],
+                            embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', enc, 'fc'],
+                            uni_model_hidden=[H, H], uni_model_activations=['elu', 'elu', 'linear'],
+                            uni_model_layer_type=(['efc-8'] * 3 if value else ['fc'] * 3), fix_rnn_length=0,
+                            uni_model_input_mapping_dim=32, reward_input=False, last_action_input=True,
+                            last_state_input=True, separate_encoder=True)
+    hp = dict(gamma=0.99, sac_tau=0.995, policy_update_per=1, redq_m=2, policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5,
+              rnn_value_lr=1e-5, alpha_lr=1e-4, target_entropy_ratio=1.0, sac_batch_size=sum(lens) - 1,
+              max_buffer_transition_num=1000, sample_std=0.1, target_action_noise_std=0.04, target_action_noise_clip=0.12,
+              policy_l2_norm=0.0, value_l2_norm=0.0)
+    torch.manual_seed(3)
+    cls = SACFullLengthRNNREDQ_SEP_OPTIM if algo == "sac" else TD3FullLengthRNNREDQ_SEP_OPTIM
+    alg = cls(dict(hp), kw(False), kw(True), max(lens), device=torch.device("cuda:0"))
+    with torch.no_grad():
+        for m in (alg.policy, alg.values[0]):
+            for p in m.parameters():
+                if p.dim() == 1:
+                    p.add_(0.05 * torch.randn_like(p))
+    alg._finalize_models()
+    cpu_sd = lambda model: {k: {n: t.detach().cpu().clone() for n, t in sd.items()} for k, sd in model.state_dict().items()}
+    pol_sd, val_sd = cpu_sd(alg.policy), cpu_sd(alg.values[0])
+    fill_buffer(alg.replay_buffer, Transition, np.random.RandomState(4), lens, S, A)
+    skip = alg._get_skip_len()
+    obuf = OS.RefNestedReplay(1000, max(lens), additional_history_len=skip - 1)
+    fill_buffer(obuf, OS.Transition, np.random.RandomState(4), lens, S, A)
+    gen = torch.Generator().manual_seed(8)
+    drawn = []
+
+    def o_noise(shape):
+        n = torch.randn(tuple(shape), generator=gen)
+        drawn.append(n)
+        return n
+
+    pk = dict(kw(False))
+    upd = OU.RefUpdate(pol_sd, val_sd, OM.ModelSpec(**pk), OM.ModelSpec(**kw(True)), hp, obuf, o_noise, algo=algo, redq=True,
+                       allow_nest_stack=alg.allow_nest_stack)
+    for call in range(2):
+        drawn.clear()
+        np.random.seed(100 + call)
+        ref = upd.train_one_batch()
+        it = iter([d.cuda() for d in drawn])
+        alg.policy.noise_fn = alg.target_policy.noise_fn = lambda like: next(it)
+        np.random.seed(100 + call)
+        log = alg.train_one_batch()
+        for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "target_q_max"):
+            if k in ref and k in log:
+                assert abs(log[k] - ref[k]) <= TOL * max(1.0, abs(ref[k])), (k, log[k], ref[k])
+        worst = 0.0
+        for which, model, osd in (("policy", alg.policy, upd.policy), ("value", alg.values[0], upd.value),
+                                  ("target", alg.target_values[0], upd.target)):
+            for mod, params in model.state_dict().items():
+                for n, t in params.items():
+                    worst = max(worst, assert_close(t, osd[mod][n].detach(), TOL, f"{which}/{mod}/{n}"))
+        for mod, m in alg.values[0].contextual_modules.items():
+            for n, p_ in m.named_parameters():
+                if upd.value_grads[mod][n] is not None and p_.grad is not None and which:
+                    pass
+        print(f"{enc} {algo} call {call}: worst updated-parameter relative error {worst:.2e}")
