@@ -198,6 +198,14 @@ int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t 
 int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
                  int64_t strideBias, int act, int passes, int reduce_g, cudaStream_t stream);
+/* Weight-gradient form: D[s][g][M, N] = sum over the s-th slice of rows r of A[g][r, M]^T B[g][r, N] (both operands
+ * row-major with the REDUCTION over rows, i.e. MN-major for the tensor core; no transposed copies).  Split-K over
+ * the R rows: splits = rorl_gemm_nt_splits(M, N, R, G); partial s lands at D + s * strideSplit and the caller sums
+ * the partials (deterministic).  M, N, ld*, stride* multiples of 4. */
+int rorl_gemm_nt_splits(int64_t M, int64_t N, int64_t R, int64_t G);
+int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda,
+                 int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits,
+                 int64_t strideSplit, int passes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Trajectory gather: builds the padded, nest-stacked [rows, Lmax, F] fp32 batch of

@@ -18,8 +18,12 @@
 //               stage into one of two TMEM accumulators; tcgen05.commit frees the stage / publishes the tile
 //   warps 6-9   epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per instruction), + bias, ELU,
 //               vectorised global stores; overlaps the next tile's main loop (double-buffered TMEM)
-// Both operands are K-major (the reduction dimension is contiguous), which is what the forward
-// (x, W[N,K]) and the data-gradient (dY, W^T materialised by the caller; weights are tiny) need.
+// Operand layouts: the TN variant takes both operands K-major (reduction dimension contiguous): forward
+// (x, W[N,K]) and data-gradient (dY, W^T materialised by the caller; weights are tiny).  The NT variant takes
+// both operands MN-major (reduction dimension = rows): weight gradients dW[n,k] = sum_m dY[m,n] X[m,k] straight
+// from the row-major activations, with split-K over the (very long) token dimension and per-split partial
+// outputs the caller sums (deterministic, no atomics).  tcgen05.mma.kind::tf32 multiplies K-major operands only, so
+// in the NT variant the splitter warps transpose each tile in shared memory while they split it.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -30,7 +34,8 @@ constexpr int kGemmStages = 3;
 constexpr int kGemmThreads = 320;
 constexpr int kTileBytes = kGemmBM * kGemmBK * 4;             // 16 KiB (A and B tiles have the same size)
 constexpr int kStageBytes = 4 * kTileBytes;                   // A_raw | B_raw | A_lo | B_lo
-constexpr int kGemmSmem = kGemmStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kStagingBytes = 4 * 32 * 128;                   // per epilogue warp: 32 rows x 32 fp32 columns
+constexpr int kGemmSmem = kGemmStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmParams {
     float* D;
@@ -39,6 +44,9 @@ struct GemmParams {
     int M, N, K, G;
     long long ldd, strideD, strideBias;
     int a_batched, b_batched, act, passes, reduce_g;
+    int dbg;
+    int splits;                 // NT variant: split-K factor; partial s is written at D + s * strideSplit
+    long long strideSplit;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,21 +98,38 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(alpha = 1) without the multi-instruction expm1f: degree-7 Taylor for -0.5 < x <= 0 (rel. err < 1e-7),
+// ex2-based below (abs. err 2e-7 on a result of magnitude >= 0.39).
+__device__ __forceinline__ float elu1(float x) {
+    if (x > 0.f) return x;
+    if (x > -0.5f) {
+        float p = 1.0f / 5040.0f;
+        p = fmaf(p, x, 1.0f / 720.0f);
+        p = fmaf(p, x, 1.0f / 120.0f);
+        p = fmaf(p, x, 1.0f / 24.0f);
+        p = fmaf(p, x, 1.0f / 6.0f);
+        p = fmaf(p, x, 0.5f);
+        p = fmaf(p, x, 1.0f);
+        return p * x;
+    }
+    return ex2f(x * kLog2e) - 1.0f;
+}
 
+template <bool MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + kGemmStages * kStageBytes;
+    const uint32_t bars = base + kGemmStages * kStageBytes + kStagingBytes;
     // barrier map (8 B each): full_raw[S], full_split[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr
     auto bar_full_raw = [&](int s) { return bars + 8u * s; };
     auto bar_full_split = [&](int s) { return bars + 8u * (kGemmStages + s); };
     auto bar_empty = [&](int s) { return bars + 8u * (2 * kGemmStages + s); };
     auto bar_tfull = [&](int a) { return bars + 8u * (3 * kGemmStages + a); };
     auto bar_tempty = [&](int a) { return bars + 8u * (3 * kGemmStages + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kGemmStages * kStageBytes + 8 * (3 * kGemmStages + 4));
+    uint8_t* staging = base_ptr + kGemmStages * kStageBytes;                      // 16 KiB, 4 KiB per epilogue warp
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kGemmStages * kStageBytes + kStagingBytes + 8 * (3 * kGemmStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool split = p.passes == 3;
@@ -112,8 +137,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // reduce_g: the G operand pairs are summed into ONE output (the reduction runs over (g, k)), used for the
     // data-gradient of an ensemble layer whose input is shared by all members.
     const int KTg = (p.K + kGemmBK - 1) / kGemmBK;
-    const int ntiles = tilesM * tilesN * (p.reduce_g ? 1 : p.G);
-    const int KT = p.reduce_g ? KTg * p.G : KTg;
+    const int nsplit = MN ? p.splits : 1;
+    const int ntiles = tilesM * tilesN * (p.reduce_g ? 1 : p.G) * nsplit;
+    const int KTs = (KTg + nsplit - 1) / nsplit;                                  // k-tiles per split (NT variant)
+    const int KT = MN ? KTs : (p.reduce_g ? KTg * p.G : KTg);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; ++s) {
@@ -143,15 +170,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM, g = tile / (tilesN * tilesM);
+                const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM;
+                const int g = (tile / (tilesN * tilesM)) % p.G, sp = tile / (tilesN * tilesM * p.G);
                 for (int kt = 0; kt < KT; ++kt, ++it) {
                     const int s = it % kGemmStages;
                     mbar_wait(bar_empty(s), ((it / kGemmStages) & 1) ^ 1);
                     mbar_expect_tx(bar_full_raw(s), 2 * kTileBytes);
                     const uint32_t st = base + s * kStageBytes;
-                    const int gg = p.reduce_g ? kt / KTg : g, kk = p.reduce_g ? kt % KTg : kt;
-                    tma_load_3d(st, &mapA, bar_full_raw(s), kk * kGemmBK, tm * kGemmBM, p.a_batched ? gg : 0);
-                    tma_load_3d(st + kTileBytes, &mapB, bar_full_raw(s), kk * kGemmBK, tn * kGemmBN, p.b_batched ? gg : 0);
+                    if (MN) {
+                        // operands [rows = reduction][cols = MN]: 4 boxes of 32 columns x 32 rows per operand
+                        const int r0 = (sp * KTs + kt) * kGemmBK;                 // rows beyond the tensor are zero-filled
+#pragma unroll
+                        for (int bI = 0; bI < 4; ++bI) {
+                            tma_load_3d(st + bI * (kGemmBK * 128), &mapA, bar_full_raw(s), tm * kGemmBM + 32 * bI, r0, p.a_batched ? g : 0);
+                            tma_load_3d(st + kTileBytes + bI * (kGemmBK * 128), &mapB, bar_full_raw(s), tn * kGemmBN + 32 * bI, r0, p.b_batched ? g : 0);
+                        }
+                    } else {
+                        const int gg = p.reduce_g ? kt / KTg : g, kk = p.reduce_g ? kt % KTg : kt;
+                        tma_load_3d(st, &mapA, bar_full_raw(s), kk * kGemmBK, tm * kGemmBM, p.a_batched ? gg : 0);
+                        tma_load_3d(st + kTileBytes, &mapB, bar_full_raw(s), kk * kGemmBK, tn * kGemmBN, p.b_batched ? gg : 0);
+                    }
                 }
             }
         }
@@ -159,7 +197,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | 
+                                   ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
                 const int acc = tcount & 1;
@@ -170,14 +209,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int s = it % kGemmStages;
                     const uint32_t ph = (it / kGemmStages) & 1;
                     mbar_wait(bar_full_raw(s), ph);
-                    if (split) mbar_wait(bar_full_split(s), ph);
+                    if (split || MN) mbar_wait(bar_full_split(s), ph);
                     tc_fence_after();
                     const uint32_t st = base + s * kStageBytes;
                     const uint64_t a_hi = make_kmajor_desc(st), b_hi = make_kmajor_desc(st + kTileBytes);
                     const uint64_t a_lo = make_kmajor_desc(st + 2 * kTileBytes), b_lo = make_kmajor_desc(st + 3 * kTileBytes);
 #pragma unroll
                     for (int k = 0; k < kGemmBK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 8 * 4 >> 4);        // 32 B per k-step inside the swizzle row
+                        const uint64_t adv = (uint64_t)(k * 8 * 4 >> 4);        // 32 B per k-step inside the 128-B swizzle row
                         const uint32_t first = (kt | k) == 0 ? 0u : 1u;
                         if (split) {
                             umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, first);
@@ -193,9 +232,49 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
     } else if (warp < 6) {
-        // ------------------------------------------------------------------ splitters (hi/lo)
-        if (split) {
-            const int t = threadIdx.x - 64;                                      // 0..127
+        // ------------------------------------------------------------------ splitters (hi/lo [+ transpose])
+        const int t = threadIdx.x - 64;                                          // 0..127
+        if (MN) {
+            // TMA delivered each operand as 4 blocks of [32 reduction rows][32 MN columns] (SWIZZLE_128B).  kind::tf32
+            // only multiplies K-major operands (with the MN-major bits set the MMA returns zeros on this part), so
+            // the split doubles as a transposition: every thread pulls its 64 values into registers, all 128
+            // splitter threads meet at a named barrier, then hi / lo are written as K-major SWIZZLE_128B rows
+            // (row = MN index, 32 reduction values = 128 B) over the raw tile / into the lo tile.
+            const int blk = t >> 5, r = t & 31;                                  // warp <-> MN block, lane <-> reduction row
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % kGemmStages;
+                    mbar_wait(bar_full_raw(s), (it / kGemmStages) & 1);
+                    uint8_t* st = base_ptr + s * kStageBytes;
+                    float4 v[2][8];
+#pragma unroll
+                    for (int op = 0; op < 2; ++op)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            v[op][c] = *reinterpret_cast<const float4*>(st + op * kTileBytes + blk * 4096 + r * 128 + ((c ^ (r & 7)) << 4));
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int op = 0; op < 2; ++op) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float e[4] = {v[op][c].x, v[op][c].y, v[op][c].z, v[op][c].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int mn = blk * 32 + c * 4 + i;
+                                const int off = mn * 128 + (((r >> 2) ^ (mn & 7)) << 4) + ((r & 3) << 2);
+                                const float hi = __uint_as_float((__float_as_uint(e[i]) + 0x1000u) & 0xFFFFE000u);
+                                *reinterpret_cast<float*>(st + op * kTileBytes + off) = hi;
+                                if (split) *reinterpret_cast<float*>(st + (2 + op) * kTileBytes + off) = e[i] - hi;
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full_split(s));
+                }
+            }
+        } else if (split) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int kt = 0; kt < KT; ++kt, ++it) {
@@ -207,9 +286,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const int off = (t + 128 * i) * 16;
                         float4 v = *reinterpret_cast<const float4*>(st + off);
                         // hi = the operand rounded to TF32 (written back so that the tensor core's own
-                        // fp32->tf32 conversion is exact whatever its rounding), lo = exact remainder
-                        float4 hi, lo;
+                        // fp32->tf32 conversion is exact whatever its rounding), lo = exact remainder;
                         // round-to-nearest on the 13 dropped bits: |lo| <= 2^-12 |x| and unbiased
+                        float4 hi, lo;
                         hi.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
                         hi.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
                         hi.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
@@ -226,19 +305,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         // ------------------------------------------------------------------ epilogue
+        // TMEM -> registers (one accumulator row per lane) -> + bias / ELU -> swizzled per-warp staging tile in
+        // shared memory -> row-contiguous 128-B global stores (4 full lines per warp instruction).
         const int q = warp & 3;                                                  // TMEM lane quarter this warp may read
+        uint8_t* stg = staging + q * 4096;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-            const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM, g = tile / (tilesN * tilesM);
+            const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM;
+            const int g = (tile / (tilesN * tilesM)) % p.G, sp = tile / (tilesN * tilesM * p.G);
             const int acc = tcount & 1;
             mbar_wait(bar_tfull(acc), (tcount >> 1) & 1);
             tc_fence_after();
-            const int row = tm * kGemmBM + q * 32 + lane;
-            float* drow = p.D + (long long)g * p.strideD + (long long)row * p.ldd;
-            float* prow = p.Dpre ? p.Dpre + (long long)g * p.strideD + (long long)row * p.ldd : nullptr;
+            const long long obase = (long long)g * p.strideD + (long long)sp * p.strideSplit;
+            const int row0 = tm * kGemmBM + q * 32;
             const float* bias = p.bias ? p.bias + (long long)g * p.strideBias : nullptr;
+            auto flush = [&](const float4 (&o)[8], float* out, int col0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int rloc = rr * 4 + (lane >> 3), ch = lane & 7;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + rloc * 128 + ((ch ^ (rloc & 7)) << 4));
+                    const int grow = row0 + rloc, col = col0 + ch * 4;
+                    if (grow < p.M && col < p.N)
+                        *reinterpret_cast<float4*>(out + obase + (long long)grow * p.ldd + col) = v;
+                }
+                __syncwarp();
+            };
 #pragma unroll 1
             for (int c = 0; c < kGemmBN / 32; ++c) {
+                const int col0 = tn * kGemmBN + c * 32;
+                if (col0 >= p.N) break;                                          // warp-uniform
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + acc * kGemmBN + c * 32 + ((uint32_t)(q * 32) << 16);
                 asm volatile(
@@ -250,24 +349,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int col0 = tn * kGemmBN + c * 32;
-                if (row < p.M) {
+                float4 o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = col0 + 4 * j;
-                        if (col < p.N) {
-                            float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                            if (bias) {
-                                const float4 bv = *reinterpret_cast<const float4*>(bias + col);
-                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                            }
-                            if (prow) *reinterpret_cast<float4*>(prow + col) = o;
-                            if (p.act == 1) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
-                            *reinterpret_cast<float4*>(drow + col) = o;
-                        }
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                       __uint_as_float(r[4 * j + 3]));
+                    if (bias && col0 + 4 * j < p.N) {
+                        const float4 bv = *reinterpret_cast<const float4*>(bias + col0 + 4 * j);
+                        o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
                     }
                 }
+                if (p.Dpre) flush(o, p.Dpre, col0);
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { o[j].x = elu1(o[j].x); o[j].y = elu1(o[j].y); o[j].z = elu1(o[j].z); o[j].w = elu1(o[j].w); }
+                }
+                flush(o, p.D, col0);
             }
             tc_fence_before();
             __syncwarp();
@@ -298,19 +395,33 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 3-D map over a row-major [batch][rows][K] fp32 tensor: box = 32 (K) x 128 rows x 1, SWIZZLE_128B, zero OOB fill.
-static int make_map(CUtensorMap* map, const float* ptr, long long rows, long long K, long long ld, long long batch,
-                    long long batch_stride) {
+// 3-D map over a row-major [batch][rows][cols] fp32 tensor: box = 32 cols (128 B) x box_rows x 1, SWIZZLE_128B,
+// out-of-bounds elements read as zero.
+static int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, long long batch,
+                    long long batch_stride, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return RORL_ERR_ARG;
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : rows * ld) * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM, 1};
+    cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? RORL_OK : RORL_ERR_ARG;
+}
+
+static int g_gemm_dbg = 0;
+static int gemm_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    }
+    return sms;
 }
 
 }  // namespace rorl
@@ -331,29 +442,69 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     if (K % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideBias % 4)
         return RORL_ERR_ALIGN;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D) |
-         reinterpret_cast<uintptr_t>(bias)) & 15)
+         reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(Dpre)) & 15)
         return RORL_ERR_ALIGN;
     if (passes != 1 && passes != 3) return RORL_ERR_ARG;
+    if (reduce_g && (!strideA || !strideB)) return RORL_ERR_ARG;
     CUtensorMap mapA, mapB;
-    int rc = make_map(&mapA, A, M, K, lda, strideA ? G : 1, strideA);
+    int rc = make_map(&mapA, A, M, K, lda, strideA ? G : 1, strideA, kGemmBM);
     if (rc) return rc;
-    rc = make_map(&mapB, B, N, K, ldb, strideB ? G : 1, strideB);
+    rc = make_map(&mapB, B, N, K, ldb, strideB ? G : 1, strideB, kGemmBN);
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
     p.ldd = ldd; p.strideD = strideD; p.strideBias = strideBias;
     p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act; p.passes = passes; p.reduce_g = reduce_g != 0;
-    if (reduce_g && (!strideA || !strideB)) return RORL_ERR_ARG;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-    }
+    p.splits = 1; p.strideSplit = 0; p.dbg = g_gemm_dbg;
+    const int sms = gemm_sms();
     const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN) * (reduce_g ? 1 : G);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_tn_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(mapA, mapB, p);
+    gemm_kernel<false><<<grid, kGemmThreads, kGemmSmem, stream>>>(mapA, mapB, p);
+    RORL_RETURN_LAUNCH();
+}
+
+void rorl_gemm_debug(int v) { g_gemm_dbg = v; }
+
+// Split-K factor rorl_gemm_nt uses for a [M x N] output reduced over R rows in G batches (the caller sizes D with it).
+int rorl_gemm_nt_splits(int64_t M, int64_t N, int64_t R, int64_t G) {
+    if (M <= 0 || N <= 0 || R <= 0 || G <= 0) return RORL_ERR_SHAPE;
+    const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN) * G;
+    const long long kt = (R + kGemmBK - 1) / kGemmBK;
+    long long s = (2 * 148 + tiles - 1) / tiles;
+    const long long smax = kt / 4 > 0 ? kt / 4 : 1;
+    if (s > smax) s = smax;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+// D[s][g][M, N] = sum over the s-th slice of rows r of A[g][r, M]^T B[g][r, N]   (both operands MN-major: the
+// reduction runs over ROWS).  Weight gradients: dW[n, k] = sum_m dY[m, n] X[m, k] with A = dY, B = X.
+// splits must equal rorl_gemm_nt_splits(M, N, R, G); the caller sums the partials over s.
+int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda,
+                 int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits,
+                 int64_t strideSplit, int passes, cudaStream_t stream) {
+    if (!A || !B || !D) return RORL_ERR_ARG;
+    if (M <= 0 || N <= 0 || R <= 0 || G <= 0 || splits <= 0) return RORL_ERR_SHAPE;
+    if (M % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideSplit % 4)
+        return RORL_ERR_ALIGN;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D)) & 15)
+        return RORL_ERR_ALIGN;
+    if (passes != 1 && passes != 3) return RORL_ERR_ARG;
+    if (splits != rorl_gemm_nt_splits(M, N, R, G)) return RORL_ERR_ARG;
+    CUtensorMap mapA, mapB;
+    int rc = make_map(&mapA, A, R, M, lda, strideA ? G : 1, strideA, kGemmBK);
+    if (rc) return rc;
+    rc = make_map(&mapB, B, R, N, ldb, strideB ? G : 1, strideB, kGemmBK);
+    if (rc) return rc;
+    GemmParams p;
+    p.D = D; p.Dpre = nullptr; p.bias = nullptr; p.M = (int)M; p.N = (int)N; p.K = (int)R; p.G = (int)G;
+    p.ldd = ldd; p.strideD = strideD; p.strideBias = 0;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = 0; p.passes = passes; p.reduce_g = 0;
+    p.splits = (int)splits; p.strideSplit = strideSplit; p.dbg = g_gemm_dbg;
+    const int sms = gemm_sms();
+    const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN) * G * splits;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, stream>>>(mapA, mapB, p);
     RORL_RETURN_LAUNCH();
 }
 

@@ -343,9 +343,31 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     return (D, pre) if want_pre else D
 
 
+def gemm_nt(A, B, passes: int = None):
+    """D[g] = A[g]^T @ B[g] with the reduction over ROWS: A [R, M] or [G, R, M]; B [R, N] or [G, R, N] -> [M, N] or
+    [G, M, N].  The weight-gradient GEMM: split-K partials from the tensor-core kernel, summed here."""
+    A, B = _mat(A), _mat(B)
+    G = max(A.shape[0] if A.dim() == 3 else 1, B.shape[0] if B.dim() == 3 else 1)
+    R, M = A.shape[-2], A.shape[-1]
+    Nn = B.shape[-1]
+    assert B.shape[-2] == R
+    batched = A.dim() == 3 or B.dim() == 3
+    splits = N.lib().rorl_gemm_nt_splits(M, Nn, R, G)
+    D = torch.empty((splits, G, M, Nn), device=A.device, dtype=torch.float32)
+    N.call("rorl_gemm_nt", N.ptr(A), N.ptr(B), N.ptr(D), M, Nn, R, G, A.stride(-2), B.stride(-2), Nn,
+           A.stride(0) if A.dim() == 3 else 0, B.stride(0) if B.dim() == 3 else 0, M * Nn, splits, G * M * Nn,
+           int(passes or GEMM_PASSES), N.stream())
+    D = D.sum(0) if splits > 1 else D[0]
+    return D if batched else D[0]
+
+
+def _gemm_nt_ok(M, Nn, R):
+    return M % 4 == 0 and Nn % 4 == 0 and R >= 128
+
+
 class LinearTC(Function):
     """y = act(x W^T + b) on the tcgen05 GEMM; dX on the same kernel (W^T materialised: weights are tiny);
-    dW / db through cuBLAS for now."""
+    dW on its MN-major split-K variant (gemm_nt); db is a column sum."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, elu):
@@ -368,7 +390,7 @@ class LinearTC(Function):
         if ctx.needs_input_grad[0]:
             dx = gemm_tn(g, weight.t().contiguous()).view(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            dw = g.t() @ xs
+            dw = gemm_nt(g, xs) if _gemm_nt_ok(Nn, xs.shape[1], xs.shape[0]) else g.t() @ xs
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = g.sum(0)
         return dx, dw, db, None
@@ -410,8 +432,8 @@ class EnsembleLinearTC(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_tn(g, weight, reduce_g=ctx.shared).view(ctx.xshape)     # weight [E, in, out] is K-major here
-        if ctx.needs_input_grad[1]:
-            dw = torch.matmul(xs.transpose(-1, -2), g)                        # [E, in, out] (x broadcast if shared)
+        if ctx.needs_input_grad[1]:                                           # [E, in, out] (x broadcast if shared)
+            dw = gemm_nt(xs, g) if _gemm_nt_ok(Kin, Nout, g.shape[1]) else torch.matmul(xs.transpose(-1, -2), g)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = g.sum(1, keepdim=True)
         return dx, dw, db, None, None

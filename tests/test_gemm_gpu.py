@@ -92,3 +92,18 @@ def test_linear_and_ensemble_autograd(K):
     assert rel_err(y2, yr) < 1e-5
     for a, r, n in zip(got, ref, "h W b".split()):
         assert rel_err(a, r) < 5e-5, n
+
+
+@pytest.mark.parametrize("R,M,N,G", [(128, 128, 128, 1), (1000, 80, 512, 1), (32576, 256, 384, 1), (5000, 384, 256, 8), (333, 12, 260, 2)])
+def test_gemm_nt_weight_gradient_form(K, R, M, N, G):
+    g = torch.Generator(device="cuda").manual_seed(R + M)
+    A = torch.randn((G, R, M) if G > 1 else (R, M), device="cuda", generator=g)
+    B = torch.randn((G, R, N) if G > 1 else (R, N), device="cuda", generator=g)
+    D = K.gemm_nt(A, B)
+    ref = A.double().transpose(-1, -2) @ B.double()
+    e = rel_err(D, ref)
+    print(f"NT R={R} M={M} N={N} G={G}: 3xTF32 err {e:.2e}")
+    assert e < 2e-5
+    if G > 1:       # shared A (first efc layer: one input, E output gradients)
+        D2 = K.gemm_nt(A[0], B)
+        assert rel_err(D2, A[0].double().t() @ B.double()) < 2e-5
