@@ -208,6 +208,27 @@ int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N,
                  int64_t strideSplit, int passes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * GRU recurrence as a persistent thread-block-cluster kernel (W_hh resident in registers across a
+ * cluster of H / 64 CTAs, h_t exchanged through distributed shared memory each step).
+ * Replaces the recurrent part of torch.nn.GRU(input, H, batch_first=True) on the `gru` encoder path
+ * (ref: offpolicy_rnn/models/rnn_base.py:59,245-247,454; gate order r, z, n as in torch.nn.GRU).
+ * gi [B, L, 3H] = x W_ih^T + b_ih is computed by the caller (one GEMM); w_hh [3H, H]; b_hh [3H] or
+ * NULL; h0 [B, H] or NULL (= 0).  out [B, L, H] = h_t for every step; h_last [B, H] (may be NULL);
+ * save [B, L, 4H] = (r, z, n, W_hn h + b_hn) for the backward (NULL when no backward follows).
+ * H in {128, 256}.
+ * Backward: dout [B, L, H] (gradient w.r.t. out), dh_last [B, H] or NULL -> dgi [B, L, 3H] (gradient
+ * w.r.t. gi = gradient w.r.t. the r and z rows of gh as well), dghn [B, L, H] (gradient w.r.t.
+ * W_hn h + b_hn), dh0 [B, H] (may be NULL).  Weight gradients are GEMMs over all steps, left to the
+ * caller: dW_hh = [dgi_r, dgi_z, dghn]^T h_{t-1}.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_gru_save_floats_per_step(int64_t H);
+int rorl_gru_fwd(const float* gi, const float* w_hh, const float* b_hh, const float* h0, float* out, float* save,
+                 float* h_last, int64_t B, int64_t L, int64_t H, cudaStream_t stream);
+int rorl_gru_bwd(const float* dout, const float* dh_last, const float* w_hh, const float* save, const float* out,
+                 const float* h0, float* dgi, float* dghn, float* dh0, int64_t B, int64_t L, int64_t H,
+                 cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Trajectory gather: builds the padded, nest-stacked [rows, Lmax, F] fp32 batch of
  * NestedMemoryArray.sample_trajs directly from a device-resident fp32 ring buffer, following a
  * host-computed plan (ref: offpolicy_rnn/buffers/transition_buffer/nested_replay_memory.py:103-185;

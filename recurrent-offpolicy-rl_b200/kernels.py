@@ -6,6 +6,7 @@ Each Function is the B200 counterpart of one autograd Function / fused op of the
   LRUScan / complex_scan                <- TritonSequentialScan_Complex (ref: offpolicy_rnn/models/lru/scan_triton/complex_rnn.py:174-244)
   SelectiveScan / selective_scan_fn     <- SelectiveScanFn (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/selective_scan_interface_new.py:19-93)
   AddNorm / layer_norm_fn, rms_norm_fn  <- LayerNormFn (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/triton/layernorm.py:464-478)
+  GRUScan                               <- torch.nn.GRU recurrence (ref: offpolicy_rnn/models/rnn_base.py:59,245-247,454)
   CausalConv1dSiLU                      <- mask * x -> nn.Conv1d -> SiLU (ref: offpolicy_rnn/models/smamba/mamba.py:207-212)
 
 All of them require CUDA tensors: there is no CPU implementation (the oracle under oracle/ is test
@@ -128,6 +129,61 @@ class LRUScan(Function):
 
 def complex_scan(v_re, v_im, f_re, f_im, h0_re=None, h0_im=None, grad_detach=None):
     return LRUScan.apply(v_re, v_im, f_re, f_im, h0_re, h0_im, grad_detach)
+
+
+# ------------------------------------------------------------------------------------------------
+# GRU (persistent cluster kernel for the recurrence; the input / weight-gradient GEMMs are tensor-core GEMMs)
+# ------------------------------------------------------------------------------------------------
+class GRUScan(Function):
+    """out, h_last = GRU recurrence over gi = x W_ih^T + b_ih.  gi [B, L, 3H]; w_hh [3H, H]; b_hh [3H]; h0 [B, H]."""
+
+    @staticmethod
+    def forward(ctx, gi, w_hh, b_hh, h0):
+        gi, w = _f32c(gi), _f32c(w_hh)
+        B, L, H3 = gi.shape
+        H = H3 // 3
+        b = None if b_hh is None else _f32c(b_hh)
+        h0c = None if h0 is None else _f32c(h0.reshape(B, H))
+        out = torch.empty((B, L, H), device=gi.device, dtype=torch.float32)
+        h_last = torch.empty((B, H), device=gi.device, dtype=torch.float32)
+        save = torch.empty((B, L, 4 * H), device=gi.device, dtype=torch.float32) if any(ctx.needs_input_grad) else None
+        N.call("rorl_gru_fwd", N.ptr(gi), N.ptr(w), N.ptr(b), N.ptr(h0c), N.ptr(out), N.ptr(save), N.ptr(h_last),
+               B, L, H, N.stream())
+        ctx.save_for_backward(w, save, out, h0c)
+        ctx.has_bias, ctx.h0_shape = b is not None, (None if h0 is None else h0.shape)
+        ctx.set_materialize_grads(False)
+        return out, h_last
+
+    @staticmethod
+    def backward(ctx, dout, dh_last):
+        w, save, out, h0c = ctx.saved_tensors
+        B, L, H = out.shape
+        dev = out.device
+        dout = torch.zeros_like(out) if dout is None else _f32c(dout)
+        dh_last = None if dh_last is None else _f32c(dh_last.reshape(B, H))
+        dgi = torch.empty((B, L, 3 * H), device=dev, dtype=torch.float32)
+        dghn = torch.empty((B, L, H), device=dev, dtype=torch.float32)
+        dh0 = torch.empty((B, H), device=dev, dtype=torch.float32)
+        N.call("rorl_gru_bwd", N.ptr(dout), N.ptr(dh_last), N.ptr(w), N.ptr(save), N.ptr(out), N.ptr(h0c), N.ptr(dgi),
+               N.ptr(dghn), N.ptr(dh0), B, L, H, N.stream())
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            first = torch.zeros((B, 1, H), device=dev, dtype=torch.float32) if h0c is None else h0c.unsqueeze(1)
+            h_prev = torch.cat((first, out[:, :-1]), dim=1).reshape(B * L, H)
+            g2 = dgi.view(B * L, 3 * H)
+            gn = dghn.view(B * L, H)
+            if _gemm_nt_ok(2 * H, H, B * L):
+                dw = torch.cat((gemm_nt(g2[:, :2 * H], h_prev), gemm_nt(gn, h_prev)), dim=0)
+            else:
+                dw = torch.cat((g2[:, :2 * H].t() @ h_prev, gn.t() @ h_prev), dim=0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.cat((dgi.view(B * L, 3 * H)[:, :2 * H].sum(0), dghn.view(B * L, H).sum(0)))
+        dh0_out = dh0.view(ctx.h0_shape) if (ctx.h0_shape is not None and ctx.needs_input_grad[3]) else None
+        return dgi, dw, db, dh0_out
+
+
+def gru_scan(gi, w_hh, b_hh=None, h0=None):
+    return GRUScan.apply(gi, w_hh, b_hh, h0)
 
 
 # ------------------------------------------------------------------------------------------------

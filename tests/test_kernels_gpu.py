@@ -245,3 +245,40 @@ def test_addnorm_vs_oracle(K, C, rms):
     got = torch.autograd.grad((y, res), gin[:3] + ([] if rms else [gin[3]]), (dy.cuda(), dres.cuda()))
     for a, c, n in zip(got, ref, ("dx", "dr", "dw", "db")):
         assert_close(a, c, TOL, n)
+
+
+# ------------------------------------------------------------------------------------------------ gru
+@pytest.mark.parametrize("shape", [(3, 41, 16, 16), (5, 17, 12, 32), (2, 9, 64, 64), (6, 50, 128, 128), (4, 33, 256, 256),
+                                   (32, 1002, 256, 256), (150, 7, 64, 256)])
+@pytest.mark.parametrize("with_h0", [False, True])
+def test_gru_vs_torch_cpu(K, shape, with_h0):
+    """Persistent cluster GRU (csrc/gru.cu + tensor-core input GEMM) vs torch.nn.GRU on CPU, the reference's own
+    `gru` layer (ref: offpolicy_rnn/models/rnn_base.py:59,245-247,454): outputs, final state, input / state /
+    parameter gradients."""
+    from rorl_b200.models.gru.gru import GRULayer
+    B, L, I, H = shape
+    if B * L > 20000 and with_h0:
+        pytest.skip("one large case is enough")
+    torch.manual_seed(B * 100 + L)
+    ref = torch.nn.GRU(I, H, batch_first=True)
+    mine = GRULayer(I, H, batch_first=True)
+    mine.load_state_dict(ref.state_dict())
+    mine.cuda()
+    x = torch.randn(B, L, I)
+    h0 = 0.5 * torch.randn(1, B, H) if with_h0 else None
+    dy, dhl = torch.randn(B, L, H), torch.randn(1, B, H)
+    xr = x.clone().requires_grad_()
+    h0r = None if h0 is None else h0.clone().requires_grad_()
+    yr, hr = ref(xr, h0r)
+    (yr * dy).sum().backward(retain_graph=True) if False else ((yr * dy).sum() + (hr * dhl).sum()).backward()
+    xg = x.cuda().requires_grad_()
+    h0g = None if h0 is None else h0.cuda().requires_grad_()
+    yg, hg = mine(xg, h0g)
+    ((yg * dy.cuda()).sum() + (hg * dhl.cuda()).sum()).backward()
+    assert_close(yg, yr, TOL, "out")
+    assert_close(hg, hr, TOL, "h_n")
+    assert_close(xg.grad, xr.grad, TOL, "dx")
+    if with_h0:
+        assert_close(h0g.grad, h0r.grad, TOL, "dh0")
+    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, TOL, n)
