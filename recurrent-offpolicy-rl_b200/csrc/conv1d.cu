@@ -11,11 +11,14 @@
 namespace rorl {
 
 constexpr int kConvThreads = 128;
-constexpr int kConvSeg = 128;   // steps per CTA segment
+constexpr int kConvSeg = 128;   // steps per CTA segment (multiple of every supported K)
 
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_fast(x); }
 
-template <int K>
+// All loads of a K-step batch are issued branch-free (time index clamped to the segment, the valid-step mask
+// either compiled in or out) one batch ahead of their use, so each thread keeps 2K independent loads in flight;
+// a branch per element (bounds / mask tests) had left the kernel latency-bound at ~0.9 TB/s.
+template <int K, bool MASK>
 __global__ void __launch_bounds__(kConvThreads) conv1d_silu_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
     const float* __restrict__ mask, float* __restrict__ y, int L, int D, int ld_x, int ld_y) {
@@ -25,38 +28,47 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_silu_fwd_kernel(
     if (d >= D) return;
     float wk[K], win[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) wk[k] = w[(size_t)d * K + k];
-    const float bs = bias ? bias[d] : 0.f;
+    for (int k = 0; k < K; ++k) wk[k] = __ldg(w + (size_t)d * K + k);
+    const float bs = bias ? __ldg(bias + d) : 0.f;
     const size_t row0 = (size_t)b * L;
-    // preload the K-1 halo steps: win slot (t mod K) holds xm[t]
-#pragma unroll
-    for (int k = 0; k < K; ++k) win[k] = 0.f;
-    // Align the main loop so that (t - t0) % K is static: halo fills slots for t0-(K-1) .. t0-1.
-    // Use local time s = t - t0 + K (so halo has s in [1, K-1], main loop starts at s = K).
+    const float* xp = x + row0 * ld_x + d;
+    const float* mp = mask + row0;
+    // halo: win slot k holds xm[t0 - K + k] for k = 1..K-1 (slot s % K with local time s = t - t0 + K)
+    win[0] = 0.f;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        int t = t0 - K + k;
-        float v = 0.f;
-        if (t >= 0) {
-            v = x[(row0 + t) * ld_x + d];
-            if (mask) v *= mask[row0 + t];
-        }
-        win[k] = v;  // slot s % K with s = k
+        const int t = t0 - K + k, tc = max(t, 0);
+        float v = __ldg(xp + (size_t)tc * ld_x);
+        if (MASK) v *= __ldg(mp + tc);
+        win[k] = t >= 0 ? v : 0.f;
     }
-    for (int tb = t0; tb < t1; tb += K) {
+    float nx[K];
+    auto fetch = [&](int tb) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            int t = tb + j;
-            if (t < t1) {
-                float v = x[(row0 + t) * ld_x + d];
-                if (mask) v *= mask[row0 + t];
-                win[j] = v;  // s = t - t0 + K, s % K == j
-                // taps: xm[t - (K-1) + k] lives in slot (j + 1 + k) % K
-                float acc = bs;
+            const int tc = min(tb + j, t1 - 1);
+            nx[j] = __ldg(xp + (size_t)tc * ld_x);
+        }
+        if (MASK) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc = fmaf(wk[k], win[(j + 1 + k) % K], acc);
-                y[(row0 + t) * ld_y + d] = siluf_(acc);
-            }
+            for (int j = 0; j < K; ++j) nx[j] *= __ldg(mp + min(tb + j, t1 - 1));
+        }
+    };
+    fetch(t0);
+    for (int tb = t0; tb < t1; tb += K) {
+        float cx[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) cx[j] = nx[j];
+        fetch(min(tb + K, t1 - 1));
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int t = tb + j;
+            win[j] = cx[j];
+            // taps: xm[t - (K-1) + k] lives in slot (j + 1 + k) % K
+            float acc = bs;
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc = fmaf(wk[k], win[(j + 1 + k) % K], acc);
+            if (t < t1) y[(row0 + t) * ld_y + d] = siluf_(acc);
         }
     }
 }
@@ -65,7 +77,7 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_silu_fwd_kernel(
 //   dxm_s = sum_k w[k] * dpre[s + (K-1) - k];  dw[k] = sum_t dpre_t * xm[t - (K-1) + k];  db = sum_t dpre_t.
 // A segment owns dx for s in [t0, t1): it evaluates dpre on [t0, t1 + K - 1) but only counts
 // t in [t0, t1) towards dw / dbias.
-template <int K>
+template <int K, bool MASK>
 __global__ void __launch_bounds__(kConvThreads) conv1d_silu_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
     const float* __restrict__ mask, const float* __restrict__ dy, float* __restrict__ dx,
@@ -77,56 +89,69 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_silu_bwd_kernel(
     float wk[K], win[K], acc_dx[K], dwk[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        wk[k] = w[(size_t)d * K + k];
-        win[k] = 0.f; acc_dx[k] = 0.f; dwk[k] = 0.f;
+        wk[k] = __ldg(w + (size_t)d * K + k);
+        acc_dx[k] = 0.f; dwk[k] = 0.f;
     }
-    const float bs = bias ? bias[d] : 0.f;
+    const float bs = bias ? __ldg(bias + d) : 0.f;
     float db = 0.f;
     const size_t row0 = (size_t)b * L;
+    const float* xp = x + row0 * ld_x + d;
+    const float* gp = dy + row0 * ld_dy + d;
+    const float* mp = mask + row0;
+    win[0] = 0.f;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        int t = t0 - K + k;
-        float v = 0.f;
-        if (t >= 0) {
-            v = x[(row0 + t) * ld_x + d];
-            if (mask) v *= mask[row0 + t];
-        }
-        win[k] = v;
+        const int t = t0 - K + k, tc = max(t, 0);
+        float v = __ldg(xp + (size_t)tc * ld_x);
+        if (MASK) v *= __ldg(mp + tc);
+        win[k] = t >= 0 ? v : 0.f;
     }
-    const int tend = min(L, t1 + K - 1);
+    const int tend = min(L, t1 + K - 1);       // dpre is needed on [t0, tend)
+    const int tstop = tend + K - 1;            // positions up to t1 - 1 complete by step tend + K - 2
     // acc_dx slot (s % K) accumulates dxm for position t = s - K + t0; position t - (K-1) completes at step t.
-    for (int tb = t0; tb < tend + K - 1; tb += K) {
+    float nx[K], ng[K];
+    auto fetch = [&](int tb) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            int t = tb + j;
-            if (t < tend + K - 1) {
-                float dpre = 0.f;
-                if (t < tend) {
-                    float v = x[(row0 + t) * ld_x + d];
-                    if (mask) v *= mask[row0 + t];
-                    win[j] = v;
-                    float pre = bs;
+            const int tc = min(tb + j, tend - 1);
+            nx[j] = __ldg(xp + (size_t)tc * ld_x);
+            ng[j] = __ldg(gp + (size_t)tc * ld_dy);
+        }
+        if (MASK) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) pre = fmaf(wk[k], win[(j + 1 + k) % K], pre);
-                    float sg = sigmoidf_fast(pre);
-                    dpre = dy[(row0 + t) * ld_dy + d] * sg * (1.0f + pre * (1.0f - sg));
-                    if (t < t1) {
-                        db += dpre;
+            for (int j = 0; j < K; ++j) nx[j] *= __ldg(mp + min(tb + j, tend - 1));
+        }
+    };
+    fetch(t0);
+    for (int tb = t0; tb < tstop; tb += K) {
+        float cx[K], cg[K];
 #pragma unroll
-                        for (int k = 0; k < K; ++k) dwk[k] = fmaf(dpre, win[(j + 1 + k) % K], dwk[k]);
-                    }
-                }
-                // scatter dpre_t into positions t-(K-1)+k (slot (j+1+k)%K); slot j is the newest (k = K-1)
-                acc_dx[j] = 0.f;
+        for (int j = 0; j < K; ++j) { cx[j] = nx[j]; cg[j] = ng[j]; }
+        fetch(min(tb + K, tend - 1));
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc_dx[(j + 1 + k) % K] = fmaf(wk[k], dpre, acc_dx[(j + 1 + k) % K]);
-                // position t-(K-1) (slot (j+1)%K) has now received all its contributions
-                int s = t - (K - 1);
-                if (s >= t0 && s < t1) {
-                    float g = acc_dx[(j + 1) % K];
-                    if (mask) g *= mask[row0 + s];
-                    dx[(row0 + s) * ld_dx + d] = g;
-                }
+        for (int j = 0; j < K; ++j) {
+            const int t = tb + j;
+            win[j] = cx[j];
+            float pre = bs;
+#pragma unroll
+            for (int k = 0; k < K; ++k) pre = fmaf(wk[k], win[(j + 1 + k) % K], pre);
+            const float sg = sigmoidf_fast(pre);
+            const float dfull = cg[j] * sg * (1.0f + pre * (1.0f - sg));
+            const float dpre = t < tend ? dfull : 0.f;          // steps past the sequence / halo end contribute nothing
+            const float down = t < t1 ? dpre : 0.f;             // dw / dbias count this segment's own steps only
+            db += down;
+#pragma unroll
+            for (int k = 0; k < K; ++k) dwk[k] = fmaf(down, win[(j + 1 + k) % K], dwk[k]);
+            // scatter dpre_t into positions t-(K-1)+k (slot (j+1+k)%K); slot j is the newest (k = K-1)
+            acc_dx[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc_dx[(j + 1 + k) % K] = fmaf(wk[k], dpre, acc_dx[(j + 1 + k) % K]);
+            // position t-(K-1) (slot (j+1)%K) has now received all its contributions
+            const int sp = t - (K - 1);
+            if (sp >= t0 && sp < t1) {
+                float g = acc_dx[(j + 1) % K];
+                if (MASK) g *= __ldg(mp + sp);
+                dx[(row0 + sp) * ld_dx + d] = g;
             }
         }
     }
@@ -144,14 +169,19 @@ extern "C" {
 
 int rorl_conv1d_nseg(int64_t L) { return (int)((L + kConvSeg - 1) / kConvSeg); }
 
-#define CONV_DISPATCH(KERN, ...)                                                   \
-    switch (K) {                                                                   \
-        case 2: KERN<2><<<grid, kConvThreads, 0, stream>>>(__VA_ARGS__); break;    \
-        case 3: KERN<3><<<grid, kConvThreads, 0, stream>>>(__VA_ARGS__); break;    \
-        case 4: KERN<4><<<grid, kConvThreads, 0, stream>>>(__VA_ARGS__); break;    \
-        case 8: KERN<8><<<grid, kConvThreads, 0, stream>>>(__VA_ARGS__); break;    \
-        case 16: KERN<16><<<grid, kConvThreads, 0, stream>>>(__VA_ARGS__); break;  \
-        default: return RORL_ERR_SHAPE;                                            \
+#define CONV_CASE(KERN, KK, ...)                                                        \
+    case KK:                                                                            \
+        if (mask) KERN<KK, true><<<grid, kConvThreads, 0, stream>>>(__VA_ARGS__);       \
+        else KERN<KK, false><<<grid, kConvThreads, 0, stream>>>(__VA_ARGS__);           \
+        break;
+#define CONV_DISPATCH(KERN, ...)                   \
+    switch (K) {                                   \
+        CONV_CASE(KERN, 2, __VA_ARGS__)            \
+        CONV_CASE(KERN, 3, __VA_ARGS__)            \
+        CONV_CASE(KERN, 4, __VA_ARGS__)            \
+        CONV_CASE(KERN, 8, __VA_ARGS__)            \
+        CONV_CASE(KERN, 16, __VA_ARGS__)           \
+        default: return RORL_ERR_SHAPE;            \
     }
 
 int rorl_conv1d_silu_fwd(const float* x, const float* w, const float* bias, const float* mask, float* y,

@@ -16,8 +16,11 @@
 //               fence.proxy.async, arrive
 //   warp 1      MMA issuer (one elected lane): 4 k-steps x 3 tcgen05.mma.kind::tf32 (M128 x N128 x K8) per
 //               stage into one of two TMEM accumulators; tcgen05.commit frees the stage / publishes the tile
-//   warps 6-9   epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per instruction), + bias, ELU,
-//               vectorised global stores; overlaps the next tile's main loop (double-buffered TMEM)
+//   warps 6-13  epilogue: two warps per TMEM lane quarter, each owning two of the four 32-column chunks:
+//               tcgen05.ld (32 lanes x 32 columns per instruction), + bias, branch-free ELU, shared-memory
+//               transposition, 128-B-row global stores; overlaps the next tile's main loop (double-buffered
+//               TMEM).  One warp per scheduler was latency bound (ncu: the epilogue, not the MMA, set the tile
+//               time), hence eight
 // Operand layouts: the TN variant takes both operands K-major (reduction dimension contiguous): forward
 // (x, W[N,K]) and data-gradient (dY, W^T materialised by the caller; weights are tiny).  The NT variant takes
 // both operands MN-major (reduction dimension = rows): weight gradients dW[n,k] = sum_m dY[m,n] X[m,k] straight
@@ -31,10 +34,11 @@ namespace rorl {
 
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 32;     // BK fp32 = one 128-byte swizzle row
 constexpr int kGemmStages = 3;
-constexpr int kGemmThreads = 320;
+constexpr int kGemmThreads = 448;                                // TMA, MMA, 4 splitter and 8 epilogue warps
+constexpr int kGemmEpiWarps = 8;
 constexpr int kTileBytes = kGemmBM * kGemmBK * 4;             // 16 KiB (A and B tiles have the same size)
 constexpr int kStageBytes = 4 * kTileBytes;                   // A_raw | B_raw | A_lo | B_lo
-constexpr int kStagingBytes = 4 * 32 * 128;                   // per epilogue warp: 32 rows x 32 fp32 columns
+constexpr int kStagingBytes = kGemmEpiWarps * 32 * 128;       // per epilogue warp: 32 rows x 32 fp32 columns
 constexpr int kGemmSmem = kGemmStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmParams {
@@ -49,27 +53,6 @@ struct GemmParams {
     long long strideSplit;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -98,21 +81,12 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
     return d;
 }
 
-// ELU(alpha = 1) without the multi-instruction expm1f: degree-7 Taylor for -0.5 < x <= 0 (rel. err < 1e-7),
-// ex2-based below (abs. err 2e-7 on a result of magnitude >= 0.39).
+// ELU(alpha = 1), branch-free: ex2 on min(x, 0) and a select (5 instructions, no divergence).  Absolute error
+// ~1e-7 (ex2.approx is 2 ulp on a result in (0, 1]); relative to the layer's activations that is far inside
+// the 1e-3 parity budget.
 __device__ __forceinline__ float elu1(float x) {
-    if (x > 0.f) return x;
-    if (x > -0.5f) {
-        float p = 1.0f / 5040.0f;
-        p = fmaf(p, x, 1.0f / 720.0f);
-        p = fmaf(p, x, 1.0f / 120.0f);
-        p = fmaf(p, x, 1.0f / 24.0f);
-        p = fmaf(p, x, 1.0f / 6.0f);
-        p = fmaf(p, x, 0.5f);
-        p = fmaf(p, x, 1.0f);
-        return p * x;
-    }
-    return ex2f(x * kLog2e) - 1.0f;
+    const float e = ex2f(fminf(x, 0.f) * kLog2e) - 1.0f;
+    return x > 0.f ? x : e;
 }
 
 template <bool MN>
@@ -150,7 +124,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull(a), 1);
-            mbar_init(bar_tempty(a), 4);
+            mbar_init(bar_tempty(a), kGemmEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -308,7 +282,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // TMEM -> registers (one accumulator row per lane) -> + bias / ELU -> swizzled per-warp staging tile in
         // shared memory -> row-contiguous 128-B global stores (4 full lines per warp instruction).
         const int q = warp & 3;                                                  // TMEM lane quarter this warp may read
-        uint8_t* stg = staging + q * 4096;
+        const int hf = (warp - 6) >> 2;                                          // which pair of 32-column chunks
+        uint8_t* stg = staging + (warp - 6) * 4096;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM;
@@ -334,28 +309,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 }
                 __syncwarp();
             };
-#pragma unroll 1
-            for (int c = 0; c < kGemmBN / 32; ++c) {
-                const int col0 = tn * kGemmBN + c * 32;
-                if (col0 >= p.N) break;                                          // warp-uniform
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + acc * kGemmBN + c * 32 + ((uint32_t)(q * 32) << 16);
+            // both of this warp's chunks are pulled out of TMEM up front, so the accumulator is released to the MMA
+            // warp before the (long) bias / activation / store tail
+            uint32_t r[2][32];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const uint32_t taddr = tmem_base + acc * kGemmBN + (2 * hf + cc) * 32 + ((uint32_t)(q * 32) << 16);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "=r"(r[cc][0]), "=r"(r[cc][1]), "=r"(r[cc][2]), "=r"(r[cc][3]), "=r"(r[cc][4]), "=r"(r[cc][5]), "=r"(r[cc][6]), "=r"(r[cc][7]),
+                      "=r"(r[cc][8]), "=r"(r[cc][9]), "=r"(r[cc][10]), "=r"(r[cc][11]), "=r"(r[cc][12]), "=r"(r[cc][13]), "=r"(r[cc][14]), "=r"(r[cc][15]),
+                      "=r"(r[cc][16]), "=r"(r[cc][17]), "=r"(r[cc][18]), "=r"(r[cc][19]), "=r"(r[cc][20]), "=r"(r[cc][21]), "=r"(r[cc][22]), "=r"(r[cc][23]),
+                      "=r"(r[cc][24]), "=r"(r[cc][25]), "=r"(r[cc][26]), "=r"(r[cc][27]), "=r"(r[cc][28]), "=r"(r[cc][29]), "=r"(r[cc][30]), "=r"(r[cc][31])
                     : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(acc));
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int col0 = tn * kGemmBN + (2 * hf + cc) * 32;
+                if (col0 >= p.N) break;                                          // warp-uniform
                 float4 o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                       __uint_as_float(r[4 * j + 3]));
+                    o[j] = make_float4(__uint_as_float(r[cc][4 * j]), __uint_as_float(r[cc][4 * j + 1]), __uint_as_float(r[cc][4 * j + 2]),
+                                       __uint_as_float(r[cc][4 * j + 3]));
                     if (bias && col0 + 4 * j < p.N) {
-                        const float4 bv = *reinterpret_cast<const float4*>(bias + col0 + 4 * j);
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * j));
                         o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
                     }
                 }
@@ -366,9 +349,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 }
                 flush(o, p.D, col0);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty(acc));
         }
     }
     tc_fence_before();

@@ -50,157 +50,283 @@ struct SelFwdParams {
     int L, D;
     int ld_u, ld_delta, ld_z, ld_B, ld_C, ld_y;
     int nckpt;
+    int dbg;
 };
 
-template <int N, bool HAS_Z, bool SOFTPLUS>
-__global__ void __launch_bounds__(kSelThreads) selscan_fwd_kernel(const SelFwdParams p) {
-    using Cfg = SelCfg<N>;
-    constexpr int S = Cfg::S, LPD = Cfg::LPD, DPW = Cfg::DPW, DT = Cfg::DT, QPR = Cfg::QPR;
-    constexpr int TC = 32;                                  // steps per staged tile
-    constexpr int STAGE = TC * (3 * DT + 2 * N) + TC;       // u, delta, z, B, C, start
-    constexpr int NQ = TC * QPR / kSelThreads;              // float4 per thread per [TC x DT] tile
-    constexpr int NQB = (TC * N / 4 + kSelThreads - 1) / kSelThreads;
-    extern __shared__ __align__(16) float smem[];
+// Forward decomposition (warp specialised, shared-memory-bandwidth aware).
+//
+// The scan is serial in time per (d, n); the only parallelism is B x D x N and the arithmetic floor is the MUFU
+// pipe: one ex2 per (t, d, n), 16 per clock per SM (measured with tools/microbench/pipes.cu: 15.9 / clk / SM;
+// fma.f32x2 = 117 fma / clk / SM; a scan-like mix sustains 15.6 ex2 / clk / SM from 16 warps).  What the ncu
+// captures of the earlier versions showed, in order:
+//   * every warp running load -> transform -> barrier -> scan -> barrier -> write-back phases cost 176 us for the
+//     data-movement skeleton alone, not overlapped with the scan (tools/sel_phases.py)  => warp specialisation;
+//   * with one channel x 8 states per thread the time loop reads B_t and C_t (64 B per thread per step) through
+//     LDS.128, which is 4 shared-memory wavefronts per instruction however much of it is a broadcast: 26 wavefronts
+//     per warp-step, l1tex shared pipe 83 % busy, 439 cycles per step against 256 for the MUFU pipe
+//     => two channels per thread share one copy of B_t / C_t (22 wavefronts per 16 states instead of 26 per 8).
+// Roles per CTA (DT channels of one batch row):
+//   * 8 SCAN warps, thread = 2 adjacent channels x 4 states (state, A, B, C as float2 pairs): per step LDS.64 of
+//     (delta or +inf) and delta*u for the channel pair, 2 LDS.128 of B/C, 8 ex2 issued one step ahead of the state
+//     update they feed and interleaved with it, packed fma/mul.f32x2, one STS.64 of the lane's partial sums of h.C.
+//     No shuffles, branches or block barriers in the time loop; tiles are handed over through mbarriers.
+//   * 4 HELPER warps: cp.async of the raw tile three tiles ahead (4-stage ring), the per-(t, d) transform
+//     (softplus, delta*u, reset folded into the exponent argument as +inf so that ex2(-inf) = 0, silu(z) and
+//     the D*u skip pre-multiplied by it), and the write-back of y = partials * silu(z) + skip as coalesced rows.
+template <int N>
+struct SelFwdCfg {
+#ifndef RORL_SEL_S
+#define RORL_SEL_S 4
+#endif
+    static constexpr int S = RORL_SEL_S;                  // states per scan thread (per channel)
+    static constexpr int CH = 2;                          // channels per scan thread
+    static constexpr int LPD = N / S;                     // lanes per channel pair
+    static constexpr int PPW = 32 / LPD;                  // channel pairs per warp
+    static constexpr int NSCAN = 32 * 32 / RORL_SEL_S;    // scan threads (8 warps at S = 4)
+    static constexpr int DT = (NSCAN / 32) * PPW * CH;    // channels per CTA
+    static constexpr int QPR = DT / 4;                    // float4 quads per tile row
+    static constexpr int TC = 2 * RORL_SEL_S;             // steps per tile
+    static constexpr int NST = 4;                         // raw stages in flight
+    static constexpr int STAGE = TC * (4 * DT + 2 * N);   // u->skip, delta->dtA, z->silu(z), du, B, C
+    static constexpr int PROW = DT * LPD + DT;            // partial-sum row: [DT/4 quads][2 pairs][LPD][2] + 4 floats of skew per quad
+    static constexpr int PART = TC * PROW;                // (the skew makes the helpers' LDS.128 of a quad bank-conflict free)
+    static constexpr int NHELP = 128;                     // helper threads
+    static constexpr int NTHREADS = NSCAN + NHELP;
+    static constexpr size_t SMEM = sizeof(float) * (NST * STAGE + 2 * PART) + 128;
+};
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int dl = lane / LPD, ng = lane % LPD;
-    const int dloc = warp * DPW + dl;
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+template <int N, bool HAS_Z, bool SOFTPLUS>
+__global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(const SelFwdParams p) {
+    using Cfg = SelFwdCfg<N>;
+    constexpr int S = Cfg::S, LPD = Cfg::LPD, PPW = Cfg::PPW, DT = Cfg::DT, QPR = Cfg::QPR, TC = Cfg::TC, STAGE = Cfg::STAGE;
+    constexpr int NST = Cfg::NST, PART = Cfg::PART, PROW = Cfg::PROW, NHELP = Cfg::NHELP, NSCAN = Cfg::NSCAN, H2 = S / 2;
+    extern __shared__ __align__(16) float smem[];
+    float* s_part = smem + NST * STAGE;                     // [2][TC][DT/2][LPD][2]
+    const uint32_t bars = smem_u32(s_part + 2 * PART);      // full[NST], done[2], freep[2]
+    auto bar_full = [&](int st) { return bars + 8u * st; };
+    auto bar_done = [&](int pb) { return bars + 8u * (NST + pb); };
+    auto bar_freep = [&](int pb) { return bars + 8u * (NST + 2 + pb); };
+
+    const int tid = threadIdx.x;
     const int b = blockIdx.y, d0 = blockIdx.x * DT;
-    const int d = d0 + dloc;
-    const bool dvalid = d < p.D;
     const int L = p.L;
     const size_t row0 = (size_t)b * L;
     const int ntiles = (L + TC - 1) / TC;
-    const int myq = tid % QPR;                               // this thread's quad column (fixed)
-    const bool qvalid = (d0 + myq * 4) < p.D;
-
-    float A2[S], h[S];
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        A2[j] = dvalid ? p.A[(size_t)d * N + ng * S + j] * kLog2e : 0.f;
-        h[j] = 0.f;
+    if (tid == 0) {
+        for (int st = 0; st < NST; ++st) mbar_init(bar_full(st), NHELP / 32);
+        for (int pb = 0; pb < 2; ++pb) {
+            mbar_init(bar_done(pb), NSCAN / 32);
+            mbar_init(bar_freep(pb), NHELP / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const float Dd = (dvalid && p.Dskip) ? p.Dskip[d] : 0.f;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.dbias && qvalid) bias4 = *reinterpret_cast<const float4*>(p.dbias + d0 + myq * 4);
+    __syncthreads();
 
-    auto issue = [&](int tile) {
-        if (tile < ntiles) {
-            float* st = smem + (tile & 1) * STAGE;
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                int idx = tid + i * kSelThreads, r = idx / QPR, t = tile * TC + r;
-                bool ok = qvalid && t < L;
-                size_t row = row0 + (ok ? t : 0);
-                int col = d0 + myq * 4;
-                cp_async16(st + r * DT + myq * 4, p.u + row * p.ld_u + col, ok);
-                cp_async16(st + TC * DT + r * DT + myq * 4, p.delta + row * p.ld_delta + col, ok);
-                if (HAS_Z) cp_async16(st + 2 * TC * DT + r * DT + myq * 4, p.z + row * p.ld_z + col, ok);
-            }
-#pragma unroll
-            for (int i = 0; i < NQB; ++i) {
-                int idx = tid + i * kSelThreads;
-                if (idx < TC * N / 4) {
-                    int r = idx / (N / 4), q = idx % (N / 4), t = tile * TC + r;
-                    bool ok = t < L;
-                    size_t row = row0 + (ok ? t : 0);
-                    cp_async16(st + 3 * TC * DT + r * N + q * 4, p.Bm + row * p.ld_B + q * 4, ok);
-                    cp_async16(st + 3 * TC * DT + TC * N + r * N + q * 4, p.Cm + row * p.ld_C + q * 4, ok);
+    if (tid >= NSCAN) {
+        // ------------------------------------------------------------------------------------ helper warps
+        const int ht = tid - NSCAN;
+        auto issue = [&](int tile) {
+            if (tile < ntiles) {
+                float* st = smem + (tile % NST) * STAGE;
+                for (int idx = ht; idx < TC * QPR; idx += NHELP) {
+                    const int r = idx / QPR, q = idx % QPR, t = tile * TC + r, col = d0 + q * 4;
+                    const bool ok = col < p.D && t < L;
+                    const size_t row = row0 + (ok ? t : 0);
+                    cp_async16(st + r * DT + q * 4, p.u + row * p.ld_u + (ok ? col : 0), ok);
+                    cp_async16(st + TC * DT + r * DT + q * 4, p.delta + row * p.ld_delta + (ok ? col : 0), ok);
+                    if (HAS_Z) cp_async16(st + 2 * TC * DT + r * DT + q * 4, p.z + row * p.ld_z + (ok ? col : 0), ok);
+                }
+                for (int idx = ht; idx < TC * N / 4; idx += NHELP) {
+                    const int r = idx / (N / 4), q = idx % (N / 4), t = tile * TC + r;
+                    const bool ok = t < L;
+                    const size_t row = row0 + (ok ? t : 0);
+                    cp_async16(st + 4 * TC * DT + r * N + q * 4, p.Bm + row * p.ld_B + q * 4, ok);
+                    cp_async16(st + 4 * TC * DT + TC * N + r * N + q * 4, p.Cm + row * p.ld_C + q * 4, ok);
                 }
             }
-            if (tid < TC) {
-                int t = tile * TC + tid;
-                bool ok = p.start != nullptr && t < L;
-                cp_async4(st + 3 * TC * DT + 2 * TC * N + tid, p.start + (ok ? row0 + t : 0), ok);
+            cp_async_commit();
+        };
+        // per-(t, d) transform of the elements this thread staged itself (visible to it after wait_group)
+        auto transform = [&](int tile) {
+            float* st = smem + (tile % NST) * STAGE;
+            for (int idx = ht; idx < TC * QPR; idx += NHELP) {
+                const int r = idx / QPR, q = idx % QPR, t = tile * TC + r, col = d0 + q * 4;
+                // reset flag first: its (L2) latency overlaps the arithmetic below
+                const float rs = (p.start != nullptr && t < L) ? __ldg(p.start + row0 + t) : 0.f;
+                float4* pu = reinterpret_cast<float4*>(st + r * DT + q * 4);
+                float4* pd = reinterpret_cast<float4*>(st + TC * DT + r * DT + q * 4);
+                float4* pz = reinterpret_cast<float4*>(st + 2 * TC * DT + r * DT + q * 4);
+                float4 x = *pd;
+                const float4 uu = *pu;
+                if (p.dbias && col < p.D) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.dbias + col));
+                    x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                }
+                if (SOFTPLUS) {
+                    x.x = softplusf_fast(x.x); x.y = softplusf_fast(x.y);
+                    x.z = softplusf_fast(x.z); x.w = softplusf_fast(x.w);
+                }
+                // rows past the end of the sequence: delta = 0 (a = 1, du = 0) leaves the state untouched
+                if (t >= L) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(st + 3 * TC * DT + r * DT + q * 4) =
+                    make_float4(x.x * uu.x, x.y * uu.y, x.z * uu.z, x.w * uu.w);
+                float4 gz = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (HAS_Z) {
+                    const float4 zz = *pz;
+                    gz = make_float4(zz.x * sigmoidf_fast(zz.x), zz.y * sigmoidf_fast(zz.y), zz.z * sigmoidf_fast(zz.z),
+                                     zz.w * sigmoidf_fast(zz.w));
+                }
+                float4 D4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.Dskip && col < p.D) D4 = __ldg(reinterpret_cast<const float4*>(p.Dskip + col));
+                *pz = gz;
+                *pu = make_float4(D4.x * uu.x * gz.x, D4.y * uu.y * gz.y, D4.z * uu.z * gz.z, D4.w * uu.w * gz.w);
+                // reset: the scan multiplies this slot by A * log2(e) < 0, so +inf gives a = ex2(-inf) = 0
+                if (rs != 0.f) x = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                *pd = x;
+            }
+        };
+        for (int k = 0; k < NST - 1; ++k) issue(k);
+        cp_async_wait<NST - 2>();
+        transform(0);
+        __syncwarp();
+        if ((ht & 31) == 0) mbar_arrive(bar_full(0));
+        for (int k = 0; k < ntiles; ++k) {
+            // stage (k + NST - 1) % NST held tile k - 1, whose write-back finished behind the helper barrier below
+            issue(k + NST - 1);
+            if (k + 1 < ntiles) {
+                cp_async_wait<NST - 2>();
+                transform(k + 1);
+                __syncwarp();
+                if ((ht & 31) == 0) mbar_arrive(bar_full((k + 1) % NST));
+            }
+            // write-back of tile k once the scan warps have left its partial sums
+            mbar_wait(bar_done(k & 1), (k >> 1) & 1);
+            const float* st = smem + (k % NST) * STAGE;
+            const float* part = s_part + (k & 1) * PART;
+            for (int idx = ht; idx < TC * QPR; idx += NHELP) {
+                const int r = idx / QPR, q = idx % QPR, t = k * TC + r, col = d0 + q * 4;
+                if (col < p.D && t < L) {
+                    const float4 skip = *reinterpret_cast<const float4*>(st + r * DT + q * 4);
+                    const float4 gz = *reinterpret_cast<const float4*>(st + 2 * TC * DT + r * DT + q * 4);
+                    float yv[4];
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp) {         // the quad's two channel pairs
+                        const float2* pp = reinterpret_cast<const float2*>(part + r * PROW + q * (4 * LPD + 4) + cp * 2 * LPD);
+                        float2 sum = f2(0.f, 0.f);
+#pragma unroll
+                        for (int kk = 0; kk < LPD; ++kk) {
+                            const float2 v = pp[kk];
+                            sum.x += v.x; sum.y += v.y;
+                        }
+                        yv[2 * cp] = sum.x; yv[2 * cp + 1] = sum.y;
+                    }
+                    *reinterpret_cast<float4*>(p.y + (row0 + t) * p.ld_y + col) =
+                        make_float4(fmaf(yv[0], gz.x, skip.x), fmaf(yv[1], gz.y, skip.y), fmaf(yv[2], gz.z, skip.z), fmaf(yv[3], gz.w, skip.w));
+                }
+            }
+            __syncwarp();
+            if ((ht & 31) == 0) mbar_arrive(bar_freep(k & 1));
+            asm volatile("bar.sync 1, %0;" ::"n"(NHELP) : "memory");   // all helpers are done reading stage k % NST
+        }
+    } else {
+        // ------------------------------------------------------------------------------------ scan warps
+        const int lane = tid & 31, warp = tid >> 5;
+        const int pl = lane / LPD, ng = lane % LPD;
+        const int ploc = warp * PPW + pl;                   // channel pair within the CTA
+        const int dloc = ploc * 2;
+        const int d = d0 + dloc;
+        float2 A2[2][H2], h[2][H2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const bool ok = d + c < p.D;
+#pragma unroll
+            for (int j = 0; j < H2; ++j) {
+                A2[c][j] = ok ? f2(p.A[(size_t)(d + c) * N + ng * S + 2 * j] * kLog2e, p.A[(size_t)(d + c) * N + ng * S + 2 * j + 1] * kLog2e)
+                              : f2(0.f, 0.f);
+                h[c][j] = f2(0.f, 0.f);
             }
         }
-        cp_async_commit();
-    };
-
-    issue(0);
-    for (int tile = 0; tile < ntiles; ++tile) {
-        float* st = smem + (tile & 1) * STAGE;
-        float* s_u = st;
-        float* s_dt = st + TC * DT;
-        float* s_z = st + 2 * TC * DT;
-        float* s_B = st + 3 * TC * DT;
-        float* s_C = s_B + TC * N;
-        float* s_start = s_C + TC * N;
-        cp_async_wait<0>();
-        // transform the elements this thread staged itself (visible to it without a barrier)
+        for (int k = 0; k < ntiles; ++k) {
+            const float* st = smem + (k % NST) * STAGE;
+            const float* s_dt = st + TC * DT;
+            const float* s_du = st + 3 * TC * DT;
+            const float* s_B = st + 4 * TC * DT;
+            const float* s_C = s_B + TC * N;
+            float* part = s_part + (k & 1) * PART;
+            mbar_wait(bar_full(k % NST), (k / NST) & 1);
+            if (k >= 2) mbar_wait(bar_freep(k & 1), ((k >> 1) - 1) & 1);
+            // software pipeline: a[][] holds exp(delta_i A) for the step about to be applied
+            float2 a[2][H2];
+            {
+                const float2 dt = *reinterpret_cast<const float2*>(s_dt + dloc);
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int idx = tid + i * kSelThreads, r = idx / QPR;
-            float4* pd = reinterpret_cast<float4*>(s_dt + r * DT + myq * 4);
-            float4 x = *pd;
-            x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-            if (SOFTPLUS) {
-                x.x = softplusf_fast(x.x); x.y = softplusf_fast(x.y);
-                x.z = softplusf_fast(x.z); x.w = softplusf_fast(x.w);
+                for (int j = 0; j < H2; ++j) {
+                    const float2 e0 = __fmul2_rn(f2(dt.x, dt.x), A2[0][j]);
+                    const float2 e1 = __fmul2_rn(f2(dt.y, dt.y), A2[1][j]);
+                    a[0][j] = f2(ex2f(e0.x), ex2f(e0.y));
+                    a[1][j] = f2(ex2f(e1.x), ex2f(e1.y));
+                }
             }
-            *pd = x;
-            if (HAS_Z) {
-                float4* pz = reinterpret_cast<float4*>(s_z + r * DT + myq * 4);
-                float4 zz = *pz;
-                zz.x *= sigmoidf_fast(zz.x); zz.y *= sigmoidf_fast(zz.y);
-                zz.z *= sigmoidf_fast(zz.z); zz.w *= sigmoidf_fast(zz.w);
-                *pz = zz;
+#pragma unroll
+            for (int i = 0; i < TC; ++i) {
+                const float2 du = *reinterpret_cast<const float2*>(s_du + i * DT + dloc);
+                const float2 dtn = (i + 1 < TC) ? *reinterpret_cast<const float2*>(s_dt + (i + 1) * DT + dloc) : f2(0.f, 0.f);
+                float2 Bv[H2], Cv[H2];
+#pragma unroll
+                for (int j = 0; j < H2; j += 2) {
+                    const float4 bq = *reinterpret_cast<const float4*>(s_B + i * N + ng * S + 2 * j);
+                    const float4 cq = *reinterpret_cast<const float4*>(s_C + i * N + ng * S + 2 * j);
+                    Bv[j] = f2(bq.x, bq.y); Bv[j + 1] = f2(bq.z, bq.w);
+                    Cv[j] = f2(cq.x, cq.y); Cv[j + 1] = f2(cq.z, cq.w);
+                }
+                float2 acc[2] = {f2(0.f, 0.f), f2(0.f, 0.f)};
+#pragma unroll
+                for (int j = 0; j < H2; ++j) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float duc = c ? du.y : du.x;
+                        h[c][j] = __ffma2_rn(a[c][j], h[c][j], __fmul2_rn(f2(duc, duc), Bv[j]));
+                        acc[c] = __ffma2_rn(h[c][j], Cv[j], acc[c]);
+                        if (i + 1 < TC) {          // next step's decay, issued between this step's FMAs
+                            const float dtc = c ? dtn.y : dtn.x;
+                            const float2 e = __fmul2_rn(f2(dtc, dtc), A2[c][j]);
+                            a[c][j] = f2(ex2f(e.x), ex2f(e.y));
+                        }
+                    }
+                }
+                *reinterpret_cast<float2*>(part + i * PROW + (ploc >> 1) * (4 * LPD + 4) + (ploc & 1) * 2 * LPD + 2 * ng) =
+                    f2(acc[0].x + acc[0].y, acc[1].x + acc[1].y);
+                if (((i + 1) % (TC < kCkptEvery ? TC : kCkptEvery)) == 0 && ((k * TC + i) % kCkptEvery) == kCkptEvery - 1) {
+                    const int ck = (k * TC + i) / kCkptEvery;
+                    if (p.ckpt != nullptr && ck < p.nckpt) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (d + c < p.D) {
+                                float* cpt = p.ckpt + (((size_t)b * p.nckpt + ck) * p.D + d + c) * N + ng * S;
+#pragma unroll
+                                for (int j = 0; j < H2; j += 2)
+                                    *reinterpret_cast<float4*>(cpt + 2 * j) = make_float4(h[c][j].x, h[c][j].y, h[c][j + 1].x, h[c][j + 1].y);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_done(k & 1));
+        }
+        if (p.last_state != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (d + c < p.D) {
+                    float* cpt = p.last_state + ((size_t)b * p.D + d + c) * N + ng * S;
+#pragma unroll
+                    for (int j = 0; j < H2; j += 2)
+                        *reinterpret_cast<float4*>(cpt + 2 * j) = make_float4(h[c][j].x, h[c][j].y, h[c][j + 1].x, h[c][j + 1].y);
+                }
             }
         }
-        __syncthreads();
-        issue(tile + 1);
-
-        const int tbase = tile * TC;
-        const int tcount = min(TC, L - tbase);
-#pragma unroll 2
-        for (int i = 0; i < tcount; ++i) {
-            const float dt = s_dt[i * DT + dloc];
-            const float uu = s_u[i * DT + dloc];
-            const float du = dt * uu;
-            if (s_start[i] != 0.f) {
-#pragma unroll
-                for (int j = 0; j < S; ++j) h[j] = 0.f;
-            }
-            float Bv[S], Cv[S];
-            *reinterpret_cast<float4*>(Bv) = *reinterpret_cast<const float4*>(s_B + i * N + ng * S);
-            *reinterpret_cast<float4*>(Bv + 4) = *reinterpret_cast<const float4*>(s_B + i * N + ng * S + 4);
-            *reinterpret_cast<float4*>(Cv) = *reinterpret_cast<const float4*>(s_C + i * N + ng * S);
-            *reinterpret_cast<float4*>(Cv + 4) = *reinterpret_cast<const float4*>(s_C + i * N + ng * S + 4);
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                float a = ex2f(dt * A2[j]);
-                h[j] = fmaf(a, h[j], du * Bv[j]);
-                acc = fmaf(h[j], Cv[j], acc);
-            }
-#pragma unroll
-            for (int o = 1; o < LPD; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (ng == 0) {
-                float yv = fmaf(Dd, uu, acc);
-                if (HAS_Z) yv *= s_z[i * DT + dloc];
-                s_z[i * DT + dloc] = yv;
-            }
-            const int t = tbase + i;
-            if (p.ckpt != nullptr && (t % kCkptEvery) == kCkptEvery - 1 && dvalid) {
-                float* c = p.ckpt + (((size_t)b * p.nckpt + t / kCkptEvery) * p.D + d) * N + ng * S;
-                *reinterpret_cast<float4*>(c) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(c + 4) = make_float4(h[4], h[5], h[6], h[7]);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int idx = tid + i * kSelThreads, r = idx / QPR, t = tbase + r;
-            if (qvalid && t < L) {
-                float4 v = *reinterpret_cast<const float4*>(s_z + r * DT + myq * 4);
-                *reinterpret_cast<float4*>(p.y + (row0 + t) * p.ld_y + d0 + myq * 4) = v;
-            }
-        }
-    }
-    if (p.last_state != nullptr && dvalid) {
-        float* c = p.last_state + ((size_t)b * p.D + d) * N + ng * S;
-        *reinterpret_cast<float4*>(c) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(c + 4) = make_float4(h[4], h[5], h[6], h[7]);
     }
 }
 
@@ -501,7 +627,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) selscan_bwd_kernel(const SelBw
 
 template <int N>
 constexpr size_t sel_fwd_smem() {
-    return sizeof(float) * 2 * (32 * (3 * SelCfg<N>::DT + 2 * N) + 32);
+    return SelFwdCfg<N>::SMEM;
 }
 template <int N>
 constexpr size_t sel_bwd_smem() {
@@ -513,6 +639,7 @@ constexpr size_t sel_bwd_smem() {
 
 using namespace rorl;
 
+static int g_sel_dbg = 0;
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int N, bool HAS_Z, bool SP>
@@ -521,8 +648,8 @@ static int launch_fwd(const SelFwdParams& p, int64_t B, cudaStream_t stream) {
     constexpr size_t smem = sel_fwd_smem<N>();
     static bool once = (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;
-    dim3 grid((unsigned)((p.D + SelCfg<N>::DT - 1) / SelCfg<N>::DT), (unsigned)B);
-    kern<<<grid, kSelThreads, smem, stream>>>(p);
+    dim3 grid((unsigned)((p.D + SelFwdCfg<N>::DT - 1) / SelFwdCfg<N>::DT), (unsigned)B);
+    kern<<<grid, SelFwdCfg<N>::NTHREADS, smem, stream>>>(p);
     RORL_RETURN_LAUNCH();
 }
 template <int N, bool HAS_Z, bool SP>
@@ -561,6 +688,9 @@ int rorl_selscan_dtile(int64_t N) {
 
 int rorl_selscan_ckpt_every(void) { return kCkptEvery; }
 
+/* diagnostic only (tools/): bit mask that disables phases of the forward kernel for phase timing */
+void rorl_selscan_debug(int v) { g_sel_dbg = v; }
+
 int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
                      const float* Dskip, const float* z, const float* delta_bias, const float* start, float* y,
                      float* ckpt, float* last_state, int64_t B, int64_t L, int64_t D, int64_t N, int64_t ld_u,
@@ -581,6 +711,7 @@ int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const f
     p.ld_u = (int)ld_u; p.ld_delta = (int)ld_delta; p.ld_z = (int)ld_z; p.ld_B = (int)ld_B; p.ld_C = (int)ld_C;
     p.ld_y = (int)ld_y;
     p.nckpt = (int)(L / kCkptEvery);
+    p.dbg = g_sel_dbg;
     const bool has_z = z != nullptr, sp = delta_softplus != 0;
     SEL_DISPATCH(launch_fwd, p, B, stream);
 }

@@ -429,19 +429,19 @@ class LinearTC(Function):
     def forward(ctx, x, weight, bias, elu):
         K, Nn = weight.shape[1], weight.shape[0]
         xs = _mat(x.reshape(-1, K))
-        need_pre = elu and any(ctx.needs_input_grad)
-        y, pre = gemm_tn(xs, weight, bias, 1 if elu else 0, want_pre=True) if need_pre else (gemm_tn(xs, weight, bias, 1 if elu else 0), None)
-        ctx.save_for_backward(xs, weight, pre)
+        y = gemm_tn(xs, weight, bias, 1 if elu else 0)
+        # ELU backward from the OUTPUT (elu' = y + 1 for y <= 0): no pre-activation copy is written or kept
+        ctx.save_for_backward(xs, weight, y if elu else None)
         ctx.elu, ctx.has_bias, ctx.xshape = elu, bias is not None, x.shape
         return y.view(*x.shape[:-1], Nn)
 
     @staticmethod
     def backward(ctx, dy):
-        xs, weight, pre = ctx.saved_tensors
+        xs, weight, yout = ctx.saved_tensors
         Nn = weight.shape[0]
         g = _f32c(dy.reshape(-1, Nn))
-        if ctx.elu:   # exact derivative from the saved pre-activation (y + 1 would cancel for saturated units)
-            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, False, pre)
+        if ctx.elu:
+            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, True, yout)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_tn(g, weight.t().contiguous()).view(ctx.xshape)
@@ -471,20 +471,19 @@ class EnsembleLinearTC(Function):
         xs = _mat(x.reshape(-1, Kin) if shared else x.reshape(E, -1, Kin))
         wt = weight.transpose(1, 2).contiguous()                  # [E, out, in]: K-major B operand
         b2 = None if bias is None else bias.reshape(E, Nout)
-        need_pre = elu and any(ctx.needs_input_grad)
-        y, pre = gemm_tn(xs, wt, b2, 1 if elu else 0, want_pre=True) if need_pre else (gemm_tn(xs, wt, b2, 1 if elu else 0), None)
-        ctx.save_for_backward(xs, weight, pre)
+        y = gemm_tn(xs, wt, b2, 1 if elu else 0)
+        ctx.save_for_backward(xs, weight, y if elu else None)
         ctx.elu, ctx.has_bias, ctx.shared, ctx.xshape = elu, bias is not None, shared, x.shape
         lead = x.shape[:-1] if shared else x.shape[1:-1]
         return y.view(E, *lead, Nout)
 
     @staticmethod
     def backward(ctx, dy):
-        xs, weight, pre = ctx.saved_tensors
+        xs, weight, yout = ctx.saved_tensors
         E, Kin, Nout = weight.shape
         g = _f32c(dy.reshape(E, -1, Nout))
         if ctx.elu:
-            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, False, pre)
+            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, True, yout)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_tn(g, weight, reduce_g=ctx.shared).view(ctx.xshape)     # weight [E, in, out] is K-major here

@@ -1,0 +1,202 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmark at the workload shapes: CUDA-event time per launch, algorithmic
+bytes / FLOPs, fraction of the measured peak.  Inputs are larger than L2 or rotated so launches do not hit in cache.
+
+    python tools/bench_kernels.py [--only gilr,lru,selscan,conv,addnorm,gru,gemm] [--out gpurun_out/kernels.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import rorl_b200.kernels as K  # noqa: E402
+import rorl_b200._native as N  # noqa: E402
+
+dev = torch.device("cuda:0")
+try:
+    PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+except Exception:
+    PEAKS = {}
+HBM = float(PEAKS.get("hbm_gbs", 6650.0))
+TF = float(PEAKS.get("bf16_tflops", 1590.0))
+
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e-3
+
+
+def rn(*s):
+    return torch.randn(*s, device=dev)
+
+
+RES = {}
+
+
+def rec(name, t, nbytes=None, flops=None, note=""):
+    r = {"us": t * 1e6}
+    if nbytes:
+        r.update(GBps=nbytes / t / 1e9, hbm_frac=nbytes / t / 1e9 / HBM, bytes=nbytes)
+    if flops:
+        r.update(TFLOPs=flops / t / 1e12, bf16_peak_frac=flops / t / 1e12 / TF, flops=flops)
+    if note:
+        r["note"] = note
+    RES[name] = r
+    print(name, json.dumps(r), flush=True)
+
+
+def bench_gilr():
+    B, L, C = 32, 1002, 256
+    uv, uf, dh = rn(B, L, C), rn(B, L, C), rn(B, L, C)
+    start = torch.zeros(B, L, device=dev); start[:, 0] = 1
+    h = torch.empty_like(uv)
+    du, df = torch.empty_like(uv), torch.empty_like(uv)
+    S = N.stream()
+    rec("gilr_fused_fwd", timeit(lambda: N.call("rorl_gilr_fused_fwd", N.ptr(uv), N.ptr(uf), N.ptr(start), N.ptr(h), B, L, C, S)),
+        12 * B * L * C)
+    rec("gilr_fused_bwd", timeit(lambda: N.call("rorl_gilr_fused_bwd", N.ptr(dh), N.ptr(uv), N.ptr(uf), N.ptr(h), N.ptr(start),
+                                                N.ptr(du), N.ptr(df), B, L, C, S)), 24 * B * L * C)
+    # L2-cold variant: 8 rotating operand sets (8 x 98 MB > 126 MB L2)
+    sets = [(rn(B, L, C), rn(B, L, C), torch.empty(B, L, C, device=dev)) for _ in range(8)]
+    it = [0]
+
+    def cold():
+        a, b, c = sets[it[0] % 8]
+        it[0] += 1
+        N.call("rorl_gilr_fused_fwd", N.ptr(a), N.ptr(b), N.ptr(start), N.ptr(c), B, L, C, S)
+    rec("gilr_fused_fwd_L2cold", timeit(cold, n=24), 12 * B * L * C)
+
+
+def bench_lru():
+    B, L, C = 32, 1002, 256
+    vr, vi, fr, fi = rn(B, L, C), rn(B, L, C), 0.9 * torch.rand(B, L, C, device=dev), 0.1 * rn(B, L, C)
+    hr, hi = torch.empty_like(vr), torch.empty_like(vr)
+    S = N.stream()
+    rec("lru_scan_fwd", timeit(lambda: N.call("rorl_lru_scan_fwd", N.ptr(vr), N.ptr(vi), N.ptr(fr), N.ptr(fi), None, None,
+                                              N.ptr(hr), N.ptr(hi), B, L, C, S)), 24 * B * L * C,
+        note="per-step decay tensors as the reference materialises them: 6 x [B,L,C] floats")
+    g1, g2 = rn(B, L, C), rn(B, L, C)
+    o = [torch.empty_like(vr) for _ in range(4)]
+    rec("lru_scan_bwd", timeit(lambda: N.call("rorl_lru_scan_bwd", N.ptr(g1), N.ptr(g2), N.ptr(fr), N.ptr(fi), N.ptr(hr), N.ptr(hi),
+                                              None, None, None, N.ptr(o[0]), N.ptr(o[1]), N.ptr(o[2]), N.ptr(o[3]), B, L, C, S)),
+        40 * B * L * C)
+
+
+def bench_selscan():
+    B, L, D, Ns = 32, 1018, 512, 32
+    u, delta, z = rn(B, L, D).requires_grad_(), (0.5 * rn(B, L, D) - 1).requires_grad_(), rn(B, L, D).requires_grad_()
+    Bm, Cm = rn(B, L, Ns).requires_grad_(), rn(B, L, Ns).requires_grad_()
+    A = (-torch.exp(0.3 * rn(D, Ns))).requires_grad_()
+    Dk, bias = rn(D).requires_grad_(), rn(D).requires_grad_()
+    start = torch.zeros(B, L, device=dev); start[:, :18] = 1
+    dy = rn(B, L, D)
+    with torch.no_grad():
+        t_fwd = timeit(lambda: K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True))
+    t_fwd_ck = timeit(lambda: K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True), n=10)
+    t_both = timeit(lambda: torch.autograd.grad(K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True),
+                                                (u, delta, A, Bm, Cm, Dk, z, bias), dy), n=10)
+    bf = 4 * (4 * B * D * L + 2 * B * Ns * L + B * L)
+    bb = 4 * (7 * B * D * L + 4 * B * Ns * L)
+    rec("selscan_fwd", t_fwd, bf, note="MUFU floor ~115 us (App. F)")
+    rec("selscan_fwd_ckpt", t_fwd_ck, bf)
+    rec("selscan_bwd(+partial sums)", t_both - t_fwd_ck, bb)
+
+
+def bench_conv():
+    B, L, D, Kc = 32, 1018, 512, 16
+    x, w, b = rn(B, L, D).requires_grad_(), rn(D, 1, Kc).requires_grad_(), rn(D).requires_grad_()
+    mask = torch.ones(B, L, device=dev)
+    dy = rn(B, L, D)
+    with torch.no_grad():
+        t_f = timeit(lambda: K.causal_conv1d_silu(x, w, b, mask))
+    t_fb = timeit(lambda: torch.autograd.grad(K.causal_conv1d_silu(x, w, b, mask), (x, w, b), dy), n=10)
+    rec("conv1d_silu_fwd", t_f, 8 * B * L * D)
+    rec("conv1d_silu_bwd(+partials)", t_fb - t_f, 12 * B * L * D)
+
+
+def bench_addnorm():
+    rows, C = 32 * 1018, 256
+    x, r, w, b = rn(rows, C).requires_grad_(), rn(rows, C).requires_grad_(), rn(C).requires_grad_(), rn(C).requires_grad_()
+    dy = rn(rows, C)
+    with torch.no_grad():
+        t_f = timeit(lambda: K.layer_norm_fn(x, w, b, r, 1e-5, True))
+    rec("addnorm_fwd", t_f, 16 * rows * C)
+    t_fb = timeit(lambda: torch.autograd.grad(K.layer_norm_fn(x, w, b, r, 1e-5, True), (x, r, w, b), (dy, dy)), n=10)
+    rec("addnorm_bwd", t_fb - t_f, 16 * rows * C)
+
+
+def bench_gru():
+    from rorl_b200.models.gru.gru import GRULayer
+    B, L, H = 32, 1002, 256
+    gi, w, bh = rn(B, L, 3 * H), 0.06 * rn(3 * H, H), rn(3 * H)
+    out, hl, save = torch.empty(B, L, H, device=dev), torch.empty(B, H, device=dev), torch.empty(B, L, 4 * H, device=dev)
+    S = N.stream()
+    t = timeit(lambda: N.call("rorl_gru_fwd", N.ptr(gi), N.ptr(w), N.ptr(bh), None, N.ptr(out), N.ptr(save), N.ptr(hl), B, L, H, S), n=10)
+    rec("gru_fwd_persistent", t, note=f"{t / L * 1e6:.3f} us/step, {B} rows, H={H}")
+    dout = rn(B, L, H)
+    dgi, dghn, dh0 = torch.empty(B, L, 3 * H, device=dev), torch.empty(B, L, H, device=dev), torch.empty(B, H, device=dev)
+    t = timeit(lambda: N.call("rorl_gru_bwd", N.ptr(dout), None, N.ptr(w), N.ptr(save), N.ptr(out), None, N.ptr(dgi), N.ptr(dghn),
+                              N.ptr(dh0), B, L, H, S), n=10)
+    rec("gru_bwd_persistent", t, note=f"{t / L * 1e6:.3f} us/step")
+    ref = torch.nn.GRU(H, H, batch_first=True).to(dev)
+    x = rn(B, L, H)
+    with torch.no_grad():
+        t = timeit(lambda: ref(x), n=10)
+    rec("cudnn_gru_fwd(library, for scale)", t, note=f"{t / L * 1e6:.3f} us/step")
+    mine = GRULayer(H, H).to(dev)
+    xg = x.clone().requires_grad_()
+    t = timeit(lambda: torch.autograd.grad(mine(xg)[0], [xg] + list(mine.parameters()), dout), n=10)
+    rec("gru_layer_fwd+bwd(ours, incl. GEMMs)", t)
+    xr = x.clone().requires_grad_()
+    t = timeit(lambda: torch.autograd.grad(ref(xr)[0], [xr] + list(ref.parameters()), dout), n=10)
+    rec("cudnn_gru_fwd+bwd(library, for scale)", t)
+
+
+def bench_gemm():
+    M = 32 * 1018
+    for (n, k, g, tag) in [(256, 256, 1, "fc 256x256"), (1024, 256, 1, "in_proj"), (256, 512, 1, "out_proj"), (256, 384, 8, "efc-8 L1 (shared x)"),
+                           (256, 256, 8, "efc-8 L2")]:
+        a = rn(M, k) if (g == 1 or k == 384) else rn(g, M, k)
+        b = rn(n, k) if g == 1 else rn(g, n, k)
+        bias = rn(n) if g == 1 else rn(g, n)
+        for passes in (3, 1):
+            t = timeit(lambda: K.gemm_tn(a, b, bias, 1, passes=passes))
+            fl = 2.0 * M * n * k * g
+            rec(f"gemm_tn {tag} passes={passes}", t, flops=fl * passes, nbytes=4 * (a.numel() + b.numel() + M * n * g),
+                note=f"useful fp32 TFLOP/s {fl / t / 1e12:.1f}")
+    # weight gradient
+    gq, xq = rn(M, 256), rn(M, 256)
+    t = timeit(lambda: K.gemm_nt(gq, xq))
+    rec("gemm_nt 256x256 R=32576 passes=3", t, flops=3 * 2.0 * M * 256 * 256, nbytes=4 * (gq.numel() + xq.numel()))
+    c = torch.empty(M, 256, device=dev)
+    a2, w2 = rn(M, 256), rn(256, 256)
+    t = timeit(lambda: torch.mm(a2, w2, out=c))
+    rec("cublas sgemm 32576x256x256 (library, for scale)", t, flops=2.0 * M * 256 * 256)
+
+
+ALL = {"gilr": bench_gilr, "lru": bench_lru, "selscan": bench_selscan, "conv": bench_conv, "addnorm": bench_addnorm,
+       "gru": bench_gru, "gemm": bench_gemm}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    names = [n for n in a.only.split(",") if n] or list(ALL)
+    for n in names:
+        ALL[n]()
+    if a.out:
+        os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+        json.dump({"peaks": {"hbm_gbs": HBM, "bf16_tflops": TF}, "kernels": RES}, open(a.out, "w"), indent=1)
