@@ -32,6 +32,7 @@ from .. import _native as N
 from ..buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
 from ..policy_value_models.make_models import make_policy_model, make_value_model
 from ..utility.q_value_guard import QValueGuard
+from .data_parallel import BucketedGradSync, sync_count_and_guard
 
 DEFAULTS = dict(utd=1, policy_utd=1, randomize_mask=False, valid_number_post_randomized=0, random_trunc_traj=False,
                 randomize_first_hidden=False, gamma=0.99, sac_tau=0.995, policy_update_per=1, no_alpha_auto_tune=False,
@@ -227,6 +228,14 @@ class FullLengthRNNUpdate:
         self.policy.train()
         for q in self.target_arena.params + list(self.target_policy.parameters(True)):
             q.requires_grad_(False)
+        # data parallel: bucketed gradient all-reduce overlapped with the backward pass (algorithm/data_parallel.py)
+        for old in (getattr(self, '_sync_value', None), getattr(self, '_sync_policy', None)):
+            if old is not None:
+                old.remove()
+        self._sync_value = self._sync_policy = None
+        if self.dist_group is not None:
+            self._sync_value = BucketedGradSync(self.value_arena.params, self.value_arena.offsets, self.value_arena.grad, self.dist_group)
+            self._sync_policy = BucketedGradSync(self.policy_arena.params, self.policy_arena.offsets, self.policy_arena.grad, self.dist_group)
 
     def load_models(self, policy_sd=None, value_sd=None):
         if policy_sd is not None:
@@ -352,8 +361,11 @@ class FullLengthRNNUpdate:
         N.call("rorl_q_loss_fwd_bwd", N.ptr(qc), N.ptr(tq_c), N.ptr(mask_c), N.ptr(n_valid),
                N.ptr(self._stats[2:3]), N.ptr(dq), N.ptr(self._work), E, M, N.stream())
         self.optimizer_value.zero_grad()
+        if self._sync_value is not None:
+            self._sync_value.begin()
         qc.backward(dq.view_as(qc))
-        self._allreduce(self.value_arena.grad)
+        if self._sync_value is not None:
+            self._sync_value.finish()
         self.optimizer_value.step(tau=p.sac_tau)   # + Polyak (ref :395)
         for v in self.values:
             v.eval()
@@ -378,11 +390,14 @@ class FullLengthRNNUpdate:
                    N.ptr(self.log_sac_alpha.data), float(self.target_entropy), 1 if self.use_redq else 0,
                    N.ptr(self._stats[4:8]), N.ptr(dqp), N.ptr(dlogp), N.ptr(self._work), E, M, N.stream())
             self.optimizer_policy.zero_grad()
+            if self._sync_policy is not None:
+                self._sync_policy.begin()
             if td3:
                 qpc.backward(dqp.view_as(qpc))
             else:
                 torch.autograd.backward([qpc, logp_c], [dqp.view_as(qpc), dlogp.view_as(logp_c)])
-            self._allreduce(self.policy_arena.grad)
+            if self._sync_policy is not None:
+                self._sync_policy.finish()
             self.optimizer_policy.step()
             if not p.no_alpha_auto_tune:
                 self.alpha_arena.grad.copy_(self._stats[7:8])
@@ -409,8 +424,4 @@ class FullLengthRNNUpdate:
 
     def _sync_guard_and_count(self):
         """Data-parallel: make n_valid and the guard state identical on every rank."""
-        import torch.distributed as dist
-        self._allreduce(self._stats[1:2])
-        lo, hi = self.Q_guard.state[0:1], self.Q_guard.state[1:2]
-        self._allreduce(lo, dist.ReduceOp.MIN)
-        self._allreduce(hi, dist.ReduceOp.MAX)
+        sync_count_and_guard(self._stats[1:2], self.Q_guard.state[0:1], self.Q_guard.state[1:2], self.dist_group)
