@@ -327,7 +327,9 @@ class FullLengthRNNUpdate:
         k = min(traj_len_array.shape[1], L)
         att[:, :k] = torch.from_numpy(traj_len_array[:, :k]).to(torch.int32)
         tgt_att = torch.cat((att[:, 1:], torch.zeros((B, 1), dtype=torch.int32)), dim=-1)
+        att_h, tgt_h = att.numpy(), tgt_att.numpy()
         att, tgt_att = att.to(dev, non_blocking=True), tgt_att.to(dev, non_blocking=True)
+        att._host, tgt_att._host = att_h, tgt_h              # host copy for the cgpt work list (no device->host sync)
         mk = lambda model: model.make_init_state(B, device=dev)
         policy_hidden, target_policy_hidden = mk(self.policy), mk(self.policy)
         target_hidden, value_hidden = mk(self.target_values[0]), mk(self.values[0])

@@ -426,10 +426,11 @@ class LinearTC(Function):
     dW on its MN-major split-K variant (gemm_nt); db is a column sum."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, elu):
+    def forward(ctx, x, weight, bias, elu, passes=None):
         K, Nn = weight.shape[1], weight.shape[0]
         xs = _mat(x.reshape(-1, K))
-        y = gemm_tn(xs, weight, bias, 1 if elu else 0)
+        ctx.passes = passes
+        y = gemm_tn(xs, weight, bias, 1 if elu else 0, passes=passes)
         # ELU backward from the OUTPUT (elu' = y + 1 for y <= 0): no pre-activation copy is written or kept
         ctx.save_for_backward(xs, weight, y if elu else None)
         ctx.elu, ctx.has_bias, ctx.xshape = elu, bias is not None, x.shape
@@ -444,20 +445,21 @@ class LinearTC(Function):
             g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, True, yout)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm_tn(g, weight.t().contiguous()).view(ctx.xshape)
+            dx = gemm_tn(g, weight.t().contiguous(), passes=ctx.passes).view(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            dw = gemm_nt(g, xs) if _gemm_nt_ok(Nn, xs.shape[1], xs.shape[0]) else g.t() @ xs
+            dw = gemm_nt(g, xs, passes=ctx.passes) if _gemm_nt_ok(Nn, xs.shape[1], xs.shape[0]) else g.t() @ xs
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = g.sum(0)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def linear(x, weight, bias=None, elu=False):
+def linear(x, weight, bias=None, elu=False, passes=None):
     """nn.Linear forward (+ optional fused ELU).  Shapes the tensor-core kernel cannot take (K % 4, N % 4, K < 32)
-    go through cuBLAS; both are GPU paths."""
+    go through cuBLAS; both are GPU paths.  passes=1: single TF32 pass (used where the reference itself runs the
+    layer in bf16 autocast), default 3xTF32 = fp32 parity."""
     M = x.numel() // x.shape[-1]
     if x.is_cuda and _gemm_ok(M, weight.shape[0], weight.shape[1]):
-        return LinearTC.apply(x, weight, bias, elu)
+        return LinearTC.apply(x, weight, bias, elu, passes)
     y = torch.nn.functional.linear(x, weight, bias)
     return torch.nn.functional.elu(y) if elu else y
 
@@ -500,3 +502,75 @@ def ensemble_linear(x, weight, bias, elu, shared):
     if x.is_cuda and _gemm_ok(M, Nout, Kin):
         return EnsembleLinearTC.apply(x, weight, bias, elu, shared)
     return None
+
+
+# ------------------------------------------------------------------------------------------------
+# causal variable-length attention with ALiBi (tcgen05, bf16 operands) -- the cgpt encoder's attention
+# ------------------------------------------------------------------------------------------------
+class AttnVarlen(Function):
+    """out[T, H*64] = attention(qkv[T, 3, H, 64]) per sequence.  `tiles` int32 [ntiles, 4] and `gmap` int32 [Ta] on the
+    device come from attention_tiles (see include/rorl_b200.h for the two token spaces); slopes [H] fp32."""
+
+    @staticmethod
+    def forward(ctx, qkv, tiles, gmap, slopes, softmax_scale):
+        T, three, H, hd = qkv.shape
+        assert three == 3 and hd == 64, "the tcgen05 attention kernel is built for head dimension 64"
+        qkv = _f32c(qkv)
+        dev = qkv.device
+        Ta = gmap.shape[0]
+        Tp = (Ta + 63) // 64 * 64
+        need_grad = ctx.needs_input_grad[0]
+        rm = torch.empty((3, Ta, H, 64), device=dev, dtype=torch.bfloat16)
+        tr = torch.empty((3, H, 64, Tp), device=dev, dtype=torch.bfloat16)
+        N.call("rorl_attn_prep", N.ptr(qkv), 3 * H * 64, 3, H, Ta, Tp, N.ptr(gmap), N.ptr(rm), N.ptr(tr), None, 0, None, N.stream())
+        out = torch.zeros((T, H * 64), device=dev, dtype=torch.float32)        # rows outside every sequence stay 0
+        lse = torch.zeros((H, Tp), device=dev, dtype=torch.float32) if need_grad else None
+        N.call("rorl_attn_fwd", N.ptr(rm[0]), N.ptr(rm[1]), N.ptr(tr[2]), N.ptr(tiles), tiles.shape[0], N.ptr(slopes),
+               float(softmax_scale), N.ptr(out), H * 64, N.ptr(lse), H, Ta, Tp, N.stream())
+        ctx.save_for_backward(rm, tr, out, lse, tiles, gmap, slopes)
+        ctx.scale, ctx.dims = float(softmax_scale), (T, H, Ta, Tp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rm, tr, out, lse, tiles, gmap, slopes = ctx.saved_tensors
+        T, H, Ta, Tp = ctx.dims
+        dev = out.device
+        dout = _f32c(dout)
+        do_rm = torch.empty((Ta, H, 64), device=dev, dtype=torch.bfloat16)
+        do_tr = torch.empty((H, 64, Tp), device=dev, dtype=torch.bfloat16)
+        D = torch.empty((H, Tp), device=dev, dtype=torch.float32)
+        N.call("rorl_attn_prep", N.ptr(dout), H * 64, 1, H, Ta, Tp, N.ptr(gmap), N.ptr(do_rm), N.ptr(do_tr), N.ptr(out), H * 64,
+               N.ptr(D), N.stream())
+        dqkv = torch.zeros((T, 3, H, 64), device=dev, dtype=torch.float32)
+        N.call("rorl_attn_bwd", N.ptr(rm[0]), N.ptr(rm[1]), N.ptr(rm[2]), N.ptr(do_rm), N.ptr(tr[0]), N.ptr(tr[1]), N.ptr(do_tr),
+               N.ptr(lse), N.ptr(D), N.ptr(tiles), tiles.shape[0], N.ptr(slopes), ctx.scale, N.ptr(dqkv[:, 0]), N.ptr(dqkv[:, 1]),
+               N.ptr(dqkv[:, 2]), 3 * H * 64, H, Ta, Tp, N.stream())
+        return dqkv, None, None, None, None
+
+
+def attn_varlen_alibi(qkv, tiles, gmap, slopes, softmax_scale):
+    return AttnVarlen.apply(qkv, tiles, gmap, slopes, softmax_scale)
+
+
+def attention_tiles(seq_starts, seq_lens):
+    """Host helper.  Lays the sequences (first token row, length; zero-length entries skipped) out on 8-token
+    boundaries of the attention token space and returns CPU tensors (tiles int32 [ntiles, 4], gmap int32 [Ta]):
+    tiles rows are (first attention-space token, length, 128-row tile index, first source/output row)."""
+    import numpy as np
+    rows, maps, pos = [], [], 0
+    for s, n in zip(seq_starts, seq_lens):
+        s, n = int(s), int(n)
+        if n <= 0:
+            continue
+        for t in range((n + 127) // 128):
+            rows.append((pos, n, t, s))
+        slot = (n + 7) // 8 * 8
+        m = np.full(slot, -1, dtype=np.int32)
+        m[:n] = np.arange(s, s + n, dtype=np.int32)
+        maps.append(m)
+        pos += slot
+    if not rows:
+        rows.append((0, 0, 0, 0))
+        maps.append(np.full(8, -1, dtype=np.int32))
+    return torch.tensor(rows, dtype=torch.int32), torch.from_numpy(np.concatenate(maps))

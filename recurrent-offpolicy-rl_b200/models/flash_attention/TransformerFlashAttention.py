@@ -1,0 +1,161 @@
+"""`cgpt_*` encoder: pre-norm causal transformer with ALiBi attention over the trajectories packed in each row.
+
+API- and state_dict-compatible with the reference's TransformerDecoder / DecoderLayer / PositionWiseFeedForward /
+RMSNorm (ref: offpolicy_rnn/models/flash_attention/TransformerFlashAttention.py:29-121) and with the parameter
+names of flash_attn's MHA it embeds (`mha.Wqkv.{weight,bias}`, `mha.out_proj.{weight,bias}`).
+
+What runs where:
+  * attention: csrc/attn.cu (tcgen05, bf16 operands, fp32 accumulation) -- the reference runs flash-attn 2 in bf16
+    autocast (ref :80-82);
+  * Wqkv / out_proj: tcgen05 GEMM, single TF32 pass (the reference runs them in bf16 under the same autocast; TF32
+    keeps 3 more mantissa bits, inside the 1e-2 budget of this path);
+  * FFN (fc1 -> GELU -> fc2), norms, output_fc: fp32 as in the reference (3xTF32 GEMM, fused add+norm kernels).
+Differences, deliberate: tokens are NOT unpadded / re-padded (ref :104-121): every per-token operation runs on the
+padded [B*L] token axis, the attention kernel walks the sequences through a (start, length) work list, and the
+padding tokens are zeroed once at the end, which is what pad_input produces.  Attention-probability dropout
+(flash-attn's `dropout_p`) is not implemented: with p > 0 in training mode only the three nn.Dropout sites are
+active (the reference's own parity recipe runs cgpt with p0.0).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import kernels as K
+from ..linear import Linear
+from ..RNNHidden import InferenceParams  # noqa: F401  (re-exported under the reference's name)
+
+
+def get_alibi_slopes(nheads: int):
+    """Same schedule as flash_attn.modules.mha.get_alibi_slopes (geometric in 2^(-8/n))."""
+    def pow2(n):
+        start = 2 ** (-(2 ** -(math.log2(n) - 3)))
+        return [start * start ** i for i in range(n)]
+    if math.log2(nheads).is_integer():
+        return pow2(nheads)
+    closest = 2 ** math.floor(math.log2(nheads))
+    return pow2(closest) + get_alibi_slopes(2 * closest)[0::2][:nheads - closest]
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, d_model: int, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d_model))
+
+    def forward(self, x):
+        return K.rms_norm_fn(x, self.weight, None, eps=self.eps)
+
+
+class LayerNorm(nn.LayerNorm):
+    def forward(self, x):
+        return K.layer_norm_fn(x, self.weight, self.bias, eps=self.eps)
+
+
+class MHA(nn.Module):
+    """Self-attention block with flash_attn.modules.mha.MHA's parameter names (fused Wqkv, out_proj)."""
+
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0):
+        super().__init__()
+        assert embed_dim % num_heads == 0
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        if self.head_dim != 64:
+            raise NotImplementedError('the tcgen05 attention kernel is built for head dimension 64 (cgpt: 512 / 8)')
+        self.attn_dropout = dropout
+        self.Wqkv = Linear(embed_dim, 3 * embed_dim)
+        self.out_proj = Linear(embed_dim, embed_dim)
+        self.register_buffer('alibi_slopes', torch.tensor(get_alibi_slopes(num_heads), dtype=torch.float32), persistent=False)
+
+    def forward(self, x, tiles):
+        """x: [T, C] tokens; tiles: device (work list, gather map) of the sequences (kernels.attention_tiles)."""
+        T = x.shape[0]
+        qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=1)
+        o = K.attn_varlen_alibi(qkv.view(T, 3, self.num_heads, self.head_dim), tiles[0], tiles[1], self.alibi_slopes,
+                                1.0 / math.sqrt(self.head_dim))
+        return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=1)
+
+
+class PositionWiseFeedForward(nn.Module):
+    def __init__(self, d_model, d_ff, dropout=0.1):
+        super().__init__()
+        self.fc1 = Linear(d_model, d_ff)
+        self.fc2 = Linear(d_ff, d_model)
+        self.act = nn.GELU()
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x):
+        return self.fc2(self.dropout(self.act(self.fc1(x))))
+
+
+class DecoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, d_ff, dropout=0.1, layer_idx=None, ln=True):
+        super().__init__()
+        self.mha = MHA(d_model, nhead, dropout)
+        self.ffn = PositionWiseFeedForward(d_model, d_ff, dropout)
+        self.dropout = nn.Dropout(dropout)
+        self.mha_norm = LayerNorm(d_model) if ln else RMSNorm(d_model)
+        self.ffn_norm = LayerNorm(d_model) if ln else RMSNorm(d_model)
+
+    def forward(self, x, tiles):
+        x = self.dropout(self.mha(self.mha_norm(x), tiles)) + x                  # ref :76-83
+        return self.dropout(self.ffn(self.ffn_norm(x))) + x                      # ref :84 (pre_norm)
+
+
+def sequences_of(seqlens_host: np.ndarray, L: int):
+    """Row-packed sequence lengths [B, <=L] -> (starts, lengths) on the padded token axis b * L + position, plus the
+    number of real tokens per row.  Mirrors how unpad_input_for_concatenated_sequences reads the same array."""
+    starts, lens, row_tokens = [], [], []
+    for b in range(seqlens_host.shape[0]):
+        pos = 0
+        for n in seqlens_host[b]:
+            n = int(n)
+            if n > 0:
+                starts.append(b * L + pos)
+                lens.append(n)
+                pos += n
+        assert pos <= L, 'sequence lengths exceed the padded row length'
+        row_tokens.append(pos)
+    return starts, lens, row_tokens
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, d_model, n_head, d_ff, n_layer, dropout=0.1, ln=True):
+        super().__init__()
+        self.d_model, self.n_head, self.d_ff, self.n_layer = d_model, n_head, d_ff, n_layer
+        self.decoder_layers = nn.ModuleList([DecoderLayer(d_model, n_head, d_ff, dropout=dropout, layer_idx=i, ln=ln)
+                                             for i in range(n_layer)])
+        self.output_ln = LayerNorm(d_model) if ln else RMSNorm(d_model)
+        self.output_fc = Linear(d_model, d_model)
+
+    def forward(self, x, inference_params=None, seqlens=None):
+        """x: [B, L, C].  seqlens: [B, L] lengths of the sequences packed in each row (zeros padded), as the update
+        path passes them (ref :104-112); None = every row is one full-length sequence.  A host copy attached as
+        `seqlens._host` (numpy) avoids a device->host sync."""
+        if not x.is_cuda:
+            raise RuntimeError('the cgpt encoder runs on sm_100a kernels only; there is no CPU path')
+        if inference_params is not None and seqlens is None and x.shape[-2] == 1:
+            raise NotImplementedError('single-step kv-cache decoding (rollout) is outside the update hot path')
+        B, L, C = x.shape
+        if seqlens is None:
+            host = np.zeros((B, 1), dtype=np.int64)
+            host[:, 0] = L
+        else:
+            host = getattr(seqlens, '_host', None)
+            if host is None:
+                host = seqlens.detach().cpu().numpy()
+        starts, lens, row_tokens = sequences_of(np.asarray(host), L)
+        tiles = tuple(t.to(x.device, non_blocking=True) for t in K.attention_tiles(starts, lens))
+        h = x.reshape(B * L, C)
+        for layer in self.decoder_layers:
+            h = layer(h, tiles)
+        h = self.output_fc(self.output_ln(h)).view(B, L, C)
+        if any(n < L for n in row_tokens):                                       # pad_input: padding tokens -> 0
+            keep = torch.zeros((B, L, 1), dtype=h.dtype)
+            for b, n in enumerate(row_tokens):
+                keep[b, :n] = 1
+            h = h * keep.to(x.device, non_blocking=True)
+        return h

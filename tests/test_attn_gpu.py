@@ -1,0 +1,116 @@
+"""GPU parity of the tcgen05 attention kernels and of the cgpt encoder built on them.  Tolerance 1e-2 relative
+(max-norm): the path computes with bf16 operands like the reference's flash-attn autocast region (BASELINE.json)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _seqs(lens, gaps):
+    starts, pos = [], 0
+    for n, g in zip(lens, gaps):
+        pos += g
+        starts.append(pos)
+        pos += n
+    return starts, pos
+
+
+@pytest.mark.parametrize("lens,gaps", [([1, 130, 1, 300, 64, 128, 129], [0, 0, 3, 0, 1, 0, 5]), ([1001, 1, 1001], [0, 0, 0]),
+                                       ([17], [2]), ([256, 512], [0, 0])])
+def test_attention_vs_oracle(lens, gaps):
+    import rorl_b200.kernels as K
+    from oracle import attention as OA
+    H, hd = 8, 64
+    starts, used = _seqs(lens, gaps)
+    T = used + 7
+    gen = torch.Generator().manual_seed(T)
+    qkv = torch.randn(T, 3, H, hd, generator=gen)
+    dout = torch.randn(T, H * hd, generator=gen)
+    slopes = OA.alibi_slopes(H)
+    scale = 1.0 / math.sqrt(hd)
+    ref_in = qkv.clone().requires_grad_()
+    ref = OA.attention_varlen(ref_in, starts, lens, slopes, scale)
+    inside = torch.zeros(T, 1)
+    for s, n in zip(starts, lens):
+        inside[s:s + n] = 1
+    (ref * dout * inside).sum().backward()
+    x = qkv.cuda().requires_grad_()
+    tiles, gmap = (t.cuda() for t in K.attention_tiles(starts, lens))
+    out = K.attn_varlen_alibi(x, tiles, gmap, torch.tensor(slopes, dtype=torch.float32, device="cuda"), scale)
+    (out * (dout * inside).cuda()).sum().backward()
+    assert_close(out, ref, TOL, "out")
+    assert float(out.cpu()[inside[:, 0] == 0].abs().max() if (inside == 0).any() else 0.0) == 0.0
+    for i, name in enumerate("qkv"):
+        assert_close(x.grad[:, i], ref_in.grad[:, i], TOL, f"d{name}")
+
+
+def test_attention_vs_flash_attn():
+    """Pins the third-party arithmetic: flash-attn's own varlen kernel (bf16) on the same inputs."""
+    fa = pytest.importorskip("flash_attn")
+    import rorl_b200.kernels as K
+    from oracle import attention as OA
+    H, hd = 8, 64
+    lens = [1, 1001, 1, 700, 301]
+    starts, T = _seqs(lens, [0] * len(lens))
+    gen = torch.Generator().manual_seed(3)
+    qkv = torch.randn(T, 3, H, hd, generator=gen).cuda()
+    dout = torch.randn(T, H * hd, generator=gen).cuda()
+    slopes = torch.tensor(OA.alibi_slopes(H), dtype=torch.float32, device="cuda")
+    scale = 1.0 / math.sqrt(hd)
+    cu = torch.tensor(np.concatenate(([0], np.cumsum(lens))), dtype=torch.int32, device="cuda")
+    a = qkv.to(torch.bfloat16).requires_grad_()
+    try:
+        ref = fa.flash_attn_varlen_qkvpacked_func(a, cu, max(lens), 0.0, softmax_scale=scale, causal=True, alibi_slopes=slopes)
+    except Exception as e:  # pragma: no cover - flash-attn build without this GPU's kernels
+        pytest.skip(f"flash-attn cannot run here: {e}")
+    ref.backward(dout.view(T, H, hd).to(torch.bfloat16))
+    x = qkv.clone().requires_grad_()
+    tiles, gmap = (t.cuda() for t in K.attention_tiles(starts, lens))
+    out = K.attn_varlen_alibi(x, tiles, gmap, slopes, scale)
+    out.backward(dout)
+    assert_close(out, ref.float().reshape(T, H * hd), 2e-2, "out vs flash-attn (both bf16)")
+    assert_close(x.grad, a.grad.float(), 3e-2, "dqkv vs flash-attn (both bf16)")
+
+
+@pytest.mark.parametrize("case", ["stacked_ln", "rows_rms"])
+def test_cgpt_encoder_vs_oracle(case):
+    from oracle import attention as OA
+    from rorl_b200.models.flash_attention.TransformerFlashAttention import TransformerDecoder
+    torch.manual_seed(0)
+    C, Hh = 512, 8
+    if case == "stacked_ln":
+        B, L, ln, nl = 3, 300, True, 2
+        seq = np.zeros((B, L), dtype=np.int64)
+        seq[0, :2] = (200, 100); seq[1, :3] = (1, 150, 99); seq[2, :1] = (212,)
+    else:
+        B, L, ln, nl = 2, 1002, False, 2
+        seq = np.zeros((B, L), dtype=np.int64)
+        seq[:, 0] = 1; seq[:, 1] = 1001
+    net = TransformerDecoder(C, Hh, 4 * C, nl, dropout=0.0, ln=ln)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items()}
+    x = torch.randn(B, L, C)
+    dy = torch.randn(B, L, C)
+    xr = x.clone().requires_grad_()
+    ref = OA.decoder_forward(sd, xr, seq, Hh, ln)
+    (ref * dy).sum().backward()
+    net.cuda().train()
+    xg = x.cuda().requires_grad_()
+    s_dev = torch.from_numpy(seq).to(torch.int32).cuda()
+    s_dev._host = seq
+    out = net(xg, None, s_dev)
+    (out * dy.cuda()).sum().backward()
+    assert_close(out, ref, TOL, "y")
+    assert_close(xg.grad, xr.grad, TOL, "dx")
+    worst = 0.0
+    for n, p in net.named_parameters():
+        worst = max(worst, assert_close(p.grad, sd[n].grad, 2e-2, n))
