@@ -38,7 +38,8 @@ ALGO = os.environ.get("RORL_BENCH_ALGO", "sac")
 METRIC = "sac_update_trajectory_steps_per_s"
 
 
-def model_kwargs(enc, value, hidden=256):
+def model_kwargs(enc, value, hidden=None):
+    hidden = hidden or (512 if enc.startswith("cgpt") else 256)      # encoder width 256 (cgpt: 512)
     return dict(state_dim=S_DIM, action_dim=A_DIM, embedding_size=128, embedding_hidden=[hidden, hidden],
                 embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', enc, 'fc'],
                 uni_model_hidden=[256, 256], uni_model_activations=['elu', 'elu', 'linear'],

@@ -135,6 +135,22 @@ def gru_layer(p, pre, x, side: Side):
     return out
 
 
+def cgpt_layer(p, pre, x, side: Side, layer_id: str):
+    """TransformerDecoder on the rows' packed sequences (eval / p = 0 semantics).
+    ref: offpolicy_rnn/models/rnn_base.py:222-236 (grammar), :437-452 (call), flash_attention/TransformerFlashAttention.py:104-121"""
+    from . import attention as OA
+    nhead, ln = 8, True
+    for tok in layer_id.split('_')[1:]:
+        if tok.startswith('h'):
+            nhead = int(tok[1:])
+        elif tok.startswith('rms'):
+            ln = False
+    seq = side.attention_concat_mask
+    seq = None if seq is None else seq.detach().cpu().numpy().astype('int64')
+    sub = {k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}
+    return OA.decoder_forward(sub, x, seq, nhead, ln)
+
+
 def rnn_base(p: Dict[str, torch.Tensor], layer_types: List[str], acts: List[str], x, side: Optional[Side] = None,
              desire_ndim=None):
     """RNNBase.meta_forward.  ref: offpolicy_rnn/models/rnn_base.py:397-472"""
@@ -153,6 +169,8 @@ def rnn_base(p: Dict[str, torch.Tensor], layer_types: List[str], acts: List[str]
             x = smamba_layer(p, pre, x, side, lt)
         elif lt == 'gru':
             x = gru_layer(p, pre, x, side)
+        elif lt.startswith('cgpt'):
+            x = cgpt_layer(p, pre, x, side, lt)
         else:
             raise NotImplementedError(lt)
         if '+' in act:

@@ -117,7 +117,8 @@ def test_sampler_device_bit_exact():
             assert st[2] == int(g[f"c{call}/rng_pos"])
 
 
-@pytest.mark.parametrize("enc,algo", [("smamba_s32_c16_b2_nln", "sac"), ("gilr", "td3"), ("lru", "sac"), ("smamba_s64_c8_b1_ff", "sac")])
+@pytest.mark.parametrize("enc,algo", [("smamba_s32_c16_b2_nln", "sac"), ("gilr", "td3"), ("lru", "sac"), ("smamba_s64_c8_b1_ff", "sac"),
+                                      ("gru", "td3"), ("cgpt_h1_l2_p0.0_rms", "sac"), ("cgpt_h1_l1_p0.0", "td3")])
 def test_update_vs_oracle_wide(enc, algo):
     """Same comparison at widths that route every projection through the tcgen05 GEMM (K >= 32), against the
     pinned oracle's CPU update (no reference fixture exists at this size)."""
@@ -127,6 +128,7 @@ def test_update_vs_oracle_wide(enc, algo):
     from rorl_b200.buffers.transition_buffer.replay_memory import Transition
     S, A, H = 5, 3, 64
     lens = [40, 33, 25, 37]
+    TOL = 1e-2 if enc.startswith("cgpt") else 1e-3          # bf16 attention path: BASELINE.json's 1e-2
     kw = lambda value: dict(state_dim=S, action_dim=A, embedding_size=32, embedding_hidden=[H, H],
                             embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', enc, 'fc'],
                             uni_model_hidden=[H, H], uni_model_activations=['elu', 'elu', 'linear'],
@@ -174,14 +176,28 @@ def test_update_vs_oracle_wide(enc, algo):
         for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "target_q_max"):
             if k in ref and k in log:
                 assert abs(log[k] - ref[k]) <= TOL * max(1.0, abs(ref[k])), (k, log[k], ref[k])
+        # gradients left in the arenas (critic grads in the value arena, actor grads in the policy arena)
+        gworst = 0.0
+        for grads, model in ((upd.value_grads, alg.values[0]), (upd.policy_grads, alg.policy)):
+            for mod, m in model.contextual_modules.items():
+                for n, p_ in m.named_parameters():
+                    if grads[mod][n] is not None and p_.grad is not None:
+                        gworst = max(gworst, assert_close(p_.grad, grads[mod][n], TOL, f"grad/{mod}/{n}"))
+        # Updated parameters.  AdamW normalises every gradient entry to a step of about +-lr, so where the bf16
+        # attention path perturbs a near-zero gradient entry the step itself flips; the fp32 oracle and a bf16
+        # implementation (the reference's flash-attn included) can therefore differ by ~2 lr / |w| on single entries.
+        # So for cgpt the bound on a parameter is 1e-2 relative PLUS one flipped step (2 lr) per update taken.
         worst = 0.0
         for which, model, osd in (("policy", alg.policy, upd.policy), ("value", alg.values[0], upd.value),
                                   ("target", alg.target_values[0], upd.target)):
             for mod, params in model.state_dict().items():
                 for n, t in params.items():
-                    worst = max(worst, assert_close(t, osd[mod][n].detach(), TOL, f"{which}/{mod}/{n}"))
-        for mod, m in alg.values[0].contextual_modules.items():
-            for n, p_ in m.named_parameters():
-                if upd.value_grads[mod][n] is not None and p_.grad is not None and which:
-                    pass
-        print(f"{enc} {algo} call {call}: worst updated-parameter relative error {worst:.2e}")
+                    r = osd[mod][n].detach()
+                    if enc.startswith("cgpt"):
+                        bound = TOL * float(r.abs().max()) + 2.2 * hp["value_lr"] * (call + 1)
+                        diff = float((t.cpu() - r).abs().max())
+                        assert diff <= bound, f"{which}/{mod}/{n}: |diff| {diff:.3e} > {bound:.3e}"
+                        worst = max(worst, diff / (float(r.abs().max()) + 1e-30))
+                    else:
+                        worst = max(worst, assert_close(t, r, TOL, f"{which}/{mod}/{n}"))
+        print(f"{enc} {algo} call {call}: worst gradient rel. error {gworst:.2e}, worst updated-parameter rel. error {worst:.2e}")
