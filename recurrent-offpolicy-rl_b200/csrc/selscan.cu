@@ -32,7 +32,7 @@
 namespace rorl {
 
 constexpr int kSelThreads = 256;
-constexpr int kCkptEvery = 16;
+constexpr int kCkptEvery = 8;
 
 template <int N>
 struct SelCfg {
@@ -341,286 +341,373 @@ struct SelBwdParams {
     int nckpt;
 };
 
-// Reduce-scatter 8 per-lane values across the DPW channel-lanes of a warp (lane bits above the
-// LPD state-group bits).  On return v[0..KEEP) hold sums over all channels of the warp for the
-// state indices [first, first + KEEP).
+// Backward decomposition (warp specialised like the forward).
+//
+// Per element (t, d, n) the adjoint needs h_t (recomputed from a checkpoint: 1 ex2), a_t again for
+// lambda_t = g_t C_t + a_{t+1} lambda_{t+1} (1 ex2) and ~14 fp32 operations, plus two reductions: over n for
+// d(delta), du, dz (per-lane partial sums left in shared memory, finished by the helper warps) and over d for dB, dC
+// (shuffle reduce-scatter across the warp's channels, shared-memory sum across warps, one partial tile per CTA in
+// global memory, summed by the caller: deterministic, no atomics).
+// The forward checkpoints h every kCkptEvery = 8 steps; a chunk of 8 steps is walked forward (h_t kept in
+// registers: 32 per thread) and then backward.  The register file, not the pipes, limits residency here: 12
+// registers of state per (d, n) element, so a CTA holds 64 channels with 16 MAIN warps (thread = 1 channel x 4
+// states: 4 warps per scheduler) + 4 HELPER warps, one CTA per SM.  The helpers run the same cp.async / transform
+// / write-back pipeline as in the forward: softplus and its derivative, delta*u, g = dy * silu(z), the reset as
+// delta = +inf, and afterwards d(delta) = (sum_n t1 A ln2... see below) * softplus', du, dz, the dD / dbias
+// accumulators and the cross-warp dB / dC sums.
+template <int N>
+struct SelBwdCfg {
+    static constexpr int S = 4;                           // states per main thread
+    static constexpr int LPD = N / S;                     // lanes per channel
+    static constexpr int DPW = 32 / LPD;                  // channels per warp
+    static constexpr int NMAINW = 16;                     // main warps
+    static constexpr int NMAIN = NMAINW * 32;
+    static constexpr int DT = NMAINW * DPW;               // channels per CTA
+    static constexpr int QPR = DT / 4;                    // float4 quads per tile row
+    static constexpr int TC = kCkptEvery;                 // steps per chunk
+    static constexpr int NST = 3;                         // stages in flight
+    static constexpr int NARR = 7;                        // u | dtA | du | g | dt | softplus' | dz coefficient
+    static constexpr int STAGE = TC * (NARR * DT + 2 * N);
+    static constexpr int QS = 4 * LPD + 4;                // partial-sum quad stride (4 channels x LPD lanes + skew)
+    static constexpr int PROW = QPR * QS;                 // partial-sum row
+    static constexpr int PLANE = TC * PROW;               // one plane (sB | sA | y) of per-lane partial sums
+    static constexpr int RED = NMAINW * TC * 2 * N;       // per-warp dB | dC
+    static constexpr int NHELP = 128;
+    static constexpr int NTHREADS = NMAIN + NHELP;
+    static constexpr size_t SMEM = sizeof(float) * (NST * STAGE + 3 * PLANE + RED + 2 * DT * (NHELP / QPR)) + 128;
+};
+
+// Reduce-scatter 4 per-lane values across the DPW channel-lanes of a warp (lane bits above the LPD state-group
+// bits).  Returns the number of values this lane keeps (sums over all channels of the warp); `first` is the state
+// index (within the lane's group of 4) of v[0]; `writer` is false for the duplicate lanes when DPW > 4.
 template <int LPD>
-__device__ __forceinline__ void channel_reduce_scatter(float (&v)[8], int dl) {
+__device__ __forceinline__ int channel_reduce_scatter4(float (&v)[4], int dl, int& first, bool& writer) {
     constexpr int DPW = 32 / LPD;
-    int cnt = 8;
-#pragma unroll
-    for (int m = DPW / 2; m >= 1; m >>= 1) {
-        const bool up = (dl & m) != 0;
-        if (cnt > 1) {
-            const int half = cnt / 2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < half) {
-                    float send = up ? v[i] : v[i + half];
-                    float keep = up ? v[i + half] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m * LPD);
-                }
-            }
-            cnt = half;
-        } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], m * LPD);
-        }
+    writer = true;
+    if (DPW == 1) { first = 0; return 4; }
+    if (DPW == 2) {
+        const bool up = (dl & 1) != 0;
+        const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+        const float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];
+        v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, LPD);
+        v[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, LPD);
+        first = up ? 2 : 0;
+        return 2;
     }
+    // DPW >= 4: the two highest channel bits select the state, lower bits (DPW = 8) are plain butterflies
+    constexpr int HB = DPW / 2, LB = DPW / 4;            // lane-bit values (in units of channels) of the two rounds
+    {
+        const bool up = (dl & HB) != 0;
+        const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+        const float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];
+        v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, HB * LPD);
+        v[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, HB * LPD);
+    }
+    {
+        const bool up = (dl & LB) != 0;
+        const float sd = up ? v[0] : v[1], kp = up ? v[1] : v[0];
+        v[0] = kp + __shfl_xor_sync(0xffffffffu, sd, LB * LPD);
+    }
+    first = ((dl & HB) ? 2 : 0) + ((dl & LB) ? 1 : 0);
+#pragma unroll
+    for (int m = LB / 2; m >= 1; m >>= 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], m * LPD);
+        writer = writer && ((dl & m) == 0);
+    }
+    return 1;
 }
 
 template <int N, bool HAS_Z, bool SOFTPLUS>
-__global__ void __launch_bounds__(kSelThreads, 1) selscan_bwd_kernel(const SelBwdParams p) {
-    using Cfg = SelCfg<N>;
-    constexpr int S = Cfg::S, LPD = Cfg::LPD, DPW = Cfg::DPW, DT = Cfg::DT, QPR = Cfg::QPR;
-    constexpr int TC = kCkptEvery;
-    constexpr int STAGE = TC * (4 * DT + 2 * N) + TC;          // u, delta, z, dy, B, C, start
-    constexpr int NQ = (TC * QPR + kSelThreads - 1) / kSelThreads;
-    constexpr int NQB = (TC * N / 4 + kSelThreads - 1) / kSelThreads;
-    // number of state values each lane keeps after the channel reduce-scatter, and its first index
-    constexpr int KEEP = (DPW >= 8) ? 1 : (8 / DPW);
+__global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(const SelBwdParams p) {
+    using Cfg = SelBwdCfg<N>;
+    constexpr int S = Cfg::S, LPD = Cfg::LPD, DPW = Cfg::DPW, DT = Cfg::DT, QPR = Cfg::QPR, TC = Cfg::TC, STAGE = Cfg::STAGE;
+    constexpr int NST = Cfg::NST, QS = Cfg::QS, PROW = Cfg::PROW, PLANE = Cfg::PLANE, RED = Cfg::RED, NHELP = Cfg::NHELP;
+    constexpr int NMAIN = Cfg::NMAIN, NMAINW = Cfg::NMAINW;
     extern __shared__ __align__(16) float smem[];
-    float* s_sigdt = smem + 2 * STAGE;          // [TC][DT] d softplus / d raw
-    float* s_sigz = s_sigdt + TC * DT;          // [TC][DT] sigmoid(z)
-    float* s_ypre = s_sigz + TC * DT;           // [TC][DT] y before the gate
-    float* s_red = s_ypre + TC * DT;            // [8 warps][TC][2N]
+    float* s_pl = smem + NST * STAGE;                       // [3][TC][PROW]: sB, sA, y partials per lane
+    float* s_red = s_pl + 3 * PLANE;                        // [NMAINW][TC][2N]
+    float* s_acc = s_red + RED;                             // [2][NHELP / QPR][DT]: dD / dbias partials of the helpers
+    const uint32_t bars = smem_u32(s_acc + 2 * DT * (NHELP / QPR));
+    auto bar_full = [&](int st) { return bars + 8u * st; };
+    const uint32_t bar_done = bars + 8u * NST, bar_freep = bars + 8u * (NST + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int dl = lane / LPD, ng = lane % LPD;
-    const int dloc = warp * DPW + dl;
+    const int tid = threadIdx.x;
     const int b = blockIdx.y, d0 = blockIdx.x * DT;
-    const int d = d0 + dloc;
-    const bool dvalid = d < p.D;
     const int L = p.L;
     const size_t row0 = (size_t)b * L;
-    const int nchunks = (L + TC - 1) / TC;
-    const int myq = tid % QPR;
-    const bool qvalid = (d0 + myq * 4) < p.D;
-    // state index this lane owns after the reduce-scatter
-    const int jfirst = (DPW >= 8) ? (dl >> (DPW == 16 ? 1 : 0)) : dl * KEEP;
-    const bool red_writer = (DPW == 16) ? ((dl & 1) == 0) : true;
-
-    float A2[S], dA[S], lam[S];
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        A2[j] = dvalid ? p.A[(size_t)d * N + ng * S + j] * kLog2e : 0.f;
-        dA[j] = 0.f;
-        lam[j] = 0.f;   // a_{t+1} * lambda_{t+1}
+    const int nch = (L + TC - 1) / TC;                      // chunks; processing order c = 0 .. nch-1 is chunk nch-1-c
+    if (tid == 0) {
+        for (int st = 0; st < NST; ++st) mbar_init(bar_full(st), NHELP / 32);
+        mbar_init(bar_done, NMAINW);
+        mbar_init(bar_freep, NHELP / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const float Dd = (dvalid && p.Dskip) ? p.Dskip[d] : 0.f;
-    float dD_acc = 0.f, dbias_acc = 0.f;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.dbias && qvalid) bias4 = *reinterpret_cast<const float4*>(p.dbias + d0 + myq * 4);
+    __syncthreads();
 
-    auto issue = [&](int k) {
-        if (k >= 0) {
-            float* st = smem + (k & 1) * STAGE;
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                int idx = tid + i * kSelThreads;
-                if (idx < TC * QPR) {
-                    int r = idx / QPR, t = k * TC + r;
-                    bool ok = qvalid && t < L;
-                    size_t row = row0 + (ok ? t : 0);
-                    int col = d0 + myq * 4;
-                    cp_async16(st + r * DT + myq * 4, p.u + row * p.ld_u + col, ok);
-                    cp_async16(st + TC * DT + r * DT + myq * 4, p.delta + row * p.ld_delta + col, ok);
-                    if (HAS_Z) cp_async16(st + 2 * TC * DT + r * DT + myq * 4, p.z + row * p.ld_z + col, ok);
+    if (tid >= NMAIN) {
+        // ------------------------------------------------------------------------------------ helper warps
+        const int ht = tid - NMAIN;
+        const int myq = ht % QPR;                           // this thread's quad column is fixed (NHELP % QPR == 0)
+        const int mycol = d0 + myq * 4;
+        const bool colok = mycol < p.D;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), D4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dbias && colok) bias4 = __ldg(reinterpret_cast<const float4*>(p.dbias + mycol));
+        if (p.Dskip && colok) D4 = __ldg(reinterpret_cast<const float4*>(p.Dskip + mycol));
+        float4 accD = make_float4(0.f, 0.f, 0.f, 0.f), accB = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto issue = [&](int c) {
+            if (c < nch) {
+                const int k = nch - 1 - c;
+                float* st = smem + (c % NST) * STAGE;
+                for (int idx = ht; idx < TC * QPR; idx += NHELP) {
+                    const int r = idx / QPR, t = k * TC + r;
+                    const bool ok = colok && t < L;
+                    const size_t row = row0 + (ok ? t : 0);
+                    const int col = ok ? mycol : 0;
+                    cp_async16(st + 0 * TC * DT + r * DT + myq * 4, p.u + row * p.ld_u + col, ok);
+                    cp_async16(st + 4 * TC * DT + r * DT + myq * 4, p.delta + row * p.ld_delta + col, ok);
                     cp_async16(st + 3 * TC * DT + r * DT + myq * 4, p.dy + row * p.ld_dy + col, ok);
+                    if (HAS_Z) cp_async16(st + 6 * TC * DT + r * DT + myq * 4, p.z + row * p.ld_z + col, ok);
+                }
+                for (int idx = ht; idx < TC * N / 4; idx += NHELP) {
+                    const int r = idx / (N / 4), q = idx % (N / 4), t = k * TC + r;
+                    const bool ok = t < L;
+                    const size_t row = row0 + (ok ? t : 0);
+                    cp_async16(st + Cfg::NARR * TC * DT + r * N + q * 4, p.Bm + row * p.ld_B + q * 4, ok);
+                    cp_async16(st + Cfg::NARR * TC * DT + TC * N + r * N + q * 4, p.Cm + row * p.ld_C + q * 4, ok);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < NQB; ++i) {
-                int idx = tid + i * kSelThreads;
-                if (idx < TC * N / 4) {
-                    int r = idx / (N / 4), q = idx % (N / 4), t = k * TC + r;
-                    bool ok = t < L;
-                    size_t row = row0 + (ok ? t : 0);
-                    cp_async16(st + 4 * TC * DT + r * N + q * 4, p.Bm + row * p.ld_B + q * 4, ok);
-                    cp_async16(st + 4 * TC * DT + TC * N + r * N + q * 4, p.Cm + row * p.ld_C + q * 4, ok);
-                }
-            }
-            if (tid < TC) {
-                int t = k * TC + tid;
-                bool ok = p.start != nullptr && t < L;
-                cp_async4(st + 4 * TC * DT + 2 * TC * N + tid, p.start + (ok ? row0 + t : 0), ok);
-            }
-        }
-        cp_async_commit();
-    };
-
-    issue(nchunks - 1);
-    for (int k = nchunks - 1; k >= 0; --k) {
-        float* st = smem + (k & 1) * STAGE;
-        float* s_u = st;
-        float* s_dt = st + TC * DT;
-        float* s_z = st + 2 * TC * DT;
-        float* s_dy = st + 3 * TC * DT;
-        float* s_B = st + 4 * TC * DT;
-        float* s_C = s_B + TC * N;
-        float* s_start = s_C + TC * N;
-
-        // state entering the chunk (h at t = 16k - 1)
-        float h[S];
-        if (k > 0 && dvalid) {
-            const float* c = p.ckpt + (((size_t)b * p.nckpt + (k - 1)) * p.D + d) * N + ng * S;
-            float4 c0 = *reinterpret_cast<const float4*>(c), c1 = *reinterpret_cast<const float4*>(c + 4);
-            h[0] = c0.x; h[1] = c0.y; h[2] = c0.z; h[3] = c0.w;
-            h[4] = c1.x; h[5] = c1.y; h[6] = c1.z; h[7] = c1.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < S; ++j) h[j] = 0.f;
-        }
-
-        cp_async_wait<0>();
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int idx = tid + i * kSelThreads;
-            if (idx < TC * QPR) {
-                int r = idx / QPR;
-                float4* pd = reinterpret_cast<float4*>(s_dt + r * DT + myq * 4);
-                float4 x = *pd, sg;
+            cp_async_commit();
+        };
+        auto transform = [&](int c) {
+            const int k = nch - 1 - c;
+            float* st = smem + (c % NST) * STAGE;
+            for (int idx = ht; idx < TC * QPR; idx += NHELP) {
+                const int r = idx / QPR, t = k * TC + r, o = r * DT + myq * 4;
+                const float rs = (p.start != nullptr && t < L) ? __ldg(p.start + row0 + t) : 0.f;
+                const float4 uu = *reinterpret_cast<const float4*>(st + o);
+                float4 x = *reinterpret_cast<const float4*>(st + 4 * TC * DT + o);
+                const float4 dyv = *reinterpret_cast<const float4*>(st + 3 * TC * DT + o);
                 x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+                float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (SOFTPLUS) {
                     sg = make_float4(sigmoidf_fast(x.x), sigmoidf_fast(x.y), sigmoidf_fast(x.z), sigmoidf_fast(x.w));
-                    x.x = softplusf_fast(x.x); x.y = softplusf_fast(x.y);
-                    x.z = softplusf_fast(x.z); x.w = softplusf_fast(x.w);
-                } else {
-                    sg = make_float4(1.f, 1.f, 1.f, 1.f);
+                    x.x = softplusf_fast(x.x); x.y = softplusf_fast(x.y); x.z = softplusf_fast(x.z); x.w = softplusf_fast(x.w);
                 }
-                *pd = x;
-                *reinterpret_cast<float4*>(s_sigdt + r * DT + myq * 4) = sg;
+                if (t >= L) x = make_float4(0.f, 0.f, 0.f, 0.f);      // a = 1, du = 0 and (zero-filled dy) g = 0: a no-op step
+                *reinterpret_cast<float4*>(st + 4 * TC * DT + o) = x;                                     // delta
+                *reinterpret_cast<float4*>(st + 5 * TC * DT + o) = sg;                                    // d softplus
+                *reinterpret_cast<float4*>(st + 2 * TC * DT + o) = make_float4(x.x * uu.x, x.y * uu.y, x.z * uu.z, x.w * uu.w);
+                const float4 xa = rs != 0.f ? make_float4(INFINITY, INFINITY, INFINITY, INFINITY) : x;
+                *reinterpret_cast<float4*>(st + 1 * TC * DT + o) = xa;                                    // delta or +inf
+                float4 g = dyv;
                 if (HAS_Z) {
-                    float4 zz = *reinterpret_cast<const float4*>(s_z + r * DT + myq * 4);
-                    *reinterpret_cast<float4*>(s_sigz + r * DT + myq * 4) =
-                        make_float4(sigmoidf_fast(zz.x), sigmoidf_fast(zz.y), sigmoidf_fast(zz.z), sigmoidf_fast(zz.w));
+                    const float4 zz = *reinterpret_cast<const float4*>(st + 6 * TC * DT + o);
+                    const float4 sz = make_float4(sigmoidf_fast(zz.x), sigmoidf_fast(zz.y), sigmoidf_fast(zz.z), sigmoidf_fast(zz.w));
+                    g = make_float4(dyv.x * zz.x * sz.x, dyv.y * zz.y * sz.y, dyv.z * zz.z * sz.z, dyv.w * zz.w * sz.w);
+                    *reinterpret_cast<float4*>(st + 6 * TC * DT + o) =
+                        make_float4(dyv.x * sz.x * (1.f + zz.x * (1.f - sz.x)), dyv.y * sz.y * (1.f + zz.y * (1.f - sz.y)),
+                                    dyv.z * sz.z * (1.f + zz.z * (1.f - sz.z)), dyv.w * sz.w * (1.f + zz.w * (1.f - sz.w)));
                 }
+                *reinterpret_cast<float4*>(st + 3 * TC * DT + o) = g;
             }
-        }
-        __syncthreads();
-        issue(k - 1);
-
-        const int tbase = k * TC;
-        // ---- phase F: recompute h_t inside the chunk ----
-        float hb[TC][S];
-#pragma unroll
-        for (int i = 0; i < TC; ++i) {
-            if (tbase + i < L) {
-                const float dt = s_dt[i * DT + dloc];
-                const float uu = s_u[i * DT + dloc];
-                const float du = dt * uu;
-                const bool rst = s_start[i] != 0.f;
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    float a = rst ? 0.f : ex2f(dt * A2[j]);
-                    h[j] = fmaf(a, h[j], du * s_B[i * N + ng * S + j]);
-                    hb[i][j] = h[j];
-                    acc = fmaf(h[j], s_C[i * N + ng * S + j], acc);
-                }
-                if (HAS_Z) {
-#pragma unroll
-                    for (int o = 1; o < LPD; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (ng == 0) s_ypre[i * DT + dloc] = fmaf(Dd, uu, acc);
-                }
+        };
+        for (int c = 0; c < NST - 1; ++c) issue(c);
+        cp_async_wait<NST - 2>();
+        transform(0);
+        __syncwarp();
+        if ((ht & 31) == 0) mbar_arrive(bar_full(0));
+        for (int c = 0; c < nch; ++c) {
+            const int k = nch - 1 - c;
+            issue(c + NST - 1);
+            if (c + 1 < nch) {
+                cp_async_wait<NST - 2>();
+                transform(c + 1);
+                __syncwarp();
+                if ((ht & 31) == 0) mbar_arrive(bar_full((c + 1) % NST));
             }
-        }
-        // ---- phase R: adjoint recurrence, latest step first ----
+            mbar_wait(bar_done, c & 1);
+            const float* st = smem + (c % NST) * STAGE;
+            for (int idx = ht; idx < TC * QPR; idx += NHELP) {
+                const int r = idx / QPR, t = k * TC + r, o = r * DT + myq * 4;
+                if (colok && t < L) {
+                    float sB[4], sA[4], yp[4];
 #pragma unroll
-        for (int i = TC - 1; i >= 0; --i) {
-            if (tbase + i < L) {
-                const float dt = s_dt[i * DT + dloc];
-                const float uu = s_u[i * DT + dloc];
-                const float du = dt * uu;
-                const float dyv = s_dy[i * DT + dloc];
-                const bool rst = s_start[i] != 0.f;
-                float g = dyv;
-                float dzv = 0.f;
-                if (HAS_Z) {
-                    const float zr = s_z[i * DT + dloc], sg = s_sigz[i * DT + dloc];
-                    g = dyv * zr * sg;
-                    dzv = dyv * s_ypre[i * DT + dloc] * sg * (1.0f + zr * (1.0f - sg));
-                }
-                float dC[S], dB[S];
-                float sB = 0.f, sA = 0.f;
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const float* pb = s_pl + r * PROW + myq * QS + ch * LPD;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    const float Bj = s_B[i * N + ng * S + j], Cj = s_C[i * N + ng * S + j];
-                    const float l = fmaf(g, Cj, lam[j]);
-                    dC[j] = g * hb[i][j];
-                    dB[j] = l * du;
-                    sB = fmaf(l, Bj, sB);
-                    const float ahp = fmaf(-du, Bj, hb[i][j]);   // a_t * h_{t-1}
-                    const float t1 = l * ahp;
-                    dA[j] = fmaf(t1, dt, dA[j]);
-                    sA = fmaf(t1, A2[j], sA);
-                    const float a = rst ? 0.f : ex2f(dt * A2[j]);
-                    lam[j] = a * l;
-                }
-#pragma unroll
-                for (int o = 1; o < LPD; o <<= 1) {
-                    sB += __shfl_xor_sync(0xffffffffu, sB, o);
-                    sA += __shfl_xor_sync(0xffffffffu, sA, o);
-                }
-                if (ng == 0) {
-                    const float ddt = fmaf(sA, kLn2, uu * sB) * s_sigdt[i * DT + dloc];
-                    dbias_acc += ddt;
-                    dD_acc = fmaf(g, uu, dD_acc);
-                    s_u[i * DT + dloc] = fmaf(g, Dd, dt * sB);
-                    s_dt[i * DT + dloc] = ddt;
-                    if (HAS_Z) s_z[i * DT + dloc] = dzv;
-                }
-                channel_reduce_scatter<LPD>(dC, dl);
-                channel_reduce_scatter<LPD>(dB, dl);
-                if (red_writer) {
-                    float* r = s_red + ((size_t)warp * TC + i) * (2 * N) + ng * S + jfirst;
-#pragma unroll
-                    for (int q = 0; q < KEEP; ++q) {
-                        r[q] = dB[q];
-                        r[N + q] = dC[q];
+                        for (int kk = 0; kk < LPD; kk += 4) {
+                            const float4 v0 = *reinterpret_cast<const float4*>(pb + kk);
+                            const float4 v1 = *reinterpret_cast<const float4*>(pb + PLANE + kk);
+                            a0 += (v0.x + v0.y) + (v0.z + v0.w);
+                            a1 += (v1.x + v1.y) + (v1.z + v1.w);
+                            if (HAS_Z) {
+                                const float4 v2 = *reinterpret_cast<const float4*>(pb + 2 * PLANE + kk);
+                                a2 += (v2.x + v2.y) + (v2.z + v2.w);
+                            }
+                        }
+                        sB[ch] = a0; sA[ch] = a1; yp[ch] = a2;
+                    }
+                    const float4 uu = *reinterpret_cast<const float4*>(st + o);
+                    const float4 g = *reinterpret_cast<const float4*>(st + 3 * TC * DT + o);
+                    const float4 dt = *reinterpret_cast<const float4*>(st + 4 * TC * DT + o);
+                    const float4 sg = *reinterpret_cast<const float4*>(st + 5 * TC * DT + o);
+                    // sA was accumulated against A * log2(e): * ln2 restores sum_n t1 A
+                    const float4 ddt = make_float4(fmaf(sA[0], kLn2, uu.x * sB[0]) * sg.x, fmaf(sA[1], kLn2, uu.y * sB[1]) * sg.y,
+                                                   fmaf(sA[2], kLn2, uu.z * sB[2]) * sg.z, fmaf(sA[3], kLn2, uu.w * sB[3]) * sg.w);
+                    const float4 duo = make_float4(fmaf(g.x, D4.x, dt.x * sB[0]), fmaf(g.y, D4.y, dt.y * sB[1]),
+                                                   fmaf(g.z, D4.z, dt.z * sB[2]), fmaf(g.w, D4.w, dt.w * sB[3]));
+                    accB.x += ddt.x; accB.y += ddt.y; accB.z += ddt.z; accB.w += ddt.w;
+                    accD.x = fmaf(g.x, uu.x, accD.x); accD.y = fmaf(g.y, uu.y, accD.y);
+                    accD.z = fmaf(g.z, uu.z, accD.z); accD.w = fmaf(g.w, uu.w, accD.w);
+                    const size_t row = row0 + t;
+                    *reinterpret_cast<float4*>(p.du + row * p.ld_du + mycol) = duo;
+                    *reinterpret_cast<float4*>(p.ddelta + row * p.ld_ddelta + mycol) = ddt;
+                    if (HAS_Z) {
+                        const float4 zc = *reinterpret_cast<const float4*>(st + 6 * TC * DT + o);
+                        *reinterpret_cast<float4*>(p.dz + row * p.ld_dz + mycol) =
+                            make_float4(zc.x * fmaf(D4.x, uu.x, yp[0]), zc.y * fmaf(D4.y, uu.y, yp[1]),
+                                        zc.z * fmaf(D4.z, uu.z, yp[2]), zc.w * fmaf(D4.w, uu.w, yp[3]));
                     }
                 }
             }
-        }
-        __syncthreads();
-        // ---- copy out du / ddelta / dz and the per-CTA dB|dC partial ----
+            for (int idx = ht; idx < TC * 2 * N; idx += NHELP) {
+                const int r = idx / (2 * N), t = k * TC + r;
+                if (t < L) {
+                    float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int idx = tid + i * kSelThreads;
-            if (idx < TC * QPR) {
-                int r = idx / QPR, t = tbase + r;
-                if (qvalid && t < L) {
-                    size_t row = row0 + t;
-                    int col = d0 + myq * 4;
-                    *reinterpret_cast<float4*>(p.du + row * p.ld_du + col) =
-                        *reinterpret_cast<const float4*>(s_u + r * DT + myq * 4);
-                    *reinterpret_cast<float4*>(p.ddelta + row * p.ld_ddelta + col) =
-                        *reinterpret_cast<const float4*>(s_dt + r * DT + myq * 4);
-                    if (HAS_Z)
-                        *reinterpret_cast<float4*>(p.dz + row * p.ld_dz + col) =
-                            *reinterpret_cast<const float4*>(s_z + r * DT + myq * 4);
+                    for (int w = 0; w < NMAINW; ++w) sum += s_red[w * TC * 2 * N + idx];
+                    p.dBC_part[(((size_t)blockIdx.x * p.Bsz + b) * L + t) * (2 * N) + (idx % (2 * N))] = sum;
                 }
             }
+            __syncwarp();
+            if ((ht & 31) == 0) mbar_arrive(bar_freep);
+            asm volatile("bar.sync 1, %0;" ::"n"(NHELP) : "memory");
         }
-        for (int idx = tid; idx < TC * 2 * N; idx += kSelThreads) {
-            int r = idx / (2 * N), t = tbase + r;
-            if (t < L) {
-                float s = 0.f;
+        // per-channel sums over time: combine the NHELP / QPR helper threads that share a quad column
+        float* aD = s_acc + (ht / QPR) * DT + myq * 4;
+        float* aB = aD + (NHELP / QPR) * DT;
+        *reinterpret_cast<float4*>(aD) = accD;
+        *reinterpret_cast<float4*>(aB) = accB;
+        asm volatile("bar.sync 1, %0;" ::"n"(NHELP) : "memory");
+        for (int ch = ht; ch < DT; ch += NHELP) {
+            if (d0 + ch < p.D) {
+                float sD = 0.f, sBb = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) s += s_red[(size_t)w * TC * 2 * N + idx];
-                p.dBC_part[(((size_t)blockIdx.x * p.Bsz + b) * L + t) * (2 * N) + (idx % (2 * N))] = s;
+                for (int w = 0; w < NHELP / QPR; ++w) {
+                    sD += s_acc[w * DT + ch];
+                    sBb += s_acc[(NHELP / QPR + w) * DT + ch];
+                }
+                p.dD_part[(size_t)b * p.D + d0 + ch] = sD;
+                p.dbias_part[(size_t)b * p.D + d0 + ch] = sBb;
             }
         }
-        // the next iteration's pre-barrier writes touch s_sigdt/s_sigz only; s_red and the stage
-        // are protected by that barrier.
-    }
-    if (dvalid) {
-        float* a = p.dA_part + ((size_t)b * p.D + d) * N + ng * S;
-        // dA accumulates t1 * delta with t1 = lambda * a_t h_{t-1}
-        *reinterpret_cast<float4*>(a) = make_float4(dA[0], dA[1], dA[2], dA[3]);
-        *reinterpret_cast<float4*>(a + 4) = make_float4(dA[4], dA[5], dA[6], dA[7]);
-        if (ng == 0) {
-            p.dD_part[(size_t)b * p.D + d] = dD_acc;
-            p.dbias_part[(size_t)b * p.D + d] = dbias_acc;
+    } else {
+        // ------------------------------------------------------------------------------------ main warps
+        constexpr int H2 = S / 2;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int dl = lane / LPD, ng = lane % LPD;
+        const int dloc = warp * DPW + dl;
+        const int d = d0 + dloc;
+        const bool dvalid = d < p.D;
+        float2 A2[H2], dA[H2], lam[H2];
+#pragma unroll
+        for (int j = 0; j < H2; ++j) {
+            // channels past D: any negative A keeps (+inf) * A = -inf at reset steps (0 would give NaN, and this
+            // thread's zero contributions still enter the cross-channel dB / dC sums)
+            A2[j] = dvalid ? f2(p.A[(size_t)d * N + ng * S + 2 * j] * kLog2e, p.A[(size_t)d * N + ng * S + 2 * j + 1] * kLog2e)
+                           : f2(-1.f, -1.f);
+            dA[j] = f2(0.f, 0.f);
+            lam[j] = f2(0.f, 0.f);                          // a_{t+1} * lambda_{t+1}
+        }
+        const int poff = (dloc >> 2) * QS + (dloc & 3) * LPD + ng;      // this lane's slot in a partial-sum row
+        auto ld_ckpt = [&](int k) {                         // state entering chunk k
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k > 0 && dvalid) v = __ldg(reinterpret_cast<const float4*>(p.ckpt + (((size_t)b * p.nckpt + (k - 1)) * p.D + d) * N + ng * S));
+            return v;
+        };
+        float4 hin = ld_ckpt(nch - 1);
+        for (int c = 0; c < nch; ++c) {
+            const int k = nch - 1 - c;
+            const float* st = smem + (c % NST) * STAGE;
+            const float* s_dtA = st + 1 * TC * DT;
+            const float* s_du = st + 2 * TC * DT;
+            const float* s_g = st + 3 * TC * DT;
+            const float* s_B = st + Cfg::NARR * TC * DT;
+            const float* s_C = s_B + TC * N;
+            mbar_wait(bar_full(c % NST), (c / NST) & 1);
+            // ---- phase F: recompute h_t inside the chunk
+            float2 h[H2] = {f2(hin.x, hin.y), f2(hin.z, hin.w)};
+            hin = ld_ckpt(k - 1);                           // prefetch the next chunk's entry state
+            float2 hb[TC][H2];
+#pragma unroll
+            for (int i = 0; i < TC; ++i) {
+                const float dtA = s_dtA[i * DT + dloc], du = s_du[i * DT + dloc];
+                const float4 bq = *reinterpret_cast<const float4*>(s_B + i * N + ng * S);
+                const float2 Bv[H2] = {f2(bq.x, bq.y), f2(bq.z, bq.w)};
+#pragma unroll
+                for (int j = 0; j < H2; ++j) {
+                    const float2 e = __fmul2_rn(f2(dtA, dtA), A2[j]);
+                    const float2 a = f2(ex2f(e.x), ex2f(e.y));
+                    h[j] = __ffma2_rn(a, h[j], __fmul2_rn(f2(du, du), Bv[j]));
+                    hb[i][j] = h[j];
+                }
+            }
+            // the partial-sum planes and s_red are single-buffered: the helpers must have finished chunk c-1
+            if (c >= 1) mbar_wait(bar_freep, (c - 1) & 1);
+            // ---- phase R: adjoint recurrence, latest step first
+#pragma unroll
+            for (int i = TC - 1; i >= 0; --i) {
+                const float dtA = s_dtA[i * DT + dloc], du = s_du[i * DT + dloc], g = s_g[i * DT + dloc];
+                const float dt = (dtA == INFINITY) ? 0.f : dtA;     // at a reset a_t h_{t-1} = 0, so dt is immaterial there
+                const float4 bq = *reinterpret_cast<const float4*>(s_B + i * N + ng * S);
+                const float4 cq = *reinterpret_cast<const float4*>(s_C + i * N + ng * S);
+                const float2 Bv[H2] = {f2(bq.x, bq.y), f2(bq.z, bq.w)};
+                const float2 Cv[H2] = {f2(cq.x, cq.y), f2(cq.z, cq.w)};
+                const float2 g2 = f2(g, g), du2 = f2(du, du), dt2 = f2(dt, dt);
+                float2 sB2 = f2(0.f, 0.f), sA2 = f2(0.f, 0.f), yp2 = f2(0.f, 0.f);
+                float dBv[4], dCv[4];
+#pragma unroll
+                for (int j = 0; j < H2; ++j) {
+                    const float2 l = __ffma2_rn(g2, Cv[j], lam[j]);
+                    const float2 dc = __fmul2_rn(g2, hb[i][j]);
+                    const float2 db = __fmul2_rn(l, du2);
+                    dCv[2 * j] = dc.x; dCv[2 * j + 1] = dc.y;
+                    dBv[2 * j] = db.x; dBv[2 * j + 1] = db.y;
+                    sB2 = __ffma2_rn(l, Bv[j], sB2);
+                    const float2 ahp = __ffma2_rn(f2(-du, -du), Bv[j], hb[i][j]);     // a_t * h_{t-1}
+                    const float2 t1 = __fmul2_rn(l, ahp);
+                    dA[j] = __ffma2_rn(t1, dt2, dA[j]);
+                    sA2 = __ffma2_rn(t1, A2[j], sA2);
+                    if (HAS_Z) yp2 = __ffma2_rn(hb[i][j], Cv[j], yp2);
+                    const float2 e = __fmul2_rn(f2(dtA, dtA), A2[j]);
+                    lam[j] = __fmul2_rn(f2(ex2f(e.x), ex2f(e.y)), l);
+                }
+                float* pl = s_pl + i * PROW + poff;
+                pl[0] = sB2.x + sB2.y;
+                pl[PLANE] = sA2.x + sA2.y;
+                if (HAS_Z) pl[2 * PLANE] = yp2.x + yp2.y;
+                int fB, fC;
+                bool wB, wC;
+                const int nB = channel_reduce_scatter4<LPD>(dBv, dl, fB, wB);
+                channel_reduce_scatter4<LPD>(dCv, dl, fC, wC);
+                if (wB) {
+                    float* rr = s_red + ((size_t)warp * TC + i) * (2 * N) + ng * S + fB;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < nB) {
+                            rr[q] = dBv[q];
+                            rr[N + q] = dCv[q];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_done);
+        }
+        if (dvalid) {
+            float* a = p.dA_part + ((size_t)b * p.D + d) * N + ng * S;
+            *reinterpret_cast<float4*>(a) = make_float4(dA[0].x, dA[0].y, dA[1].x, dA[1].y);
         }
     }
 }
@@ -631,8 +718,7 @@ constexpr size_t sel_fwd_smem() {
 }
 template <int N>
 constexpr size_t sel_bwd_smem() {
-    return sizeof(float) * (2 * (kCkptEvery * (4 * SelCfg<N>::DT + 2 * N) + kCkptEvery) +
-                            3 * kCkptEvery * SelCfg<N>::DT + 8 * kCkptEvery * 2 * N);
+    return SelBwdCfg<N>::SMEM;
 }
 
 }  // namespace rorl
@@ -658,8 +744,8 @@ static int launch_bwd(const SelBwdParams& p, int64_t B, cudaStream_t stream) {
     constexpr size_t smem = sel_bwd_smem<N>();
     static bool once = (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;
-    dim3 grid((unsigned)((p.D + SelCfg<N>::DT - 1) / SelCfg<N>::DT), (unsigned)B);
-    kern<<<grid, kSelThreads, smem, stream>>>(p);
+    dim3 grid((unsigned)((p.D + SelBwdCfg<N>::DT - 1) / SelBwdCfg<N>::DT), (unsigned)B);
+    kern<<<grid, SelBwdCfg<N>::NTHREADS, smem, stream>>>(p);
     RORL_RETURN_LAUNCH();
 }
 
@@ -680,9 +766,9 @@ static int launch_bwd(const SelBwdParams& p, int64_t B, cudaStream_t stream) {
 extern "C" {
 
 int rorl_selscan_dtile(int64_t N) {
-    if (N == 16) return SelCfg<16>::DT;
-    if (N == 32) return SelCfg<32>::DT;
-    if (N == 64) return SelCfg<64>::DT;
+    if (N == 16) return SelBwdCfg<16>::DT;
+    if (N == 32) return SelBwdCfg<32>::DT;
+    if (N == 64) return SelBwdCfg<64>::DT;
     return RORL_ERR_SHAPE;
 }
 
