@@ -571,13 +571,16 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
                     }
                 }
             }
-            for (int idx = ht; idx < TC * 2 * N; idx += NHELP) {
+            for (int idx = ht * 4; idx < TC * 2 * N; idx += NHELP * 4) {
                 const int r = idx / (2 * N), t = k * TC + r;
                 if (t < L) {
-                    float sum = 0.f;
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int w = 0; w < NMAINW; ++w) sum += s_red[w * TC * 2 * N + idx];
-                    p.dBC_part[(((size_t)blockIdx.x * p.Bsz + b) * L + t) * (2 * N) + (idx % (2 * N))] = sum;
+                    for (int w = 0; w < NMAINW; ++w) {
+                        const float4 v = *reinterpret_cast<const float4*>(s_red + w * TC * 2 * N + idx);
+                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    }
+                    *reinterpret_cast<float4*>(p.dBC_part + (((size_t)blockIdx.x * p.Bsz + b) * L + t) * (2 * N) + (idx % (2 * N))) = sum;
                 }
             }
             __syncwarp();
