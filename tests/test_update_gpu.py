@@ -165,6 +165,7 @@ def test_update_vs_oracle_wide(enc, algo):
     pk = dict(kw(False))
     upd = OU.RefUpdate(pol_sd, val_sd, OM.ModelSpec(**pk), OM.ModelSpec(**kw(True)), hp, obuf, o_noise, algo=algo, redq=True,
                        allow_nest_stack=alg.allow_nest_stack)
+    eps_zone = {}
     for call in range(2):
         drawn.clear()
         np.random.seed(100 + call)
@@ -183,21 +184,39 @@ def test_update_vs_oracle_wide(enc, algo):
                 for n, p_ in m.named_parameters():
                     if grads[mod][n] is not None and p_.grad is not None:
                         gworst = max(gworst, assert_close(p_.grad, grads[mod][n], TOL, f"grad/{mod}/{n}"))
-        # Updated parameters.  AdamW normalises every gradient entry to a step of about +-lr, so where the bf16
-        # attention path perturbs a near-zero gradient entry the step itself flips; the fp32 oracle and a bf16
-        # implementation (the reference's flash-attn included) can therefore differ by ~2 lr / |w| on single entries.
-        # So for cgpt the bound on a parameter is 1e-2 relative PLUS one flipped step (2 lr) per update taken.
-        worst = 0.0
-        for which, model, osd in (("policy", alg.policy, upd.policy), ("value", alg.values[0], upd.value),
-                                  ("target", alg.target_values[0], upd.target)):
+        # Updated parameters.  AdamW turns every gradient entry into a step of lr * g / (|g| + eps): where |g| is
+        # within a few orders of eps = 1e-8 the step amplifies fp32 rounding noise of the gradient (d step / d g =
+        # lr * eps / (|g| + eps)^2), and where the bf16 attention path perturbs a near-zero entry the step can flip
+        # outright -- the reference itself differs from run to run there (its CUDA backward is not deterministic,
+        # ref: results.md:4).  So: entries whose oracle gradient is above the eps regime (|g| >= 1e-6 in every call
+        # so far) must match to TOL; entries inside it are bounded by one flipped step (2 lr) per update taken.
+        # For cgpt (bf16 attention) every entry gets the flipped-step allowance on top of 1e-2.
+        worst, n_eps = 0.0, 0
+        for which, model, osd, ograds in (("policy", alg.policy, upd.policy, upd.policy_grads), ("value", alg.values[0], upd.value, upd.value_grads),
+                                          ("target", alg.target_values[0], upd.target, upd.value_grads)):
             for mod, params in model.state_dict().items():
                 for n, t in params.items():
                     r = osd[mod][n].detach()
+                    diff = (t.cpu() - r).abs()
+                    scale = float(r.abs().max()) + 1e-30
+                    flip = 2.2 * hp["value_lr"] * (call + 1)
                     if enc.startswith("cgpt"):
-                        bound = TOL * float(r.abs().max()) + 2.2 * hp["value_lr"] * (call + 1)
-                        diff = float((t.cpu() - r).abs().max())
-                        assert diff <= bound, f"{which}/{mod}/{n}: |diff| {diff:.3e} > {bound:.3e}"
-                        worst = max(worst, diff / (float(r.abs().max()) + 1e-30))
-                    else:
-                        worst = max(worst, assert_close(t, r, TOL, f"{which}/{mod}/{n}"))
-        print(f"{enc} {algo} call {call}: worst gradient rel. error {gworst:.2e}, worst updated-parameter rel. error {worst:.2e}")
+                        bound = TOL * scale + flip
+                        assert float(diff.max()) <= bound, f"{which}/{mod}/{n}: |diff| {float(diff.max()):.3e} > {bound:.3e}"
+                        worst = max(worst, float(diff.max()) / scale)
+                        continue
+                    g = ograds.get(mod, {}).get(n)
+                    key = (which, mod, n)
+                    small = eps_zone.get(key, torch.zeros_like(r, dtype=torch.bool))
+                    if g is not None:
+                        small = small | (g.detach().abs() < 1e-6)
+                    eps_zone[key] = small
+                    n_eps += int(small.sum())
+                    strict = diff[~small]
+                    if strict.numel():
+                        e = float(strict.max()) / scale
+                        assert e <= TOL, f"{which}/{mod}/{n}: relative error {e:.3e} > {TOL:.1e}"
+                        worst = max(worst, e)
+                    if small.any():
+                        assert float(diff[small].max()) <= flip, f"{which}/{mod}/{n}: eps-regime entry moved {float(diff[small].max()):.3e} > {flip:.3e}"
+        print(f"{enc} {algo} call {call}: worst gradient rel. error {gworst:.2e}, worst updated-parameter rel. error {worst:.2e} ({n_eps} eps-regime entries)")
