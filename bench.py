@@ -178,7 +178,7 @@ def run_ours(args):
         res = alg.update_on_host_batch(host_batch, host_valid, plan.total_size, plan.lens, sync=True)
         assert np.isfinite(res["critic_loss"])
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(args.warmup):          # >= 3: eager, graph capture, first replay
         step_e2e()
     e2e_steps = max(3, args.steps // 2)
     ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps

@@ -76,6 +76,8 @@ int rorl_lru_scan_bwd(const float* g_re, const float* g_im, const float* f_re, c
  * Token-major layout: u, delta, z, y: [B, L, D] with row strides ld_*; Bm, Cm: [B, L, N] with row
  * strides ld_B, ld_C; A: [D, N] (already -exp(A_log)); Dskip, delta_bias: [D] or NULL; z may be NULL;
  * start: [B, L] (1 = reset the state before this step) or NULL.  N in {16, 32, 64}; D % 4 == 0.
+ * h0 (may be NULL = 0): [B, D, N] state carried into the call (the s6 layer's `initial_state`,
+ * ref: offpolicy_rnn/models/s6/selective_scan/cpu_scan.py:52-53); a constant: no gradient is produced for it.
  * ckpt (may be NULL when no backward follows): [B, L / rorl_selscan_ckpt_every(), D, N] state
  * checkpoints the backward consumes; last_state (may be NULL): [B, D, N].
  *
@@ -88,12 +90,12 @@ int rorl_lru_scan_bwd(const float* g_re, const float* g_im, const float* f_re, c
 int rorl_selscan_dtile(int64_t N);
 int rorl_selscan_ckpt_every(void);
 int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
-                     const float* Dskip, const float* z, const float* delta_bias, const float* start, float* y,
-                     float* ckpt, float* last_state, int64_t B, int64_t L, int64_t D, int64_t N, int64_t ld_u,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start, const float* h0,
+                     float* y, float* ckpt, float* last_state, int64_t B, int64_t L, int64_t D, int64_t N, int64_t ld_u,
                      int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_y, int delta_softplus,
                      cudaStream_t stream);
 int rorl_selscan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
-                     const float* Dskip, const float* z, const float* delta_bias, const float* start,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start, const float* h0,
                      const float* dy, const float* ckpt, float* du, float* ddelta, float* dz, float* dBC_part,
                      float* dA_part, float* dD_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t N,
                      int64_t ld_u, int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_dy,
@@ -271,6 +273,26 @@ int rorl_attn_bwd(const void* q_rm, const void* k_rm, const void* v_rm, const vo
 int rorl_traj_gather(const float* ring, int64_t F, const int64_t* plan, int64_t ntraj, const int32_t* colmap,
                      int64_t start_col, float* batch, float* valid, int64_t rows, int64_t Lmax, int64_t skip,
                      int64_t max_len, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Deterministic row reductions of the backward pass (csrc/reduce.cu): no atomics, per-CTA partials in `work`.
+ * Replace ATen `sum(0)` / `mm` launches autograd issues for the reference's nn.Linear / EnsembleLinear biases and
+ * narrow-input weights (ref: offpolicy_rnn/models/ensemble_linear_model.py:29-60; torch.nn.Linear backward).
+ *   rorl_colsum          out[g, n] = sum_m x[g, m, n]      x: G groups of [M, N], row stride ldx, group stride gsx
+ *   rorl_elu_bwd_colsum  gout = dy * (y > 0 ? 1 : y + 1)   ELU backward from the layer OUTPUT y, fused with the
+ *                        out[g, n] = sum_m gout[g, m, n]   bias gradient of that layer
+ *   rorl_skinny_wgrad    dW[n, k] = sum_m g[m, n] x[m, k]  K <= 16 (obs / action encoders, dt_proj)
+ * N % 4 == 0 and 16-byte aligned rows for the column sums; `work` holds rorl_*_work_floats() floats.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t rorl_colsum_work_floats(int64_t G, int64_t M, int64_t N);
+int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, int64_t N, int64_t ldx, int64_t gsx,
+                cudaStream_t stream);
+int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
+                        int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
+                        cudaStream_t stream);
+int64_t rorl_skinny_wgrad_work_floats(int64_t M, int64_t N, int64_t K);
+int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, int64_t M, int64_t N, int64_t K,
+                      int64_t ldg, int64_t ldx, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

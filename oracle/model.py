@@ -5,7 +5,7 @@ names are the reference's own.  Plain PyTorch ops + autogra
 ref: offpolicy_rnn/models/rnn_base.py (RNNBase), contextual_model.py (ContextualModel),
      policy_value_models/contextual_sac_policy_single_head.py, contextual_sac_value.py,
      contextual_td3_policy.py, models/smamba/mamba.py (GPU path = forward_sequential),
-     models/gilr/gilr.py, models/lru/lru.py, torch.nn.GRU.
+     models/gilr/gilr.py, models/lru/lru.py, models/s6/mamba.py (+ s6/selective_scan/cpu_scan.py), torch.nn.GRU.
 """
 from __future__ import annotations
 
@@ -126,6 +126,55 @@ def smamba_layer(p, pre, x, side: Side, layer_id: str):
     return ff_block(p, pre + 'head.', x, eps)
 
 
+def parse_s6(layer_id: str):
+    """ref: rnn_base.py:118-136"""
+    cfg = dict(d_state=16, d_conv=4, ff=True)
+    for tok in layer_id.split('_')[1:]:
+        if tok.startswith('s'):
+            cfg['d_state'] = int(tok[1:])
+        elif tok.startswith('c'):
+            cfg['d_conv'] = int(tok[1:])
+        elif tok.startswith('no') and tok[2:] == 'ff':
+            cfg['ff'] = False
+    return cfg
+
+
+def s6_layer(p, pre, x, side: Side, layer_id: str, hidden=None):
+    """MambaResidualBlock: RMSNorm -> MambaBlock -> + x -> feed-forward tail; returns (out, hidden [B,1,D*N+(K-1)*D]).
+    ref: offpolicy_rnn/models/s6/mamba.py:41-67 (block), :146-191 (mixer), :133-144 (conv with explicit left
+    state, padding 0), :193-237 (ssm), RMSNorm :240-251 (eps 1e-5), PositionWiseFeedForward :256-267."""
+    cfg = parse_s6(layer_id)
+    N, K = cfg['d_state'], cfg['d_conv']
+    Bsz, L, _ = x.shape
+    m = pre + 'mixer.'
+    rms = lambda t, w: t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-5) * w
+    xz = F.linear(rms(x, p[pre + 'norm.weight']), p[m + 'in_proj.weight'])
+    Dm = xz.shape[-1] // 2
+    xs, res = xz[..., :Dm], xz[..., Dm:]
+    if hidden is None:
+        h_ssm, h_conv = torch.zeros((Bsz, Dm, N)), torch.zeros((Bsz, K - 1, Dm))
+    else:
+        h_ssm, h_conv = torch.split(hidden, [Dm * N, Dm * (K - 1)], dim=-1)
+        h_ssm, h_conv = h_ssm.reshape(Bsz, Dm, N), h_conv.reshape(Bsz, K - 1, Dm)
+    if side.mask is not None:
+        xs = xs * side.mask
+    x_in = torch.cat((h_conv, xs), dim=-2)                                        # :139
+    xs = F.conv1d(x_in.transpose(1, 2), p[m + 'conv1d.weight'], p[m + 'conv1d.bias'], groups=Dm)[:, :, :L].transpose(1, 2)
+    h_conv = x_in[:, -(K - 1):, :]
+    xs = F.silu(xs)
+    x_dbl = F.linear(xs, p[m + 'x_proj.weight'])
+    R = x_dbl.shape[-1] - 2 * N
+    dt, Bm, Cm = torch.split(x_dbl, [R, N, N], dim=-1)
+    delta = F.softplus(F.linear(dt, p[m + 'dt_proj.weight'], p[m + 'dt_proj.bias']))
+    start = side.rnn_start if side.rnn_start is not None else torch.zeros((Bsz, L, 1))
+    y, h_ssm = ops.s6_scan(xs, delta, -torch.exp(p[m + 'A_log'].float()), Bm, Cm, p[m + 'D'].float(), start, h_ssm)
+    out = F.linear(y * F.silu(res), p[m + 'out_proj.weight']) + x
+    h_out = torch.cat((h_ssm.reshape(Bsz, 1, -1), h_conv.reshape(Bsz, 1, -1)), dim=-1)
+    if cfg['ff']:
+        return ff_block(p, pre + 'ff.', out), h_out
+    return F.linear(rms(out, p[pre + 'norm_f.weight']), p[pre + 'ff.weight']), h_out
+
+
 def gru_layer(p, pre, x, side: Side):
     """torch.nn.GRU(batch_first=True), zero initial state.  ref: rnn_base.py:59,245-247,454"""
     hidden = p[pre + 'weight_hh_l0'].shape[1]
@@ -167,6 +216,9 @@ def rnn_base(p: Dict[str, torch.Tensor], layer_types: List[str], acts: List[str]
             x = lru_layer(p, pre, x, side)
         elif lt.startswith('smamba'):
             x = smamba_layer(p, pre, x, side, lt)
+        elif lt.startswith('mamba'):
+            x, h = s6_layer(p, pre, x, side, lt, side.h0.get(i))
+            side.h_out = h
         elif lt == 'gru':
             x = gru_layer(p, pre, x, side)
         elif lt.startswith('cgpt'):

@@ -79,6 +79,24 @@ def selective_scan(u, delta, A, B, C, start=None, D=None, z=None, delta_bias=Non
     return (out, x) if return_last_state else out
 
 
+def s6_scan(u, delta, A, B, C, D, start, h0=None):
+    """The s6 layer's CPU scan, token-major u/delta [B,L,D], B/C [B,L,N], start [B,L,1]; returns (y, final state).
+    ref: offpolicy_rnn/models/s6/selective_scan/cpu_scan.py:6-61 (deltaA with reset :44-45, deltaB_u :46,
+    initial state :52-53, recurrence :55-58, D skip :61).  Step-by-step, no [B,L,D,N] materialisation."""
+    Bsz, L, Dm = u.shape
+    x = torch.zeros((Bsz, Dm, A.shape[1]), dtype=torch.float32)
+    if h0 is not None:
+        x = x + h0
+    keep = 1 - start.reshape(Bsz, L)
+    ys = []
+    for t in range(L):
+        dA = torch.exp(delta[:, t, :, None] * A[None]) * keep[:, t, None, None]
+        x = dA * x + (delta[:, t] * u[:, t])[..., None] * B[:, t, None, :]
+        ys.append((x * C[:, t, None, :]).sum(-1))
+    y = torch.stack(ys, dim=1)
+    return y + u * D[None, None, :], x
+
+
 def add_norm(x, weight, bias, residual=None, eps=1e-6, prenorm=False, is_rms=False):
     """residual add then LayerNorm / RMSNorm; prenorm=True also returns the sum.
     ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/triton/layernorm_cpu.py:6-35"""

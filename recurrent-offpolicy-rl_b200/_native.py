@@ -19,7 +19,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(REPO_ROOT, "include", "rorl_b200.h")
 LIB_PATH = os.environ.get("RORL_B200_LIB") or os.path.join(CSRC, "librorl_b200.so")   # override: A/B experiments only
 SOURCES = ["scan_real.cu", "scan_complex.cu", "selscan.cu", "conv1d.cu", "addnorm.cu", "losses.cu", "optim.cu",
-           "gather.cu", "gru.cu", "gemm.cu", "attn.cu"]
+           "gather.cu", "gru.cu", "gemm.cu", "attn.cu", "reduce.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -155,6 +155,12 @@ def call(name: str, *args) -> None:
     global _launches
     _launches += 1
     check(getattr(lib(), name)(*args), name)
+
+
+def add_launches(n: int) -> None:
+    """Kernel launches replayed from a captured CUDA graph (counted once at capture time, per replay here)."""
+    global _launches
+    _launches += int(n)
 
 
 def launch_count() -> int:

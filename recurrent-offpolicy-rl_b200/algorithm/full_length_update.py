@@ -22,6 +22,7 @@ with the B200-native restructuring:
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional
 
@@ -36,7 +37,7 @@ from .data_parallel import BucketedGradSync, sync_count_and_guard
 
 DEFAULTS = dict(utd=1, policy_utd=1, randomize_mask=False, valid_number_post_randomized=0, random_trunc_traj=False,
                 randomize_first_hidden=False, gamma=0.99, sac_tau=0.995, policy_update_per=1, no_alpha_auto_tune=False,
-                policy_max_gradnorm=None, policy_embedding_max_gradnorm=None, value_max_gradnorm=None,
+                use_cuda_graph=True, policy_max_gradnorm=None, policy_embedding_max_gradnorm=None, value_max_gradnorm=None,
                 value_embedding_max_gradnorm=None, redq_m=2, target_action_noise_std=0.04,
                 target_action_noise_clip=0.12, policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5, rnn_value_lr=1e-4,
                 alpha_lr=1e-2, policy_l2_norm=0.0, value_l2_norm=0.0, sample_std=0.1, target_entropy_ratio=1.5,
@@ -200,11 +201,20 @@ class FullLengthRNNUpdate:
         # scratch for the fused reductions
         self._work = torch.zeros(int(N.lib().rorl_loss_work_floats(0)), dtype=torch.float32, device=self.device)
         self._stats = torch.zeros(16, dtype=torch.float32, device=self.device)
-        self._sel_all = None
+        self._ensemble_size = int(value_args['uni_model_layer_type'][-1].split('-')[-1])
+        self._sel_pinned = torch.zeros(max(self._ensemble_size, 1), dtype=torch.int32).pin_memory()
+        self._h2d_stage = None
+        self._has_gpt = any('gpt' in lid for net in (self.values[0].embedding_network, self.policy.embedding_network,
+                                                     self.values[0].uni_network, self.policy.uni_network) for lid in net.layer_type)
+        env = os.environ.get('RORL_CUDA_GRAPH')
+        self.use_cuda_graph = bool(hp.get('use_cuda_graph', True)) if env is None else env not in ('0', 'false', 'off')
+        self._graphs: Dict = {}
+        self._graph_pool = None
 
     # ---- construction helpers ---------------------------------------------------------------------------------
     def _finalize_models(self):
         """(Re)build arenas + optimizers after weights are in place; call again after load_state_dict."""
+        self._graphs, self._graph_pool = {}, None       # captured graphs point into the old arenas
         self._value_update(tau=0.0)
         self.target_policy.copy_weight_from(self.policy, tau=0.0)
         self.policy_arena = FlatArena(self.policy, self.device)
@@ -252,6 +262,8 @@ class FullLengthRNNUpdate:
             for lid, layer in zip(net.layer_type, net.layer_list):
                 if 'smamba' in lid:
                     skip = max(skip, layer.d_conv)
+                elif 'mamba' in lid:
+                    skip = max(skip, layer.mixer.d_conv)
         return skip + 1
 
     def allow_nest_stack_trajs(self):
@@ -273,7 +285,7 @@ class FullLengthRNNUpdate:
         stats[0] = max|y|, stats[1] = n_valid."""
         E, M = q_next.shape[0], q_next[0].numel()
         m = torch.empty(M, dtype=torch.float32, device=self.device)
-        sel = torch.as_tensor(np.asarray(sel_idx), dtype=torch.int32).to(self.device, non_blocking=True)
+        sel = sel_idx                                                  # int32 device tensor [m]
         # every operand is bound to a local until both launches are enqueued: a temporary freed right after
         # data_ptr() would hand its block to the next temporary and the pointers would alias.
         qn = q_next.contiguous()
@@ -305,11 +317,95 @@ class FullLengthRNNUpdate:
                              traj_len_array: np.ndarray, sync: bool = True) -> Dict:
         """End-to-end entry for callers that sample on the host, as the reference does (ref :313-332): the
         [rows, W, F] fp32 batch and [rows, W, 1] valid indicator come from (pinned) host memory."""
-        batch = host_batch.to(self.device, non_blocking=True)
-        valid = host_valid.to(self.device, non_blocking=True)
+        stage = self._h2d_stage
+        if stage is None or stage[0].shape != host_batch.shape or stage[1].shape != host_valid.shape:
+            stage = self._h2d_stage = (torch.empty(host_batch.shape, dtype=torch.float32, device=self.device),
+                                       torch.empty(host_valid.shape, dtype=torch.float32, device=self.device))
+        batch, valid = stage                         # persistent device staging: same addresses every step (graph replay)
+        batch.copy_(host_batch, non_blocking=True)
+        valid.copy_(host_valid, non_blocking=True)
         return self.update_on_batch(self.replay_buffer.array_to_transition(batch), batch_size, valid, traj_len_array, sync=sync)
 
     def update_on_batch(self, batch, batch_size, valid_ind, traj_len_array, sync: bool = True) -> Dict:
+        """One update on a device-resident batch.  Host side: the REDQ subset draw (numpy global RNG, same call
+        order as the reference: after the sampler's draws, ref :313 then sac_full_length_rnn_redq.py:28), the
+        attention length tables, the policy-update cadence.  Device side: `_update_core`, either launched eagerly
+        or -- when the batch lives in persistent buffers and nothing host-dependent is baked into the launch
+        sequence -- replayed from a CUDA graph captured on the second sighting of the same (buffers, shape,
+        length table, cadence) key."""
+        p = self.parameter
+        dev = self.device
+        B, L = batch.state.shape[0], batch.state.shape[1]
+        E = self._ensemble_size
+        sel_np = np.random.permutation(E)[:p.redq_m] if self.use_redq else np.arange(E)
+        did_policy = self.grad_num % p.policy_update_per == 0
+        self._sel_pinned[:len(sel_np)] = torch.from_numpy(np.asarray(sel_np, dtype=np.int32))
+        att_np = np.zeros((B, L), dtype=np.int32)                                                      # ref :358-366
+        k = min(traj_len_array.shape[1], L)
+        att_np[:, :k] = traj_len_array[:, :k].astype(np.int32)
+        tgt_np = np.concatenate((att_np[:, 1:], np.zeros((B, 1), dtype=np.int32)), axis=-1)
+        key = None
+        if self._graph_allowed():
+            key = (batch.state.data_ptr(), valid_ind.data_ptr(), B, L, tuple(batch.state.stride()), did_policy,
+                   len(sel_np), att_np.tobytes())
+        entry = self._graphs.get(key) if key is not None else None
+        if entry is not None and entry != 'seen':
+            entry['sel'].copy_(self._sel_pinned[:len(sel_np)], non_blocking=True)
+            entry['graph'].replay()
+            N.add_launches(entry['launches'])
+        else:
+            sel = torch.empty(len(sel_np), dtype=torch.int32, device=dev)
+            sel.copy_(self._sel_pinned[:len(sel_np)], non_blocking=True)
+            att = torch.from_numpy(att_np).pin_memory().to(dev, non_blocking=True)
+            tgt_att = torch.from_numpy(tgt_np).pin_memory().to(dev, non_blocking=True)
+            att._host, tgt_att._host = att_np, tgt_np      # host copy for the cgpt work list (no device->host sync)
+            if entry == 'seen':
+                # second sighting: capture (nothing executes during capture), then replay once for this step
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                l0 = N.launch_count()
+                with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode="thread_local"):
+                    self._update_core(batch, valid_ind, att, tgt_att, sel, did_policy)
+                if self._graph_pool is None:
+                    self._graph_pool = graph.pool()
+                launches = N.launch_count() - l0
+                self._graphs[key] = {'graph': graph, 'sel': sel, 'att': att, 'tgt_att': tgt_att, 'launches': launches,
+                                     'keep': (batch, valid_ind)}
+                graph.replay()
+            else:
+                if key is not None:
+                    if len(self._graphs) >= 8:                          # bounded: drop the oldest key
+                        self._graphs.pop(next(iter(self._graphs)))
+                    self._graphs[key] = 'seen'
+                self._update_core(batch, valid_ind, att, tgt_att, sel, did_policy)
+        self.grad_num += 1
+        # logged scalars: one device vector, one read-back ------------------------------------------------------ ref :435-467
+        out = {'real_batch_size': batch_size, 'real_batch_traj_num': B, 'policy_updated': did_policy}
+        if not sync:
+            out['stats_device'] = self._stats
+            return out
+        s = self._stats.tolist()
+        g = self.Q_guard.state.tolist()
+        out.update({'critic_loss': s[2], 'target_q_max': s[0], 'log_alpha': float(self.log_sac_alpha.item()),
+                    'clip_min': g[0], 'clip_max': g[1], 'value_grad_norm': 0.0,
+                    'average_traj_len': self.replay_buffer.size / max(len(self.replay_buffer), 1)})
+        if did_policy:
+            out.update({'actor_loss': s[4], 'log_prob': s[5], 'policy_grad_norm': 0})
+            if not p.no_alpha_auto_tune:
+                out['alpha_loss'] = s[6]
+        return out
+
+    def _graph_allowed(self) -> bool:
+        """CUDA-graph replay needs a launch sequence that depends on nothing the host decides per step: the cgpt
+        encoder builds its attention work list on the host from the length table, and an injected `noise_fn`
+        (parity tests) returns a different tensor per call."""
+        if not self.use_cuda_graph or self._has_gpt:
+            return False
+        ok = lambda fn: fn is torch.randn_like or getattr(fn, 'graph_safe', False)   # device-only, same launches every call
+        return all(ok(getattr(m, 'noise_fn', torch.randn_like)) for m in (self.policy, self.target_policy))
+
+    def _update_core(self, batch, valid_ind, att, tgt_att, sel, did_policy):
+        """Device side of the update: launches only (no host reads, no pageable copies), so it can be captured."""
         p = self.parameter
         td3 = self.base_algorithm == 'td3'
         dev = self.device
@@ -323,13 +419,6 @@ class FullLengthRNNUpdate:
         d_start = rnn_start[:, 1:] - rnn_start[:, :-1]
         total_start = rnn_start.clone()
         total_start[:, :-1] = torch.where(d_start == -1, torch.zeros_like(d_start), total_start[:, :-1])
-        att = torch.zeros((B, L), dtype=torch.int32)                                                      # ref :358-366
-        k = min(traj_len_array.shape[1], L)
-        att[:, :k] = torch.from_numpy(traj_len_array[:, :k]).to(torch.int32)
-        tgt_att = torch.cat((att[:, 1:], torch.zeros((B, 1), dtype=torch.int32)), dim=-1)
-        att_h, tgt_h = att.numpy(), tgt_att.numpy()
-        att, tgt_att = att.to(dev, non_blocking=True), tgt_att.to(dev, non_blocking=True)
-        att._host, tgt_att._host = att_h, tgt_h              # host copy for the cgpt work list (no device->host sync)
         mk = lambda model: model.make_init_state(B, device=dev)
         policy_hidden, target_policy_hidden = mk(self.policy), mk(self.policy)
         target_hidden, value_hidden = mk(self.target_values[0]), mk(self.values[0])
@@ -347,8 +436,6 @@ class FullLengthRNNUpdate:
                 a_next = torch.clamp(a_mean + torch.clamp(noise, -p.target_action_noise_clip, p.target_action_noise_clip), -1, 1)
                 logp_next = None
             q_next = self.target_values[0].forward(next_state, state, action, a_next, target_hidden, reward)[0]
-            E = q_next.shape[0]
-            sel = np.random.permutation(E)[:p.redq_m] if self.use_redq else np.arange(E)
             target_Q = self._target_Q(q_next, sel, logp_next, reward, done, timeout, mask)
         n_valid = self._stats[1:2]
         if self.dist_group is not None:
@@ -373,7 +460,6 @@ class FullLengthRNNUpdate:
             v.eval()
         self.policy.train()
         # 5. actor + alpha ---------------------------------------------------------------------------------------- ref :116-132,405-432
-        did_policy = self.grad_num % p.policy_update_per == 0
         if did_policy:
             for w in self.value_arena.params:
                 w.requires_grad_(False)
@@ -406,23 +492,7 @@ class FullLengthRNNUpdate:
                 self._allreduce(self.alpha_arena.grad)
                 self.optimizer_alpha.step()
                 self.log_sac_alpha.data.clamp_(max=1.0)
-        self.grad_num += 1
-        # 6. logged scalars: one device vector, one read-back ---------------------------------------------------- ref :435-467
-        out = {'real_batch_size': batch_size, 'real_batch_traj_num': B, 'policy_updated': did_policy}
         self.last_target_Q = target_Q
-        if not sync:
-            out['stats_device'] = self._stats
-            return out
-        s = self._stats.tolist()
-        g = self.Q_guard.state.tolist()
-        out.update({'critic_loss': s[2], 'target_q_max': s[0], 'log_alpha': float(self.log_sac_alpha.item()),
-                    'clip_min': g[0], 'clip_max': g[1], 'value_grad_norm': 0.0,
-                    'average_traj_len': self.replay_buffer.size / max(len(self.replay_buffer), 1)})
-        if did_policy:
-            out.update({'actor_loss': s[4], 'log_prob': s[5], 'policy_grad_norm': 0})
-            if not p.no_alpha_auto_tune:
-                out['alpha_loss'] = s[6]
-        return out
 
     def _sync_guard_and_count(self):
         """Data-parallel: make n_valid and the guard state identical on every rank."""

@@ -33,13 +33,23 @@
 namespace rorl {
 
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 32;     // BK fp32 = one 128-byte swizzle row
-constexpr int kGemmStages = 3;
 constexpr int kGemmThreads = 448;                                // TMA, MMA, 4 splitter and 8 epilogue warps
 constexpr int kGemmEpiWarps = 8;
-constexpr int kTileBytes = kGemmBM * kGemmBK * 4;             // 16 KiB (A and B tiles have the same size)
-constexpr int kStageBytes = 4 * kTileBytes;                   // A_raw | B_raw | A_lo | B_lo
+constexpr int kTileBytes = kGemmBM * kGemmBK * 4;             // 16 KiB: the A tile (and the B tile at BN = 128)
 constexpr int kStagingBytes = kGemmEpiWarps * 32 * 128;       // per epilogue warp: 32 rows x 32 fp32 columns
-constexpr int kGemmSmem = kGemmStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+// Tile configuration.  The kernel is bound by L2 -> SM operand traffic and shared-memory bandwidth, not by the MMA
+// pipe (fp32 operands: a 128 x 128 tile pulls 32 KiB per k-step for 1 MFLOP; measured: the single-pass variant runs
+// at the same ~300 TFLOP/s whatever the shape).  BN = 256 (TN variant, N > 128) reads the A tile once for twice the
+// columns: 0.75x the operand bytes per FLOP and half the A-splitting work, at the cost of a 2-deep instead of a
+// 3-deep ring (227 KiB of shared memory) and both 256-column TMEM accumulators (512 columns).
+template <int BN>
+struct GemmCfg {
+    static constexpr int kTileB = BN * kGemmBK * 4;               // B tile bytes
+    static constexpr int kRaw = kTileBytes + kTileB;               // A_raw | B_raw
+    static constexpr int kStage = 2 * kRaw;                        // A_raw | B_raw | A_lo | B_lo
+    static constexpr int kStages = BN == 256 ? 2 : 3;
+    static constexpr int kSmem = kStages * kStage + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct GemmParams {
     float* D;
@@ -61,9 +71,13 @@ __device__ __forceinline__ float elu1(float x) {
     return x > 0.f ? x : e;
 }
 
-template <bool MN>
+template <bool MN, int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    static_assert(BN == 128 || (BN == 256 && !MN), "BN = 256 exists for the TN variant only");
+    using Cfg = GemmCfg<BN>;
+    constexpr int kGemmStages = Cfg::kStages, kStageBytes = Cfg::kStage, kRawBytes = Cfg::kRaw, kTileB = Cfg::kTileB;
+    constexpr int kGemmBN = BN;                                   // shadows the namespace default inside the kernel
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -121,7 +135,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 for (int kt = 0; kt < KT; ++kt, ++it) {
                     const int s = it % kGemmStages;
                     mbar_wait(bar_empty(s), ((it / kGemmStages) & 1) ^ 1);
-                    mbar_expect_tx(bar_full_raw(s), 2 * kTileBytes);
+                    mbar_expect_tx(bar_full_raw(s), kRawBytes);
                     const uint32_t st = base + s * kStageBytes;
                     if (MN) {
                         // operands [rows = reduction][cols = MN]: 4 boxes of 32 columns x 32 rows per operand
@@ -159,7 +173,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     tc_fence_after();
                     const uint32_t st = base + s * kStageBytes;
                     const uint64_t a_hi = make_kmajor_desc(st), b_hi = make_kmajor_desc(st + kTileBytes);
-                    const uint64_t a_lo = make_kmajor_desc(st + 2 * kTileBytes), b_lo = make_kmajor_desc(st + 3 * kTileBytes);
+                    const uint64_t a_lo = make_kmajor_desc(st + kRawBytes), b_lo = make_kmajor_desc(st + kRawBytes + kTileBytes);
 #pragma unroll
                     for (int k = 0; k < kGemmBK / 8; ++k) {
                         const uint64_t adv = (uint64_t)(k * 8 * 4 >> 4);        // 32 B per k-step inside the 128-B swizzle row
@@ -211,7 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                                 const int off = mn * 128 + (((r >> 2) ^ (mn & 7)) << 4) + ((r & 3) << 2);
                                 const float hi = __uint_as_float((__float_as_uint(e[i]) + 0x1000u) & 0xFFFFE000u);
                                 *reinterpret_cast<float*>(st + op * kTileBytes + off) = hi;
-                                if (split) *reinterpret_cast<float*>(st + (2 + op) * kTileBytes + off) = e[i] - hi;
+                                if (split) *reinterpret_cast<float*>(st + kRawBytes + op * kTileBytes + off) = e[i] - hi;
                             }
                         }
                     }
@@ -228,7 +242,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     mbar_wait(bar_full_raw(s), (it / kGemmStages) & 1);
                     uint8_t* st = base_ptr + s * kStageBytes;
 #pragma unroll 4
-                    for (int i = 0; i < 2 * kTileBytes / 16 / 128; ++i) {
+                    for (int i = 0; i < kRawBytes / 16 / 128; ++i) {
                         const int off = (t + 128 * i) * 16;
                         float4 v = *reinterpret_cast<const float4*>(st + off);
                         // The tensor core reads a TF32 operand by IGNORING the low 13 mantissa bits of the fp32 word, so
@@ -240,7 +254,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
                         lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
                         lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                        *reinterpret_cast<float4*>(st + 2 * kTileBytes + off) = lo;
+                        *reinterpret_cast<float4*>(st + kRawBytes + off) = lo;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -280,45 +294,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 }
                 __syncwarp();
             };
-            // both of this warp's chunks are pulled out of TMEM up front, so the accumulator is released to the MMA
-            // warp before the (long) bias / activation / store tail
-            uint32_t r[2][32];
+            // this warp's chunks are pulled out of TMEM two at a time; after the last pair the accumulator is released
+            // to the MMA warp, before the (long) bias / activation / store tail of that pair
+            constexpr int kHalves = kGemmBN / 128;
+#pragma unroll 1
+            for (int half = 0; half < kHalves; ++half) {
+                const int chunk0 = (kGemmBN / 64) * hf + 2 * half;               // first of this warp's two 32-column chunks
+                uint32_t r[2][32];
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const uint32_t taddr = tmem_base + acc * kGemmBN + (2 * hf + cc) * 32 + ((uint32_t)(q * 32) << 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(r[cc][0]), "=r"(r[cc][1]), "=r"(r[cc][2]), "=r"(r[cc][3]), "=r"(r[cc][4]), "=r"(r[cc][5]), "=r"(r[cc][6]), "=r"(r[cc][7]),
-                      "=r"(r[cc][8]), "=r"(r[cc][9]), "=r"(r[cc][10]), "=r"(r[cc][11]), "=r"(r[cc][12]), "=r"(r[cc][13]), "=r"(r[cc][14]), "=r"(r[cc][15]),
-                      "=r"(r[cc][16]), "=r"(r[cc][17]), "=r"(r[cc][18]), "=r"(r[cc][19]), "=r"(r[cc][20]), "=r"(r[cc][21]), "=r"(r[cc][22]), "=r"(r[cc][23]),
-                      "=r"(r[cc][24]), "=r"(r[cc][25]), "=r"(r[cc][26]), "=r"(r[cc][27]), "=r"(r[cc][28]), "=r"(r[cc][29]), "=r"(r[cc][30]), "=r"(r[cc][31])
-                    : "r"(taddr));
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty(acc));
+                for (int cc = 0; cc < 2; ++cc)
+                    tmem_ld32(tmem_base + acc * kGemmBN + (chunk0 + cc) * 32 + ((uint32_t)(q * 32) << 16), r[cc]);
+                tmem_ld_wait();
+                if (half == kHalves - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty(acc));
+                }
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int col0 = tn * kGemmBN + (2 * hf + cc) * 32;
-                if (col0 >= p.N) break;                                          // warp-uniform
-                float4 o[8];
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int col0 = tn * kGemmBN + (chunk0 + cc) * 32;
+                    if (col0 >= p.N) break;                                      // warp-uniform
+                    float4 o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    o[j] = make_float4(__uint_as_float(r[cc][4 * j]), __uint_as_float(r[cc][4 * j + 1]), __uint_as_float(r[cc][4 * j + 2]),
-                                       __uint_as_float(r[cc][4 * j + 3]));
-                    if (bias && col0 + 4 * j < p.N) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * j));
-                        o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
+                    for (int j = 0; j < 8; ++j) {
+                        o[j] = make_float4(__uint_as_float(r[cc][4 * j]), __uint_as_float(r[cc][4 * j + 1]), __uint_as_float(r[cc][4 * j + 2]),
+                                           __uint_as_float(r[cc][4 * j + 3]));
+                        if (bias && col0 + 4 * j < p.N) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * j));
+                            o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
+                        }
                     }
-                }
-                if (p.Dpre) flush(o, p.Dpre, col0);
-                if (p.act == 1) {
+                    if (p.Dpre) flush(o, p.Dpre, col0);
+                    if (p.act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { o[j].x = elu1(o[j].x); o[j].y = elu1(o[j].y); o[j].z = elu1(o[j].z); o[j].w = elu1(o[j].w); }
+                        for (int j = 0; j < 8; ++j) { o[j].x = elu1(o[j].x); o[j].y = elu1(o[j].y); o[j].z = elu1(o[j].z); o[j].w = elu1(o[j].w); }
+                    }
+                    flush(o, p.D, col0);
                 }
-                flush(o, p.D, col0);
             }
         }
     }
@@ -331,14 +343,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 }
 
 static int g_gemm_dbg = 0;
+static int g_gemm_bn = 0;
 static int gemm_sms() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-        cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        cudaFuncSetAttribute(gemm_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem);
+        cudaFuncSetAttribute(gemm_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmem);
+        cudaFuncSetAttribute(gemm_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem);
     }
     return sms;
 }
@@ -368,7 +382,9 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     CUtensorMap mapA, mapB;
     int rc = make_map(&mapA, A, M, K, lda, strideA ? G : 1, strideA, kGemmBM);
     if (rc) return rc;
-    rc = make_map(&mapB, B, N, K, ldb, strideB ? G : 1, strideB, kGemmBN);
+    const bool wide = N > kGemmBN && g_gemm_bn != 128;            // N > 128: 128 x 256 tiles (see GemmCfg)
+    const int bn = wide ? 256 : kGemmBN;
+    rc = make_map(&mapB, B, N, K, ldb, strideB ? G : 1, strideB, bn);
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
@@ -376,13 +392,18 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act; p.passes = passes; p.reduce_g = reduce_g != 0;
     p.splits = 1; p.strideSplit = 0; p.dbg = g_gemm_dbg;
     const int sms = gemm_sms();
-    const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN) * (reduce_g ? 1 : G);
+    const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn) * (reduce_g ? 1 : G);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<false><<<grid, kGemmThreads, kGemmSmem, stream>>>(mapA, mapB, p);
+    if (wide)
+        gemm_kernel<false, 256><<<grid, kGemmThreads, GemmCfg<256>::kSmem, stream>>>(mapA, mapB, p);
+    else
+        gemm_kernel<false, 128><<<grid, kGemmThreads, GemmCfg<128>::kSmem, stream>>>(mapA, mapB, p);
     RORL_RETURN_LAUNCH();
 }
 
 void rorl_gemm_debug(int v) { g_gemm_dbg = v; }
+/* diagnostic / A-B benchmarks only: 128 forces the 128 x 128 tile for every shape, 0 restores the default choice */
+void rorl_gemm_force_bn(int bn) { g_gemm_bn = bn; }
 
 // Split-K factor rorl_gemm_nt uses for a [M x N] output reduced over R rows in G batches (the caller sizes D with it).
 int rorl_gemm_nt_splits(int64_t M, int64_t N, int64_t R, int64_t G) {
@@ -423,7 +444,7 @@ int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N,
     const int sms = gemm_sms();
     const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN) * G * splits;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, stream>>>(mapA, mapB, p);
+    gemm_kernel<true, 128><<<grid, kGemmThreads, GemmCfg<128>::kSmem, stream>>>(mapA, mapB, p);
     RORL_RETURN_LAUNCH();
 }
 

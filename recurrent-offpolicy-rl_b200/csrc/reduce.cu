@@ -1,0 +1,224 @@
+// Deterministic row reductions of the backward pass, sm_100a.  All HBM-bound: every input byte is read once,
+// coalesced as float4, and per-CTA partials are summed by a second tiny launch (no atomics, so gradients are
+// bit-reproducible -- the reference's CUDA backward is not, ref: results.md:4).
+//
+//   colsum          out[n] = sum_m x[m, n]                      bias gradients (ref: autograd of F.linear /
+//                                                               EnsembleLinear bias, ensemble_linear_model.py:49-58)
+//                                                               and sums of per-CTA partial tiles (split-K wgrad,
+//                                                               selective-scan dB/dC/dA, conv dW)
+//   elu_bwd_colsum  g = dy * (y > 0 ? 1 : y + 1); out[n] = sum_m g[m, n]
+//                                                               ELU backward from the layer OUTPUT fused with the
+//                                                               bias gradient of the same layer
+//   skinny_wgrad    dW[n, k] = sum_m g[m, n] * x[m, k], K <= 16 weight gradient of the narrow-input projections
+//                                                               (obs / action encoders K = 6, 9; dt_proj K = dt_rank)
+//                                                               that cuBLAS runs as one-CTA SIMT sgemms (110 us each)
+#include "common.cuh"
+
+namespace rorl {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxQuads = 256;      // column quads (float4) handled by one CTA in x
+constexpr int kRedMaxBlocks = 592;     // 4 x 148 row blocks
+
+// grid: (row blocks, column chunks of 4 * kRedMaxQuads).  thread = (row lane, column quad).
+template <bool ELU>
+__global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                             float* __restrict__ g, float* __restrict__ partial,
+                                                             int64_t M, int64_t N, int64_t ldx, int64_t ldy, int64_t ldg,
+                                                             int64_t gsx, int64_t gsy, int64_t gsg, int rows_per_block) {
+    __shared__ float4 s_acc[kRedThreads];
+    x += (int64_t)blockIdx.z * gsx;                                        // group (ensemble member)
+    if (ELU) { y += (int64_t)blockIdx.z * gsy; g += (int64_t)blockIdx.z * gsg; }
+    partial += (int64_t)blockIdx.z * gridDim.x * N;
+    const int64_t q0 = (int64_t)blockIdx.y * kRedMaxQuads;
+    const int nq = (int)min((int64_t)kRedMaxQuads, N / 4 - q0);          // quads in this chunk
+    const int lanes = kRedThreads / nq;                                    // row lanes (>= 1)
+    const int q = threadIdx.x % nq, rl = threadIdx.x / nq;
+    const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t m1 = min(M, m0 + rows_per_block);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes) {
+        const int64_t col = (q0 + q) * 4;
+        for (int64_t m = m0 + rl; m < m1; m += lanes) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + m * ldx + col));
+            if (ELU) {
+                const float4 o = __ldg(reinterpret_cast<const float4*>(y + m * ldy + col));
+                v.x *= o.x > 0.f ? 1.f : o.x + 1.f;
+                v.y *= o.y > 0.f ? 1.f : o.y + 1.f;
+                v.z *= o.z > 0.f ? 1.f : o.z + 1.f;
+                v.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+                *reinterpret_cast<float4*>(g + m * ldg + col) = v;
+            }
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            const float4 v = s_acc[l * nq + q];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * N + (q0 + q) * 4) = acc;
+    }
+}
+
+// out[n] = sum_b partial[b, n]
+__global__ void __launch_bounds__(kRedThreads) partial_sum_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                                  int nblk, int64_t N) {
+    const int64_t q = (int64_t)blockIdx.x * kRedThreads + threadIdx.x;
+    if (q * 4 >= N) return;
+    partial += (int64_t)blockIdx.y * nblk * N;
+    out += (int64_t)blockIdx.y * N;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < nblk; ++b) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)b * N + q * 4));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + q * 4) = acc;
+}
+
+// dW[n, k] = sum_m g[m, n] x[m, k].  grid: (row blocks, column chunks of 256); thread = output column n; x rows are
+// staged in shared memory and read back as warp-wide broadcasts.
+constexpr int kSkinnyRows = 64;
+template <int KP>        // K padded to a multiple of 4, <= 16
+__global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                                   float* __restrict__ partial, int64_t M, int64_t N, int K,
+                                                                   int64_t ldg, int64_t ldx, int rows_per_block) {
+    __shared__ __align__(16) float s_x[kSkinnyRows * KP];
+    const int64_t n = (int64_t)blockIdx.y * kRedThreads + threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t m1 = min(M, m0 + rows_per_block);
+    float acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+    for (int64_t mb = m0; mb < m1; mb += kSkinnyRows) {
+        const int rows = (int)min((int64_t)kSkinnyRows, m1 - mb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += kRedThreads) {
+            const int r = i / KP, k = i % KP;
+            s_x[i] = (r < rows && k < K) ? __ldg(x + (mb + r) * ldx + k) : 0.f;
+        }
+        __syncthreads();
+        if (n < N) {
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) {
+                const float gv = __ldg(g + (mb + r) * ldg + n);
+#pragma unroll
+                for (int k4 = 0; k4 < KP; k4 += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(s_x + r * KP + k4);
+                    acc[k4] = fmaf(gv, xv.x, acc[k4]);
+                    acc[k4 + 1] = fmaf(gv, xv.y, acc[k4 + 1]);
+                    acc[k4 + 2] = fmaf(gv, xv.z, acc[k4 + 2]);
+                    acc[k4 + 3] = fmaf(gv, xv.w, acc[k4 + 3]);
+                }
+            }
+        }
+    }
+    if (n < N) {
+        float* o = partial + ((int64_t)blockIdx.x * N + n) * KP;
+#pragma unroll
+        for (int k4 = 0; k4 < KP; k4 += 4)
+            *reinterpret_cast<float4*>(o + k4) = make_float4(acc[k4], acc[k4 + 1], acc[k4 + 2], acc[k4 + 3]);
+    }
+}
+
+// dW[n, k] = sum_b partial[b, n, kp]  (drops the K padding)
+__global__ void __launch_bounds__(kRedThreads) skinny_finish_kernel(const float* __restrict__ partial, float* __restrict__ dW,
+                                                                    int nblk, int64_t N, int K, int KP) {
+    const int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x;
+    if (i >= N * K) return;
+    const int64_t n = i / K;
+    const int k = (int)(i % K);
+    float acc = 0.f;
+    for (int b = 0; b < nblk; ++b) acc += __ldg(partial + ((int64_t)b * N + n) * KP + k);
+    dW[i] = acc;
+}
+
+static inline int red_blocks(int64_t M, int* rows_per_block) {
+    int nblk = (int)((M + 63) / 64);                     // at least 64 rows per block
+    if (nblk > kRedMaxBlocks) nblk = kRedMaxBlocks;
+    if (nblk < 1) nblk = 1;
+    const int rpb = (int)((M + nblk - 1) / nblk);
+    *rows_per_block = rpb;
+    return (int)((M + rpb - 1) / rpb);
+}
+
+}  // namespace rorl
+
+using namespace rorl;
+
+static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" {
+
+int64_t rorl_colsum_work_floats(int64_t G, int64_t M, int64_t N) {
+    int rpb;
+    return G * (int64_t)red_blocks(M, &rpb) * N;
+}
+
+int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, int64_t N, int64_t ldx, int64_t gsx,
+                cudaStream_t stream) {
+    if (!x || !out || !work) return RORL_ERR_ARG;
+    if (M <= 0 || N <= 0 || G <= 0 || G > 65535) return RORL_ERR_SHAPE;
+    if (N % 4 || ldx % 4 || gsx % 4 || !a16(x) || !a16(out) || !a16(work)) return RORL_ERR_ALIGN;
+    int rpb;
+    const int nblk = red_blocks(M, &rpb);
+    const int chunks = (int)((N / 4 + kRedMaxQuads - 1) / kRedMaxQuads);
+    if (chunks > 65535) return RORL_ERR_SHAPE;
+    dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
+    colsum_kernel<false><<<grid, kRedThreads, 0, stream>>>(x, nullptr, nullptr, nblk == 1 ? out : work, M, N, ldx, 0, 0, gsx, 0, 0, rpb);
+    if (nblk > 1) {
+        dim3 g2((unsigned)((N / 4 + kRedThreads - 1) / kRedThreads), (unsigned)G);
+        partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
+    }
+    RORL_RETURN_LAUNCH();
+}
+
+int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
+                        int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
+                        cudaStream_t stream) {
+    if (!dy || !y || !g || !out || !work) return RORL_ERR_ARG;
+    if (M <= 0 || N <= 0 || G <= 0 || G > 65535) return RORL_ERR_SHAPE;
+    if (N % 4 || ld_dy % 4 || ld_y % 4 || ld_g % 4 || gs_dy % 4 || gs_y % 4 || gs_g % 4 || !a16(dy) || !a16(y) || !a16(g) ||
+        !a16(out) || !a16(work))
+        return RORL_ERR_ALIGN;
+    int rpb;
+    const int nblk = red_blocks(M, &rpb);
+    const int chunks = (int)((N / 4 + kRedMaxQuads - 1) / kRedMaxQuads);
+    if (chunks > 65535) return RORL_ERR_SHAPE;
+    dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
+    colsum_kernel<true><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb);
+    if (nblk > 1) {
+        dim3 g2((unsigned)((N / 4 + kRedThreads - 1) / kRedThreads), (unsigned)G);
+        partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
+    }
+    RORL_RETURN_LAUNCH();
+}
+
+int64_t rorl_skinny_wgrad_work_floats(int64_t M, int64_t N, int64_t K) {
+    int rpb;
+    const int64_t KP = (K + 3) / 4 * 4;
+    return (int64_t)red_blocks(M, &rpb) * N * KP;
+}
+
+int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, int64_t M, int64_t N, int64_t K,
+                      int64_t ldg, int64_t ldx, cudaStream_t stream) {
+    if (!g || !x || !dW || !work) return RORL_ERR_ARG;
+    if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
+    if (!a16(work)) return RORL_ERR_ALIGN;
+    int rpb;
+    const int nblk = red_blocks(M, &rpb);
+    const int KP = (int)((K + 3) / 4 * 4);
+    dim3 grid((unsigned)nblk, (unsigned)((N + kRedThreads - 1) / kRedThreads));
+    switch (KP) {
+        case 4: skinny_wgrad_kernel<4><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
+        case 8: skinny_wgrad_kernel<8><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
+        case 12: skinny_wgrad_kernel<12><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
+        default: skinny_wgrad_kernel<16><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
+    }
+    skinny_finish_kernel<<<(unsigned)((N * K + kRedThreads - 1) / kRedThreads), kRedThreads, 0, stream>>>(work, dW, nblk, N, (int)K, KP);
+    RORL_RETURN_LAUNCH();
+}
+
+}  // extern "C"

@@ -45,7 +45,7 @@ struct SelCfg {
 };
 
 struct SelFwdParams {
-    const float *u, *delta, *z, *Bm, *Cm, *A, *Dskip, *dbias, *start;
+    const float *u, *delta, *z, *Bm, *Cm, *A, *Dskip, *dbias, *start, *h0;
     float *y, *ckpt, *last_state;
     int L, D;
     int ld_u, ld_delta, ld_z, ld_B, ld_C, ld_y;
@@ -246,6 +246,10 @@ __global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(
                 A2[c][j] = ok ? f2(p.A[(size_t)(d + c) * N + ng * S + 2 * j] * kLog2e, p.A[(size_t)(d + c) * N + ng * S + 2 * j + 1] * kLog2e)
                               : f2(0.f, 0.f);
                 h[c][j] = f2(0.f, 0.f);
+                if (p.h0 != nullptr && ok) {                // carried state entering the call: [B, D, N]
+                    const float* hp = p.h0 + ((size_t)b * p.D + d + c) * N + ng * S + 2 * j;
+                    h[c][j] = f2(__ldg(hp), __ldg(hp + 1));
+                }
             }
         }
         for (int k = 0; k < ntiles; ++k) {
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(
 // backward
 // ---------------------------------------------------------------------------------------------
 struct SelBwdParams {
-    const float *u, *delta, *z, *Bm, *Cm, *A, *Dskip, *dbias, *start, *dy, *ckpt;
+    const float *u, *delta, *z, *Bm, *Cm, *A, *Dskip, *dbias, *start, *dy, *ckpt, *h0;
     float *du, *ddelta, *dz, *dBC_part, *dA_part, *dD_part, *dbias_part;
     int L, D, Bsz;
     int ld_u, ld_delta, ld_z, ld_B, ld_C, ld_dy, ld_du, ld_ddelta, ld_dz;
@@ -627,6 +631,7 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
         auto ld_ckpt = [&](int k) {                         // state entering chunk k
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k > 0 && dvalid) v = __ldg(reinterpret_cast<const float4*>(p.ckpt + (((size_t)b * p.nckpt + (k - 1)) * p.D + d) * N + ng * S));
+            if (k == 0 && dvalid && p.h0 != nullptr) v = __ldg(reinterpret_cast<const float4*>(p.h0 + ((size_t)b * p.D + d) * N + ng * S));
             return v;
         };
         float4 hin = ld_ckpt(nch - 1);
@@ -781,8 +786,8 @@ int rorl_selscan_ckpt_every(void) { return kCkptEvery; }
 void rorl_selscan_debug(int v) { g_sel_dbg = v; }
 
 int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
-                     const float* Dskip, const float* z, const float* delta_bias, const float* start, float* y,
-                     float* ckpt, float* last_state, int64_t B, int64_t L, int64_t D, int64_t N, int64_t ld_u,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start, const float* h0,
+                     float* y, float* ckpt, float* last_state, int64_t B, int64_t L, int64_t D, int64_t N, int64_t ld_u,
                      int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_y, int delta_softplus,
                      cudaStream_t stream) {
     if (!u || !delta || !A || !Bm || !Cm || !y) return RORL_ERR_ARG;
@@ -791,11 +796,11 @@ int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const f
     if (D % 4 || ld_u % 4 || ld_delta % 4 || ld_B % 4 || ld_C % 4 || ld_y % 4 || (z && ld_z % 4)) return RORL_ERR_ALIGN;
     if (!aligned16(u) || !aligned16(delta) || !aligned16(Bm) || !aligned16(Cm) || !aligned16(y) ||
         (z && !aligned16(z)) || (delta_bias && !aligned16(delta_bias)) || (ckpt && !aligned16(ckpt)) ||
-        (last_state && !aligned16(last_state)))
+        (last_state && !aligned16(last_state)) || (h0 && !aligned16(h0)))
         return RORL_ERR_ALIGN;
     SelFwdParams p;
     p.u = u; p.delta = delta; p.z = z; p.Bm = Bm; p.Cm = Cm; p.A = A; p.Dskip = Dskip; p.dbias = delta_bias;
-    p.start = start; p.y = y; p.ckpt = ckpt; p.last_state = last_state;
+    p.start = start; p.h0 = h0; p.y = y; p.ckpt = ckpt; p.last_state = last_state;
     p.L = (int)L; p.D = (int)D;
     p.ld_u = (int)ld_u; p.ld_delta = (int)ld_delta; p.ld_z = (int)ld_z; p.ld_B = (int)ld_B; p.ld_C = (int)ld_C;
     p.ld_y = (int)ld_y;
@@ -806,7 +811,7 @@ int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const f
 }
 
 int rorl_selscan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
-                     const float* Dskip, const float* z, const float* delta_bias, const float* start,
+                     const float* Dskip, const float* z, const float* delta_bias, const float* start, const float* h0,
                      const float* dy, const float* ckpt, float* du, float* ddelta, float* dz, float* dBC_part,
                      float* dA_part, float* dD_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t N,
                      int64_t ld_u, int64_t ld_delta, int64_t ld_z, int64_t ld_B, int64_t ld_C, int64_t ld_dy,
@@ -823,11 +828,11 @@ int rorl_selscan_bwd(const float* u, const float* delta, const float* A, const f
         return RORL_ERR_ALIGN;
     if (!aligned16(u) || !aligned16(delta) || !aligned16(Bm) || !aligned16(Cm) || !aligned16(dy) || !aligned16(du) ||
         !aligned16(ddelta) || (z && (!aligned16(z) || !aligned16(dz))) || (delta_bias && !aligned16(delta_bias)) ||
-        (ckpt && !aligned16(ckpt)) || !aligned16(dA_part))
+        (ckpt && !aligned16(ckpt)) || !aligned16(dA_part) || (h0 && !aligned16(h0)))
         return RORL_ERR_ALIGN;
     SelBwdParams p;
     p.u = u; p.delta = delta; p.z = z; p.Bm = Bm; p.Cm = Cm; p.A = A; p.Dskip = Dskip; p.dbias = delta_bias;
-    p.start = start; p.dy = dy; p.ckpt = ckpt;
+    p.start = start; p.h0 = h0; p.dy = dy; p.ckpt = ckpt;
     p.du = du; p.ddelta = ddelta; p.dz = dz; p.dBC_part = dBC_part; p.dA_part = dA_part; p.dD_part = dD_part;
     p.dbias_part = dbias_part;
     p.L = (int)L; p.D = (int)D; p.Bsz = (int)B;

@@ -44,6 +44,90 @@ def _flag(t, B, L):
 
 
 # ------------------------------------------------------------------------------------------------
+# deterministic row reductions (csrc/reduce.cu)
+# ------------------------------------------------------------------------------------------------
+def _red_ok(t: torch.Tensor, n: int) -> bool:
+    return t.is_cuda and t.dtype == torch.float32 and n % 4 == 0 and t.data_ptr() % 16 == 0
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """[M, N] -> [N] or [G, M, N] -> [G, N]: sum over the row axis (bias gradients)."""
+    G = x.shape[0] if x.dim() == 3 else 1
+    M, Nn = x.shape[-2], x.shape[-1]
+    if not (_red_ok(x, Nn) and x.stride(-1) == 1 and x.stride(-2) % 4 == 0 and (x.dim() == 2 or x.stride(0) % 4 == 0)):
+        return x.sum(-2)
+    out = torch.empty((G, Nn) if x.dim() == 3 else (Nn,), device=x.device, dtype=torch.float32)
+    work = torch.empty(int(N.lib().rorl_colsum_work_floats(G, M, Nn)), device=x.device, dtype=torch.float32)
+    N.call("rorl_colsum", N.ptr(x), N.ptr(out), N.ptr(work), G, M, Nn, x.stride(-2), x.stride(0) if x.dim() == 3 else 0, N.stream())
+    return out
+
+
+def sum_leading(t: torch.Tensor) -> torch.Tensor:
+    """t.sum(0) for a contiguous [P, ...] stack of per-CTA partial results."""
+    if t.shape[0] == 1:
+        return t[0]
+    n = t[0].numel()
+    if not (t.is_contiguous() and _red_ok(t, n)):
+        return t.sum(0)
+    return colsum(t.view(t.shape[0], n)).view(t.shape[1:])
+
+
+def elu_bwd_colsum(dy: torch.Tensor, y: torch.Tensor):
+    """ELU backward from the layer output fused with the bias gradient: dy, y [M, N] or [G, M, N] contiguous ->
+    (g = dy * elu'(y), g.sum(rows))."""
+    G = dy.shape[0] if dy.dim() == 3 else 1
+    M, Nn = dy.shape[-2], dy.shape[-1]
+    if not (_red_ok(dy, Nn) and _red_ok(y, Nn) and dy.is_contiguous() and y.is_contiguous()):
+        g = torch.ops.aten.elu_backward(dy, 1.0, 1.0, 1.0, True, y)
+        return g, g.sum(-2)
+    g = torch.empty_like(dy)
+    out = torch.empty((G, Nn) if dy.dim() == 3 else (Nn,), device=dy.device, dtype=torch.float32)
+    work = torch.empty(int(N.lib().rorl_colsum_work_floats(G, M, Nn)), device=dy.device, dtype=torch.float32)
+    N.call("rorl_elu_bwd_colsum", N.ptr(dy), N.ptr(y), N.ptr(g), N.ptr(out), N.ptr(work), G, M, Nn, Nn, Nn, Nn, M * Nn, M * Nn,
+           M * Nn, N.stream())
+    return g, out
+
+
+def skinny_wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW [N, K] = g[M, N]^T x[M, K] for K <= 16 (unit inner strides, any row stride)."""
+    M, Nn = g.shape
+    K = x.shape[1]
+    dW = torch.empty((Nn, K), device=g.device, dtype=torch.float32)
+    work = torch.empty(int(N.lib().rorl_skinny_wgrad_work_floats(M, Nn, K)), device=g.device, dtype=torch.float32)
+    N.call("rorl_skinny_wgrad", N.ptr(g), N.ptr(x), N.ptr(dW), N.ptr(work), M, Nn, K, g.stride(0), x.stride(0), N.stream())
+    return dW
+
+
+class LinearSkinny(Function):
+    """nn.Linear with a narrow input (K <= 16: obs / action encoders, dt_proj).  Forward and data gradient stay on
+    cuBLAS (tiny); the weight gradient, a [N, K] reduction over ~32 k rows that cuBLAS runs as a single-CTA SIMT
+    sgemm (110 us), and the bias gradient run on the deterministic reduction kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        Nn, K = weight.shape
+        g = _f32c(dy.reshape(-1, Nn))
+        x2 = x.reshape(-1, K)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (g @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = skinny_wgrad(g, x2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(g)
+        return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------------
 # GILR
 # ------------------------------------------------------------------------------------------------
 class GILRScan(Function):
@@ -194,7 +278,7 @@ class SelectiveScan(Function):
     D / delta_bias [D], start [B, L].  Returns y [B, L, D] (and last_state [B, D, N])."""
 
     @staticmethod
-    def forward(ctx, u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state):
+    def forward(ctx, u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state, h0=None):
         u, delta, Bm, Cm = _rows(u), _rows(delta), _rows(Bm), _rows(Cm)
         z = None if z is None else _rows(z)
         A = _f32c(A)
@@ -203,6 +287,8 @@ class SelectiveScan(Function):
         B, L, D = u.shape
         Ns = A.shape[1]
         start = _flag(start, B, L)
+        if h0 is not None:                                   # carried state [B, D, N] (constant: no gradient)
+            h0 = _f32c(h0.detach().reshape(B, D, Ns))
         y = torch.empty((B, L, D), device=u.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad)
         every = N.lib().rorl_selscan_ckpt_every()
@@ -210,12 +296,12 @@ class SelectiveScan(Function):
         ckpt = torch.empty((B, nck, D, Ns), device=u.device, dtype=torch.float32) if (need_grad and nck > 0) else None
         last = torch.empty((B, D, Ns), device=u.device, dtype=torch.float32) if return_last_state else None
         N.call("rorl_selscan_fwd", N.ptr(u), N.ptr(delta), N.ptr(A), N.ptr(Bm), N.ptr(Cm), N.ptr(Dskip), N.ptr(z),
-               N.ptr(delta_bias), N.ptr(start), N.ptr(y), N.ptr(ckpt), N.ptr(last), B, L, D, Ns,
+               N.ptr(delta_bias), N.ptr(start), N.ptr(h0), N.ptr(y), N.ptr(ckpt), N.ptr(last), B, L, D, Ns,
                u.stride(1), delta.stride(1), 0 if z is None else z.stride(1), Bm.stride(1), Cm.stride(1), D,
                int(bool(delta_softplus)), N.stream())
         ctx.delta_softplus = bool(delta_softplus)
         ctx.return_last_state = return_last_state
-        ctx.save_for_backward(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, ckpt)
+        ctx.save_for_backward(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, ckpt, h0)
         if return_last_state:
             ctx.mark_non_differentiable(last)
             return y, last
@@ -223,7 +309,7 @@ class SelectiveScan(Function):
 
     @staticmethod
     def backward(ctx, dy, *unused):
-        u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, ckpt = ctx.saved_tensors
+        u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, ckpt, h0 = ctx.saved_tensors
         dy = _rows(dy)
         B, L, D = u.shape
         Ns = A.shape[1]
@@ -237,19 +323,19 @@ class SelectiveScan(Function):
         dD = torch.empty((B, D), device=dev, dtype=torch.float32)
         dbias = torch.empty((B, D), device=dev, dtype=torch.float32)
         N.call("rorl_selscan_bwd", N.ptr(u), N.ptr(delta), N.ptr(A), N.ptr(Bm), N.ptr(Cm), N.ptr(Dskip), N.ptr(z),
-               N.ptr(delta_bias), N.ptr(start), N.ptr(dy), N.ptr(ckpt), N.ptr(du), N.ptr(ddelta), N.ptr(dz),
+               N.ptr(delta_bias), N.ptr(start), N.ptr(h0), N.ptr(dy), N.ptr(ckpt), N.ptr(du), N.ptr(ddelta), N.ptr(dz),
                N.ptr(dBC), N.ptr(dA), N.ptr(dD), N.ptr(dbias), B, L, D, Ns,
                u.stride(1), delta.stride(1), 0 if z is None else z.stride(1), Bm.stride(1), Cm.stride(1),
                dy.stride(1), D, D, D, int(ctx.delta_softplus), N.stream())
-        dBC = dBC.sum(0) if ntile > 1 else dBC[0]
-        return (du, ddelta, dA.sum(0), dBC[..., :Ns], dBC[..., Ns:],
-                None if Dskip is None else dD.sum(0), dz,
-                None if delta_bias is None else dbias.sum(0), None, None, None)
+        dBC = sum_leading(dBC)
+        return (du, ddelta, sum_leading(dA), dBC[..., :Ns], dBC[..., Ns:],
+                None if Dskip is None else sum_leading(dD), dz,
+                None if delta_bias is None else sum_leading(dbias), None, None, None, None)
 
 
 def selective_scan_tm(u, delta, A, Bm, Cm, Dskip=None, z=None, delta_bias=None, start=None, delta_softplus=False,
-                      return_last_state=False):
-    return SelectiveScan.apply(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state)
+                      return_last_state=False, h0=None):
+    return SelectiveScan.apply(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state, h0)
 
 
 def selective_scan_fn(u, delta, A, B, C, start, D=None, z=None, delta_bias=None, delta_softplus=False,
@@ -297,7 +383,7 @@ class CausalConv1dSiLU(Function):
         db = torch.empty((P, D), device=x.device, dtype=torch.float32)
         N.call("rorl_conv1d_silu_bwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(mask), N.ptr(dy), N.ptr(dx), N.ptr(dw),
                N.ptr(db), B, L, D, K, x.stride(1), dy.stride(1), D, N.stream())
-        return dx, dw.sum(0).reshape(ctx.wshape), (None if bias is None else db.sum(0)), None
+        return dx, sum_leading(dw).reshape(ctx.wshape), (None if bias is None else sum_leading(db)), None
 
 
 def causal_conv1d_silu(x, weight, bias=None, mask=None):
@@ -348,7 +434,7 @@ class AddNorm(Function):
         N.call("rorl_addnorm_bwd", N.ptr(dy), N.ptr(dres), N.ptr(r), N.ptr(w), N.ptr(mean), N.ptr(rstd), N.ptr(dx),
                N.ptr(dw), N.ptr(db), rows, C, int(ctx.is_rms), int(ctx.has_bias), N.stream())
         dx = dx.reshape(ctx.shape)
-        return dx, dw.sum(0), (db.sum(0) if ctx.has_bias else None), (dx if ctx.has_res else None), None, None, None
+        return dx, sum_leading(dw), (sum_leading(db) if ctx.has_bias else None), (dx if ctx.has_res else None), None, None, None
 
 
 def layer_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False, is_rms_norm=False):
@@ -413,7 +499,7 @@ def gemm_nt(A, B, passes: int = None):
     N.call("rorl_gemm_nt", N.ptr(A), N.ptr(B), N.ptr(D), M, Nn, R, G, A.stride(-2), B.stride(-2), Nn,
            A.stride(0) if A.dim() == 3 else 0, B.stride(0) if B.dim() == 3 else 0, M * Nn, splits, G * M * Nn,
            int(passes or GEMM_PASSES), N.stream())
-    D = D.sum(0) if splits > 1 else D[0]
+    D = sum_leading(D)
     return D if batched else D[0]
 
 
@@ -441,15 +527,18 @@ class LinearTC(Function):
         xs, weight, yout = ctx.saved_tensors
         Nn = weight.shape[0]
         g = _f32c(dy.reshape(-1, Nn))
-        if ctx.elu:
-            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, True, yout)
         dx = dw = db = None
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.elu:
+            g, db = elu_bwd_colsum(g, yout)                  # ELU' and the bias gradient in one pass over dy
+        elif want_db:
+            db = colsum(g)
+        if not want_db:
+            db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_tn(g, weight.t().contiguous(), passes=ctx.passes).view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             dw = gemm_nt(g, xs, passes=ctx.passes) if _gemm_nt_ok(Nn, xs.shape[1], xs.shape[0]) else g.t() @ xs
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g.sum(0)
         return dx, dw, db, None, None
 
 
@@ -460,7 +549,10 @@ def linear(x, weight, bias=None, elu=False, passes=None):
     M = x.numel() // x.shape[-1]
     if x.is_cuda and _gemm_ok(M, weight.shape[0], weight.shape[1]):
         return LinearTC.apply(x, weight, bias, elu, passes)
-    y = torch.nn.functional.linear(x, weight, bias)
+    if x.is_cuda and weight.shape[1] <= 16 and M >= 1024 and x.dtype == torch.float32:
+        y = LinearSkinny.apply(x, weight, bias)
+    else:
+        y = torch.nn.functional.linear(x, weight, bias)
     return torch.nn.functional.elu(y) if elu else y
 
 
@@ -484,15 +576,17 @@ class EnsembleLinearTC(Function):
         xs, weight, yout = ctx.saved_tensors
         E, Kin, Nout = weight.shape
         g = _f32c(dy.reshape(E, -1, Nout))
-        if ctx.elu:
-            g = torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, True, yout)
         dx = dw = db = None
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.elu:
+            g, db = elu_bwd_colsum(g, yout)
+            db = db.unsqueeze(1) if want_db else None
+        elif want_db:
+            db = colsum(g).unsqueeze(1)
         if ctx.needs_input_grad[0]:
             dx = gemm_tn(g, weight, reduce_g=ctx.shared).view(ctx.xshape)     # weight [E, in, out] is K-major here
         if ctx.needs_input_grad[1]:                                           # [E, in, out] (x broadcast if shared)
             dw = gemm_nt(xs, g) if _gemm_nt_ok(Kin, Nout, g.shape[1]) else torch.matmul(xs.transpose(-1, -2), g)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g.sum(1, keepdim=True)
         return dx, dw, db, None, None
 
 

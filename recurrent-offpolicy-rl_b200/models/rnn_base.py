@@ -22,6 +22,7 @@ from .linear import Linear
 from .gilr.gilr import GILRLayer
 from .lru.lru import LRULayer
 from .smamba.mamba import BlockList as MambaBlockList
+from .s6.mamba import MambaResidualBlock
 from .gru.gru import GRULayer
 
 try:
@@ -64,6 +65,19 @@ def parse_layer_id(layer_id: str) -> Tuple[str, Dict]:
             else:
                 raise ValueError(f'Pattern {t} has not been implemented!')
         return 'smamba', cfg
+    if layer_id.startswith('mamba'):                           # s6 layer, ref: rnn_base.py:118-136
+        cfg = dict(d_state=16, d_conv=4, use_ff=True)
+        for t in toks:
+            if t.startswith('s'):
+                cfg['d_state'] = int(t[1:])
+            elif t.startswith('c'):
+                cfg['d_conv'] = int(t[1:])
+            elif t.startswith('no'):
+                if t[2:] == 'ff':
+                    cfg['use_ff'] = False
+            else:
+                raise ValueError(f'Pattern {t} has not been implemented!')
+        return 'mamba', cfg
     if layer_id.startswith('cgpt'):
         cfg = dict(nhead=8, nlayer=4, pdrop=0.1, maxlength=1024, ln=True)
         for t in toks:
@@ -84,7 +98,7 @@ def parse_layer_id(layer_id: str) -> Tuple[str, Dict]:
         return layer_id, {}
     raise NotImplementedError(
         f'layer type {layer_id!r} is outside the update hot path this package covers '
-        f'(fc, efc-E, gru, lru, gilr, smamba_*, cgpt_*)')
+        f'(fc, efc-E, gru, lru, gilr, smamba_*, mamba_*, cgpt_*)')
 
 
 class RNNBase(nn.Module):
@@ -129,6 +143,10 @@ class RNNBase(nn.Module):
                                          rms_norm=cfg['rms_norm'], use_ff=cfg['use_ff'])
                     self.layer_list.append(blk)
                     self.rnn_hidden_state_input_size.append(blk.desired_hidden_dim)
+                elif kind == 'mamba':
+                    blk = MambaResidualBlock(width_in, width, d_conv=cfg['d_conv'], d_state=cfg['d_state'], use_ff=cfg['use_ff'])
+                    self.layer_list.append(blk)
+                    self.rnn_hidden_state_input_size.append(blk.mixer.desired_hidden_dim)
                 elif kind == 'cgpt':
                     if TransformerDecoder is None:
                         raise RuntimeError('cgpt encoder unavailable in this build')
@@ -171,7 +189,7 @@ class RNNBase(nn.Module):
                 nn.init.xavier_uniform_(m.out_proj.weight)
                 nn.init.constant_(m.out_proj.bias, 0)
                 self._xavier_efc(m.in_proj)
-            elif isinstance(m, MambaBlockList) or (TransformerDecoder is not None and isinstance(m, TransformerDecoder)):
+            elif isinstance(m, (MambaBlockList, MambaResidualBlock)) or (TransformerDecoder is not None and isinstance(m, TransformerDecoder)):
                 pass
             else:   # GRU and anything else with plain weight/bias tensors
                 for name, param in m.named_parameters():
@@ -223,6 +241,8 @@ class RNNBase(nn.Module):
                     x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.grad_detach)
                 elif lid.startswith('smamba'):
                     x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.mask)
+                elif lid.startswith('mamba'):
+                    x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.mask, hidden_state.grad_detach)
                 elif lid.startswith('cgpt'):
                     if x.dim() == 3 and x.shape[-2] > 1:
                         cache, seqlens = None, hidden_state.attention_concat_mask

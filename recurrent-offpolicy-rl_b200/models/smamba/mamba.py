@@ -77,14 +77,17 @@ class Mamba(nn.Module):
         reference's GPU path (ref: mamba.py:160-164)."""
         Bsz, L, _ = x.shape
         Dn, N, R = self.d_inner, self.d_state, self.dt_rank
-        xz = self.in_proj(x)                                           # [B, L, 2D]
-        xs, z = xz[..., :Dn], xz[..., Dn:]                             # column slices, no copy
+        # the two halves of in_proj as two GEMMs on row slices of the weight: xs and z come out as separate
+        # contiguous tensors, so no column-slice gradients ([B, L, 2D] zero-fill + copy + add) exist in the backward
+        Wi, bi = self.in_proj.weight, self.in_proj.bias
+        xs = K.linear(x, Wi[:Dn], None if bi is None else bi[:Dn])     # [B, L, D]
+        z = K.linear(x, Wi[Dn:], None if bi is None else bi[Dn:])
         if self.use_conv:
             xs = K.causal_conv1d_silu(xs, self.conv1d.weight, self.conv1d.bias, mask)
         elif mask is not None:
             xs = xs * mask
         x_dbl = self.x_proj(xs)                                        # [B, L, R + 2N]
-        delta = F.linear(x_dbl[..., :R], self.dt_proj.weight)          # bias + softplus happen in the scan
+        delta = K.linear(x_dbl[..., :R], self.dt_proj.weight)          # bias + softplus happen in the scan
         A = -torch.exp(self.A_log.float())
         y = K.selective_scan_tm(xs, delta, A, x_dbl[..., R:R + N], x_dbl[..., R + N:], self.D.float(), z,
                                 self.dt_proj.bias.float(), rnn_start, True)

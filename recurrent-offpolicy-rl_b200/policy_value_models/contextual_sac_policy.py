@@ -15,6 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from ..models.contextual_model import ContextualModel
+from ..models.linear import Linear
 from ..models.RNNHidden import RNNHidden
 from .utils import nearest_power_of_two, nearest_power_of_two_half
 
@@ -31,10 +32,10 @@ class _InputEncoders:
         self.separate_encoder = separate_encoder
         if separate_encoder:
             w = 128
-            self.state_encoder = torch.nn.Linear(state_dim, w)
-            self.last_act_encoder = torch.nn.Linear(self.last_act_dim, w) if self.last_act_dim else None
-            self.reward_encoder = torch.nn.Linear(self.reward_dim, w) if self.reward_dim else None
-            self.last_obs_encoder = torch.nn.Linear(self.last_obs_dim, w) if self.last_obs_dim else None
+            self.state_encoder = Linear(state_dim, w)
+            self.last_act_encoder = Linear(self.last_act_dim, w) if self.last_act_dim else None
+            self.reward_encoder = Linear(self.reward_dim, w) if self.reward_dim else None
+            self.last_obs_encoder = Linear(self.last_obs_dim, w) if self.last_obs_dim else None
             return w * (1 + sum(e is not None for e in (self.last_act_encoder, self.last_obs_encoder, self.reward_encoder)))
         self.state_encoder = self.last_act_encoder = self.reward_encoder = self.last_obs_encoder = torch.nn.Identity()
         return state_dim + self.reward_dim + self.last_act_dim + self.last_obs_dim

@@ -11,6 +11,7 @@ from typing import Optional
 import torch
 
 from ..models.contextual_model import ContextualModel
+from ..models.linear import Linear
 from ..models.RNNHidden import RNNHidden
 from ..models.rnn_base import ACTIVATIONS
 from .contextual_sac_policy import _InputEncoders
@@ -32,8 +33,8 @@ class ContextualSACValue(ContextualModel, _InputEncoders):
         self.state_input_encoder = torch.nn.Identity()
         self.action_input_encoder = torch.nn.Identity()
         if uni_model_input_mapping_dim > 0 and separate_encoder:
-            self.state_input_encoder = torch.nn.Linear(state_dim, uni_model_input_mapping_dim)
-            self.action_input_encoder = torch.nn.Linear(action_dim, uni_model_input_mapping_dim)
+            self.state_input_encoder = Linear(state_dim, uni_model_input_mapping_dim)
+            self.action_input_encoder = Linear(action_dim, uni_model_input_mapping_dim)
             uni_in = uni_model_input_mapping_dim * 2
             uni_model_input_mapping_dim = 0
         ContextualModel.__init__(self, embedding_input_size=cum_dim, embedding_size=embedding_size,

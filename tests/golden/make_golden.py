@@ -106,12 +106,16 @@ def gen_ops():
 # layer-level
 # ------------------------------------------------------------------------------------------------
 LAYER_IDS = {"gilr": "gilr", "lru": "lru", "gru": "gru", "smamba_rms": "smamba_s16_c4_b2",
-             "smamba_ln": "smamba_s32_c8_b1_nln", "smamba_ff": "smamba_s16_c8_b1_ff"}
+             "smamba_ln": "smamba_s32_c8_b1_nln", "smamba_ff": "smamba_s16_c8_b1_ff",
+             # s6 layer: reference CPU path = selective_scan_cpu, explicit conv left state
+             "mamba_ff": "mamba_s16_c4", "mamba_noff": "mamba_s32_c8_noff", "mamba_h0": "mamba_s16_c4"}
 
 
-def gen_layers():
+def gen_layers(only=None):
     from offpolicy_rnn.models.rnn_base import RNNBase
     for tag, lid in LAYER_IDS.items():
+        if only and tag not in only:
+            continue
         torch.manual_seed(7)
         net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
         with torch.no_grad():   # make every parameter non-trivial (zero biases hide bugs)
@@ -130,11 +134,16 @@ def gen_layers():
         if 'gru' not in lid:
             hid.set_rnn_start(start)
             hid.set_mask(mask)
-        y, _, _ = net.meta_forward(x, hid)
+        if tag == "mamba_h0":       # carried (non-zero) SSM + conv state entering the call
+            hid[0] = 0.3 * torch.randn_like(hid[0])
+        h_in = [h.clone() for h in hid] if lid.startswith('mamba') else None
+        y, h_out, _ = net.meta_forward(x, hid)
         dy = torch.randn_like(y)
         params = dict(net.named_parameters())
         grads = torch.autograd.grad(y, [x] + list(params.values()), dy, allow_unused=True)
         arrs = {"x": x, "start": start, "mask": mask, "y": y, "dy": dy, "dx": grads[0]}
+        if h_in is not None:
+            arrs["h_in"], arrs["h_out"] = h_in[0], h_out[0]
         for (n, p), gr in zip(params.items(), grads[1:]):
             arrs["p/" + n] = p
             if gr is not None:   # e.g. GILRLayer.layer_norm is constructed but never used
@@ -367,7 +376,7 @@ if __name__ == "__main__":
     if "ops" in which:
         gen_ops()
     if "layers" in which:
-        gen_layers()
+        gen_layers([w[len("layer_"):] for w in which if w.startswith("layer_")] or None)
     if "sampler" in which:
         gen_sampler()
     if "updates" in which:

@@ -18,7 +18,7 @@ def K():
 
 
 @pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (300, 12, 256), (1000, 80, 512), (32576, 256, 384), (4097, 1024, 256),
-                                     (77, 132, 36)])
+                                     (77, 132, 36), (513, 260, 64), (2000, 200, 96), (129, 2048, 384)])
 def test_gemm_tn_plain(K, M, N, K_):
     g = torch.Generator(device="cuda").manual_seed(M + N)
     A = torch.randn(M, K_, device="cuda", generator=g)

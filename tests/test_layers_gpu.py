@@ -1,0 +1,40 @@
+"""Encoder layers on the CUDA path against the layer-level golden fixtures recorded from the UNMODIFIED reference
+(tests/golden/layer_*.npz: RNNBase(['fc', <ID>, 'fc']) forward, input and parameter gradients, and for the s6
+`mamba_*` layer the returned hidden state incl. a carried non-zero state).  fp32 tolerance 1e-3 (BASELINE.json)."""
+import pytest
+import torch
+
+from helpers import T, assert_close, load_npz
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "smamba_rms", "smamba_ln", "smamba_ff", "mamba_ff", "mamba_noff", "mamba_h0"])
+def test_layer_golden(tag):
+    from rorl_b200.models.rnn_base import RNNBase
+    g = load_npz(f"layer_{tag}.npz")
+    lid = str(g["layer_id"])
+    net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
+    sd = {k[2:]: T(v) for k, v in g.items() if k.startswith("p/")}
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    net.cuda()
+    x = T(g["x"], "cuda", grad=True)
+    hid = net.make_init_state(x.shape[0], x.device)
+    if lid != "gru":
+        hid.set_rnn_start(T(g["start"], "cuda"))
+        hid.set_mask(T(g["mask"], "cuda"))
+    if tag == "mamba_h0":
+        hid[0] = T(g["h_in"], "cuda")
+    y, h_out, _ = net.meta_forward(x, hid)
+    assert_close(y, g["y"], TOL, "y")
+    if "h_out" in g:
+        assert tuple(h_out[0].shape) == g["h_out"].shape
+        assert_close(h_out[0], g["h_out"], TOL, "h_out")
+    params = dict(net.named_parameters())
+    names = [k[2:] for k in g if k.startswith("g/")]
+    gs = torch.autograd.grad(y, [x] + [params[n] for n in names], T(g["dy"], "cuda"))
+    assert_close(gs[0], g["dx"], TOL, "dx")
+    for n, got in zip(names, gs[1:]):
+        assert_close(got, g["g/" + n], TOL, n)

@@ -65,15 +65,20 @@ def test_addnorm_op():
         assert_close(got, g[k], TOL, k)
 
 
-@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "smamba_rms", "smamba_ln", "smamba_ff"])
+@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "smamba_rms", "smamba_ln", "smamba_ff", "mamba_ff", "mamba_noff", "mamba_h0"])
 def test_encoder_layer(tag):
     g = load_npz(f"layer_{tag}.npz")
     lid = str(g["layer_id"])
     p = {k[2:]: T(v, grad=True) for k, v in g.items() if k.startswith("p/")}
     x = T(g["x"], grad=True)
     side = OM.Side() if lid == "gru" else OM.Side(T(g["start"]), T(g["mask"]))
+    if "h_in" in g:
+        side.h0 = {1: T(g["h_in"])}
     y = OM.rnn_base(p, ['fc', lid, 'fc'], ['elu', 'elu', 'linear'], x, side)
     assert_close(y, g["y"], TOL, "y")
+    if "h_out" in g:        # s6 layer: [ssm state | conv window], batch-first (ref: s6/mamba.py:187-190)
+        assert side.h_out.shape == g["h_out"].shape
+        assert_close(side.h_out, g["h_out"], TOL, "h_out")
     names = [k[2:] for k in g if k.startswith("g/")]
     gs = torch.autograd.grad(y, [x] + [p[n] for n in names], T(g["dy"]))
     assert_close(gs[0], g["dx"], 1e-4, "dx")

@@ -1,0 +1,72 @@
+"""Deterministic reduction kernels (csrc/reduce.cu) against float64 sums: bias-gradient column sums, the fused
+ELU-backward + column sum, partial-stack sums and the narrow-input weight gradient."""
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import rorl_b200.kernels as K
+    return K
+
+
+@pytest.mark.parametrize("M,N", [(1, 4), (63, 12), (1000, 80), (32576, 256), (32576, 128), (5000, 1028), (70000, 2052)])
+def test_colsum(K, M, N):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    assert rel_err(K.colsum(x), x.double().sum(0)) < 2e-6
+    wide = torch.randn(M, 2 * N, device="cuda", generator=g)
+    sl = wide[:, N:]                                   # row-strided view
+    assert rel_err(K.colsum(sl), sl.double().sum(0)) < 2e-6
+    a, b = K.colsum(x), K.colsum(x)
+    assert torch.equal(a, b), "must be deterministic"
+
+
+def test_colsum_grouped_and_leading(K):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(8, 3001, 256, device="cuda", generator=g)
+    assert rel_err(K.colsum(x), x.double().sum(1)) < 2e-6
+    parts = torch.randn(8, 32, 1018, 64, device="cuda", generator=g)
+    assert rel_err(K.sum_leading(parts), parts.double().sum(0)) < 1e-6
+    assert K.sum_leading(parts[:1]).data_ptr() == parts.data_ptr()
+    odd = torch.randn(5, 7, 3, device="cuda", generator=g)          # not a multiple of 4: ATen path
+    assert rel_err(K.sum_leading(odd), odd.double().sum(0)) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(777, 64), (8, 2000, 256), (32576, 256)])
+def test_elu_bwd_colsum(K, shape):
+    g = torch.Generator(device="cuda").manual_seed(shape[-1])
+    pre = torch.randn(*shape, device="cuda", generator=g)
+    y = torch.nn.functional.elu(pre)
+    dy = torch.randn(*shape, device="cuda", generator=g)
+    gout, db = K.elu_bwd_colsum(dy, y)
+    ref = dy.double() * torch.where(pre > 0, torch.ones_like(pre), pre.exp()).double()
+    assert rel_err(gout, ref) < 1e-6
+    assert rel_err(db, ref.sum(-2)) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,Kk", [(32576, 128, 9), (32576, 128, 6), (32576, 512, 16), (5000, 300, 1), (100, 8, 3), (2049, 1030, 13)])
+def test_skinny_wgrad(K, M, N, Kk):
+    gen = torch.Generator(device="cuda").manual_seed(M + Kk)
+    g = torch.randn(M, N, device="cuda", generator=gen)
+    big = torch.randn(M, 45, device="cuda", generator=gen)
+    x = big[:, 7:7 + Kk]                               # column slice of a wider batch row, like the replay fields
+    dW = K.skinny_wgrad(g, x)
+    assert rel_err(dW, g.double().t() @ x.double()) < 2e-6
+
+
+def test_linear_skinny_autograd(K):
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(32, 1018, 9, device="cuda", generator=gen, requires_grad=True)
+    W = torch.randn(128, 9, device="cuda", generator=gen, requires_grad=True)
+    b = torch.randn(128, device="cuda", generator=gen, requires_grad=True)
+    dy = torch.randn(32, 1018, 128, device="cuda", generator=gen)
+    got = torch.autograd.grad(K.linear(x, W, b), (x, W, b), dy)
+    xd, Wd, bd = (t.detach().double().requires_grad_() for t in (x, W, b))
+    ref = torch.autograd.grad(torch.nn.functional.linear(xd, Wd, bd), (xd, Wd, bd), dy.double())
+    for a, r, n in zip(got, ref, "x W b".split()):
+        assert rel_err(a, r) < 1e-5, n

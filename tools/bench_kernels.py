@@ -176,6 +176,11 @@ def bench_gemm():
             fl = 2.0 * M * n * k * g
             rec(f"gemm_tn {tag} passes={passes}", t, flops=fl * passes, nbytes=4 * (a.numel() + b.numel() + M * n * g),
                 note=f"useful fp32 TFLOP/s {fl / t / 1e12:.1f}")
+        if n > 128:                      # A/B: the 128 x 128 tile on the same shape
+            N.lib().rorl_gemm_force_bn(128)
+            t = timeit(lambda: K.gemm_tn(a, b, bias, 1, passes=3))
+            N.lib().rorl_gemm_force_bn(0)
+            rec(f"gemm_tn {tag} passes=3 BN=128 (A/B)", t, flops=fl * 3, note=f"useful fp32 TFLOP/s {fl / t / 1e12:.1f}")
     # weight gradient
     gq, xq = rn(M, 256), rn(M, 256)
     t = timeit(lambda: K.gemm_nt(gq, xq))
@@ -186,7 +191,28 @@ def bench_gemm():
     rec("cublas sgemm 32576x256x256 (library, for scale)", t, flops=2.0 * M * 256 * 256)
 
 
-ALL = {"gilr": bench_gilr, "lru": bench_lru, "selscan": bench_selscan, "conv": bench_conv, "addnorm": bench_addnorm,
+def bench_reduce():
+    M = 32 * 1018
+    for n in (128, 256, 1024):
+        x = rn(M, n)
+        t = timeit(lambda: K.colsum(x))
+        rec(f"colsum [{M},{n}]", t, 4 * M * n)
+        t = timeit(lambda: x.sum(0))
+        rec(f"aten sum(0) [{M},{n}] (library, for scale)", t, 4 * M * n)
+    dy, y = rn(8, M, 256), rn(8, M, 256)
+    t = timeit(lambda: K.elu_bwd_colsum(dy, y))
+    rec("elu_bwd_colsum [8,32576,256]", t, 12 * dy.numel())
+    t = timeit(lambda: torch.ops.aten.elu_backward(dy, 1.0, 1.0, 1.0, True, y).sum(1))
+    rec("aten elu_backward + sum (library, for scale)", t, 12 * dy.numel())
+    for n, k in ((128, 9), (512, 16)):
+        g, x = rn(M, n), rn(M, k)
+        t = timeit(lambda: K.skinny_wgrad(g, x))
+        rec(f"skinny_wgrad N={n} K={k}", t, 4 * M * (n + k))
+        t = timeit(lambda: g.t() @ x)
+        rec(f"cublas wgrad N={n} K={k} (library, for scale)", t, 4 * M * (n + k))
+
+
+ALL = {"reduce": bench_reduce, "gilr": bench_gilr, "lru": bench_lru, "selscan": bench_selscan, "conv": bench_conv, "addnorm": bench_addnorm,
        "gru": bench_gru, "gemm": bench_gemm}
 
 if __name__ == "__main__":
