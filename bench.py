@@ -251,11 +251,20 @@ def scan_roofline(alg, dev, ms_per_step):
     # per update: 2 blocks x (5 forward, 2 backward) launches
     share_fwd, share_bwd = 10 * t_fwd / (ms_per_step * 1e-3), 4 * t_bwd / (ms_per_step * 1e-3)
     if share_bwd > share_fwd:
-        name, ach, traffic = "selscan_bwd_kernel<32>", bytes_bwd / t_bwd / 1e9, bytes_bwd
+        name, ach, alg_bytes = "selscan_bwd_kernel<32>", bytes_bwd / t_bwd / 1e9, bytes_bwd
     else:
-        name, ach, traffic = "selscan_fwd_kernel<32>", bytes_fwd / t_fwd / 1e9, bytes_fwd
+        name, ach, alg_bytes = "selscan_fwd_kernel<32>", bytes_fwd / t_fwd / 1e9, bytes_fwd
+    # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/): not measurable live
+    traffic, xu = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "selscan_ncu_traffic.json")))[name]
+        traffic, xu = cap["dram_bytes_read"] + cap["dram_bytes_write"], cap.get("xu_pipe_pct")
+    except Exception:
+        pass
     return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "algorithmic_bytes_per_launch": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+            "traffic": traffic, "traffic_source": "profiles/selscan_ncu_traffic.json (ncu --set full, same shape)",
+            "xu_pipe_pct_ncu": xu,
+            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
             "fwd": {"us": t_fwd * 1e6, "GBps": bytes_fwd / t_fwd / 1e9, "share_of_step": share_fwd},
             "bwd": {"us": t_bwd * 1e6, "GBps": bytes_bwd / t_bwd / 1e9, "share_of_step": share_bwd},
             "note": "selective scan at d_state=32 is MUFU/FMA-pipe bound, not HBM bound (SURVEY.md App. F)"}

@@ -281,7 +281,8 @@ int rorl_traj_gather(const float* ring, int64_t F, const int64_t* plan, int64_t 
  *   rorl_colsum          out[g, n] = sum_m x[g, m, n]      x: G groups of [M, N], row stride ldx, group stride gsx
  *   rorl_elu_bwd_colsum  gout = dy * (y > 0 ? 1 : y + 1)   ELU backward from the layer OUTPUT y, fused with the
  *                        out[g, n] = sum_m gout[g, m, n]   bias gradient of that layer
- *   rorl_skinny_wgrad    dW[n, k] = sum_m g[m, n] x[m, k]  K <= 16 (obs / action encoders, dt_proj)
+ *   rorl_skinny_wgrad    dW[n, k] = sum_m g[m, n] x[m, k]  K <= 16 (obs / action encoders, dt_proj); dW is [N, KP],
+ *                        KP = K rounded up to a multiple of 4, columns >= K are zero
  * N % 4 == 0 and 16-byte aligned rows for the column sums; `work` holds rorl_*_work_floats() floats.
  * ---------------------------------------------------------------------------------------------- */
 int64_t rorl_colsum_work_floats(int64_t G, int64_t M, int64_t N);

@@ -126,6 +126,42 @@ def smamba_layer(p, pre, x, side: Side, layer_id: str):
     return ff_block(p, pre + 'head.', x, eps)
 
 
+def smamba_step(p, pre, x, hidden, layer_id: str):
+    """Rollout path: ONE time step through every block's Mamba.step with the carried hidden
+    [1, B, blocks * (D*d_conv + D*d_state)] (per block: conv window first, then SSM state).  rnn_start / mask are not
+    consulted on this path.  ref: offpolicy_rnn/models/smamba/mamba.py:133-159 (dispatch), :257-305 (step),
+    :492-526 (BlockList: hidden chunked per block, outputs concatenated)."""
+    cfg = parse_smamba(layer_id)
+    N, Kc, eps = cfg['d_state'], cfg['d_conv'], 1e-8
+    Bsz = x.shape[0]
+    hs = torch.chunk(hidden, cfg['blocks'], dim=-1)
+    residual, outs = None, []
+    for i in range(cfg['blocks']):
+        b = f'{pre}layers.{i}.'
+        m = b + 'mixer.'
+        xin, residual = ops.add_norm(x, p[b + 'norm.weight'], p.get(b + 'norm.bias'), residual, eps, prenorm=True, is_rms=cfg['rms'])
+        xz = F.linear(xin.squeeze(1), p[m + 'in_proj.weight'])
+        Dm = xz.shape[-1] // 2
+        xs, z = xz[:, :Dm], xz[:, Dm:]
+        conv = hs[i][0, :, :Dm * Kc].reshape(Bsz, Dm, Kc)
+        ssm = hs[i][0, :, Dm * Kc:].reshape(Bsz, Dm, N)
+        conv = torch.cat((conv[:, :, 1:], xs.unsqueeze(-1)), dim=-1)                       # :264-266
+        xs = F.silu((conv * p[m + 'conv1d.weight'][:, 0, :]).sum(-1) + p[m + 'conv1d.bias'])
+        x_db = F.linear(xs, p[m + 'x_proj.weight'])
+        R = x_db.shape[-1] - 2 * N
+        dt, Bm, Cm = torch.split(x_db, [R, N, N], dim=-1)
+        dt = F.softplus(F.linear(dt, p[m + 'dt_proj.weight']) + p[m + 'dt_proj.bias'])      # :283,289
+        A = -torch.exp(p[m + 'A_log'].float())
+        ssm = ssm * torch.exp(dt[..., None] * A) + xs[..., None] * (dt[..., None] * Bm[:, None, :])   # :290-292
+        y = (ssm * Cm[:, None, :]).sum(-1) + p[m + 'D'] * xs
+        x = F.linear(y * F.silu(z), p[m + 'out_proj.weight']).unsqueeze(1)
+        outs.append(torch.cat((conv.reshape(1, Bsz, -1), ssm.reshape(1, Bsz, -1)), dim=-1))
+    if not cfg['ff']:
+        x = ops.add_norm(x, p[pre + 'norm_f.weight'], p.get(pre + 'norm_f.bias'), residual, eps, prenorm=False, is_rms=cfg['rms'])
+        return F.linear(x, p[pre + 'head.weight']), torch.cat(outs, dim=-1)
+    return ff_block(p, pre + 'head.', x + residual, eps), torch.cat(outs, dim=-1)
+
+
 def parse_s6(layer_id: str):
     """ref: rnn_base.py:118-136"""
     cfg = dict(d_state=16, d_conv=4, ff=True)

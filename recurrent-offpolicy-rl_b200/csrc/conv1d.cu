@@ -42,23 +42,23 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_silu_fwd_kernel(
         if (MASK) v *= __ldg(mp + tc);
         win[k] = t >= 0 ? v : 0.f;
     }
-    float nx[K];
+    // the mask is only LOADED here and applied when the batch is consumed: multiplying inside fetch() made every
+    // batch wait for its own loads right after issuing them (ncu: 56 % of the stalls were long-scoreboard on those
+    // multiplies), i.e. no load ever overlapped the arithmetic of the previous batch
+    float nx[K], nm[K];
     auto fetch = [&](int tb) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int tc = min(tb + j, t1 - 1);
             nx[j] = __ldg(xp + (size_t)tc * ld_x);
-        }
-        if (MASK) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) nx[j] *= __ldg(mp + min(tb + j, t1 - 1));
+            if (MASK) nm[j] = __ldg(mp + tc);
         }
     };
     fetch(t0);
     for (int tb = t0; tb < t1; tb += K) {
         float cx[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) cx[j] = nx[j];
+        for (int j = 0; j < K; ++j) cx[j] = MASK ? nx[j] * nm[j] : nx[j];
         fetch(min(tb + K, t1 - 1));
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -109,24 +109,21 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_silu_bwd_kernel(
     const int tend = min(L, t1 + K - 1);       // dpre is needed on [t0, tend)
     const int tstop = tend + K - 1;            // positions up to t1 - 1 complete by step tend + K - 2
     // acc_dx slot (s % K) accumulates dxm for position t = s - K + t0; position t - (K-1) completes at step t.
-    float nx[K], ng[K];
+    float nx[K], ng[K], nm[K];
     auto fetch = [&](int tb) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int tc = min(tb + j, tend - 1);
             nx[j] = __ldg(xp + (size_t)tc * ld_x);
             ng[j] = __ldg(gp + (size_t)tc * ld_dy);
-        }
-        if (MASK) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) nx[j] *= __ldg(mp + min(tb + j, tend - 1));
+            if (MASK) nm[j] = __ldg(mp + tc);            // applied at consumption (see the forward kernel)
         }
     };
     fetch(t0);
     for (int tb = t0; tb < tstop; tb += K) {
         float cx[K], cg[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) { cx[j] = nx[j]; cg[j] = ng[j]; }
+        for (int j = 0; j < K; ++j) { cx[j] = MASK ? nx[j] * nm[j] : nx[j]; cg[j] = ng[j]; }
         fetch(min(tb + K, tend - 1));
 #pragma unroll
         for (int j = 0; j < K; ++j) {

@@ -39,14 +39,36 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __rest
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (rl < lanes) {
         const int64_t col = (q0 + q) * 4;
-        for (int64_t m = m0 + rl; m < m1; m += lanes) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(x + m * ldx + col));
+        auto elu_grad = [&](float4& v, const float4& o) {
+            v.x *= o.x > 0.f ? 1.f : o.x + 1.f;
+            v.y *= o.y > 0.f ? 1.f : o.y + 1.f;
+            v.z *= o.z > 0.f ? 1.f : o.z + 1.f;
+            v.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+        };
+        int64_t m = m0 + rl;
+        // four rows per iteration: all loads are issued before the first use (memory-level parallelism; a one-row
+        // loop left each thread with a single 16-byte load in flight and ran at a quarter of the HBM rate)
+        for (; m + 3 * (int64_t)lanes < m1; m += 4 * (int64_t)lanes) {
+            float4 v[4], o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(x + (m + u * lanes) * ldx + col));
             if (ELU) {
-                const float4 o = __ldg(reinterpret_cast<const float4*>(y + m * ldy + col));
-                v.x *= o.x > 0.f ? 1.f : o.x + 1.f;
-                v.y *= o.y > 0.f ? 1.f : o.y + 1.f;
-                v.z *= o.z > 0.f ? 1.f : o.z + 1.f;
-                v.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[u] = __ldcs(reinterpret_cast<const float4*>(y + (m + u * lanes) * ldy + col));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    elu_grad(v[u], o[u]);
+                    *reinterpret_cast<float4*>(g + (m + u * lanes) * ldg + col) = v[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; m < m1; m += lanes) {
+            float4 v = __ldcs(reinterpret_cast<const float4*>(x + m * ldx + col));
+            if (ELU) {
+                const float4 o = __ldcs(reinterpret_cast<const float4*>(y + m * ldy + col));
+                elu_grad(v, o);
                 *reinterpret_cast<float4*>(g + m * ldg + col) = v;
             }
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -63,19 +85,33 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __rest
     }
 }
 
-// out[n] = sum_b partial[b, n]
+// out[n] = sum_b partial[b, n]: a CTA owns 32 column quads, 8 lanes split the nblk partial rows, shared-memory combine
+// (a single thread walking hundreds of dependent-latency loads per column made this tiny stage the longer one)
 __global__ void __launch_bounds__(kRedThreads) partial_sum_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                                   int nblk, int64_t N) {
-    const int64_t q = (int64_t)blockIdx.x * kRedThreads + threadIdx.x;
-    if (q * 4 >= N) return;
+    __shared__ float4 s_acc[kRedThreads];
     partial += (int64_t)blockIdx.y * nblk * N;
     out += (int64_t)blockIdx.y * N;
+    const int ql = threadIdx.x & 31, rl = threadIdx.x >> 5;               // 32 quads x 8 row lanes
+    const int64_t q = (int64_t)blockIdx.x * 32 + ql;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = 0; b < nblk; ++b) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)b * N + q * 4));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (q * 4 < N) {
+#pragma unroll 4
+        for (int b = rl; b < nblk; b += 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)b * N + q * 4));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
-    *reinterpret_cast<float4*>(out + q * 4) = acc;
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0 && q * 4 < N) {
+#pragma unroll
+        for (int l = 1; l < 8; ++l) {
+            const float4 v = s_acc[l * 32 + ql];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + q * 4) = acc;
+    }
 }
 
 // dW[n, k] = sum_m g[m, n] x[m, k].  grid: (row blocks, column chunks of 256); thread = output column n; x rows are
@@ -101,16 +137,20 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
         }
         __syncthreads();
         if (n < N) {
-#pragma unroll 4
-            for (int r = 0; r < rows; ++r) {
-                const float gv = __ldg(g + (mb + r) * ldg + n);
+            for (int r0 = 0; r0 < rows; r0 += 8) {
+                float gv[8];
 #pragma unroll
-                for (int k4 = 0; k4 < KP; k4 += 4) {
-                    const float4 xv = *reinterpret_cast<const float4*>(s_x + r * KP + k4);
-                    acc[k4] = fmaf(gv, xv.x, acc[k4]);
-                    acc[k4 + 1] = fmaf(gv, xv.y, acc[k4 + 1]);
-                    acc[k4 + 2] = fmaf(gv, xv.z, acc[k4 + 2]);
-                    acc[k4 + 3] = fmaf(gv, xv.w, acc[k4 + 3]);
+                for (int u = 0; u < 8; ++u) gv[u] = (r0 + u < rows) ? __ldg(g + (mb + r0 + u) * ldg + n) : 0.f;   // 8 loads in flight
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int k4 = 0; k4 < KP; k4 += 4) {
+                        const float4 xv = *reinterpret_cast<const float4*>(s_x + (r0 + u) * KP + k4);     // rows past `rows` are zero
+                        acc[k4] = fmaf(gv[u], xv.x, acc[k4]);
+                        acc[k4 + 1] = fmaf(gv[u], xv.y, acc[k4 + 1]);
+                        acc[k4 + 2] = fmaf(gv[u], xv.z, acc[k4 + 2]);
+                        acc[k4 + 3] = fmaf(gv[u], xv.w, acc[k4 + 3]);
+                    }
                 }
             }
         }
@@ -123,21 +163,11 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
     }
 }
 
-// dW[n, k] = sum_b partial[b, n, kp]  (drops the K padding)
-__global__ void __launch_bounds__(kRedThreads) skinny_finish_kernel(const float* __restrict__ partial, float* __restrict__ dW,
-                                                                    int nblk, int64_t N, int K, int KP) {
-    const int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x;
-    if (i >= N * K) return;
-    const int64_t n = i / K;
-    const int k = (int)(i % K);
-    float acc = 0.f;
-    for (int b = 0; b < nblk; ++b) acc += __ldg(partial + ((int64_t)b * N + n) * KP + k);
-    dW[i] = acc;
-}
-
-static inline int red_blocks(int64_t M, int* rows_per_block) {
+static inline int red_blocks(int64_t M, int* rows_per_block, int64_t G = 1, int64_t chunks = 1) {
     int nblk = (int)((M + 63) / 64);                     // at least 64 rows per block
-    if (nblk > kRedMaxBlocks) nblk = kRedMaxBlocks;
+    int cap = (int)(kRedMaxBlocks / (G * chunks));       // about 4 CTAs per SM over the whole grid
+    if (cap < 1) cap = 1;
+    if (nblk > cap) nblk = cap;
     if (nblk < 1) nblk = 1;
     const int rpb = (int)((M + nblk - 1) / nblk);
     *rows_per_block = rpb;
@@ -163,13 +193,13 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
     if (M <= 0 || N <= 0 || G <= 0 || G > 65535) return RORL_ERR_SHAPE;
     if (N % 4 || ldx % 4 || gsx % 4 || !a16(x) || !a16(out) || !a16(work)) return RORL_ERR_ALIGN;
     int rpb;
-    const int nblk = red_blocks(M, &rpb);
     const int chunks = (int)((N / 4 + kRedMaxQuads - 1) / kRedMaxQuads);
     if (chunks > 65535) return RORL_ERR_SHAPE;
+    const int nblk = red_blocks(M, &rpb, G, chunks);
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
     colsum_kernel<false><<<grid, kRedThreads, 0, stream>>>(x, nullptr, nullptr, nblk == 1 ? out : work, M, N, ldx, 0, 0, gsx, 0, 0, rpb);
     if (nblk > 1) {
-        dim3 g2((unsigned)((N / 4 + kRedThreads - 1) / kRedThreads), (unsigned)G);
+        dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
     }
     RORL_RETURN_LAUNCH();
@@ -184,13 +214,13 @@ int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, f
         !a16(out) || !a16(work))
         return RORL_ERR_ALIGN;
     int rpb;
-    const int nblk = red_blocks(M, &rpb);
     const int chunks = (int)((N / 4 + kRedMaxQuads - 1) / kRedMaxQuads);
     if (chunks > 65535) return RORL_ERR_SHAPE;
+    const int nblk = red_blocks(M, &rpb, G, chunks);
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
     colsum_kernel<true><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb);
     if (nblk > 1) {
-        dim3 g2((unsigned)((N / 4 + kRedThreads - 1) / kRedThreads), (unsigned)G);
+        dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
     }
     RORL_RETURN_LAUNCH();
@@ -206,18 +236,23 @@ int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, in
                       int64_t ldg, int64_t ldx, cudaStream_t stream) {
     if (!g || !x || !dW || !work) return RORL_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
-    if (!a16(work)) return RORL_ERR_ALIGN;
+    if (!a16(work) || !a16(dW)) return RORL_ERR_ALIGN;
     int rpb;
-    const int nblk = red_blocks(M, &rpb);
+    const int chunks = (int)((N + kRedThreads - 1) / kRedThreads);
+    const int nblk = red_blocks(M, &rpb, 1, chunks);
     const int KP = (int)((K + 3) / 4 * 4);
-    dim3 grid((unsigned)nblk, (unsigned)((N + kRedThreads - 1) / kRedThreads));
+    dim3 grid((unsigned)nblk, (unsigned)chunks);
+    float* dst = nblk == 1 ? dW : work;
     switch (KP) {
-        case 4: skinny_wgrad_kernel<4><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
-        case 8: skinny_wgrad_kernel<8><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
-        case 12: skinny_wgrad_kernel<12><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
-        default: skinny_wgrad_kernel<16><<<grid, kRedThreads, 0, stream>>>(g, x, work, M, N, (int)K, ldg, ldx, rpb); break;
+        case 4: skinny_wgrad_kernel<4><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        case 8: skinny_wgrad_kernel<8><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        case 12: skinny_wgrad_kernel<12><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        default: skinny_wgrad_kernel<16><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
     }
-    skinny_finish_kernel<<<(unsigned)((N * K + kRedThreads - 1) / kRedThreads), kRedThreads, 0, stream>>>(work, dW, nblk, N, (int)K, KP);
+    if (nblk > 1) {
+        dim3 g2((unsigned)((N * KP / 4 + 31) / 32), 1u);
+        partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, dW, nblk, N * KP);
+    }
     RORL_RETURN_LAUNCH();
 }
 

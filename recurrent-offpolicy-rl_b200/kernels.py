@@ -92,10 +92,11 @@ def skinny_wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """dW [N, K] = g[M, N]^T x[M, K] for K <= 16 (unit inner strides, any row stride)."""
     M, Nn = g.shape
     K = x.shape[1]
-    dW = torch.empty((Nn, K), device=g.device, dtype=torch.float32)
+    KP = (K + 3) // 4 * 4
+    dW = torch.empty((Nn, KP), device=g.device, dtype=torch.float32)       # K padded to a multiple of 4 (zero columns)
     work = torch.empty(int(N.lib().rorl_skinny_wgrad_work_floats(M, Nn, K)), device=g.device, dtype=torch.float32)
     N.call("rorl_skinny_wgrad", N.ptr(g), N.ptr(x), N.ptr(dW), N.ptr(work), M, Nn, K, g.stride(0), x.stride(0), N.stream())
-    return dW
+    return dW[:, :K]
 
 
 class LinearSkinny(Function):

@@ -77,6 +77,8 @@ class Mamba(nn.Module):
         reference's GPU path (ref: mamba.py:160-164)."""
         Bsz, L, _ = x.shape
         Dn, N, R = self.d_inner, self.d_state, self.dt_rank
+        if L == 1:
+            return self.step(x, hidden)
         # the two halves of in_proj as two GEMMs on row slices of the weight: xs and z come out as separate
         # contiguous tensors, so no column-slice gradients ([B, L, 2D] zero-fill + copy + add) exist in the backward
         Wi, bi = self.in_proj.weight, self.in_proj.bias
@@ -95,6 +97,38 @@ class Mamba(nn.Module):
         if hidden is None:
             hidden = torch.zeros((1, Bsz, self.desired_hidden_dim), device=x.device)
         return out, hidden
+
+
+    def step(self, x, hidden=None):
+        """Single-step (rollout / decoding) path, taken for L == 1 as in the reference (ref: mamba.py:133-159
+        dispatch, :257-305 step).  hidden [1, B, D*d_conv + D*d_state] = [conv window | SSM state], conv FIRST;
+        the window is rolled and the new input appended, the SSM state advances by one step of the same scan
+        kernel (carried state in, final state out).  As in the reference, `rnn_start` and `mask` are NOT looked
+        at on this path."""
+        Bsz = x.shape[0]
+        Dn, N, R, Kc = self.d_inner, self.d_state, self.dt_rank, self.d_conv
+        if hidden is None:
+            conv_state = x.new_zeros((Bsz, Dn, Kc)) if self.use_conv else None
+            ssm_state = x.new_zeros((Bsz, Dn, N))
+        else:
+            conv_state = hidden[0, :, :self.conv_hidden_dim].reshape(Bsz, Dn, Kc) if self.use_conv else None
+            ssm_state = hidden[0, :, self.conv_hidden_dim:].reshape(Bsz, Dn, N)
+        xz = self.in_proj(x)                                           # [B, 1, 2D]
+        xs, z = xz[..., :Dn], xz[..., Dn:]
+        if self.use_conv:
+            conv_state = torch.cat((conv_state[:, :, 1:], xs.transpose(1, 2)), dim=-1)      # roll left, append
+            xs = torch.sum(conv_state * self.conv1d.weight[:, 0, :], dim=-1)
+            if self.conv1d.bias is not None:
+                xs = xs + self.conv1d.bias
+            xs = F.silu(xs).unsqueeze(1)                               # [B, 1, D]
+        x_dbl = self.x_proj(xs)
+        delta = K.linear(x_dbl[..., :R], self.dt_proj.weight)
+        A = -torch.exp(self.A_log.float())
+        y, last = K.selective_scan_tm(xs.contiguous(), delta, A, x_dbl[..., R:R + N], x_dbl[..., R + N:], self.D.float(),
+                                      z, self.dt_proj.bias.float(), None, True, True, ssm_state)
+        out = self.out_proj(y)
+        parts = ([conv_state.reshape(1, Bsz, -1)] if self.use_conv else []) + [last.reshape(1, Bsz, -1)]
+        return out, torch.cat(parts, dim=-1)
 
 
 def _init_weights(module, n_layer, rescale_prenorm_residual=True, n_residuals_per_layer=1):

@@ -7,6 +7,7 @@ Fixtures:
   ops_*.npz      op-level in/out/grad of the reference's own restatements (scan_cpu, complex_scan_cpu,
                  selective_scan_ref, layernorm_cpu)
   layer_*.npz    RNNBase(['fc', <ID>, 'fc']) forward + input/parameter gradients for each encoder ID
+  step_*.npz     smamba rollout path: L single steps through Mamba.step() with a carried hidden (reference CPU path)
   sampler_*.npz  NestedMemoryArray.sample_trajs outputs for seeded buffers
   update_*.npz   one or two full train_one_batch() calls of the reference algorithm classes (App. D harness)
 """
@@ -149,6 +150,50 @@ def gen_layers(only=None):
             if gr is not None:   # e.g. GILRLayer.layer_norm is constructed but never used
                 arrs["g/" + n] = gr
         save(f"layer_{tag}.npz", layer_id=np.array(lid), **arrs)
+
+
+def gen_steps():
+    """Rollout step path of the smamba layer: the UNMODIFIED reference on CPU walks Mamba.step() once per time step
+    (ref: smamba/mamba.py:133-159,257-305) -- its natural CPU path, no patching (a fresh import would be needed to
+    undo _refload's forward_sequential routing, so the original forward is recovered from the class dict)."""
+    import importlib
+    import offpolicy_rnn.models.smamba.mamba as smamba
+    src = importlib.util.find_spec("offpolicy_rnn.models.smamba.mamba").origin
+    ns = {}
+    orig_forward = None
+    # re-exec the module source in a scratch namespace to get the original Mamba.forward function object
+    spec = importlib.util.spec_from_file_location("_smamba_orig", src, submodule_search_locations=None)
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = "offpolicy_rnn.models.smamba"
+    spec.loader.exec_module(mod)
+    orig_forward = mod.Mamba.forward
+    patched = smamba.Mamba.forward
+    smamba.Mamba.forward = orig_forward
+    try:
+        from offpolicy_rnn.models.rnn_base import RNNBase
+        for tag, lid in (("smamba_rms", "smamba_s16_c4_b2"), ("smamba_ln16", "smamba_s32_c16_b1_nln")):
+            torch.manual_seed(11)
+            net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
+            with torch.no_grad():
+                for p in net.parameters():
+                    if p.dim() == 1 or p.abs().max() == 0:
+                        p.add_(0.1 * torch.randn_like(p))
+            B, L = 3, 7
+            x = torch.randn(B, L, 12)
+            hid = net.make_init_state(B)
+            hid[0] = 0.3 * torch.randn_like(hid[0])
+            h_in = hid[0].clone()
+            ys, h = [], hid
+            with torch.no_grad():
+                for t in range(L):
+                    y, h, _ = net.meta_forward(x[:, t:t + 1], h)
+                    ys.append(y)
+            arrs = {"x": x, "h_in": h_in, "y": torch.cat(ys, dim=1), "h_out": h[0]}
+            for n, p in net.named_parameters():
+                arrs["p/" + n] = p
+            save(f"step_{tag}.npz", layer_id=np.array(lid), **arrs)
+    finally:
+        smamba.Mamba.forward = patched
 
 
 # ------------------------------------------------------------------------------------------------
@@ -372,11 +417,13 @@ def gen_updates():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "layers", "sampler", "updates"]
+    which = sys.argv[1:] or ["ops", "layers", "steps", "sampler", "updates"]
     if "ops" in which:
         gen_ops()
     if "layers" in which:
         gen_layers([w[len("layer_"):] for w in which if w.startswith("layer_")] or None)
+    if "steps" in which:
+        gen_steps()
     if "sampler" in which:
         gen_sampler()
     if "updates" in which:

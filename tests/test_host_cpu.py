@@ -36,7 +36,9 @@ def test_layer_id_grammar():
     assert parse_layer_id('smamba') == ('smamba', dict(d_state=16, d_conv=4, block_num=2, rms_norm=True, use_ff=False))
     assert parse_layer_id('cgpt_h8_l6_p0.1_ml1024_rms') == ('cgpt', dict(nhead=8, nlayer=6, pdrop=0.1, maxlength=1024, ln=False))
     assert parse_layer_id('efc-8') == ('efc', {'ensemble': 8})
-    for lid in ('gru', 'lru', 'gilr', 'smamba_s16', 'cgpt_h8'):
+    assert parse_layer_id('mamba_s32_c16') == ('mamba', dict(d_state=32, d_conv=16, use_ff=True))
+    assert parse_layer_id('mamba_noff')[1] == dict(d_state=16, d_conv=4, use_ff=False)
+    for lid in ('gru', 'lru', 'gilr', 'smamba_s16', 'cgpt_h8', 'mamba_s16'):
         assert check_is_rnn(lid)
     assert not check_is_rnn('fc') and not check_is_rnn('efc-8')
     with pytest.raises(NotImplementedError):
@@ -127,3 +129,40 @@ def test_sampler_plan_bit_exact(tag):
         assert np.array_equal(np.array(st[1][:4], dtype=np.int64), g[f"c{call}/rng_next"]) and st[2] == int(g[f"c{call}/rng_pos"])
     with pytest.raises(RuntimeError, match="no CPU path"):
         buf.gather_device(plan)
+
+
+def test_s6_layer_state_dict_keys_and_hidden_size():
+    """s6 `mamba_*` layer: parameter names / shapes and the hidden width of the reference (layer_mamba_*.npz were
+    recorded from the unmodified reference's RNNBase)."""
+    from rorl_b200.models.rnn_base import RNNBase
+    for tag in ("mamba_ff", "mamba_noff"):
+        g = load_npz(f"layer_{tag}.npz")
+        net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', str(g["layer_id"]), 'fc'])
+        ref = {k[2:]: v.shape for k, v in g.items() if k.startswith("p/")}
+        mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        assert list(ref) == list(mine)
+        for k in ref:
+            assert tuple(ref[k]) == mine[k], k
+        assert net.rnn_hidden_state_input_size == [g["h_in"].shape[-1]]
+
+
+def test_checkpoint_files_follow_reference_naming(tmp_path):
+    """save()/load() write one `{name}-{index}-{module}.pt` state_dict per contextual module, the reference's
+    checkpoint layout (ref: offpolicy_rnn/models/contextual_model.py:135-153)."""
+    import os
+    from rorl_b200.policy_value_models.make_models import make_policy_model
+    kw = dict(state_dim=5, action_dim=3, embedding_size=8, embedding_hidden=[16, 16], embedding_activations=['elu', 'elu', 'linear'],
+              embedding_layer_type=['fc', 'gilr', 'fc'], uni_model_hidden=[16, 16], uni_model_activations=['elu', 'elu', 'linear'],
+              uni_model_layer_type=['fc'] * 3, fix_rnn_length=0, uni_model_input_mapping_dim=8, reward_input=False,
+              last_action_input=True, last_state_input=True, separate_encoder=True)
+    torch.manual_seed(0)
+    a = make_policy_model(kw, 'sac', False)
+    torch.manual_seed(1)
+    b = make_policy_model(kw, 'sac', False)
+    a.save(str(tmp_path), 7)
+    files = sorted(os.listdir(tmp_path))
+    assert files == sorted(f"{a.name}-7-{k}.pt" for k in a.contextual_modules)
+    b.load(str(tmp_path), 7)
+    for k, sd in a.state_dict().items():
+        for n, t in sd.items():
+            assert torch.equal(t, b.state_dict()[k][n]), (k, n)

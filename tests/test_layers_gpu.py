@@ -38,3 +38,26 @@ def test_layer_golden(tag):
     assert_close(gs[0], g["dx"], TOL, "dx")
     for n, got in zip(names, gs[1:]):
         assert_close(got, g["g/" + n], TOL, n)
+
+
+@pytest.mark.parametrize("tag", ["smamba_rms", "smamba_ln16"])
+def test_smamba_rollout_step_golden(tag):
+    """The L == 1 rollout path (conv window roll + one step of the scan kernel with the carried SSM state) against the
+    reference's own Mamba.step loop on CPU (tests/golden/step_*.npz)."""
+    from rorl_b200.models.rnn_base import RNNBase
+    g = load_npz(f"step_{tag}.npz")
+    lid = str(g["layer_id"])
+    net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
+    net.load_state_dict({k[2:]: T(v) for k, v in g.items() if k.startswith("p/")})
+    net.cuda()
+    x = T(g["x"], "cuda")
+    h = net.make_init_state(x.shape[0], x.device)
+    h[0] = T(g["h_in"], "cuda")
+    ys = []
+    with torch.no_grad():
+        for t in range(x.shape[1]):
+            y, h, _ = net.meta_forward(x[:, t:t + 1], h)
+            ys.append(y)
+    assert_close(torch.cat(ys, dim=1), g["y"], TOL, "y")
+    assert tuple(h[0].shape) == g["h_out"].shape
+    assert_close(h[0], g["h_out"], TOL, "h_out")

@@ -4,6 +4,7 @@
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from helpers import T, assert_close, cfg_of, load_npz, nested_sd
 from oracle import model as OM
@@ -84,6 +85,22 @@ def test_encoder_layer(tag):
     assert_close(gs[0], g["dx"], 1e-4, "dx")
     for n, got in zip(names, gs[1:]):
         assert_close(got, g["g/" + n], 2e-4, n)
+
+
+@pytest.mark.parametrize("tag", ["smamba_rms", "smamba_ln16"])
+def test_smamba_rollout_step(tag):
+    """Oracle restatement of the L == 1 rollout path against the reference's own step loop (carried hidden)."""
+    g = load_npz(f"step_{tag}.npz")
+    lid = str(g["layer_id"])
+    p = {k[2:]: T(v) for k, v in g.items() if k.startswith("p/")}
+    x, h = T(g["x"]), T(g["h_in"])
+    ys = []
+    for t in range(x.shape[1]):
+        e = F.elu(F.linear(x[:, t:t + 1], p['layer_list.0.weight'], p['layer_list.0.bias']))
+        e, h = OM.smamba_step(p, 'layer_list.1.', e, h, lid)
+        ys.append(F.linear(F.elu(e), p['layer_list.2.weight'], p['layer_list.2.bias']))
+    assert_close(torch.cat(ys, dim=1), g["y"], TOL, "y")
+    assert_close(h, g["h_out"], TOL, "h_out")
 
 
 def _fill(buf, rng, lens, S, A):

@@ -26,13 +26,31 @@ TF = float(PEAKS.get("bf16_tflops", 1590.0))
 
 
 def timeit(fn, n=20, warm=3):
+    """CUDA-event time per call.  The n calls are captured into one CUDA graph and replayed, so that what is
+    measured is device time, not the Python / ctypes launch path (tens of microseconds per call, which hides
+    kernels shorter than that); falls back to eager launches if the callable cannot be captured."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    graph = None
+    if not os.environ.get("RORL_BENCH_EAGER"):
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                for _ in range(n):
+                    fn()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception:
+            graph = None
+            torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        fn()
+    if graph is not None:
+        graph.replay()
+    else:
+        for _ in range(n):
+            fn()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e-3
@@ -63,11 +81,10 @@ def bench_gilr():
     start = torch.zeros(B, L, device=dev); start[:, 0] = 1
     h = torch.empty_like(uv)
     du, df = torch.empty_like(uv), torch.empty_like(uv)
-    S = N.stream()
-    rec("gilr_fused_fwd", timeit(lambda: N.call("rorl_gilr_fused_fwd", N.ptr(uv), N.ptr(uf), N.ptr(start), N.ptr(h), B, L, C, S)),
+    rec("gilr_fused_fwd", timeit(lambda: N.call("rorl_gilr_fused_fwd", N.ptr(uv), N.ptr(uf), N.ptr(start), N.ptr(h), B, L, C, N.stream())),
         12 * B * L * C)
     rec("gilr_fused_bwd", timeit(lambda: N.call("rorl_gilr_fused_bwd", N.ptr(dh), N.ptr(uv), N.ptr(uf), N.ptr(h), N.ptr(start),
-                                                N.ptr(du), N.ptr(df), B, L, C, S)), 24 * B * L * C)
+                                                N.ptr(du), N.ptr(df), B, L, C, N.stream())), 24 * B * L * C)
     # L2-cold variant: 8 rotating operand sets (8 x 98 MB > 126 MB L2)
     sets = [(rn(B, L, C), rn(B, L, C), torch.empty(B, L, C, device=dev)) for _ in range(8)]
     it = [0]
@@ -75,7 +92,7 @@ def bench_gilr():
     def cold():
         a, b, c = sets[it[0] % 8]
         it[0] += 1
-        N.call("rorl_gilr_fused_fwd", N.ptr(a), N.ptr(b), N.ptr(start), N.ptr(c), B, L, C, S)
+        N.call("rorl_gilr_fused_fwd", N.ptr(a), N.ptr(b), N.ptr(start), N.ptr(c), B, L, C, N.stream())
     rec("gilr_fused_fwd_L2cold", timeit(cold, n=24), 12 * B * L * C)
 
 
@@ -83,14 +100,13 @@ def bench_lru():
     B, L, C = 32, 1002, 256
     vr, vi, fr, fi = rn(B, L, C), rn(B, L, C), 0.9 * torch.rand(B, L, C, device=dev), 0.1 * rn(B, L, C)
     hr, hi = torch.empty_like(vr), torch.empty_like(vr)
-    S = N.stream()
     rec("lru_scan_fwd", timeit(lambda: N.call("rorl_lru_scan_fwd", N.ptr(vr), N.ptr(vi), N.ptr(fr), N.ptr(fi), None, None,
-                                              N.ptr(hr), N.ptr(hi), B, L, C, S)), 24 * B * L * C,
+                                              N.ptr(hr), N.ptr(hi), B, L, C, N.stream())), 24 * B * L * C,
         note="per-step decay tensors as the reference materialises them: 6 x [B,L,C] floats")
     g1, g2 = rn(B, L, C), rn(B, L, C)
     o = [torch.empty_like(vr) for _ in range(4)]
     rec("lru_scan_bwd", timeit(lambda: N.call("rorl_lru_scan_bwd", N.ptr(g1), N.ptr(g2), N.ptr(fr), N.ptr(fi), N.ptr(hr), N.ptr(hi),
-                                              None, None, None, N.ptr(o[0]), N.ptr(o[1]), N.ptr(o[2]), N.ptr(o[3]), B, L, C, S)),
+                                              None, None, None, N.ptr(o[0]), N.ptr(o[1]), N.ptr(o[2]), N.ptr(o[3]), B, L, C, N.stream())),
         40 * B * L * C)
 
 
@@ -142,13 +158,12 @@ def bench_gru():
     B, L, H = 32, 1002, 256
     gi, w, bh = rn(B, L, 3 * H), 0.06 * rn(3 * H, H), rn(3 * H)
     out, hl, save = torch.empty(B, L, H, device=dev), torch.empty(B, H, device=dev), torch.empty(B, L, 4 * H, device=dev)
-    S = N.stream()
-    t = timeit(lambda: N.call("rorl_gru_fwd", N.ptr(gi), N.ptr(w), N.ptr(bh), None, N.ptr(out), N.ptr(save), N.ptr(hl), B, L, H, S), n=10)
+    t = timeit(lambda: N.call("rorl_gru_fwd", N.ptr(gi), N.ptr(w), N.ptr(bh), None, N.ptr(out), N.ptr(save), N.ptr(hl), B, L, H, N.stream()), n=10)
     rec("gru_fwd_persistent", t, note=f"{t / L * 1e6:.3f} us/step, {B} rows, H={H}")
     dout = rn(B, L, H)
     dgi, dghn, dh0 = torch.empty(B, L, 3 * H, device=dev), torch.empty(B, L, H, device=dev), torch.empty(B, H, device=dev)
     t = timeit(lambda: N.call("rorl_gru_bwd", N.ptr(dout), None, N.ptr(w), N.ptr(save), N.ptr(out), None, N.ptr(dgi), N.ptr(dghn),
-                              N.ptr(dh0), B, L, H, S), n=10)
+                              N.ptr(dh0), B, L, H, N.stream()), n=10)
     rec("gru_bwd_persistent", t, note=f"{t / L * 1e6:.3f} us/step")
     ref = torch.nn.GRU(H, H, batch_first=True).to(dev)
     x = rn(B, L, H)

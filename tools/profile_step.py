@@ -18,4 +18,4 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     alg.train_one_batch(sync=False)
     torch.cuda.synchronize()
-print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=45, max_shapes_column_width=70))
+print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=110, max_name_column_width=45, max_shapes_column_width=70))
