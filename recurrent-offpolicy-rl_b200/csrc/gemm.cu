@@ -42,12 +42,16 @@ constexpr int kStagingBytes = kGemmEpiWarps * 32 * 128;       // per epilogue wa
 // at the same ~300 TFLOP/s whatever the shape).  BN = 256 (TN variant, N > 128) reads the A tile once for twice the
 // columns: 0.75x the operand bytes per FLOP and half the A-splitting work, at the cost of a 2-deep instead of a
 // 3-deep ring (227 KiB of shared memory) and both 256-column TMEM accumulators (512 columns).
-template <int BN>
+// BK = 16 (64-byte swizzle rows) halves the stage so that the same 192 KiB ring is twice as deep (4 stages at BN = 256,
+// 6 at BN = 128): the TMA round trip (~1 us from L2) then hides behind the other stages' MMAs, which a 2-deep ring of
+// 96-KiB stages cannot do.
+template <int BN, int BK = kGemmBK>
 struct GemmCfg {
-    static constexpr int kTileB = BN * kGemmBK * 4;               // B tile bytes
-    static constexpr int kRaw = kTileBytes + kTileB;               // A_raw | B_raw
+    static constexpr int kTileA = kGemmBM * BK * 4;                // A tile bytes
+    static constexpr int kTileB = BN * BK * 4;                     // B tile bytes
+    static constexpr int kRaw = kTileA + kTileB;                   // A_raw | B_raw
     static constexpr int kStage = 2 * kRaw;                        // A_raw | B_raw | A_lo | B_lo
-    static constexpr int kStages = BN == 256 ? 2 : 3;
+    static constexpr int kStages = (192 * 1024) / kStage;
     static constexpr int kSmem = kStages * kStage + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -71,13 +75,17 @@ __device__ __forceinline__ float elu1(float x) {
     return x > 0.f ? x : e;
 }
 
-template <bool MN, int BN>
+template <bool MN, int BN, int BK>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
     static_assert(BN == 128 || (BN == 256 && !MN), "BN = 256 exists for the TN variant only");
-    using Cfg = GemmCfg<BN>;
+    static_assert(BK == 32 || (BK == 16 && !MN), "BK = 16 exists for the TN variant only");
+    using Cfg = GemmCfg<BN, BK>;
     constexpr int kGemmStages = Cfg::kStages, kStageBytes = Cfg::kStage, kRawBytes = Cfg::kRaw, kTileB = Cfg::kTileB;
-    constexpr int kGemmBN = BN;                                   // shadows the namespace default inside the kernel
+    constexpr int kTileBytes = Cfg::kTileA;                       // these three shadow the namespace defaults inside the kernel
+    constexpr int kGemmBN = BN;
+    constexpr int kGemmBK = BK;
+    (void)kTileB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -172,8 +180,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     if (split || MN) mbar_wait(bar_full_split(s), ph);
                     tc_fence_after();
                     const uint32_t st = base + s * kStageBytes;
-                    const uint64_t a_hi = make_kmajor_desc(st), b_hi = make_kmajor_desc(st + kTileBytes);
-                    const uint64_t a_lo = make_kmajor_desc(st + kRawBytes), b_lo = make_kmajor_desc(st + kRawBytes + kTileBytes);
+                    auto mk = [](uint32_t a) { return BK == 16 ? make_kmajor_desc_sw64(a) : make_kmajor_desc(a); };
+                    const uint64_t a_hi = mk(st), b_hi = mk(st + kTileBytes);
+                    const uint64_t a_lo = mk(st + kRawBytes), b_lo = mk(st + kRawBytes + kTileBytes);
 #pragma unroll
                     for (int k = 0; k < kGemmBK / 8; ++k) {
                         const uint64_t adv = (uint64_t)(k * 8 * 4 >> 4);        // 32 B per k-step inside the 128-B swizzle row
@@ -344,15 +353,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 
 static int g_gemm_dbg = 0;
 static int g_gemm_bn = 0;
+static int g_gemm_bk = 0;
+constexpr int kGemmDefaultBK = 32;
 static int gemm_sms() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem);
-        cudaFuncSetAttribute(gemm_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmem);
-        cudaFuncSetAttribute(gemm_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmem);
+        cudaFuncSetAttribute(gemm_kernel<false, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 32>::kSmem);
+        cudaFuncSetAttribute(gemm_kernel<false, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, 32>::kSmem);
+        cudaFuncSetAttribute(gemm_kernel<false, 128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 16>::kSmem);
+        cudaFuncSetAttribute(gemm_kernel<false, 256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, 16>::kSmem);
+        cudaFuncSetAttribute(gemm_kernel<true, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 32>::kSmem);
     }
     return sms;
 }
@@ -380,11 +393,12 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     if (passes != 1 && passes != 3) return RORL_ERR_ARG;
     if (reduce_g && (!strideA || !strideB)) return RORL_ERR_ARG;
     CUtensorMap mapA, mapB;
-    int rc = make_map(&mapA, A, M, K, lda, strideA ? G : 1, strideA, kGemmBM);
-    if (rc) return rc;
     const bool wide = N > kGemmBN && g_gemm_bn != 128;            // N > 128: 128 x 256 tiles (see GemmCfg)
     const int bn = wide ? 256 : kGemmBN;
-    rc = make_map(&mapB, B, N, K, ldb, strideB ? G : 1, strideB, bn);
+    const int bk = g_gemm_bk == 32 ? 32 : (g_gemm_bk == 16 ? 16 : kGemmDefaultBK);
+    int rc = make_map(&mapA, A, M, K, lda, strideA ? G : 1, strideA, kGemmBM, bk);
+    if (rc) return rc;
+    rc = make_map(&mapB, B, N, K, ldb, strideB ? G : 1, strideB, bn, bk);
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
@@ -394,16 +408,22 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     const int sms = gemm_sms();
     const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn) * (reduce_g ? 1 : G);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    if (wide)
-        gemm_kernel<false, 256><<<grid, kGemmThreads, GemmCfg<256>::kSmem, stream>>>(mapA, mapB, p);
+    if (wide && bk == 16)
+        gemm_kernel<false, 256, 16><<<grid, kGemmThreads, GemmCfg<256, 16>::kSmem, stream>>>(mapA, mapB, p);
+    else if (wide)
+        gemm_kernel<false, 256, 32><<<grid, kGemmThreads, GemmCfg<256, 32>::kSmem, stream>>>(mapA, mapB, p);
+    else if (bk == 16)
+        gemm_kernel<false, 128, 16><<<grid, kGemmThreads, GemmCfg<128, 16>::kSmem, stream>>>(mapA, mapB, p);
     else
-        gemm_kernel<false, 128><<<grid, kGemmThreads, GemmCfg<128>::kSmem, stream>>>(mapA, mapB, p);
+        gemm_kernel<false, 128, 32><<<grid, kGemmThreads, GemmCfg<128, 32>::kSmem, stream>>>(mapA, mapB, p);
     RORL_RETURN_LAUNCH();
 }
 
 void rorl_gemm_debug(int v) { g_gemm_dbg = v; }
 /* diagnostic / A-B benchmarks only: 128 forces the 128 x 128 tile for every shape, 0 restores the default choice */
 void rorl_gemm_force_bn(int bn) { g_gemm_bn = bn; }
+/* diagnostic / A-B benchmarks only: 16 or 32 forces the k-depth of a stage for the TN variant, 0 restores the default */
+void rorl_gemm_force_bk(int bk) { g_gemm_bk = bk; }
 
 // Split-K factor rorl_gemm_nt uses for a [M x N] output reduced over R rows in G batches (the caller sizes D with it).
 int rorl_gemm_nt_splits(int64_t M, int64_t N, int64_t R, int64_t G) {
@@ -444,7 +464,7 @@ int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N,
     const int sms = gemm_sms();
     const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN) * G * splits;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<true, 128><<<grid, kGemmThreads, GemmCfg<128>::kSmem, stream>>>(mapA, mapB, p);
+    gemm_kernel<true, 128, 32><<<grid, kGemmThreads, GemmCfg<128, 32>::kSmem, stream>>>(mapA, mapB, p);
     RORL_RETURN_LAUNCH();
 }
 

@@ -163,6 +163,54 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
     }
 }
 
+// y[m, n] = bias[n] + sum_k x[m, k] W[n, k], K <= 16: the forward of the narrow-input projections.  thread = 4 output
+// columns with their W rows in registers; x rows are staged in shared memory and read back as broadcasts; the only
+// real traffic is the coalesced float4 store of y (HBM-bound on the output).
+template <int KP>
+__global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int64_t M,
+                                                            int64_t N, int K, int64_t ldx, int64_t ldy, int rows_per_block) {
+    __shared__ __align__(16) float s_x[kSkinnyRows * KP];
+    const int64_t n0 = ((int64_t)blockIdx.y * 128 + threadIdx.x) * 4;
+    const bool act = n0 < N;
+    float w[4][KP], b4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) w[j][k] = (act && k < K) ? __ldg(W + (n0 + j) * K + k) : 0.f;
+        if (act && bias) b4[j] = __ldg(bias + n0 + j);
+    }
+    const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t m1 = min(M, m0 + rows_per_block);
+    for (int64_t mb = m0; mb < m1; mb += kSkinnyRows) {
+        const int rows = (int)min((int64_t)kSkinnyRows, m1 - mb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += 128) {
+            const int r = i / KP, k = i % KP;
+            s_x[i] = (r < rows && k < K) ? __ldg(x + (mb + r) * ldx + k) : 0.f;
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll 2
+            for (int r = 0; r < rows; ++r) {
+                float o[4] = {b4[0], b4[1], b4[2], b4[3]};
+#pragma unroll
+                for (int k4 = 0; k4 < KP; k4 += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(s_x + r * KP + k4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        o[j] = fmaf(xv.x, w[j][k4], o[j]);
+                        o[j] = fmaf(xv.y, w[j][k4 + 1], o[j]);
+                        o[j] = fmaf(xv.z, w[j][k4 + 2], o[j]);
+                        o[j] = fmaf(xv.w, w[j][k4 + 3], o[j]);
+                    }
+                }
+                *reinterpret_cast<float4*>(y + (mb + r) * ldy + n0) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
 static inline int red_blocks(int64_t M, int* rows_per_block, int64_t G = 1, int64_t chunks = 1) {
     int nblk = (int)((M + 63) / 64);                     // at least 64 rows per block
     int cap = (int)(kRedMaxBlocks / (G * chunks));       // about 4 CTAs per SM over the whole grid
@@ -252,6 +300,25 @@ int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, in
     if (nblk > 1) {
         dim3 g2((unsigned)((N * KP / 4 + 31) / 32), 1u);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, dW, nblk, N * KP);
+    }
+    RORL_RETURN_LAUNCH();
+}
+
+int rorl_skinny_linear(const float* x, const float* W, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                       int64_t ldx, int64_t ldy, cudaStream_t stream) {
+    if (!x || !W || !y) return RORL_ERR_ARG;
+    if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
+    if (N % 4 || ldy % 4 || !a16(y)) return RORL_ERR_ALIGN;
+    int rpb;
+    const int chunks = (int)((N / 4 + 127) / 128);
+    const int nblk = red_blocks(M, &rpb, 1, chunks > 1 ? chunks : 1);
+    const int KP = (int)((K + 3) / 4 * 4);
+    dim3 grid((unsigned)nblk, (unsigned)chunks);
+    switch (KP) {
+        case 4: skinny_linear_kernel<4><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        case 8: skinny_linear_kernel<8><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        case 12: skinny_linear_kernel<12><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        default: skinny_linear_kernel<16><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
     }
     RORL_RETURN_LAUNCH();
 }

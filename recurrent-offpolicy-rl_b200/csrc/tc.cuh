@@ -32,6 +32,16 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
+// K-major, SWIZZLE_64B (rows of 64 B = 16 fp32): 8-row groups are 512 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
+    return d;
+}
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -76,16 +86,16 @@ static inline EncodeTiledFn get_encode() {
 // 3-D map over a row-major [batch][rows][cols] fp32 tensor: box = 32 cols (128 B) x box_rows x 1, SWIZZLE_128B,
 // out-of-bounds elements read as zero.
 static inline int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, long long batch,
-                    long long batch_stride, int box_rows) {
+                    long long batch_stride, int box_rows, int box_cols = 32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return RORL_ERR_ARG;
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : rows * ld) * 4};
-    cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? RORL_OK : RORL_ERR_ARG;
 }
 

@@ -108,6 +108,13 @@ class LinearSkinny(Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        Nn, K = weight.shape
+        x2 = x.reshape(-1, K)
+        if Nn % 4 == 0 and x2.stride(-1) == 1 and x.dtype == torch.float32:
+            y = torch.empty((x2.shape[0], Nn), device=x.device, dtype=torch.float32)
+            N.call("rorl_skinny_linear", N.ptr(x2), N.ptr(_f32c(weight)), N.ptr(None if bias is None else _f32c(bias)), N.ptr(y),
+                   x2.shape[0], Nn, K, x2.stride(0), Nn, N.stream())
+            return y.view(*x.shape[:-1], Nn)
         return torch.nn.functional.linear(x, weight, bias)
 
     @staticmethod

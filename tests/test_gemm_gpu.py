@@ -107,3 +107,23 @@ def test_gemm_nt_weight_gradient_form(K, R, M, N, G):
     if G > 1:       # shared A (first efc layer: one input, E output gradients)
         D2 = K.gemm_nt(A[0], B)
         assert rel_err(D2, A[0].double().t() @ B.double()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (1000, 80, 512), (32576, 256, 384), (4097, 1024, 256), (77, 132, 36), (513, 260, 48)])
+def test_gemm_tn_bk16_ring(K, M, N, K_):
+    """The deeper ring of 16-wide k-stages (64-byte swizzle) must give the same result as the 32-wide one."""
+    import rorl_b200._native as NV
+    g = torch.Generator(device="cuda").manual_seed(M + N + 1)
+    A = torch.randn(M, K_, device="cuda", generator=g)
+    B = torch.randn(N, K_, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.double() @ B.double().t() + bias.double()
+    try:
+        NV.lib().rorl_gemm_force_bk(16)
+        D16 = K.gemm_tn(A, B, bias)
+        NV.lib().rorl_gemm_force_bk(32)
+        D32 = K.gemm_tn(A, B, bias)
+    finally:
+        NV.lib().rorl_gemm_force_bk(0)
+    assert rel_err(D16, ref) < 1e-5
+    assert rel_err(D32, ref) < 1e-5

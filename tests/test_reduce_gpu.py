@@ -65,7 +65,12 @@ def test_linear_skinny_autograd(K):
     W = torch.randn(128, 9, device="cuda", generator=gen, requires_grad=True)
     b = torch.randn(128, device="cuda", generator=gen, requires_grad=True)
     dy = torch.randn(32, 1018, 128, device="cuda", generator=gen)
-    got = torch.autograd.grad(K.linear(x, W, b), (x, W, b), dy)
+    y = K.linear(x, W, b)
+    assert rel_err(y, torch.nn.functional.linear(x.detach().double(), W.detach().double(), b.detach().double())) < 1e-6
+    sl = torch.randn(32, 1018, 80, device="cuda", generator=gen)[..., :16]          # dt_proj: column slice, no bias
+    W2 = torch.randn(512, 16, device="cuda", generator=gen)
+    assert rel_err(K.linear(sl, W2), sl.double() @ W2.double().t()) < 1e-6
+    got = torch.autograd.grad(y, (x, W, b), dy)
     xd, Wd, bd = (t.detach().double().requires_grad_() for t in (x, W, b))
     ref = torch.autograd.grad(torch.nn.functional.linear(xd, Wd, bd), (xd, Wd, bd), dy.double())
     for a, r, n in zip(got, ref, "x W b".split()):

@@ -191,6 +191,11 @@ def bench_gemm():
             fl = 2.0 * M * n * k * g
             rec(f"gemm_tn {tag} passes={passes}", t, flops=fl * passes, nbytes=4 * (a.numel() + b.numel() + M * n * g),
                 note=f"useful fp32 TFLOP/s {fl / t / 1e12:.1f}")
+        for bk in (16,):                 # A/B: 16-wide k-stages (twice as deep a ring)
+            N.lib().rorl_gemm_force_bk(bk)
+            t = timeit(lambda: K.gemm_tn(a, b, bias, 1, passes=3))
+            N.lib().rorl_gemm_force_bk(0)
+            rec(f"gemm_tn {tag} passes=3 BK={bk} (A/B)", t, flops=fl * 3, note=f"useful fp32 TFLOP/s {fl / t / 1e12:.1f}")
         if n > 128:                      # A/B: the 128 x 128 tile on the same shape
             N.lib().rorl_gemm_force_bn(128)
             t = timeit(lambda: K.gemm_tn(a, b, bias, 1, passes=3))
