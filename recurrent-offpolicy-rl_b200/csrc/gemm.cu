@@ -354,7 +354,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 static int g_gemm_dbg = 0;
 static int g_gemm_bn = 0;
 static int g_gemm_bk = 0;
-constexpr int kGemmDefaultBK = 32;
+constexpr int kGemmDefaultBK = 16;      // measured 3-11 % faster than 32 on every update shape (profiles/r01g_kernels.log)
 static int gemm_sms() {
     static int sms = 0;
     if (!sms) {
