@@ -10,7 +10,9 @@ synthetic HalfCheetah-V-shaped replay (obs 9, act 6) of 32 full 1000-step trajec
 Metric: trajectory-steps/s = valid transitions updated on per second, whole job.
 
   value  : K updates with the replay resident in HBM (host plan + device gather inside the step), CUDA events,
-           max over ranks.
+           max over ranks.  From the third update on the step is replayed from captured CUDA-graph segments (the
+           public API's default; RORL_CUDA_GRAPH=0 keeps the eager launch sequence); `gpu_launches` counts the
+           kernels of this library launched or replayed inside the timed region.
   e2e    : same update through the public API fed from HOST memory, the way the reference feeds it: per step a
            pinned host batch is copied H2D and the logged scalars are read back D2H, inside the timed region.
   roofline: the selective-scan kernel (forward or backward, whichever takes the larger share), timed alone
@@ -93,7 +95,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in out])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def summary(self):
         self._stop_evt.set()
@@ -359,6 +361,6 @@ if __name__ == "__main__":
         a.warmup = a.warmup if a.warmup is not None else 1
         run_reference(a)
     else:
-        a.steps = a.steps if a.steps is not None else 20
+        a.steps = a.steps if a.steps is not None else 50        # ~1 s timed region: several nvidia-smi clock samples
         a.warmup = max(3, a.warmup if a.warmup is not None else 3)
         run_ours(a)

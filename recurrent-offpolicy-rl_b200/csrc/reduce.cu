@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
                                                                    float* __restrict__ partial, int64_t M, int64_t N, int K,
                                                                    int64_t ldg, int64_t ldx, int rows_per_block) {
     __shared__ __align__(16) float s_x[kSkinnyRows * KP];
-    const int64_t n = (int64_t)blockIdx.y * kRedThreads + threadIdx.x;
+    const int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t m1 = min(M, m0 + rows_per_block);
     float acc[KP];
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
     for (int64_t mb = m0; mb < m1; mb += kSkinnyRows) {
         const int rows = (int)min((int64_t)kSkinnyRows, m1 - mb);
         __syncthreads();
-        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += kRedThreads) {
+        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += blockDim.x) {
             const int r = i / KP, k = i % KP;
             s_x[i] = (r < rows && k < K) ? __ldg(x + (mb + r) * ldx + k) : 0.f;
         }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restr
                                                             const float* __restrict__ bias, float* __restrict__ y, int64_t M,
                                                             int64_t N, int K, int64_t ldx, int64_t ldy, int rows_per_block) {
     __shared__ __align__(16) float s_x[kSkinnyRows * KP];
-    const int64_t n0 = ((int64_t)blockIdx.y * 128 + threadIdx.x) * 4;
+    const int64_t n0 = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 4;
     const bool act = n0 < N;
     float w[4][KP], b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restr
     for (int64_t mb = m0; mb < m1; mb += kSkinnyRows) {
         const int rows = (int)min((int64_t)kSkinnyRows, m1 - mb);
         __syncthreads();
-        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += 128) {
+        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += blockDim.x) {
             const int r = i / KP, k = i % KP;
             s_x[i] = (r < rows && k < K) ? __ldg(x + (mb + r) * ldx + k) : 0.f;
         }
@@ -286,16 +286,18 @@ int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, in
     if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
     if (!a16(work) || !a16(dW)) return RORL_ERR_ALIGN;
     int rpb;
-    const int chunks = (int)((N + kRedThreads - 1) / kRedThreads);
+    int threads = (int)((N + 31) / 32 * 32);                // one thread per output column
+    if (threads > kRedThreads) threads = kRedThreads;
+    const int chunks = (int)((N + threads - 1) / threads);
     const int nblk = red_blocks(M, &rpb, 1, chunks);
     const int KP = (int)((K + 3) / 4 * 4);
     dim3 grid((unsigned)nblk, (unsigned)chunks);
     float* dst = nblk == 1 ? dW : work;
     switch (KP) {
-        case 4: skinny_wgrad_kernel<4><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
-        case 8: skinny_wgrad_kernel<8><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
-        case 12: skinny_wgrad_kernel<12><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
-        default: skinny_wgrad_kernel<16><<<grid, kRedThreads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        case 4: skinny_wgrad_kernel<4><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        case 8: skinny_wgrad_kernel<8><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        case 12: skinny_wgrad_kernel<12><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        default: skinny_wgrad_kernel<16><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
     }
     if (nblk > 1) {
         dim3 g2((unsigned)((N * KP / 4 + 31) / 32), 1u);
@@ -309,16 +311,25 @@ int rorl_skinny_linear(const float* x, const float* W, const float* bias, float*
     if (!x || !W || !y) return RORL_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
     if (N % 4 || ldy % 4 || !a16(y)) return RORL_ERR_ALIGN;
+    // one thread per 4 output columns: narrow outputs (N = 128) get 32-thread CTAs instead of 128-thread CTAs that
+    // are three quarters idle, and proportionally more of them (more row blocks)
+    int threads = (int)((N / 4 + 31) / 32 * 32);
+    if (threads > 128) threads = 128;
+    const int chunks = (int)((N / 4 + threads - 1) / threads);
     int rpb;
-    const int chunks = (int)((N / 4 + 127) / 128);
-    const int nblk = red_blocks(M, &rpb, 1, chunks > 1 ? chunks : 1);
+    int nblk = (int)((M + kSkinnyRows - 1) / kSkinnyRows);
+    const int cap = 148 * 8 * (128 / threads) / (chunks > 0 ? chunks : 1);
+    if (nblk > cap) nblk = cap > 0 ? cap : 1;
+    rpb = (int)((M + nblk - 1) / nblk);
+    rpb = (rpb + kSkinnyRows - 1) / kSkinnyRows * kSkinnyRows;
+    nblk = (int)((M + rpb - 1) / rpb);
     const int KP = (int)((K + 3) / 4 * 4);
     dim3 grid((unsigned)nblk, (unsigned)chunks);
     switch (KP) {
-        case 4: skinny_linear_kernel<4><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
-        case 8: skinny_linear_kernel<8><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
-        case 12: skinny_linear_kernel<12><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
-        default: skinny_linear_kernel<16><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        case 4: skinny_linear_kernel<4><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        case 8: skinny_linear_kernel<8><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        case 12: skinny_linear_kernel<12><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        default: skinny_linear_kernel<16><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
     }
     RORL_RETURN_LAUNCH();
 }
