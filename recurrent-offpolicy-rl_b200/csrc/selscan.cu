@@ -353,9 +353,12 @@ struct SelBwdParams {
 // (shuffle reduce-scatter across the warp's channels, shared-memory sum across warps, one partial tile per CTA in
 // global memory, summed by the caller: deterministic, no atomics).
 // The forward checkpoints h every kCkptEvery = 8 steps; a chunk of 8 steps is walked forward (h_t kept in
-// registers: 32 per thread) and then backward.  The register file, not the pipes, limits residency here: 12
-// registers of state per (d, n) element, so a CTA holds 64 channels with 16 MAIN warps (thread = 1 channel x 4
-// states: 4 warps per scheduler) + 4 HELPER warps, one CTA per SM.  The helpers run the same cp.async / transform
+// registers: 32 per thread and channel) and then backward.  The register file, not the pipes, limits residency
+// here: 12 registers of state per (d, n) element, so a CTA holds 64 channels with 8 MAIN warps (thread = 2 channels
+// x 4 states, 168 registers) + 4 HELPER warps, one CTA per SM.  (The first version had 16 main warps of one channel
+// per thread: ncu showed the LSU shared-memory pipe at 70 %, most of it B_t / C_t LDS.128 broadcasts; with two
+// channels per thread sharing them it is 50 % and the kernel went 767 -> 719 us.  What remains is instruction
+// issue: ~26 thread instructions per (t, d, n) element at 0.57 IPC per scheduler with 3 warps per scheduler.)  The helpers run the same cp.async / transform
 // / write-back pipeline as in the forward: softplus and its derivative, delta*u, g = dy * silu(z), the reset as
 // delta = +inf, and afterwards d(delta) = (sum_n t1 A ln2... see below) * softplus', du, dz, the dD / dbias
 // accumulators and the cross-warp dB / dC sums.
@@ -364,9 +367,13 @@ struct SelBwdCfg {
     static constexpr int S = 4;                           // states per main thread
     static constexpr int LPD = N / S;                     // lanes per channel
     static constexpr int DPW = 32 / LPD;                  // channels per warp
-    static constexpr int NMAINW = 16;                     // main warps
+#ifndef RORL_SELBWD_CH
+#define RORL_SELBWD_CH 2
+#endif
+    static constexpr int CH = RORL_SELBWD_CH;             // channels per main thread (they share the B_t / C_t loads)
+    static constexpr int NMAINW = 16 / CH;                // main warps
     static constexpr int NMAIN = NMAINW * 32;
-    static constexpr int DT = NMAINW * DPW;               // channels per CTA
+    static constexpr int DT = NMAINW * DPW * CH;          // channels per CTA
     static constexpr int QPR = DT / 4;                    // float4 quads per tile row
     static constexpr int TC = kCkptEvery;                 // steps per chunk
     static constexpr int NST = 3;                         // stages in flight
@@ -611,90 +618,114 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
         }
     } else {
         // ------------------------------------------------------------------------------------ main warps
-        constexpr int H2 = S / 2;
+        // thread = CH channels x 4 states.  The two channels of a thread sit in different quads ((warp * CH + c) * DPW
+        // + dl), so that a warp's partial-sum stores stay bank-conflict free; what the channels share is B_t / C_t:
+        // one LDS.128 (4 shared-memory wavefronts however much of it is a broadcast) now feeds 8 elements instead
+        // of 4 -- ncu had the LSU shared-memory pipe as the busiest unit of this kernel (70 %).
+        constexpr int H2 = S / 2, CH = Cfg::CH;
         const int lane = tid & 31, warp = tid >> 5;
         const int dl = lane / LPD, ng = lane % LPD;
-        const int dloc = warp * DPW + dl;
-        const int d = d0 + dloc;
-        const bool dvalid = d < p.D;
-        float2 A2[H2], dA[H2], lam[H2];
+        int dloc[CH], poff[CH];
+        bool dvalid[CH];
+        float2 A2[CH][H2], dA[CH][H2], lam[CH][H2];
 #pragma unroll
-        for (int j = 0; j < H2; ++j) {
-            // channels past D: any negative A keeps (+inf) * A = -inf at reset steps (0 would give NaN, and this
-            // thread's zero contributions still enter the cross-channel dB / dC sums)
-            A2[j] = dvalid ? f2(p.A[(size_t)d * N + ng * S + 2 * j] * kLog2e, p.A[(size_t)d * N + ng * S + 2 * j + 1] * kLog2e)
-                           : f2(-1.f, -1.f);
-            dA[j] = f2(0.f, 0.f);
-            lam[j] = f2(0.f, 0.f);                          // a_{t+1} * lambda_{t+1}
+        for (int c = 0; c < CH; ++c) {
+            dloc[c] = (warp * CH + c) * DPW + dl;
+            const int d = d0 + dloc[c];
+            dvalid[c] = d < p.D;
+            poff[c] = (dloc[c] >> 2) * QS + (dloc[c] & 3) * LPD + ng;      // this lane's slot in a partial-sum row
+#pragma unroll
+            for (int j = 0; j < H2; ++j) {
+                // channels past D: any negative A keeps (+inf) * A = -inf at reset steps (0 would give NaN, and this
+                // thread's zero contributions still enter the cross-channel dB / dC sums)
+                A2[c][j] = dvalid[c] ? f2(p.A[(size_t)d * N + ng * S + 2 * j] * kLog2e, p.A[(size_t)d * N + ng * S + 2 * j + 1] * kLog2e)
+                                     : f2(-1.f, -1.f);
+                dA[c][j] = f2(0.f, 0.f);
+                lam[c][j] = f2(0.f, 0.f);                   // a_{t+1} * lambda_{t+1}
+            }
         }
-        const int poff = (dloc >> 2) * QS + (dloc & 3) * LPD + ng;      // this lane's slot in a partial-sum row
-        auto ld_ckpt = [&](int k) {                         // state entering chunk k
+        auto ld_ckpt = [&](int k, int c) {                  // state of channel c entering chunk k
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k > 0 && dvalid) v = __ldg(reinterpret_cast<const float4*>(p.ckpt + (((size_t)b * p.nckpt + (k - 1)) * p.D + d) * N + ng * S));
-            if (k == 0 && dvalid && p.h0 != nullptr) v = __ldg(reinterpret_cast<const float4*>(p.h0 + ((size_t)b * p.D + d) * N + ng * S));
+            const int d = d0 + dloc[c];
+            if (k > 0 && dvalid[c]) v = __ldg(reinterpret_cast<const float4*>(p.ckpt + (((size_t)b * p.nckpt + (k - 1)) * p.D + d) * N + ng * S));
+            if (k == 0 && dvalid[c] && p.h0 != nullptr) v = __ldg(reinterpret_cast<const float4*>(p.h0 + ((size_t)b * p.D + d) * N + ng * S));
             return v;
         };
-        float4 hin = ld_ckpt(nch - 1);
-        for (int c = 0; c < nch; ++c) {
-            const int k = nch - 1 - c;
-            const float* st = smem + (c % NST) * STAGE;
+        float4 hin[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) hin[c] = ld_ckpt(nch - 1, c);
+        for (int cc = 0; cc < nch; ++cc) {
+            const int k = nch - 1 - cc;
+            const float* st = smem + (cc % NST) * STAGE;
             const float* s_dtA = st + 1 * TC * DT;
             const float* s_du = st + 2 * TC * DT;
             const float* s_g = st + 3 * TC * DT;
             const float* s_B = st + Cfg::NARR * TC * DT;
             const float* s_C = s_B + TC * N;
-            mbar_wait(bar_full(c % NST), (c / NST) & 1);
+            mbar_wait(bar_full(cc % NST), (cc / NST) & 1);
             // ---- phase F: recompute h_t inside the chunk
-            float2 h[H2] = {f2(hin.x, hin.y), f2(hin.z, hin.w)};
-            hin = ld_ckpt(k - 1);                           // prefetch the next chunk's entry state
-            float2 hb[TC][H2];
+            float2 h[CH][H2];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                h[c][0] = f2(hin[c].x, hin[c].y);
+                h[c][1] = f2(hin[c].z, hin[c].w);
+                hin[c] = ld_ckpt(k - 1, c);                 // prefetch the next chunk's entry state
+            }
+            float2 hb[CH][TC][H2];
 #pragma unroll
             for (int i = 0; i < TC; ++i) {
-                const float dtA = s_dtA[i * DT + dloc], du = s_du[i * DT + dloc];
                 const float4 bq = *reinterpret_cast<const float4*>(s_B + i * N + ng * S);
                 const float2 Bv[H2] = {f2(bq.x, bq.y), f2(bq.z, bq.w)};
 #pragma unroll
-                for (int j = 0; j < H2; ++j) {
-                    const float2 e = __fmul2_rn(f2(dtA, dtA), A2[j]);
-                    const float2 a = f2(ex2f(e.x), ex2f(e.y));
-                    h[j] = __ffma2_rn(a, h[j], __fmul2_rn(f2(du, du), Bv[j]));
-                    hb[i][j] = h[j];
+                for (int c = 0; c < CH; ++c) {
+                    const float dtA = s_dtA[i * DT + dloc[c]], du = s_du[i * DT + dloc[c]];
+#pragma unroll
+                    for (int j = 0; j < H2; ++j) {
+                        const float2 e = __fmul2_rn(f2(dtA, dtA), A2[c][j]);
+                        const float2 a = f2(ex2f(e.x), ex2f(e.y));
+                        h[c][j] = __ffma2_rn(a, h[c][j], __fmul2_rn(f2(du, du), Bv[j]));
+                        hb[c][i][j] = h[c][j];
+                    }
                 }
             }
-            // the partial-sum planes and s_red are single-buffered: the helpers must have finished chunk c-1
-            if (c >= 1) mbar_wait(bar_freep, (c - 1) & 1);
+            // the partial-sum planes and s_red are single-buffered: the helpers must have finished chunk cc-1
+            if (cc >= 1) mbar_wait(bar_freep, (cc - 1) & 1);
             // ---- phase R: adjoint recurrence, latest step first
 #pragma unroll
             for (int i = TC - 1; i >= 0; --i) {
-                const float dtA = s_dtA[i * DT + dloc], du = s_du[i * DT + dloc], g = s_g[i * DT + dloc];
-                const float dt = (dtA == INFINITY) ? 0.f : dtA;     // at a reset a_t h_{t-1} = 0, so dt is immaterial there
                 const float4 bq = *reinterpret_cast<const float4*>(s_B + i * N + ng * S);
                 const float4 cq = *reinterpret_cast<const float4*>(s_C + i * N + ng * S);
                 const float2 Bv[H2] = {f2(bq.x, bq.y), f2(bq.z, bq.w)};
                 const float2 Cv[H2] = {f2(cq.x, cq.y), f2(cq.z, cq.w)};
-                const float2 g2 = f2(g, g), du2 = f2(du, du), dt2 = f2(dt, dt);
-                float2 sB2 = f2(0.f, 0.f), sA2 = f2(0.f, 0.f), yp2 = f2(0.f, 0.f);
-                float dBv[4], dCv[4];
+                float2 dB2[H2], dC2[H2];                    // the thread's channels are summed here (packed adds),
+#pragma unroll                                              // the warp's by the reduce-scatter below
+                for (int c = 0; c < CH; ++c) {
+                    const float dtA = s_dtA[i * DT + dloc[c]], du = s_du[i * DT + dloc[c]], g = s_g[i * DT + dloc[c]];
+                    const float dt = (dtA == INFINITY) ? 0.f : dtA;     // at a reset a_t h_{t-1} = 0, so dt is immaterial there
+                    const float2 g2 = f2(g, g), du2 = f2(du, du), dt2 = f2(dt, dt);
+                    float2 sB2 = f2(0.f, 0.f), sA2 = f2(0.f, 0.f), yp2 = f2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < H2; ++j) {
-                    const float2 l = __ffma2_rn(g2, Cv[j], lam[j]);
-                    const float2 dc = __fmul2_rn(g2, hb[i][j]);
-                    const float2 db = __fmul2_rn(l, du2);
-                    dCv[2 * j] = dc.x; dCv[2 * j + 1] = dc.y;
-                    dBv[2 * j] = db.x; dBv[2 * j + 1] = db.y;
-                    sB2 = __ffma2_rn(l, Bv[j], sB2);
-                    const float2 ahp = __ffma2_rn(f2(-du, -du), Bv[j], hb[i][j]);     // a_t * h_{t-1}
-                    const float2 t1 = __fmul2_rn(l, ahp);
-                    dA[j] = __ffma2_rn(t1, dt2, dA[j]);
-                    sA2 = __ffma2_rn(t1, A2[j], sA2);
-                    if (HAS_Z) yp2 = __ffma2_rn(hb[i][j], Cv[j], yp2);
-                    const float2 e = __fmul2_rn(f2(dtA, dtA), A2[j]);
-                    lam[j] = __fmul2_rn(f2(ex2f(e.x), ex2f(e.y)), l);
+                    for (int j = 0; j < H2; ++j) {
+                        const float2 l = __ffma2_rn(g2, Cv[j], lam[c][j]);
+                        const float2 dc = __fmul2_rn(g2, hb[c][i][j]);
+                        const float2 db = __fmul2_rn(l, du2);
+                        dC2[j] = c == 0 ? dc : __fadd2_rn(dC2[j], dc);
+                        dB2[j] = c == 0 ? db : __fadd2_rn(dB2[j], db);
+                        sB2 = __ffma2_rn(l, Bv[j], sB2);
+                        const float2 ahp = __ffma2_rn(f2(-du, -du), Bv[j], hb[c][i][j]);     // a_t * h_{t-1}
+                        const float2 t1 = __fmul2_rn(l, ahp);
+                        dA[c][j] = __ffma2_rn(t1, dt2, dA[c][j]);
+                        sA2 = __ffma2_rn(t1, A2[c][j], sA2);
+                        if (HAS_Z) yp2 = __ffma2_rn(hb[c][i][j], Cv[j], yp2);
+                        const float2 e = __fmul2_rn(f2(dtA, dtA), A2[c][j]);
+                        lam[c][j] = __fmul2_rn(f2(ex2f(e.x), ex2f(e.y)), l);
+                    }
+                    float* pl = s_pl + i * PROW + poff[c];
+                    pl[0] = sB2.x + sB2.y;
+                    pl[PLANE] = sA2.x + sA2.y;
+                    if (HAS_Z) pl[2 * PLANE] = yp2.x + yp2.y;
                 }
-                float* pl = s_pl + i * PROW + poff;
-                pl[0] = sB2.x + sB2.y;
-                pl[PLANE] = sA2.x + sA2.y;
-                if (HAS_Z) pl[2 * PLANE] = yp2.x + yp2.y;
+                float dBv[4] = {dB2[0].x, dB2[0].y, dB2[1].x, dB2[1].y}, dCv[4] = {dC2[0].x, dC2[0].y, dC2[1].x, dC2[1].y};
                 int fB, fC;
                 bool wB, wC;
                 const int nB = channel_reduce_scatter4<LPD>(dBv, dl, fB, wB);
@@ -713,9 +744,12 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_done);
         }
-        if (dvalid) {
-            float* a = p.dA_part + ((size_t)b * p.D + d) * N + ng * S;
-            *reinterpret_cast<float4*>(a) = make_float4(dA[0].x, dA[0].y, dA[1].x, dA[1].y);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (dvalid[c]) {
+                float* a = p.dA_part + ((size_t)b * p.D + d0 + dloc[c]) * N + ng * S;
+                *reinterpret_cast<float4*>(a) = make_float4(dA[c][0].x, dA[c][0].y, dA[c][1].x, dA[c][1].y);
+            }
         }
     }
 }
