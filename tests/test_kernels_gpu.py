@@ -282,3 +282,32 @@ def test_gru_vs_torch_cpu(K, shape, with_h0):
         assert_close(h0g.grad, h0r.grad, TOL, "dh0")
     for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
         assert_close(p.grad, q.grad, TOL, n)
+
+
+def test_selscan_full_size_chunk_composition(K):
+    """BASELINE.json's full shape (32 x 1018 x 512, N = 32), checked through a size-independent property: the scan of
+    the whole sequence equals the scan of its two halves with the state handed over (h0 in, last_state out), and a
+    reset makes everything after it independent of what came before."""
+    B, L, D, N = 32, 1018, 512, 32
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    u, delta, z = rn(B, L, D), 0.5 * rn(B, L, D) - 1, rn(B, L, D)
+    Bm, Cm = rn(B, L, N), rn(B, L, N)
+    A = -torch.exp(0.3 * rn(D, N))
+    Dk, bias = rn(D), 0.3 * rn(D)
+    start = torch.zeros(B, L, device="cuda")
+    start[:, 0] = 1
+    start[3, 500] = 1
+    y, last = K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True, True)
+    k = 509
+    sl = lambda t, a, b: t[:, a:b].contiguous()
+    y1, l1 = K.selective_scan_tm(sl(u, 0, k), sl(delta, 0, k), A, sl(Bm, 0, k), sl(Cm, 0, k), Dk, sl(z, 0, k), bias, sl(start, 0, k), True, True)
+    y2, l2 = K.selective_scan_tm(sl(u, k, L), sl(delta, k, L), A, sl(Bm, k, L), sl(Cm, k, L), Dk, sl(z, k, L), bias, sl(start, k, L), True, True, l1)
+    assert_close(torch.cat((y1, y2), dim=1), y, 1e-6, "y")
+    assert_close(l2, last, 1e-6, "last_state")
+    # reset at t = 500 in row 3: the tail of that row does not depend on the inputs before it
+    u2 = u.clone()
+    u2[3, :500] = rn(500, D)
+    y_alt = K.selective_scan_tm(u2, delta, A, Bm, Cm, Dk, z, bias, start, True)
+    assert torch.equal(y_alt[3, 500:], y[3, 500:])
+    assert torch.equal(y_alt[:3], y[:3]) and torch.equal(y_alt[4:], y[4:])

@@ -61,3 +61,35 @@ def test_smamba_rollout_step_golden(tag):
     assert_close(torch.cat(ys, dim=1), g["y"], TOL, "y")
     assert tuple(h[0].shape) == g["h_out"].shape
     assert_close(h[0], g["h_out"], TOL, "h_out")
+
+
+@pytest.mark.parametrize("lid,width", [("gilr", 64), ("lru", 64), ("gru", 64), ("mamba_s16_c4", 64), ("mamba_s32_c16_noff", 32)])
+def test_carried_state_composition(lid, width):
+    """Size-independent property of every layer that carries its state: running a sequence in two pieces, handing the
+    hidden state over, gives what the single pass gives (outputs and final state).  Exercises the carried-state
+    paths the update itself never takes (h0 of the scan kernels, the s6 conv window, the gilr correction term)."""
+    from rorl_b200.models.rnn_base import RNNBase
+    torch.manual_seed(5)
+    net = RNNBase(24, 16, [width, width], ['elu', 'elu', 'linear'], ['fc', lid, 'fc']).cuda()
+    B, L, k = 6, 203, 77
+    x = torch.randn(B, L, 24, device="cuda")
+    start = torch.zeros(B, L, 1, device="cuda")
+    start[:, 0] = 1
+    start[1, 120] = 1
+    start[2, 40] = 1
+
+    def run(xs, st, hid):
+        if lid != "gru":
+            hid.set_rnn_start(st)
+        with torch.no_grad():
+            y, h, _ = net.meta_forward(xs, hid)
+        return y, h
+
+    y_full, h_full = run(x, start, net.make_init_state(B, x.device))
+    y1, h1 = run(x[:, :k], start[:, :k], net.make_init_state(B, x.device))
+    carry = net.make_init_state(B, x.device)
+    hv = h1[0]
+    carry[0] = hv if hv.shape[0] == 1 else hv.transpose(0, 1)          # the s6 layer returns its hidden batch-first
+    y2, h2 = run(x[:, k:], start[:, k:], carry)
+    assert_close(torch.cat((y1, y2), dim=1), y_full, 1e-4, "y")
+    assert_close(h2[0].reshape(-1), h_full[0].reshape(-1), 1e-4, "final hidden")
