@@ -24,7 +24,11 @@ class PositionWiseFeedForward(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=eps)
 
     def forward(self, x):
-        return self.layer_norm(self.dropout(self.w_2(self.dropout(self.activation(self.w_1(x))))) + x)
+        y = self.dropout(self.w_2(self.dropout(self.activation(self.w_1(x)))))
+        if not x.is_cuda:
+            return self.layer_norm(y + x)
+        # residual add + LayerNorm in one kernel (ATen's LayerNorm backward ran at 240 us per call on [32, 1002, 256])
+        return K.layer_norm_fn(y, self.layer_norm.weight, self.layer_norm.bias, residual=x, eps=self.layer_norm.eps, prenorm=False)
 
 
 class GILRLayer(nn.Module):

@@ -54,7 +54,10 @@ class PositionWiseFeedForward(nn.Module):
 
     def forward(self, x):
         x_ = self.dropout(self.activation(self.w_1(x)))
-        return self.layer_norm(self.dropout(self.w_2(x_)) + x)
+        y = self.dropout(self.w_2(x_))
+        if not x.is_cuda:
+            return self.layer_norm(y + x)
+        return K.layer_norm_fn(y, self.layer_norm.weight, self.layer_norm.bias, residual=x, eps=self.layer_norm.eps, prenorm=False)
 
 
 class MambaBlock(nn.Module):
