@@ -59,8 +59,9 @@ class LayerNorm(nn.LayerNorm):
 class MHA(nn.Module):
     """Self-attention block with flash_attn.modules.mha.MHA's parameter names (fused Wqkv, out_proj)."""
 
-    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0):
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0, layer_idx=None):
         super().__init__()
+        self.layer_idx = layer_idx
         assert embed_dim % num_heads == 0
         self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
         if self.head_dim != 64:
@@ -76,6 +77,32 @@ class MHA(nn.Module):
         qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=1)
         o = K.attn_varlen_alibi(qkv.view(T, 3, self.num_heads, self.head_dim), tiles[0], tiles[1], self.alibi_slopes,
                                 1.0 / math.sqrt(self.head_dim))
+        return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=1)
+
+    def decode_step(self, x, cache):
+        """One rollout step with the kv-cache: x [B, 1, C]; `cache` is the layer stack's InferenceParams
+        (`key_value_memory_dict[layer_idx]` = [max_batch, max_seqlen, 2, H, 64] bf16, `seqlen_offset` = tokens already
+        cached).  Same arithmetic as the training kernel on one query row: bf16 q / k / v, fp32 scores with the ALiBi
+        bias -slope * (offset - j), fp32 softmax, bf16 probabilities.  (ref: flash_attn MHA with inference_params as
+        called from TransformerFlashAttention.py:76-83 and rnn_base.py:437-452.)  Tiny tensors: plain CUDA ops."""
+        B = x.shape[0]
+        H, hd = self.num_heads, self.head_dim
+        qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=1).view(B, 3, H, hd)
+        kv = cache.key_value_memory_dict.get(self.layer_idx)
+        if kv is None:
+            kv = torch.zeros((cache.max_batch_size, cache.max_seqlen, 2, H, hd), device=x.device, dtype=torch.bfloat16)
+            cache.key_value_memory_dict[self.layer_idx] = kv
+        off = int(cache.seqlen_offset)
+        if off >= kv.shape[1]:
+            raise RuntimeError(f'kv-cache of {kv.shape[1]} positions is full')
+        kv[:B, off] = qkv[:, 1:].to(torch.bfloat16)
+        q = qkv[:, 0].to(torch.bfloat16).float()                                   # [B, H, hd]
+        keys, vals = kv[:B, :off + 1, 0].float(), kv[:B, :off + 1, 1].float()      # [B, T, H, hd]
+        scores = torch.einsum('bhd,bthd->bht', q, keys) / math.sqrt(hd)
+        dist = (off - torch.arange(off + 1, device=x.device, dtype=torch.float32))
+        scores = scores - self.alibi_slopes.view(1, H, 1) * dist.view(1, 1, -1)
+        p = torch.softmax(scores, dim=-1).to(torch.bfloat16).float()
+        o = torch.einsum('bht,bthd->bhd', p, vals).reshape(B, 1, H * hd)
         return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=1)
 
 
@@ -94,7 +121,7 @@ class PositionWiseFeedForward(nn.Module):
 class DecoderLayer(nn.Module):
     def __init__(self, d_model, nhead, d_ff, dropout=0.1, layer_idx=None, ln=True):
         super().__init__()
-        self.mha = MHA(d_model, nhead, dropout)
+        self.mha = MHA(d_model, nhead, dropout, layer_idx=layer_idx)
         self.ffn = PositionWiseFeedForward(d_model, d_ff, dropout)
         self.dropout = nn.Dropout(dropout)
         self.mha_norm = LayerNorm(d_model) if ln else RMSNorm(d_model)
@@ -103,6 +130,10 @@ class DecoderLayer(nn.Module):
     def forward(self, x, tiles):
         x = self.dropout(self.mha(self.mha_norm(x), tiles)) + x                  # ref :76-83
         return self.dropout(self.ffn(self.ffn_norm(x))) + x                      # ref :84 (pre_norm)
+
+    def decode_step(self, x, cache):
+        x = self.dropout(self.mha.decode_step(self.mha_norm(x), cache)) + x
+        return self.dropout(self.ffn(self.ffn_norm(x))) + x
 
 
 def sequences_of(seqlens_host: np.ndarray, L: int):
@@ -138,7 +169,12 @@ class TransformerDecoder(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('the cgpt encoder runs on sm_100a kernels only; there is no CPU path')
         if inference_params is not None and seqlens is None and x.shape[-2] == 1:
-            raise NotImplementedError('single-step kv-cache decoding (rollout) is outside the update hot path')
+            # rollout: one token per row against the kv-cache; the caller (RNNBase.meta_forward, ref rnn_base.py:437-452)
+            # advances `seqlen_offset` after the whole stack has run
+            h = x
+            for layer in self.decoder_layers:
+                h = layer.decode_step(h, inference_params)
+            return self.output_fc(self.output_ln(h))
         B, L, C = x.shape
         if seqlens is None:
             host = np.zeros((B, 1), dtype=np.int64)

@@ -114,3 +114,25 @@ def test_cgpt_encoder_vs_oracle(case):
     worst = 0.0
     for n, p in net.named_parameters():
         worst = max(worst, assert_close(p.grad, sd[n].grad, 2e-2, n))
+
+
+def test_cgpt_kv_cache_decode_matches_full_forward():
+    """Rollout path: decoding one token at a time against the kv-cache reproduces the causal full-sequence forward
+    (same weights, eval mode) at every position -- the property flash-attn's own kv-cache path has; bf16 tolerance."""
+    from rorl_b200.models.rnn_base import RNNBase
+    torch.manual_seed(2)
+    net = RNNBase(10, 6, [128, 128], ['elu', 'elu', 'linear'], ['fc', 'cgpt_h2_l2_p0.0_ml64', 'fc']).cuda().eval()
+    B, T = 3, 37
+    x = torch.randn(B, T, 10, device="cuda")
+    with torch.no_grad():
+        y_full, _, _ = net.meta_forward(x, net.make_init_state(B, x.device))
+        hid = net.make_init_state(B, x.device)
+        ys = []
+        for t in range(T):
+            y, hid, _ = net.meta_forward(x[:, t:t + 1], hid)
+            ys.append(y)
+    assert hid[0].seqlen_offset == T
+    y_dec = torch.cat(ys, dim=1)
+    err = float((y_dec - y_full).abs().max() / y_full.abs().max())
+    print(f"kv-cache decode vs full forward: max-norm relative error {err:.2e}")
+    assert err < 1e-2
