@@ -67,6 +67,19 @@ int rorl_lru_scan_bwd(const float* g_re, const float* g_im, const float* f_re, c
                       const float* grad_detach, float* dv_re, float* dv_im, float* df_re, float* df_im,
                       int64_t B, int64_t L, int64_t C, cudaStream_t stream);
 
+/* LRU scan with the layer's own parameterisation fused in (ref: offpolicy_rnn/models/lru/lru.py:95-117 materialises
+ * gamma * u and lambda * (1 - start) as four [B, L, C] tensors before calling complex_scan):
+ *   h_t = lambda (1 - start_t) h_{t-1} + gamma u_t.   u_re, u_im: [B, L, C]; lam_re, lam_im, gamma: [C];
+ * start: [B, L] or NULL.  16 B per element forward, 24 B backward.  Backward: du [B, L, C] and the
+ * per-row partial sums dlam_re / dlam_im / dgamma [B, C] the caller reduces over axis 0.  No grad_detach here. */
+int rorl_lru_fused_fwd(const float* u_re, const float* u_im, const float* lam_re, const float* lam_im, const float* gamma,
+                       const float* start, const float* h0_re, const float* h0_im, float* h_re, float* h_im, int64_t B,
+                       int64_t L, int64_t C, cudaStream_t stream);
+int rorl_lru_fused_bwd(const float* g_re, const float* g_im, const float* lam_re, const float* lam_im, const float* gamma,
+                       const float* start, const float* h_re, const float* h_im, const float* h0_re, const float* h0_im,
+                       float* du_re, float* du_im, float* dlam_re_part, float* dlam_im_part, float* dgamma_part,
+                       int64_t B, int64_t L, int64_t C, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Mamba selective scan with reset flag.  Replaces selective_scan_cuda.fwd / .bwd as called by
  * SelectiveScanFn (ref: offpolicy_rnn/models/smamba/mamba_ssm/ops/selective_scan_interface_new.py:

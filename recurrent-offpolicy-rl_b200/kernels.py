@@ -223,6 +223,42 @@ def complex_scan(v_re, v_im, f_re, f_im, h0_re=None, h0_im=None, grad_detach=Non
     return LRUScan.apply(v_re, v_im, f_re, f_im, h0_re, h0_im, grad_detach)
 
 
+class LRUFusedScan(Function):
+    """h_t = lambda (1 - start_t) h_{t-1} + gamma u_t with lambda (complex) and gamma as [C] vectors: the LRU layer's
+    own parameterisation inside the scan kernel, so the four materialised [B, L, C] tensors of the reference
+    (ref: lru/lru.py:95-115) and their autograd elementwise chain do not exist."""
+
+    @staticmethod
+    def forward(ctx, u_re, u_im, lam_re, lam_im, gamma, start, h0_re, h0_im):
+        u_re, u_im = _f32c(u_re), _f32c(u_im)
+        lam_re, lam_im, gamma = _f32c(lam_re), _f32c(lam_im), _f32c(gamma)
+        B, L, C = u_re.shape
+        h0_re = None if h0_re is None else _f32c(h0_re.reshape(B, C))
+        h0_im = None if h0_im is None else _f32c(h0_im.reshape(B, C))
+        st = _flag(start, B, L)
+        h_re, h_im = torch.empty_like(u_re), torch.empty_like(u_im)
+        N.call("rorl_lru_fused_fwd", N.ptr(u_re), N.ptr(u_im), N.ptr(lam_re), N.ptr(lam_im), N.ptr(gamma), N.ptr(st),
+               N.ptr(h0_re), N.ptr(h0_im), N.ptr(h_re), N.ptr(h_im), B, L, C, N.stream())
+        ctx.save_for_backward(lam_re, lam_im, gamma, st, h_re, h_im, h0_re, h0_im)
+        return h_re, h_im
+
+    @staticmethod
+    def backward(ctx, g_re, g_im):
+        lam_re, lam_im, gamma, st, h_re, h_im, h0_re, h0_im = ctx.saved_tensors
+        g_re, g_im = _f32c(g_re), _f32c(g_im)
+        B, L, C = h_re.shape
+        du_re, du_im = torch.empty_like(h_re), torch.empty_like(h_im)
+        part = torch.empty((3, B, C), device=h_re.device, dtype=torch.float32)
+        N.call("rorl_lru_fused_bwd", N.ptr(g_re), N.ptr(g_im), N.ptr(lam_re), N.ptr(lam_im), N.ptr(gamma), N.ptr(st),
+               N.ptr(h_re), N.ptr(h_im), N.ptr(h0_re), N.ptr(h0_im), N.ptr(du_re), N.ptr(du_im), N.ptr(part[0]),
+               N.ptr(part[1]), N.ptr(part[2]), B, L, C, N.stream())
+        return du_re, du_im, sum_leading(part[0]), sum_leading(part[1]), sum_leading(part[2]), None, None, None
+
+
+def lru_fused_scan(u_re, u_im, lam_re, lam_im, gamma, start=None, h0_re=None, h0_im=None):
+    return LRUFusedScan.apply(u_re, u_im, lam_re, lam_im, gamma, start, h0_re, h0_im)
+
+
 # ------------------------------------------------------------------------------------------------
 # GRU (persistent cluster kernel for the recurrence; the input / weight-gradient GEMMs are tensor-core GEMMs)
 # ------------------------------------------------------------------------------------------------

@@ -47,14 +47,18 @@ class LRULayer(nn.Module):
         nu, theta, gamma = torch.exp(self.params_log)
         mag = torch.exp(-nu)
         lam_re, lam_im = mag * torch.cos(theta), mag * torch.sin(theta)
-        v_re, v_im = gamma * u[0], gamma * u[1]
-        keep = 1.0 if rnn_start is None else (1 - rnn_start)
-        f_re = (lam_re * keep).expand_as(v_re)
-        f_im = (lam_im * keep).expand_as(v_im)
         h0_re = h0_im = None
         if hidden is not None and not getattr(hidden, '_rorl_zero', False):
             h0_re, h0_im = hidden.transpose(0, 1).chunk(2, dim=-1)
-        h_re, h_im = K.complex_scan(v_re, v_im, f_re, f_im, h0_re, h0_im, grad_detach)
+        if grad_detach is None:
+            # gamma scaling and the reset-gated decay lambda * (1 - start) are formed inside the scan kernel
+            h_re, h_im = K.lru_fused_scan(u[0], u[1], lam_re, lam_im, gamma, rnn_start, h0_re, h0_im)
+        else:
+            v_re, v_im = gamma * u[0], gamma * u[1]
+            keep = 1.0 if rnn_start is None else (1 - rnn_start)
+            f_re = (lam_re * keep).expand_as(v_re)
+            f_im = (lam_im * keep).expand_as(v_im)
+            h_re, h_im = K.complex_scan(v_re, v_im, f_re, f_im, h0_re, h0_im, grad_detach)
         new_hidden = torch.cat((h_re[:, -1:, :], h_im[:, -1:, :]), dim=-1).transpose(0, 1)
         m = self.middle_proj(torch.stack((h_re, h_im), dim=0))
         out = m[0] - m[1] + u[2]

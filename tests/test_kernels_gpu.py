@@ -311,3 +311,36 @@ def test_selscan_full_size_chunk_composition(K):
     y_alt = K.selective_scan_tm(u2, delta, A, Bm, Cm, Dk, z, bias, start, True)
     assert torch.equal(y_alt[3, 500:], y[3, 500:])
     assert torch.equal(y_alt[:3], y[:3]) and torch.equal(y_alt[4:], y[4:])
+
+
+@pytest.mark.parametrize("shape", [(3, 41, 16), (2, 130, 64), (32, 1002, 256), (1, 1, 8)])
+@pytest.mark.parametrize("with_h0", [False, True])
+def test_lru_fused_matches_materialised_path(K, shape, with_h0):
+    """The fused LRU scan (lambda, gamma as [C] vectors, reset flags [B, L]) against the same recurrence fed with the
+    materialised gamma * u and lambda * (1 - start) tensors through the oracle's CPU scan, incl. d lambda, d gamma."""
+    from oracle import ops as O
+    B, L, C = shape
+    if B * L > 20000 and with_h0:
+        pytest.skip("one large case is enough")
+    gen = torch.Generator().manual_seed(B * 7 + L)
+    rn = lambda *s: torch.randn(*s, generator=gen)
+    u_re, u_im = rn(B, L, C), rn(B, L, C)
+    mag, theta = 0.9 + 0.099 * torch.rand(C, generator=gen), 6.28 * torch.rand(C, generator=gen)
+    lam_re, lam_im, gamma = mag * torch.cos(theta), mag * torch.sin(theta), 0.1 + torch.rand(C, generator=gen)
+    start = (torch.rand(B, L, 1, generator=gen) < 0.03).float()
+    start[:, 0] = 1
+    h0r, h0i = (rn(B, 1, C), rn(B, 1, C)) if with_h0 else (None, None)
+    if with_h0:
+        start[:, 0] = 0                      # otherwise the carried state is wiped at once
+    gr, gi = rn(B, L, C), rn(B, L, C)
+    cin = [t.clone().requires_grad_() for t in (u_re, u_im, lam_re, lam_im, gamma)]
+    keep = 1 - start
+    hr_ref, hi_ref = O.lru_scan(cin[4] * cin[0], cin[4] * cin[1], (cin[2] * keep).expand(B, L, C), (cin[3] * keep).expand(B, L, C), h0r, h0i, None)
+    ref = torch.autograd.grad((hr_ref, hi_ref), cin, (gr, gi))
+    gin = [t.clone().cuda().requires_grad_() for t in (u_re, u_im, lam_re, lam_im, gamma)]
+    hr, hi = K.lru_fused_scan(*gin, start.cuda(), None if h0r is None else h0r.cuda(), None if h0i is None else h0i.cuda())
+    assert_close(hr, hr_ref, TOL, "h_re")
+    assert_close(hi, hi_ref, TOL, "h_im")
+    got = torch.autograd.grad((hr, hi), gin, (gr.cuda(), gi.cuda()))
+    for a, b, n in zip(got, ref, ("du_re", "du_im", "dlam_re", "dlam_im", "dgamma")):
+        assert_close(a, b, TOL, n)

@@ -110,6 +110,19 @@ def bench_lru():
         40 * B * L * C)
 
 
+def bench_lru_fused():
+    B, L, C = 32, 1002, 256
+    u_re, u_im = rn(B, L, C).requires_grad_(), rn(B, L, C).requires_grad_()
+    lam_re, lam_im, gamma = (0.6 * torch.rand(C, device=dev)).requires_grad_(), (0.6 * torch.rand(C, device=dev)).requires_grad_(), (0.5 + torch.rand(C, device=dev)).requires_grad_()
+    start = torch.zeros(B, L, device=dev); start[:, 0] = 1
+    g1, g2 = rn(B, L, C), rn(B, L, C)
+    with torch.no_grad():
+        t_f = timeit(lambda: K.lru_fused_scan(u_re, u_im, lam_re, lam_im, gamma, start))
+    t_fb = timeit(lambda: torch.autograd.grad(K.lru_fused_scan(u_re, u_im, lam_re, lam_im, gamma, start), (u_re, u_im, lam_re, lam_im, gamma), (g1, g2)), n=10)
+    rec("lru_fused_fwd", t_f, 16 * B * L * C, note="lambda / gamma as [C] vectors, reset flags [B, L] (SURVEY.md 8d formula)")
+    rec("lru_fused_bwd(+partial sums)", t_fb - t_f, 24 * B * L * C)
+
+
 def bench_selscan():
     B, L, D, Ns = 32, 1018, 512, 32
     u, delta, z = rn(B, L, D).requires_grad_(), (0.5 * rn(B, L, D) - 1).requires_grad_(), rn(B, L, D).requires_grad_()
@@ -232,7 +245,7 @@ def bench_reduce():
         rec(f"cublas wgrad N={n} K={k} (library, for scale)", t, 4 * M * (n + k))
 
 
-ALL = {"reduce": bench_reduce, "gilr": bench_gilr, "lru": bench_lru, "selscan": bench_selscan, "conv": bench_conv, "addnorm": bench_addnorm,
+ALL = {"reduce": bench_reduce, "gilr": bench_gilr, "lru": bench_lru, "lru_fused": bench_lru_fused, "selscan": bench_selscan, "conv": bench_conv, "addnorm": bench_addnorm,
        "gru": bench_gru, "gemm": bench_gemm}
 
 if __name__ == "__main__":
