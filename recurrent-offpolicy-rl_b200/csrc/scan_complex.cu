@@ -12,6 +12,11 @@
 // h_{-1} = the supplied initial state; no gradient flows to the initial state (:242).
 #include "common.cuh"
 
+#ifndef RORL_LRU_FWD_S
+#define RORL_LRU_FWD_S 4          // steps per thread and tile of the fused forward: 128-step tiles (8 per 1002-step row) halve the
+                                  // block barriers and carry chains of 64-step tiles: 94 -> 56 us; 8 would not fit two CTAs per SM
+#endif
+
 namespace rorl {
 
 constexpr int kCThreads = 256;
@@ -413,7 +418,7 @@ int rorl_lru_fused_fwd(const float* u_re, const float* u_im, const float* lam_re
     if ((h0_re == nullptr) != (h0_im == nullptr)) return RORL_ERR_ARG;
     if (B <= 0 || L <= 0 || C <= 0 || B > 65535) return RORL_ERR_SHAPE;
     if (C % 4) return RORL_ERR_ALIGN;
-    constexpr int S = 2, NST = 3;
+    constexpr int S = RORL_LRU_FWD_S, NST = 3;
     auto kern = lru_fwd_kernel<S, NST, true>;
     constexpr size_t smem = sizeof(float) * (NST * (2 * 32 * S * 32 + 32 * S) + 2 * 8 * 8 * 16);
     static bool once = (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
