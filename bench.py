@@ -202,6 +202,7 @@ def run_ours(args):
                        "l2": "working set per step (activations > 1 GB) exceeds the 126 MB L2; no flush needed"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches)}
     line["roofline"] = scan_roofline(alg, dev, ms_per_step)
+    line["roofline_gemm"] = gemm_roofline(dev)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(encoder="gru", n_traj=N_TRAJ, updates=2, warm=1)
     print(json.dumps(line))
@@ -270,6 +271,40 @@ def scan_roofline(alg, dev, ms_per_step):
             "fwd": {"us": t_fwd * 1e6, "GBps": bytes_fwd / t_fwd / 1e9, "share_of_step": share_fwd},
             "bwd": {"us": t_bwd * 1e6, "GBps": bytes_bwd / t_bwd / 1e9, "share_of_step": share_bwd},
             "note": "selective scan at d_state=32 is MUFU/FMA-pipe bound, not HBM bound (SURVEY.md App. F)"}
+
+
+def gemm_roofline(dev):
+    """Second roofline object, for the kernel with the largest share of the step (the tcgen05 3xTF32 GEMM, ~44 %):
+    the in_proj-half shape [32576, 256] x [512, 256]^T timed alone with CUDA events.  `achieved` counts the useful
+    fp32 FLOPs (2 M N K); the kernel issues three TF32 passes for them.  `peak` is the measured dense bf16 rate of
+    MEASURED_PEAKS.json; the TF32 pipe runs at half of it."""
+    import torch
+    import rorl_b200.kernels as K
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    M, Nn, Kk = N_TRAJ * (T_LEN + 18), 512, 256
+    g = torch.Generator(device=dev).manual_seed(1)
+    a = torch.randn(M, Kk, device=dev, generator=g)
+    w = torch.randn(Nn, Kk, device=dev, generator=g)
+    for _ in range(3):
+        K.gemm_tn(a, w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        K.gemm_tn(a, w)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 20 * 1e-3
+    useful = 2.0 * M * Nn * Kk
+    return {"bound": "tensor", "kernel": "gemm_kernel<TN, BN 256, BK 16> (3xTF32)", "shape": [M, Nn, Kk], "us": t * 1e6,
+            "achieved": useful / t / 1e12, "issued_tf32": 3 * useful / t / 1e12, "peak": peak, "unit": "TFLOP/s",
+            "frac": useful / t / 1e12 / peak, "frac_issued_of_tf32_peak": 3 * useful / t / 1e12 / (peak / 2),
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); TF32 = half" if peaks else "fallback 1590 TFLOP/s bf16",
+            "tensor_pipe_pct_ncu": 44.0, "ncu_source": "profiles/r01i_step_breakdown.md (fc 256x256 shape)"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
