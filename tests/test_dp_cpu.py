@@ -102,3 +102,43 @@ def test_bucketed_allreduce_matches_single_process(tmp_path):
         assert float(r["gmin"]) == float(y.min()) and float(r["gmax"]) == float(y.max())
         err = float((r["grad"] - grad).abs().max() / grad.abs().max())
         assert err < 1e-5, err                                            # summation order only
+
+
+def test_update_stage_schedule_places_the_exchanges():
+    """The update is four device segments; which data-parallel exchange follows which segment depends on the mode:
+    single process -> none; eager + data parallel -> only the count / guard sync (gradient buckets are reduced by the
+    hooks inside the backward); CUDA-graph replay + data parallel -> one all-reduce per gradient arena between the
+    replayed segments (NCCL stays outside the captured graphs)."""
+    from types import SimpleNamespace
+    from rorl_b200.algorithm.full_length_update import FullLengthRNNUpdate
+    calls = []
+
+    class Stub:
+        parameter = SimpleNamespace(no_alpha_auto_tune=False)
+        value_arena = SimpleNamespace(grad="value_grad")
+        policy_arena = SimpleNamespace(grad="policy_grad")
+        alpha_arena = SimpleNamespace(grad="alpha_grad")
+
+        def __init__(self, group):
+            self.dist_group = group
+
+        def _sync_guard_and_count(self):
+            calls.append("count")
+
+        def _allreduce(self, t):
+            calls.append(t)
+
+    def exchanges(group, graph_mode):
+        calls.clear()
+        out = []
+        for _, comm in FullLengthRNNUpdate._stages(Stub(group), graph_mode):
+            before = len(calls)
+            if comm is not None:
+                comm()
+            out.append(tuple(calls[before:]))
+        return out
+
+    assert exchanges(None, False) == [(), (), (), ()]
+    assert exchanges(None, True) == [(), (), (), ()]
+    assert exchanges("g", False) == [("count",), (), (), ()]
+    assert exchanges("g", True) == [("count",), ("value_grad",), ("policy_grad", "alpha_grad"), ()]
