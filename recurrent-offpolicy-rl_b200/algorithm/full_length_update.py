@@ -202,7 +202,6 @@ class FullLengthRNNUpdate:
         self._work = torch.zeros(int(N.lib().rorl_loss_work_floats(0)), dtype=torch.float32, device=self.device)
         self._stats = torch.zeros(16, dtype=torch.float32, device=self.device)
         self._ensemble_size = int(value_args['uni_model_layer_type'][-1].split('-')[-1])
-        self._sel_pinned = torch.zeros(max(self._ensemble_size, 1), dtype=torch.int32).pin_memory()
         self._h2d_stage = None
         self._has_gpt = any('gpt' in lid for net in (self.values[0].embedding_network, self.policy.embedding_network,
                                                      self.values[0].uni_network, self.policy.uni_network) for lid in net.layer_type)
@@ -339,7 +338,9 @@ class FullLengthRNNUpdate:
         E = self._ensemble_size
         sel_np = np.random.permutation(E)[:p.redq_m] if self.use_redq else np.arange(E)
         did_policy = self.grad_num % p.policy_update_per == 0
-        self._sel_pinned[:len(sel_np)] = torch.from_numpy(np.asarray(sel_np, dtype=np.int32))
+        # a fresh pinned staging tensor per step: the host runs ahead of the stream, and the caching host allocator does
+        # not hand the block out again before the asynchronous copy that reads it has completed
+        sel_pinned = torch.from_numpy(np.asarray(sel_np, dtype=np.int32)).pin_memory()
         att_np = np.zeros((B, L), dtype=np.int32)                                                      # ref :358-366
         k = min(traj_len_array.shape[1], L)
         att_np[:, :k] = traj_len_array[:, :k].astype(np.int32)
@@ -350,7 +351,7 @@ class FullLengthRNNUpdate:
                    len(sel_np), att_np.tobytes())
         entry = self._graphs.get(key) if key is not None else None
         if entry is not None and entry != 'seen':
-            entry['sel'].copy_(self._sel_pinned[:len(sel_np)], non_blocking=True)
+            entry['sel'].copy_(sel_pinned, non_blocking=True)
             for graph, comm in entry['segments']:
                 graph.replay()
                 if comm is not None:
@@ -358,7 +359,7 @@ class FullLengthRNNUpdate:
             N.add_launches(entry['launches'])
         else:
             sel = torch.empty(len(sel_np), dtype=torch.int32, device=dev)
-            sel.copy_(self._sel_pinned[:len(sel_np)], non_blocking=True)
+            sel.copy_(sel_pinned, non_blocking=True)
             att = torch.from_numpy(att_np).pin_memory().to(dev, non_blocking=True)
             tgt_att = torch.from_numpy(tgt_np).pin_memory().to(dev, non_blocking=True)
             att._host, tgt_att._host = att_np, tgt_np      # host copy for the cgpt work list (no device->host sync)
