@@ -124,6 +124,13 @@ int rorl_selscan_bwd(const float* u, const float* delta, const float* A, const f
  * over axis 0.
  * ---------------------------------------------------------------------------------------------- */
 int rorl_conv1d_nseg(int64_t L);
+/* the same depthwise causal conv with the activation selectable: act = 1 SiLU (the two entry points below), act = 0 none
+ * (the `conv1d_*` encoder layer, ref: offpolicy_rnn/models/conv1d/conv1d.py:26-35) */
+int rorl_conv1d_fwd(const float* x, const float* w, const float* bias, const float* mask, float* y, int64_t B, int64_t L,
+                    int64_t D, int64_t K, int64_t ld_x, int64_t ld_y, int act, cudaStream_t stream);
+int rorl_conv1d_bwd(const float* x, const float* w, const float* bias, const float* mask, const float* dy, float* dx,
+                    float* dw_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t K, int64_t ld_x,
+                    int64_t ld_dy, int64_t ld_dx, int act, cudaStream_t stream);
 int rorl_conv1d_silu_fwd(const float* x, const float* w, const float* bias, const float* mask, float* y,
                          int64_t B, int64_t L, int64_t D, int64_t K, int64_t ld_x, int64_t ld_y,
                          cudaStream_t stream);

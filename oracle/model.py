@@ -162,6 +162,39 @@ def smamba_step(p, pre, x, hidden, layer_id: str):
     return ff_block(p, pre + 'head.', x + residual, eps), torch.cat(outs, dim=-1)
 
 
+def gilr_lstm_layer(p, pre, x, side: Side, hidden=None):
+    """ref: offpolicy_rnn/models/gilr_lstm/gilr_lstm.py:39-75 (CPU branch: scan_cpu with the carried halves)"""
+    u = ops.ensemble_linear(x, p[pre + 'in_proj.weight'], p[pre + 'in_proj.bias'], desire_ndim=4)
+    C = u.shape[-1]
+    if hidden is None:
+        h_pre = h_mid = None
+    else:
+        h_pre, h_mid = torch.chunk(hidden.transpose(0, 1), 2, -1)
+    f, v = torch.sigmoid(u[1]), torch.tanh(u[0])
+    if side.rnn_start is not None:
+        f = f * (1 - side.rnn_start)
+    v, h_pre = ops.gilr_scan(v, f, h_pre)
+    g = ops.ensemble_linear(v, p[pre + 'middle_proj.weight'], p[pre + 'middle_proj.bias'], desire_ndim=4)
+    f, i, o, z = torch.sigmoid(g[0]), torch.sigmoid(g[1]), torch.sigmoid(g[2]), torch.tanh(g[3])
+    if side.rnn_start is not None:
+        f = f * (1 - side.rnn_start)
+    out, h_mid = ops.gilr_scan(i * z, f, h_mid)
+    out = F.linear(out * o, p[pre + 'out_proj.weight'], p[pre + 'out_proj.bias'])
+    return out, torch.cat((h_pre, h_mid), dim=-1).transpose(0, 1)
+
+
+def conv1d_layer(p, pre, x, side: Side, layer_id: str, hidden=None):
+    """ref: offpolicy_rnn/models/conv1d/conv1d.py:26-52 (explicit left state, padding 0, no activation, FF tail)"""
+    Kc = int(layer_id.split('_')[-1]) if '_' in layer_id else 4
+    Bsz, L, C = x.shape
+    h = torch.zeros((Bsz, Kc - 1, C)) if hidden is None else hidden.reshape(Bsz, Kc - 1, C)
+    xm = x if side.mask is None else x * side.mask
+    x_in = torch.cat((h, xm), dim=-2)
+    y = F.conv1d(x_in.transpose(-2, -1), p[pre + 'conv1d.weight'], p[pre + 'conv1d.bias'], groups=C)[:, :, :L].transpose(-2, -1)
+    h_out = x_in[:, -(Kc - 1):, :].reshape(Bsz, 1, -1)
+    return ff_block(p, pre + 'ff.', y), h_out
+
+
 def parse_s6(layer_id: str):
     """ref: rnn_base.py:118-136"""
     cfg = dict(d_state=16, d_conv=4, ff=True)
@@ -248,6 +281,12 @@ def rnn_base(p: Dict[str, torch.Tensor], layer_types: List[str], acts: List[str]
             x = ops.ensemble_linear(x, p[pre + 'weight'], p[pre + 'bias'], desire_ndim)
         elif lt == 'gilr':
             x = gilr_layer(p, pre, x, side)
+        elif lt == 'gilr_lstm':
+            x, h = gilr_lstm_layer(p, pre, x, side, side.h0.get(i))
+            side.h_out = h
+        elif lt.startswith('conv1d'):
+            x, h = conv1d_layer(p, pre, x, side, lt, side.h0.get(i))
+            side.h_out = h
         elif lt == 'lru':
             x = lru_layer(p, pre, x, side)
         elif lt.startswith('smamba'):

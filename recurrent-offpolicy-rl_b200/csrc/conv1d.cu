@@ -21,7 +21,7 @@ __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_fast(x); 
 template <int K, bool MASK>
 __global__ void __launch_bounds__(kConvThreads) conv1d_silu_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-    const float* __restrict__ mask, float* __restrict__ y, int L, int D, int ld_x, int ld_y) {
+    const float* __restrict__ mask, float* __restrict__ y, int L, int D, int ld_x, int ld_y, int act) {
     const int d = blockIdx.x * kConvThreads + threadIdx.x;
     const int b = blockIdx.z;
     const int t0 = blockIdx.y * kConvSeg, t1 = min(L, t0 + kConvSeg);
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_silu_fwd_kernel(
             float acc = bs;
 #pragma unroll
             for (int k = 0; k < K; ++k) acc = fmaf(wk[k], win[(j + 1 + k) % K], acc);
-            if (t < t1) y[(row0 + t) * ld_y + d] = siluf_(acc);
+            if (t < t1) y[(row0 + t) * ld_y + d] = act ? siluf_(acc) : acc;      // act: warp-uniform
         }
     }
 }
@@ -81,7 +81,7 @@ template <int K, bool MASK>
 __global__ void __launch_bounds__(kConvThreads) conv1d_silu_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
     const float* __restrict__ mask, const float* __restrict__ dy, float* __restrict__ dx,
-    float* __restrict__ dw_part, float* __restrict__ db_part, int L, int D, int ld_x, int ld_dy, int ld_dx) {
+    float* __restrict__ dw_part, float* __restrict__ db_part, int L, int D, int ld_x, int ld_dy, int ld_dx, int act) {
     const int d = blockIdx.x * kConvThreads + threadIdx.x;
     const int b = blockIdx.z;
     const int t0 = blockIdx.y * kConvSeg, t1 = min(L, t0 + kConvSeg);
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_silu_bwd_kernel(
 #pragma unroll
             for (int k = 0; k < K; ++k) pre = fmaf(wk[k], win[(j + 1 + k) % K], pre);
             const float sg = sigmoidf_fast(pre);
-            const float dfull = cg[j] * sg * (1.0f + pre * (1.0f - sg));
+            const float dfull = act ? cg[j] * sg * (1.0f + pre * (1.0f - sg)) : cg[j];
             const float dpre = t < tend ? dfull : 0.f;          // steps past the sequence / halo end contribute nothing
             const float down = t < t1 ? dpre : 0.f;             // dw / dbias count this segment's own steps only
             db += down;
@@ -181,25 +181,36 @@ int rorl_conv1d_nseg(int64_t L) { return (int)((L + kConvSeg - 1) / kConvSeg); }
         default: return RORL_ERR_SHAPE;            \
     }
 
-int rorl_conv1d_silu_fwd(const float* x, const float* w, const float* bias, const float* mask, float* y,
-                         int64_t B, int64_t L, int64_t D, int64_t K, int64_t ld_x, int64_t ld_y,
-                         cudaStream_t stream) {
+int rorl_conv1d_fwd(const float* x, const float* w, const float* bias, const float* mask, float* y, int64_t B, int64_t L,
+                    int64_t D, int64_t K, int64_t ld_x, int64_t ld_y, int act, cudaStream_t stream) {
     if (!x || !w || !y) return RORL_ERR_ARG;
     if (B <= 0 || L <= 0 || D <= 0 || B > 65535) return RORL_ERR_SHAPE;
     dim3 grid((unsigned)((D + kConvThreads - 1) / kConvThreads), (unsigned)rorl_conv1d_nseg(L), (unsigned)B);
-    CONV_DISPATCH(conv1d_silu_fwd_kernel, x, w, bias, mask, y, (int)L, (int)D, (int)ld_x, (int)ld_y);
+    CONV_DISPATCH(conv1d_silu_fwd_kernel, x, w, bias, mask, y, (int)L, (int)D, (int)ld_x, (int)ld_y, act != 0);
+    RORL_RETURN_LAUNCH();
+}
+
+int rorl_conv1d_silu_fwd(const float* x, const float* w, const float* bias, const float* mask, float* y,
+                         int64_t B, int64_t L, int64_t D, int64_t K, int64_t ld_x, int64_t ld_y,
+                         cudaStream_t stream) {
+    return rorl_conv1d_fwd(x, w, bias, mask, y, B, L, D, K, ld_x, ld_y, 1, stream);
+}
+
+int rorl_conv1d_bwd(const float* x, const float* w, const float* bias, const float* mask, const float* dy, float* dx,
+                    float* dw_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t K, int64_t ld_x,
+                    int64_t ld_dy, int64_t ld_dx, int act, cudaStream_t stream) {
+    if (!x || !w || !dy || !dx || !dw_part || !dbias_part) return RORL_ERR_ARG;
+    if (B <= 0 || L <= 0 || D <= 0 || B > 65535) return RORL_ERR_SHAPE;
+    dim3 grid((unsigned)((D + kConvThreads - 1) / kConvThreads), (unsigned)rorl_conv1d_nseg(L), (unsigned)B);
+    CONV_DISPATCH(conv1d_silu_bwd_kernel, x, w, bias, mask, dy, dx, dw_part, dbias_part, (int)L, (int)D,
+                  (int)ld_x, (int)ld_dy, (int)ld_dx, act != 0);
     RORL_RETURN_LAUNCH();
 }
 
 int rorl_conv1d_silu_bwd(const float* x, const float* w, const float* bias, const float* mask, const float* dy,
                          float* dx, float* dw_part, float* dbias_part, int64_t B, int64_t L, int64_t D, int64_t K,
                          int64_t ld_x, int64_t ld_dy, int64_t ld_dx, cudaStream_t stream) {
-    if (!x || !w || !dy || !dx || !dw_part || !dbias_part) return RORL_ERR_ARG;
-    if (B <= 0 || L <= 0 || D <= 0 || B > 65535) return RORL_ERR_SHAPE;
-    dim3 grid((unsigned)((D + kConvThreads - 1) / kConvThreads), (unsigned)rorl_conv1d_nseg(L), (unsigned)B);
-    CONV_DISPATCH(conv1d_silu_bwd_kernel, x, w, bias, mask, dy, dx, dw_part, dbias_part, (int)L, (int)D,
-                  (int)ld_x, (int)ld_dy, (int)ld_dx);
-    RORL_RETURN_LAUNCH();
+    return rorl_conv1d_bwd(x, w, bias, mask, dy, dx, dw_part, dbias_part, B, L, D, K, ld_x, ld_dy, ld_dx, 1, stream);
 }
 
 }  // extern "C"

@@ -401,7 +401,7 @@ def selective_scan_fn(u, delta, A, B, C, start, D=None, z=None, delta_bias=None,
 # ------------------------------------------------------------------------------------------------
 class CausalConv1dSiLU(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, mask):
+    def forward(ctx, x, weight, bias, mask, act=True):
         x = _rows(x)
         B, L, D = x.shape
         w = _f32c(weight.reshape(D, -1))
@@ -409,10 +409,10 @@ class CausalConv1dSiLU(Function):
         bias = None if bias is None else _f32c(bias)
         mask = _flag(mask, B, L)
         y = torch.empty((B, L, D), device=x.device, dtype=torch.float32)
-        N.call("rorl_conv1d_silu_fwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(mask), N.ptr(y), B, L, D, K,
-               x.stride(1), D, N.stream())
+        N.call("rorl_conv1d_fwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(mask), N.ptr(y), B, L, D, K,
+               x.stride(1), D, int(bool(act)), N.stream())
         ctx.save_for_backward(x, w, bias, mask)
-        ctx.wshape = weight.shape
+        ctx.wshape, ctx.act = weight.shape, bool(act)
         return y
 
     @staticmethod
@@ -425,14 +425,19 @@ class CausalConv1dSiLU(Function):
         dx = torch.empty((B, L, D), device=x.device, dtype=torch.float32)
         dw = torch.empty((P, D, K), device=x.device, dtype=torch.float32)
         db = torch.empty((P, D), device=x.device, dtype=torch.float32)
-        N.call("rorl_conv1d_silu_bwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(mask), N.ptr(dy), N.ptr(dx), N.ptr(dw),
-               N.ptr(db), B, L, D, K, x.stride(1), dy.stride(1), D, N.stream())
-        return dx, sum_leading(dw).reshape(ctx.wshape), (None if bias is None else sum_leading(db)), None
+        N.call("rorl_conv1d_bwd", N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(mask), N.ptr(dy), N.ptr(dx), N.ptr(dw),
+               N.ptr(db), B, L, D, K, x.stride(1), dy.stride(1), D, int(ctx.act), N.stream())
+        return dx, sum_leading(dw).reshape(ctx.wshape), (None if bias is None else sum_leading(db)), None, None
 
 
 def causal_conv1d_silu(x, weight, bias=None, mask=None):
     """x [B, L, D] token-major; weight [D, 1, K] (nn.Conv1d depthwise layout) or [D, K]; mask [B, L(,1)]."""
-    return CausalConv1dSiLU.apply(x, weight, bias, mask)
+    return CausalConv1dSiLU.apply(x, weight, bias, mask, True)
+
+
+def causal_conv1d(x, weight, bias=None, mask=None):
+    """Same depthwise causal conv without the activation (the `conv1d_*` encoder layer)."""
+    return CausalConv1dSiLU.apply(x, weight, bias, mask, False)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -23,6 +23,8 @@ from .gilr.gilr import GILRLayer
 from .lru.lru import LRULayer
 from .smamba.mamba import BlockList as MambaBlockList
 from .s6.mamba import MambaResidualBlock
+from .conv1d.conv1d import Conv1d
+from .gilr_lstm.gilr_lstm import GILRLSTMLayer
 from .gru.gru import GRULayer
 
 try:
@@ -94,11 +96,13 @@ def parse_layer_id(layer_id: str) -> Tuple[str, Dict]:
             else:
                 raise ValueError(f'Pattern {t} has not been implemented!')
         return 'cgpt', cfg
-    if layer_id in ('gru', 'lru', 'gilr'):
+    if layer_id in ('gru', 'lru', 'gilr', 'gilr_lstm'):
         return layer_id, {}
+    if layer_id.startswith('conv1d'):                          # ref: rnn_base.py:227-234
+        return 'conv1d', {'d_conv': int(layer_id.split('_')[-1]) if '_' in layer_id else 4}
     raise NotImplementedError(
         f'layer type {layer_id!r} is outside the update hot path this package covers '
-        f'(fc, efc-E, gru, lru, gilr, smamba_*, mamba_*, cgpt_*)')
+        f'(fc, efc-E, gru, lru, gilr, gilr_lstm, conv1d_*, smamba_*, mamba_*, cgpt_*)')
 
 
 class RNNBase(nn.Module):
@@ -137,6 +141,13 @@ class RNNBase(nn.Module):
                 elif kind == 'gru':
                     self.layer_list.append(GRULayer(width_in, width, batch_first=True))
                     self.rnn_hidden_state_input_size.append(width)
+                elif kind == 'gilr_lstm':
+                    self.layer_list.append(GILRLSTMLayer(width_in, width, batch_first=True))
+                    self.rnn_hidden_state_input_size.append(width * 2)
+                elif kind == 'conv1d':
+                    blk = Conv1d(width_in, width, d_conv=cfg['d_conv'])
+                    self.layer_list.append(blk)
+                    self.rnn_hidden_state_input_size.append(blk.desired_hidden_dim)
                 elif kind == 'smamba':
                     assert width_in == width, f'mamba_simple require input_dim == output_dim, while got {width_in} and {width}'
                     blk = MambaBlockList(cfg['block_num'], width_in, d_conv=cfg['d_conv'], d_state=cfg['d_state'],
@@ -189,7 +200,12 @@ class RNNBase(nn.Module):
                 nn.init.xavier_uniform_(m.out_proj.weight)
                 nn.init.constant_(m.out_proj.bias, 0)
                 self._xavier_efc(m.in_proj)
-            elif isinstance(m, (MambaBlockList, MambaResidualBlock)) or (TransformerDecoder is not None and isinstance(m, TransformerDecoder)):
+            elif isinstance(m, GILRLSTMLayer):
+                nn.init.xavier_uniform_(m.out_proj.weight)
+                nn.init.constant_(m.out_proj.bias, 0)
+                self._xavier_efc(m.in_proj)
+                self._xavier_efc(m.middle_proj)
+            elif isinstance(m, (MambaBlockList, MambaResidualBlock, Conv1d)) or (TransformerDecoder is not None and isinstance(m, TransformerDecoder)):
                 pass
             else:   # GRU and anything else with plain weight/bias tensors
                 for name, param in m.named_parameters():
@@ -243,6 +259,8 @@ class RNNBase(nn.Module):
                     x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.mask)
                 elif lid.startswith('mamba'):
                     x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.mask, hidden_state.grad_detach)
+                elif 'conv1d' in lid:
+                    x, h = layer(x, h_in, hidden_state.mask)
                 elif lid.startswith('cgpt'):
                     if x.dim() == 3 and x.shape[-2] > 1:
                         cache, seqlens = None, hidden_state.attention_concat_mask

@@ -109,7 +109,9 @@ def gen_ops():
 LAYER_IDS = {"gilr": "gilr", "lru": "lru", "gru": "gru", "smamba_rms": "smamba_s16_c4_b2",
              "smamba_ln": "smamba_s32_c8_b1_nln", "smamba_ff": "smamba_s16_c8_b1_ff",
              # s6 layer: reference CPU path = selective_scan_cpu, explicit conv left state
-             "mamba_ff": "mamba_s16_c4", "mamba_noff": "mamba_s32_c8_noff", "mamba_h0": "mamba_s16_c4"}
+             "mamba_ff": "mamba_s16_c4", "mamba_noff": "mamba_s32_c8_noff", "mamba_h0": "mamba_s16_c4",
+             # remaining encoder IDs; *_h0 = a carried non-zero state entering the call
+             "gilr_lstm": "gilr_lstm", "gilr_lstm_h0": "gilr_lstm", "conv1d": "conv1d_8", "conv1d_h0": "conv1d"}
 
 
 def gen_layers(only=None):
@@ -135,9 +137,9 @@ def gen_layers(only=None):
         if 'gru' not in lid:
             hid.set_rnn_start(start)
             hid.set_mask(mask)
-        if tag == "mamba_h0":       # carried (non-zero) SSM + conv state entering the call
+        if tag.endswith("_h0"):     # carried (non-zero) state entering the call
             hid[0] = 0.3 * torch.randn_like(hid[0])
-        h_in = [h.clone() for h in hid] if lid.startswith('mamba') else None
+        h_in = [h.clone() for h in hid] if (lid.startswith('mamba') or lid.startswith('conv1d') or lid == 'gilr_lstm') else None
         y, h_out, _ = net.meta_forward(x, hid)
         dy = torch.randn_like(y)
         params = dict(net.named_parameters())

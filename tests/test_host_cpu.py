@@ -38,11 +38,12 @@ def test_layer_id_grammar():
     assert parse_layer_id('efc-8') == ('efc', {'ensemble': 8})
     assert parse_layer_id('mamba_s32_c16') == ('mamba', dict(d_state=32, d_conv=16, use_ff=True))
     assert parse_layer_id('mamba_noff')[1] == dict(d_state=16, d_conv=4, use_ff=False)
-    for lid in ('gru', 'lru', 'gilr', 'smamba_s16', 'cgpt_h8', 'mamba_s16'):
+    assert parse_layer_id('conv1d_8') == ('conv1d', {'d_conv': 8}) and parse_layer_id('gilr_lstm') == ('gilr_lstm', {})
+    for lid in ('gru', 'lru', 'gilr', 'smamba_s16', 'cgpt_h8', 'mamba_s16', 'gilr_lstm', 'conv1d_4'):
         assert check_is_rnn(lid)
     assert not check_is_rnn('fc') and not check_is_rnn('efc-8')
     with pytest.raises(NotImplementedError):
-        parse_layer_id('gilr_lstm')
+        parse_layer_id('cgru')
 
 
 @pytest.mark.parametrize("tag", ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru"])

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "smamba_rms", "smamba_ln", "smamba_ff", "mamba_ff", "mamba_noff", "mamba_h0"])
+@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "smamba_rms", "smamba_ln", "smamba_ff", "mamba_ff", "mamba_noff", "mamba_h0",
+                                 "gilr_lstm", "gilr_lstm_h0", "conv1d", "conv1d_h0"])
 def test_layer_golden(tag):
     from rorl_b200.models.rnn_base import RNNBase
     g = load_npz(f"layer_{tag}.npz")
@@ -25,7 +26,7 @@ def test_layer_golden(tag):
     if lid != "gru":
         hid.set_rnn_start(T(g["start"], "cuda"))
         hid.set_mask(T(g["mask"], "cuda"))
-    if tag == "mamba_h0":
+    if tag.endswith("_h0"):
         hid[0] = T(g["h_in"], "cuda")
     y, h_out, _ = net.meta_forward(x, hid)
     assert_close(y, g["y"], TOL, "y")
@@ -63,7 +64,8 @@ def test_smamba_rollout_step_golden(tag):
     assert_close(h[0], g["h_out"], TOL, "h_out")
 
 
-@pytest.mark.parametrize("lid,width", [("gilr", 64), ("lru", 64), ("gru", 64), ("mamba_s16_c4", 64), ("mamba_s32_c16_noff", 32)])
+@pytest.mark.parametrize("lid,width", [("gilr", 64), ("lru", 64), ("gru", 64), ("mamba_s16_c4", 64), ("mamba_s32_c16_noff", 32),
+                                       ("gilr_lstm", 64), ("conv1d_8", 64)])
 def test_carried_state_composition(lid, width):
     """Size-independent property of every layer that carries its state: running a sequence in two pieces, handing the
     hidden state over, gives what the single pass gives (outputs and final state).  Exercises the carried-state

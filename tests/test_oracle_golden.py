@@ -66,7 +66,8 @@ def test_addnorm_op():
         assert_close(got, g[k], TOL, k)
 
 
-@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "smamba_rms", "smamba_ln", "smamba_ff", "mamba_ff", "mamba_noff", "mamba_h0"])
+@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "smamba_rms", "smamba_ln", "smamba_ff", "mamba_ff", "mamba_noff", "mamba_h0",
+                                 "gilr_lstm", "gilr_lstm_h0", "conv1d", "conv1d_h0"])
 def test_encoder_layer(tag):
     g = load_npz(f"layer_{tag}.npz")
     lid = str(g["layer_id"])
