@@ -141,11 +141,38 @@ class RefNestedReplay:
             room.append(cap - n)
         return bins
 
-    # -- ref: nested_replay_memory.py:103-185 (randomize_mask / random_trunc_traj off) -------------
-    def sample_trajs(self, batch_size, nest_stack_trajs=True):
+    # -- ref: nested_replay_memory.py:84-100 ----------------------------------------------------------
+    @staticmethod
+    def equalized_valid_nums(lens_plus_skip, desired_total):
+        order = np.argsort(lens_plus_skip)
+        n = len(lens_plus_skip)
+        avg = int(np.ceil(desired_total / n))
+        out, got = [avg] * n, 0
+        for i in range(n):
+            tl = lens_plus_skip[order[i]] - 1
+            want = int(np.ceil((desired_total - got) / (n - i)))
+            if want <= 0:
+                want = avg
+            if want > tl:
+                want = tl
+            got += want
+            out[order[i]] = want
+        return out
+
+    # -- ref: nested_replay_memory.py:103-185 -----------------------------------------------------------
+    def sample_trajs(self, batch_size, nest_stack_trajs=True, randomize_mask=False, valid_number_post_randomized=0,
+                     equalize_data_of_each_traj=True, random_trunc_traj=False):
+        if random_trunc_traj:
+            batch_size *= 2                                                              # :109-110
         inds = self._draw(batch_size)
-        lens = [self.traj_len[i] + self.skip for i in inds]
+        if random_trunc_traj:
+            lens = [np.random.randint(0, self.traj_len[i]) + 1 + self.skip for i in inds]   # :114
+        else:
+            lens = [self.traj_len[i] + self.skip for i in inds]
         starts = [self.traj_start[i] for i in inds]
+        eq = randomize_mask and equalize_data_of_each_traj
+        if eq:
+            valid_nums = self.equalized_valid_nums(lens, valid_number_post_randomized)     # :116-117
         groups = self.pack(lens, self.row_len) if nest_stack_trajs else [[i] for i in range(len(lens))]
         rows = len(groups)
         total = int(sum(lens) - len(lens) * self.skip)
@@ -168,6 +195,9 @@ class RefNestedReplay:
                 g[r, p + self.skip - 1, self.cols['action']] = 0
                 g[r, p:p + self.skip, scol] = 1
                 valid[r, p + self.skip:p + n, :] = self.buf[s0:s0 + (n - self.skip), mcol:mcol + 1]
+                if eq:                                                                   # :166-168
+                    zeros = np.random.permutation(n - self.skip)[:-valid_nums[k]] + p + self.skip
+                    g[r, zeros, mcol] = 0
                 p += n
             width = max(width, p)
             g[r, p:, scol] = 1
@@ -178,4 +208,13 @@ class RefNestedReplay:
             lens_arr[r, :len(s)] = s
         data = g[:rows, :width, :]
         fields = [data[..., c[0]:c[-1] + 1] if len(c) else None for c in (self.cols[n] for n in FIELDS)]
-        return Transition(*fields), total, valid[:rows, :width, :], lens_arr
+        tr = Transition(*fields)
+        if randomize_mask and not equalize_data_of_each_traj:
+            # _mask_rnd_select (:78-82, called :183-184): `mask.reshape((-1,))` of the sliced batch is a COPY unless the
+            # slice spans the whole row length, so the zeroing only lands in the batch in that case; the permutation
+            # draw happens either way (and advances the global RNG)
+            m1 = tr.mask.reshape((-1,))
+            idx = m1.nonzero()[0]
+            kill = idx[np.random.permutation(idx.shape[0])[:-valid_number_post_randomized]]
+            m1[kill] = 0
+        return tr, total, valid[:rows, :width, :], lens_arr

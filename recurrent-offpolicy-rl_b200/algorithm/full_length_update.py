@@ -309,7 +309,8 @@ class FullLengthRNNUpdate:
         assert p.utd == 1, 'utd > 1: call train_one_batch repeatedly'
         # 1. sample (host plan, device gather) ------------------------------------------------------- ref :313-332
         batch, batch_size, valid_ind, traj_len_array = self.replay_buffer.sample_trajs_device(
-            p.sac_batch_size, None, equalize_data_of_each_traj=True, nest_stack_trajs=self.allow_nest_stack)
+            p.sac_batch_size, None, randomize_mask=p.randomize_mask, valid_number_post_randomized=p.valid_number_post_randomized,
+            equalize_data_of_each_traj=True, random_trunc_traj=p.random_trunc_traj, nest_stack_trajs=self.allow_nest_stack)
         return self.update_on_batch(batch, batch_size, valid_ind, traj_len_array, sync=sync)
 
     def update_on_host_batch(self, host_batch: torch.Tensor, host_valid: torch.Tensor, batch_size: int,

@@ -9,8 +9,9 @@ Same interface and bit-exact output as the reference's NestedMemoryArray.sample_
   device `rorl_traj_gather` -- all data movement, from the device-resident fp32 ring (csrc/gather.cu)
 
 `sample_trajs_device()` is what the update uses; `sample_trajs()` keeps the reference's numpy return
-type by copying that device batch back.  `randomize_mask` / `random_trunc_traj` are
-not part of the update path and are rejected.
+type by copying that device batch back.  The sampler options `random_trunc_traj` and `randomize_mask` (equalised per
+trajectory or global; ref :78-100,109-117,166-168,183-184) are part of the host plan too: the extra RNG draws happen
+in the reference's order and the mask entries to clear are applied on the device after the gather.
 """
 from __future__ import annotations
 
@@ -31,6 +32,7 @@ class SamplePlan(NamedTuple):
     width: int               # returned row width = max(ptr_end) + 1, clipped to the row length
     total_size: int          # sum of valid steps
     lens: np.ndarray         # float64 [rows, kmax]: leading 1, then len_i + skip per trajectory (traj_len_array)
+    mask_zero: np.ndarray    # int64 [k]: row * Lmax + step of batch `mask` entries cleared by randomize_mask
 
 
 class NestedMemoryArray(MemoryArray):
@@ -77,29 +79,76 @@ class NestedMemoryArray(MemoryArray):
         self._mask_range = r['mask']
         self._rnn_start_range = r['start']
 
+    def get_equalized_valid_num_each_traj(self, traj_len_added_1, desired_total_valid_number):
+        """Valid-step budget per trajectory, shortest first (ref :84-100; np.argsort's default ordering is part of it)."""
+        order = np.argsort(traj_len_added_1)
+        n = len(traj_len_added_1)
+        avg = int(np.ceil(desired_total_valid_number / n))
+        out, got = [avg for _ in range(n)], 0
+        for i in range(n):
+            tl = traj_len_added_1[order[i]] - 1
+            want = int(np.ceil((desired_total_valid_number - got) / (n - i)))
+            if want <= 0:
+                want = avg
+            if want > tl:
+                want = tl
+            got += want
+            out[order[i]] = want
+        return out
+
     # ---- host: integer plan -----------------------------------------------------------------------------------
-    def plan_trajs(self, batch_size, max_sample_size=None, get_all=False, nest_stack_trajs=True) -> SamplePlan:
-        inds = np.arange(self.available_traj_num) if get_all else self._traj_ind_sample(batch_size, max_sample_size)
+    def plan_trajs(self, batch_size, max_sample_size=None, get_all=False, nest_stack_trajs=True, randomize_mask=False,
+                   valid_number_post_randomized=0, equalize_data_of_each_traj=False, random_trunc_traj=False) -> SamplePlan:
+        if get_all:
+            inds = np.arange(self.available_traj_num)
+        else:
+            if random_trunc_traj:
+                batch_size *= 2                                                          # ref :109-110
+            inds = self._traj_ind_sample(batch_size, max_sample_size)
         skip = self._skip_step
-        lens = [self.trajectory_length[i] + skip for i in inds]
+        if random_trunc_traj:                                                            # ref :114: one draw per trajectory, in order
+            lens = [np.random.randint(0, self.trajectory_length[i]) + 1 + skip for i in inds]
+        else:
+            lens = [self.trajectory_length[i] + skip for i in inds]
         starts = [self.trajectory_start[i] for i in inds]
+        equalized = randomize_mask and equalize_data_of_each_traj
+        if equalized:
+            valid_nums = self.get_equalized_valid_num_each_traj(lens, valid_number_post_randomized)
         groups = self.load_equalize(lens, self.max_traj_step) if nest_stack_trajs else [[i] for i in range(len(lens))]
-        entries, row_end, summary, width = [], [], [], 0
+        Lmax = self.max_traj_step
+        entries, row_end, summary, width, mask_zero = [], [], [], 0, []
         for r, grp in enumerate(groups):
             p, ll = 0, [1]
             for k in grp:
                 entries.append((starts[k], r, p, lens[k] - skip))
                 ll.append(lens[k])
+                if equalized:                                                            # ref :166-168
+                    zeros = np.random.permutation(lens[k] - skip)[:-valid_nums[k]] + p + skip
+                    mask_zero.append(r * Lmax + zeros.astype(np.int64))
                 p += lens[k]
             width = max(width, p)
             row_end.append(p)
             summary.append(ll)
         width = min(width + 1, self.max_traj_step)
+        if randomize_mask and not equalize_data_of_each_traj:
+            # _mask_rnd_select on the returned batch (ref :78-82,183-184).  The draw always happens; the zeroing only
+            # lands in the batch when `mask.reshape((-1,))` of the [rows, width, 1] slice is a VIEW, i.e. when the
+            # slice spans the whole row length or there is a single row (otherwise numpy hands back a copy).
+            mcol = self._mask_range[0]
+            nz = []
+            for src, r, p, n in entries:
+                t = np.nonzero(self.memory_buffer[src:src + n, mcol])[0] + p + skip
+                nz.append(r * width + t[t < width])
+            nz = np.sort(np.concatenate(nz)) if nz else np.zeros(0, dtype=np.int64)
+            kill = nz[np.random.permutation(nz.shape[0])[:-valid_number_post_randomized]]
+            if width == self.max_traj_step or len(groups) == 1:
+                mask_zero.append((kill // width) * Lmax + kill % width)
         lens_arr = np.zeros((len(groups), max(len(s) for s in summary)))
         for r, s in enumerate(summary):
             lens_arr[r, :len(s)] = s
+        mz = np.concatenate(mask_zero).astype(np.int64) if mask_zero else np.zeros(0, dtype=np.int64)
         return SamplePlan(np.asarray(entries, dtype=np.int64).reshape(-1, 4), np.asarray(row_end, dtype=np.int64),
-                          len(groups), width, int(sum(lens) - len(lens) * skip), lens_arr)
+                          len(groups), width, int(sum(lens) - len(lens) * skip), lens_arr, mz)
 
     # ---- device: gather -----------------------------------------------------------------------------------------
     def _colmap(self):
@@ -124,18 +173,17 @@ class NestedMemoryArray(MemoryArray):
                self._rnn_start_range[0], N.ptr(batch), N.ptr(valid), rows, Lmax, self._skip_step,
                int(plan.entries[:, 3].max()), N.stream())
         dplan.record_stream(torch.cuda.current_stream())
+        if plan.mask_zero.size:                      # randomize_mask: clear the chosen entries of the batch's mask column
+            idx = torch.from_numpy(plan.mask_zero * F + self._mask_range[0]).pin_memory().to(self.device, non_blocking=True)
+            self._batch_cache[0].view(-1).index_fill_(0, idx, 0.0)
         return batch[:, :plan.width], valid[:, :plan.width].unsqueeze(-1)
-
-    def _reject_unsupported(self, randomize_mask, random_trunc_traj):
-        if randomize_mask or random_trunc_traj:
-            raise NotImplementedError('randomize_mask / random_trunc_traj are not part of the update hot path')
 
     def sample_trajs_device(self, batch_size, max_sample_size=None, get_all=False, randomize_mask=False,
                             valid_number_post_randomized=0, equalize_data_of_each_traj=False, random_trunc_traj=False,
                             copy=False, nest_stack_trajs=True):
         """-> (Transition of device fp32 views, total_size, valid indicator [rows, W, 1], traj_len_array)."""
-        self._reject_unsupported(randomize_mask, random_trunc_traj)
-        plan = self.plan_trajs(batch_size, max_sample_size, get_all, nest_stack_trajs)
+        plan = self.plan_trajs(batch_size, max_sample_size, get_all, nest_stack_trajs, randomize_mask,
+                               valid_number_post_randomized, equalize_data_of_each_traj, random_trunc_traj)
         batch, valid = self.gather_device(plan)
         return self.array_to_transition(batch), plan.total_size, valid, plan.lens
 

@@ -216,7 +216,7 @@ def fill_buffer(buf, Transition, rng, lens, S, A):
             last_s, last_a, last_r, s = s, a, np.array([[r]]), ns
 
 
-def gen_sampler():
+def gen_sampler(only=None):
     from offpolicy_rnn.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
     from offpolicy_rnn.buffers.transition_buffer.replay_memory import Transition
     cases = {
@@ -224,14 +224,32 @@ def gen_sampler():
         "b": dict(skip_extra=4, max_step=20, lens=[5, 3, 6, 4, 20, 9, 2, 12, 7], batch=40, nest=True, S=2, A=1),
         "c": dict(skip_extra=0, max_step=12, lens=[12, 12, 5, 12, 7], batch=35, nest=False, S=2, A=2),
         "d": dict(skip_extra=16, max_step=50, lens=[50] * 6, batch=6 * 50 - 1, nest=True, S=3, A=2),
+        # sampler options: randomised masks (equalised per trajectory / global) and random truncation
+        "e": dict(skip_extra=0, max_step=20, lens=[5, 3, 6, 4, 20, 9, 1, 12], batch=30, nest=True, S=3, A=2,
+                  randomize_mask=True, equalize=True, valid_num=14),
+        "f": dict(skip_extra=4, max_step=20, lens=[5, 3, 6, 4, 20, 9, 2, 12, 7], batch=20, nest=True, S=2, A=1,
+                  random_trunc=True),
+        "g": dict(skip_extra=0, max_step=12, lens=[12, 12, 5, 12, 7], batch=35, nest=False, S=2, A=2,
+                  randomize_mask=True, equalize=False, valid_num=9),
+        "h": dict(skip_extra=1, max_step=16, lens=[7, 3, 6, 4, 9, 1, 12], batch=25, nest=True, S=2, A=2,
+                  randomize_mask=True, equalize=False, valid_num=6),
+        # a row filled to the full row length: the one case in which the reference's global mask randomisation actually
+        # reaches the batch (its `mask.reshape((-1,))` is a view only then)
+        "i": dict(skip_extra=0, max_step=14, lens=[14, 6, 7], batch=26, nest=True, S=2, A=2,
+                  randomize_mask=True, equalize=False, valid_num=10),
     }
     for tag, c in cases.items():
+        if only and tag not in only:
+            continue
         buf = NestedMemoryArray(500, c["max_step"], additional_history_len=c["skip_extra"])
         fill_buffer(buf, Transition, np.random.RandomState(3), c["lens"], c["S"], c["A"])
         np.random.seed(11)
         arrs = {}
         for call in range(2):   # second call exercises the cached-array reuse path
-            tr, total, valid, lens = buf.sample_trajs(c["batch"], None, equalize_data_of_each_traj=True,
+            tr, total, valid, lens = buf.sample_trajs(c["batch"], None, randomize_mask=c.get("randomize_mask", False),
+                                                      valid_number_post_randomized=c.get("valid_num", 0),
+                                                      equalize_data_of_each_traj=c.get("equalize", True),
+                                                      random_trunc_traj=c.get("random_trunc", False),
                                                       nest_stack_trajs=c["nest"])
             for n in tr._fields:
                 v = getattr(tr, n)
@@ -427,6 +445,6 @@ if __name__ == "__main__":
     if "steps" in which:
         gen_steps()
     if "sampler" in which:
-        gen_sampler()
+        gen_sampler([w[len("sampler_"):] for w in which if w.startswith("sampler_")] or None)
     if "updates" in which:
         gen_updates()

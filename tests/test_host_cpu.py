@@ -101,10 +101,11 @@ def _apply_plan_numpy(buf, plan):
         valid[row, ptr + skip:ptr + skip + n, 0] = buf.memory_buffer[src:src + n, mc]
     for row, e in enumerate(plan.row_end):
         out[row, e:, sc] = 1
+    out[..., mc].reshape(-1)[plan.mask_zero] = 0          # randomize_mask (a view: out is contiguous)
     return out[:, :plan.width], valid[:, :plan.width]
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e", "f", "g", "h", "i"])
 def test_sampler_plan_bit_exact(tag):
     from rorl_b200.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
     from rorl_b200.buffers.transition_buffer.replay_memory import Transition
@@ -114,7 +115,9 @@ def test_sampler_plan_bit_exact(tag):
     _fill(buf, Transition, np.random.RandomState(3), c["lens"], c["S"], c["A"])
     np.random.seed(11)
     for call in range(2):
-        plan = buf.plan_trajs(c["batch"], None, nest_stack_trajs=c["nest"])
+        plan = buf.plan_trajs(c["batch"], None, nest_stack_trajs=c["nest"], randomize_mask=c.get("randomize_mask", False),
+                              valid_number_post_randomized=c.get("valid_num", 0),
+                              equalize_data_of_each_traj=c.get("equalize", True), random_trunc_traj=c.get("random_trunc", False))
         data, valid = _apply_plan_numpy(buf, plan)
         tr = buf.array_to_transition(data)
         for n in tr._fields:

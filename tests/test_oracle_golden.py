@@ -118,7 +118,7 @@ def _fill(buf, rng, lens, S, A):
             last_s, last_a, last_r, s = s, a, np.array([[r]]), ns
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e", "f", "g", "h", "i"])
 def test_sampler_bit_exact(tag):
     g = load_npz(f"sampler_{tag}.npz")
     c = cfg_of(g)
@@ -126,7 +126,10 @@ def test_sampler_bit_exact(tag):
     _fill(buf, np.random.RandomState(3), c["lens"], c["S"], c["A"])
     np.random.seed(11)
     for call in range(2):
-        tr, total, valid, lens = buf.sample_trajs(c["batch"], nest_stack_trajs=c["nest"])
+        tr, total, valid, lens = buf.sample_trajs(c["batch"], nest_stack_trajs=c["nest"], randomize_mask=c.get("randomize_mask", False),
+                                                  valid_number_post_randomized=c.get("valid_num", 0),
+                                                  equalize_data_of_each_traj=c.get("equalize", True),
+                                                  random_trunc_traj=c.get("random_trunc", False))
         for n in OS.FIELDS:
             v = getattr(tr, n)
             key = f"c{call}/{n}"

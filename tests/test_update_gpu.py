@@ -94,14 +94,17 @@ def test_sampler_device_bit_exact():
     """Device gather == reference sample_trajs bit for bit (after the fp32 cast n2t applies)."""
     from rorl_b200.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
     from rorl_b200.buffers.transition_buffer.replay_memory import Transition
-    for tag in ("a", "b", "c", "d"):
+    for tag in ("a", "b", "c", "d", "e", "f", "g", "h", "i"):
         g = load_npz(f"sampler_{tag}.npz")
         c = cfg_of(g)
         buf = NestedMemoryArray(500, c["max_step"], additional_history_len=c["skip_extra"], device=torch.device("cuda:0"))
         fill_buffer(buf, Transition, np.random.RandomState(3), c["lens"], c["S"], c["A"])
         np.random.seed(11)
         for call in range(2):
-            tr, total, valid, lens = buf.sample_trajs_device(c["batch"], None, equalize_data_of_each_traj=True,
+            tr, total, valid, lens = buf.sample_trajs_device(c["batch"], None, randomize_mask=c.get("randomize_mask", False),
+                                                            valid_number_post_randomized=c.get("valid_num", 0),
+                                                            equalize_data_of_each_traj=c.get("equalize", True),
+                                                            random_trunc_traj=c.get("random_trunc", False),
                                                             nest_stack_trajs=c["nest"])
             for n in tr._fields:
                 v = getattr(tr, n)
