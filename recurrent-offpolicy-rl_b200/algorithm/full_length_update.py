@@ -246,6 +246,13 @@ class FullLengthRNNUpdate:
             self._sync_value = BucketedGradSync(self.value_arena.params, self.value_arena.offsets, self.value_arena.grad, self.dist_group)
             self._sync_policy = BucketedGradSync(self.policy_arena.params, self.policy_arena.offsets, self.policy_arena.grad, self.dist_group)
 
+    def invalidate_graphs(self):
+        """Drop every captured CUDA graph.  Scalars that are plain Python numbers at launch time (gamma, tau, the
+        target entropy, noise scales) are baked into a captured graph, so call this after changing a hyper-parameter
+        on a live object; weights, optimizer state and learning-rate tables live in device memory and need no
+        re-capture.  (`load_models` / `_finalize_models` call it themselves: the arenas move.)"""
+        self._graphs, self._graph_pool = {}, None
+
     def load_models(self, policy_sd=None, value_sd=None):
         if policy_sd is not None:
             self.policy.load_state_dict(policy_sd)
