@@ -280,3 +280,52 @@ def test_cuda_graph_replay_matches_eager(enc, algo):
         exact = exact and torch.equal(se[k], sg[k])
         worst = max(worst, assert_close(sg[k], se[k], 2e-4, k))
     print(f"graph vs eager after 5 updates: bit-identical={exact}, worst relative difference {worst:.2e}")
+
+
+def test_host_batch_entry_matches_device_sampler():
+    """`update_on_host_batch` (the end-to-end entry for callers that keep the reference's host-side sampler: pinned fp32
+    batch in the sample_trajs layout, copied H2D inside the call) leaves exactly what `train_one_batch` leaves when it is
+    handed the batch the device sampler would have produced."""
+    from rorl_b200.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.buffers.transition_buffer.replay_memory import Transition
+    S, A, H = 5, 3, 64
+    lens = [40, 33, 25, 37]
+    enc = "smamba_s16_c4_b1"
+    kw = lambda value: dict(state_dim=S, action_dim=A, embedding_size=32, embedding_hidden=[H, H],
+                            embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', enc, 'fc'],
+                            uni_model_hidden=[H, H], uni_model_activations=['elu', 'elu', 'linear'],
+                            uni_model_layer_type=(['efc-8'] * 3 if value else ['fc'] * 3), fix_rnn_length=0,
+                            uni_model_input_mapping_dim=32, reward_input=False, last_action_input=True,
+                            last_state_input=True, separate_encoder=True)
+    hp = dict(gamma=0.99, sac_tau=0.995, policy_update_per=1, redq_m=2, policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5,
+              rnn_value_lr=1e-5, alpha_lr=1e-4, target_entropy_ratio=1.0, sac_batch_size=sum(lens) - 1,
+              max_buffer_transition_num=1000)
+
+    def noise(like):
+        return torch.cos(torch.arange(like.numel(), device=like.device, dtype=torch.float32) * 7.31).reshape(like.shape)
+    noise.graph_safe = True
+    outs = []
+    for host in (False, True):
+        torch.manual_seed(3)
+        alg = SACFullLengthRNNREDQ_SEP_OPTIM(dict(hp), kw(False), kw(True), max(lens), device=torch.device("cuda:0"))
+        alg.policy.noise_fn = alg.target_policy.noise_fn = noise
+        fill_buffer(alg.replay_buffer, Transition, np.random.RandomState(4), lens, S, A)
+        np.random.seed(50)
+        logs = []
+        for _ in range(4):
+            if not host:
+                logs.append(alg.train_one_batch())
+            else:
+                plan = alg.replay_buffer.plan_trajs(hp["sac_batch_size"], None, nest_stack_trajs=alg.allow_nest_stack)
+                b_dev, v_dev = alg.replay_buffer.gather_device(plan)
+                hb, hv = b_dev.contiguous().cpu().pin_memory(), v_dev.contiguous().cpu().pin_memory()
+                logs.append(alg.update_on_host_batch(hb, hv, plan.total_size, plan.lens))
+        sd = {f"{w}/{m}/{n}": t.detach().clone() for w, model in (("p", alg.policy), ("v", alg.values[0]), ("t", alg.target_values[0]))
+              for m, params in model.state_dict().items() for n, t in params.items()}
+        outs.append((logs, sd))
+    (la, sa), (lb, sb) = outs
+    for a, b in zip(la, lb):
+        for k in ("critic_loss", "actor_loss", "alpha_loss", "target_q_max", "real_batch_size"):
+            assert abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    for k in sa:
+        assert_close(sb[k], sa[k], 1e-5, k)
