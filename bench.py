@@ -308,11 +308,21 @@ def gemm_roofline(dev):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def oracle_update_runner(encoder, n_traj, algo="sac"):
+def oracle_update_runner(encoder, n_traj, algo="sac", s_dim=None, a_dim=None, t_len=None):
     """Build the oracle's CPU update (test infrastructure; allowed here as the cpu_baseline / reference leg)."""
     import torch
     from oracle import model as OM, sampler as OS, update as OU
     from rorl_b200.policy_value_models.make_models import make_policy_model, make_value_model
+    global S_DIM, A_DIM, T_LEN
+    saved = (S_DIM, A_DIM, T_LEN)
+    S_DIM, A_DIM, T_LEN = s_dim or S_DIM, a_dim or A_DIM, t_len or T_LEN
+    try:
+        return _oracle_update_runner(encoder, n_traj, algo, OM, OS, OU, make_policy_model, make_value_model, torch)
+    finally:
+        S_DIM, A_DIM, T_LEN = saved
+
+
+def _oracle_update_runner(encoder, n_traj, algo, OM, OS, OU, make_policy_model, make_value_model, torch):
     torch.manual_seed(0)
     np.random.seed(0)
     pk, vk = model_kwargs(encoder, False), model_kwargs(encoder, True)
@@ -321,7 +331,7 @@ def oracle_update_runner(encoder, n_traj, algo="sac"):
     buf = OS.RefNestedReplay(n_traj * T_LEN + 8, T_LEN, additional_history_len=skip - 1)
     rng = np.random.RandomState(1000)
     for _ in range(n_traj):
-        rows = synth_trajectory(rng)
+        rows = synth_trajectory(rng, T_LEN)
         if buf.buf is None:
             t = template_transition()
             buf._init(t)
@@ -350,9 +360,19 @@ def cpu_baseline(encoder, n_traj, updates, warm):
     for _ in range(updates):
         upd.train_one_batch()
     dt = (time.perf_counter() - t0) / updates
-    return {"value": valid / dt, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{updates} timed SAC updates (after {warm} warm-up) of the oracle CPU port with the {encoder} encoder on "
-                      f"{n_traj} trajectories x {T_LEN} steps, torch CPU ops on {cores} threads", "s_per_update": dt}
+    out = {"value": valid / dt, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+           "sample": f"{updates} timed SAC updates (after {warm} warm-up) of the oracle CPU port with the {encoder} encoder on "
+                     f"{n_traj} trajectories x {T_LEN} steps, torch CPU ops on {cores} threads", "s_per_update": dt}
+    # the reference's own CPU-runnable case (BASELINE.json configs[0]): Pendulum-V shapes, 8 trajectories x 200 steps
+    upd, valid = oracle_update_runner(encoder, 8, s_dim=1, a_dim=1, t_len=200)
+    upd.train_one_batch()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        upd.train_one_batch()
+    dt1 = (time.perf_counter() - t0) / 3
+    out["config1"] = {"value": valid / dt1, "unit": "trajectory-steps/s", "s_per_update": dt1,
+                      "sample": f"3 timed SAC updates (after 1 warm-up), {encoder} encoder, 8 trajectories x 200 steps, obs 1, act 1"}
+    return out
 
 
 def run_reference(args):
