@@ -328,7 +328,7 @@ def _oracle_update_runner(encoder, n_traj, algo, OM, OS, OU, make_policy_model, 
     pk, vk = model_kwargs(encoder, False), model_kwargs(encoder, True)
     pol, val = make_policy_model(pk, algo, False), make_value_model(vk, algo, False)   # weights only (CPU tensors)
     skip = 1 + max([l.d_conv for l in pol.embedding_network.layer_list if hasattr(l, 'd_conv')] + [0])
-    buf = OS.RefNestedReplay(n_traj * T_LEN + 8, T_LEN, additional_history_len=skip - 1)
+    buf = OS.RefNestedReplay(n_traj * T_LEN + 8, T_LEN, additional_history_len=skip)
     rng = np.random.RandomState(1000)
     for _ in range(n_traj):
         rows = synth_trajectory(rng, T_LEN)

@@ -196,13 +196,17 @@ int rorl_actor_loss_fwd_bwd(const float* q, const float* logp, const float* mask
  * soft-update loop (ref: offpolicy_rnn/models/rnn_base.py:475-491).
  * p, g, m, v (and target, may be NULL): flat fp32 arrays of n elements; seg_end[nseg] (int64, device)
  * and seg_lr / seg_wd [nseg] (double, device) describe contiguous LR / weight-decay groups (nseg <= 64);
- * step_ptr: device int32 count of completed steps (incremented on the stream after the update);
- * grad_clip_value: clamp every gradient to +-value first (clip_grad_value_; <= 0 = off).
+ * step_ptr: device int32 count of completed steps (incremented on the stream after the update).
+ * Gradient clipping (ref: sac_full_length_rnn_ensembleQ.py:239-250,274-287), applied to g IN PLACE before the step:
+ *   gnorm_sq != NULL: clip_grad_norm_ -- g *= min(1, max_norm / (sqrt(gnorm_sq[0]) + 1e-6)), gnorm_sq[0] = sum(g^2)
+ *                     over the model (device scalar, e.g. from rorl_sumsq);
+ *   seg_clip != NULL: clip_grad_value_ -- per-segment bound (double[nseg], <= 0 = off).
  * target <- tau * target + (1 - tau) * p_new when target != NULL.
  * ---------------------------------------------------------------------------------------------- */
-int rorl_adamw_polyak(float* p, const float* g, float* m, float* v, float* target, const int64_t* seg_end,
-                      const double* seg_lr, const double* seg_wd, int64_t nseg, int64_t n, float beta1, float beta2,
-                      float eps, float tau, int32_t* step_ptr, float grad_clip_value, cudaStream_t stream);
+int rorl_adamw_polyak(float* p, float* g, float* m, float* v, float* target, const int64_t* seg_end,
+                      const double* seg_lr, const double* seg_wd, const double* seg_clip, int64_t nseg, int64_t n,
+                      float beta1, float beta2, float eps, float tau, int32_t* step_ptr, const float* gnorm_sq,
+                      float max_norm, cudaStream_t stream);
 /* out[0] = sum(p^2) (l2_norm_square, ref rnn_base.py:531-532) */
 int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t stream);
 

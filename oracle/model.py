@@ -244,10 +244,10 @@ def s6_layer(p, pre, x, side: Side, layer_id: str, hidden=None):
     return F.linear(rms(out, p[pre + 'norm_f.weight']), p[pre + 'ff.weight']), h_out
 
 
-def gru_layer(p, pre, x, side: Side):
-    """torch.nn.GRU(batch_first=True), zero initial state.  ref: rnn_base.py:59,245-247,454"""
-    hidden = p[pre + 'weight_hh_l0'].shape[1]
-    h0 = torch.zeros((1, x.shape[0], hidden), dtype=x.dtype)
+def gru_layer(p, pre, x, side: Side, hidden=None):
+    """torch.nn.GRU(batch_first=True); initial state zero unless one is carried in ([1, B, H]).  ref: rnn_base.py:59,245-247,454"""
+    width = p[pre + 'weight_hh_l0'].shape[1]
+    h0 = torch.zeros((1, x.shape[0], width), dtype=x.dtype) if hidden is None else hidden
     flat = [p[pre + 'weight_ih_l0'], p[pre + 'weight_hh_l0'], p[pre + 'bias_ih_l0'], p[pre + 'bias_hh_l0']]
     out, _ = torch._VF.gru(x, h0, flat, True, 1, 0.0, False, False, True)
     return out
@@ -295,7 +295,7 @@ def rnn_base(p: Dict[str, torch.Tensor], layer_types: List[str], acts: List[str]
             x, h = s6_layer(p, pre, x, side, lt, side.h0.get(i))
             side.h_out = h
         elif lt == 'gru':
-            x = gru_layer(p, pre, x, side)
+            x = gru_layer(p, pre, x, side, side.h0.get(i))
         elif lt.startswith('cgpt'):
             x = cgpt_layer(p, pre, x, side, lt)
         else:

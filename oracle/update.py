@@ -22,9 +22,12 @@ def clone_sd(sd, requires_grad=False):
     return {k: {n: t.detach().clone().requires_grad_(requires_grad) for n, t in v.items()} for k, v in sd.items()}
 
 
-def param_groups(sd, rnn_lr, l2):
-    """RESeL split by module NAME: the whole embedding_model goes to the slow group.
-    ref: sac_full_length_rnn_redq_sep_optim.py:49-79"""
+def param_groups(sd, rnn_lr, l2, sep_optim=True):
+    """RESeL split by module NAME: the whole embedding_model goes to the slow group
+    (ref: sac_full_length_rnn_redq_sep_optim.py:49-79); the plain classes run one AdamW group over all parameters
+    (ref: sac.py:81-90)."""
+    if not sep_optim:
+        return [{'params': [t for mod in sd.values() for t in mod.values()]}]
     groups = []
     for k, mod in sd.items():
         params = list(mod.values())
@@ -41,7 +44,8 @@ class RefUpdate:
     """State of the reference algorithm object that `train_one_batch` touches."""
 
     def __init__(self, policy_sd, value_sd, policy_spec: M.ModelSpec, value_spec: M.ModelSpec, hp, replay,
-                 noise_fn: Callable, algo='sac', redq=True, allow_nest_stack=True, module_order=None):
+                 noise_fn: Callable, algo='sac', redq=True, allow_nest_stack=True, module_order=None, sep_optim=True,
+                 hidden_fn: Callable = None):
         self.hp = hp
         self.algo, self.redq = algo, redq
         self.pspec, self.vspec = policy_spec, value_spec
@@ -51,10 +55,11 @@ class RefUpdate:
         self.target_policy = clone_sd(policy_sd, False)
         self.log_alpha = torch.zeros(1, requires_grad=True)
         self.target_entropy = -float(policy_spec.action_dim) * hp.get('target_entropy_ratio', 1.0)
-        self.opt_pi = torch.optim.AdamW(param_groups(self.policy, hp['rnn_policy_lr'], hp.get('policy_l2_norm', 0.0)),
+        self.opt_pi = torch.optim.AdamW(param_groups(self.policy, hp['rnn_policy_lr'], hp.get('policy_l2_norm', 0.0), sep_optim),
                                         lr=hp['policy_lr'], weight_decay=hp.get('policy_l2_norm', 0.0))
-        self.opt_q = torch.optim.AdamW(param_groups(self.value, hp['rnn_value_lr'], hp.get('value_l2_norm', 0.0)),
+        self.opt_q = torch.optim.AdamW(param_groups(self.value, hp['rnn_value_lr'], hp.get('value_l2_norm', 0.0), sep_optim),
                                        lr=hp['value_lr'], weight_decay=hp.get('value_l2_norm', 0.0))
+        self.hidden_fn = hidden_fn
         self.opt_alpha = torch.optim.AdamW([self.log_alpha], lr=hp['alpha_lr'])
         self.guard = QValueGuard(decay_ratio=1 - 1e-3)
         self.replay = replay
@@ -65,7 +70,34 @@ class RefUpdate:
     def _mask_mean(self, data, mask, n):
         return (data * mask).sum() / n
 
+    def _clip(self, sd, max_norm, emb_clip):
+        """ref: sac_full_length_rnn_ensembleQ.py:239-250,274-287 -- global-norm clip, then value clip on the embedding
+        network plus the hard-coded 1e-3 on every smamba A_log; returns the logged gradient norm."""
+        norm = 0.0
+        if max_norm is not None:
+            norm = torch.nn.utils.clip_grad_norm_([t for m in sd.values() for t in m.values()], max_norm, norm_type=2).item()
+        if emb_clip is not None:
+            torch.nn.utils.clip_grad_value_(list(sd['embedding_model'].values()), emb_clip)
+            a_logs = [t for n, t in sd['embedding_model'].items() if n.endswith('mixer.A_log') and '.layers.' in n]
+            if a_logs:
+                torch.nn.utils.clip_grad_value_(a_logs, 1e-3)
+            norm = 0.0
+        return norm
+
     def train_one_batch(self) -> Dict[str, float]:
+        """utd iterations of `_one_update` with the reference's actor cadence (ref :311,405)."""
+        hp = self.hp
+        utd, cnt, out, pol = hp.get('utd', 1), 0, None, {}
+        for i in range(utd):
+            did = self.grad_num % hp.get('policy_update_per', 1) == 0 and (i + 1) / utd * hp.get('policy_utd', 1) > cnt
+            out = self._one_update(did)
+            cnt += int(did)
+            pol.update({k: out[k] for k in ('actor_loss', 'alpha_loss', 'log_prob', 'policy_grad_norm', 'policy_l2_norm_square') if k in out})
+        out.update(pol)
+        self.grad_num += 1
+        return out
+
+    def _one_update(self, did_policy) -> Dict[str, float]:
         hp = self.hp
         f32 = lambda a: torch.from_numpy(a).to(torch.float32)
         batch, total, valid_ind, len_arr = self.replay.sample_trajs(hp['sac_batch_size'], nest_stack_trajs=self.allow_nest_stack)
@@ -82,8 +114,13 @@ class RefUpdate:
         att = torch.cat((att, torch.zeros((att.shape[0], state.shape[-2] - att.shape[1]))), dim=-1)
         tgt_att = torch.cat((att[..., 1:], torch.zeros((att.shape[0], 1))), dim=-1).to(torch.int)
         att = att.to(torch.int)
-        side_t = M.Side(total_start, total_valid, tgt_att)
-        side = M.Side(rnn_start, valid_ind, att)
+        h0_pi = h0_qt = h0_q = None
+        if hp.get('randomize_first_hidden', False):       # ref :345-351 (one draw per model; both policy passes share theirs)
+            h0_pi, h0_qt, h0_q = (self.hidden_fn(spec, state.shape[0]) for spec in (self.pspec, self.vspec, self.vspec))
+        side_t = M.Side(total_start, total_valid, tgt_att, h0=h0_pi)
+        side_qt = M.Side(total_start, total_valid, tgt_att, h0=h0_qt)
+        side = M.Side(rnn_start, valid_ind, att, h0=h0_q)
+        side_pi = M.Side(rnn_start, valid_ind, att, h0=h0_pi)
         td3 = self.algo == 'td3'
         # ---- target (no grad) -------------------------------------------------------------- :83-103
         with torch.no_grad():
@@ -95,7 +132,7 @@ class RefUpdate:
                 n2 = self.noise_fn(a_mean.shape)
                 a_next = torch.clamp(a_mean + torch.clamp(n2 * hp['target_action_noise_std'], -hp['target_action_noise_clip'],
                                                           hp['target_action_noise_clip']), -1, 1)
-            q_next, _ = M.value_forward(self.target, self.vspec, next_state, state, action, a_next, side_t, reward)
+            q_next, _ = M.value_forward(self.target, self.vspec, next_state, state, action, a_next, side_qt, reward)
             if self.redq:
                 idx = np.random.permutation(q_next.shape[0])[:hp['redq_m']]
                 q_next = q_next[idx, :]
@@ -110,6 +147,7 @@ class RefUpdate:
         q_loss = self._mask_mean((q - target_q.unsqueeze(0)).pow(2).sum(dim=0), mask, n_valid)
         self.opt_q.zero_grad()
         q_loss.backward()
+        q_norm = self._clip(self.value, hp.get('value_max_gradnorm'), hp.get('value_embedding_max_gradnorm'))
         self.value_grads = {k: {n: (t.grad.clone() if t.grad is not None else None) for n, t in v.items()} for k, v in self.value.items()}
         self.opt_q.step()
         tau = hp['sac_tau']
@@ -118,11 +156,12 @@ class RefUpdate:
                 for n in self.value[k]:
                     tp = self.target[k][n]
                     tp.copy_(tp * tau + (1 - tau) * self.value[k][n])
-        out = {'critic_loss': q_loss.item(), 'target_q_max': target_q.abs().max().item(), 'real_batch_size': total}
+        out = {'critic_loss': q_loss.item(), 'target_q_max': target_q.abs().max().item(), 'real_batch_size': total,
+               'value_grad_norm': q_norm}
         # ---- actor + alpha ----------------------------------------------------------------- :116-132,405-432
-        if self.grad_num % hp.get('policy_update_per', 1) == 0:
+        if did_policy:
             noise = self.noise_fn(state.shape[:-1] + (self.pspec.action_dim,))
-            a_mean, _, a_samp, logp = M.policy_forward(self.policy, self.pspec, state, last_state, last_action, side,
+            a_mean, _, a_samp, logp = M.policy_forward(self.policy, self.pspec, state, last_state, last_action, side_pi,
                                                        reward_input, noise, td3, hp.get('sample_std', 0.1))
             a_in = a_mean if td3 else a_samp
             qp, _ = M.value_forward(self.value, self.vspec, state, last_state, last_action, a_in, side, reward_input,
@@ -131,9 +170,12 @@ class RefUpdate:
             actor_loss = self._mask_mean((-agg) if td3 else (alpha * logp - agg), mask, n_valid)
             self.opt_pi.zero_grad()
             actor_loss.backward()
+            out['policy_grad_norm'] = self._clip(self.policy, hp.get('policy_max_gradnorm'), hp.get('policy_embedding_max_gradnorm'))
             self.policy_grads = {k: {n: (t.grad.clone() if t.grad is not None else None) for n, t in v.items()} for k, v in self.policy.items()}
             self.opt_pi.step()
             out['actor_loss'] = actor_loss.item()
+            out['policy_l2_norm_square'] = sum(float((t.detach() ** 2).sum()) for k in ('embedding_model', 'universal_model', 'uni_input_mapping_network')
+                                               if k in self.policy for t in self.policy[k].values())
             if not td3:
                 alpha_loss = -self._mask_mean(self.log_alpha * (logp + self.target_entropy).detach(), mask, n_valid)
                 self.opt_alpha.zero_grad()
@@ -145,5 +187,6 @@ class RefUpdate:
                 out['log_prob'] = self._mask_mean(logp, mask, n_valid).item()
         out['log_alpha'] = self.log_alpha.item()
         out['clip_min'], out['clip_max'] = self.guard.min, self.guard.max
-        self.grad_num += 1
+        out['q1_l2_norm_square'] = sum(float((t.detach() ** 2).sum()) for k in ('embedding_model', 'universal_model', 'uni_input_mapping_network')
+                                       if k in self.value for t in self.value[k].values())   # ref :454, contextual_model.py:227-228
         return out

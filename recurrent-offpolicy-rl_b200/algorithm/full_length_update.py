@@ -102,42 +102,73 @@ class FlatArena:
 
 
 class FusedAdamW:
-    """AdamW(betas=(0.9, 0.999), eps=1e-8) over a FlatArena with contiguous lr / weight-decay segments, fused with
-    the Polyak target update when a target arena is given (csrc/optim.cu)."""
+    """AdamW(betas=(0.9, 0.999), eps=1e-8) over a FlatArena with contiguous lr / weight-decay / clip-value segments,
+    fused with the Polyak target update when a target arena is given, and with the reference's gradient clipping
+    (csrc/optim.cu): `max_norm` = clip_grad_norm_ over the whole model, `clip_values` = {id(param): bound} for
+    clip_grad_value_ (ref: sac_full_length_rnn_ensembleQ.py:239-250,274-287)."""
 
-    def __init__(self, arena: FlatArena, groups: List[dict], lr: float, weight_decay: float, target: Optional[FlatArena] = None):
+    def __init__(self, arena: FlatArena, groups: List[dict], lr: float, weight_decay: float, target: Optional[FlatArena] = None,
+                 max_norm: Optional[float] = None, clip_values: Optional[Dict[int, float]] = None, work: Optional[torch.Tensor] = None,
+                 gnorm_out: Optional[torch.Tensor] = None):
         self.arena, self.target = arena, target
         dev = arena.flat.device
         self.m = torch.zeros_like(arena.flat)
         self.v = torch.zeros_like(arena.flat)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        per_param = {}
+        self.max_norm = None if max_norm is None else float(max_norm)
+        self.gnorm_sq = gnorm_out if gnorm_out is not None else torch.zeros(1, dtype=torch.float32, device=dev)
+        self._work = work
+        self._per_param = {}
         for g in groups:
             for p in g["params"]:
-                per_param[id(p)] = (g.get("lr", lr), g.get("weight_decay", weight_decay))
-        ends, lrs, wds = [], [], []
-        for p, off in zip(arena.params, arena.offsets):
-            cfg = per_param[id(p)]
+                self._per_param[id(p)] = (g.get("lr", lr), g.get("weight_decay", weight_decay))
+        self._clip_values = dict(clip_values or {})
+        self._frozen = set()
+        self._build_segments()
+
+    def _build_segments(self):
+        dev = self.arena.flat.device
+        ends, cfgs = [], []
+        for p, off in zip(self.arena.params, self.arena.offsets):
+            lr_, wd_ = self._per_param[id(p)]
+            if id(p) in self._frozen:            # torch.optim skips parameters whose .grad is None: no step, no decay
+                lr_, wd_ = 0.0, 0.0
+            cfg = (lr_, wd_, float(self._clip_values.get(id(p), 0.0)))
             end = off + (p.numel() + 3) // 4 * 4
-            if lrs and (lrs[-1], wds[-1]) == cfg:
+            if cfgs and cfgs[-1] == cfg:
                 ends[-1] = end
             else:
-                ends.append(end), lrs.append(cfg[0]), wds.append(cfg[1])
+                ends.append(end), cfgs.append(cfg)
         assert len(ends) <= 64, 'too many lr segments; order modules so that groups are contiguous'
-        self.param_groups = [{"lr": a, "weight_decay": b, "end": e} for a, b, e in zip(lrs, wds, ends)]
+        self.param_groups = [{"lr": c[0], "weight_decay": c[1], "clip_value": c[2], "end": e} for c, e in zip(cfgs, ends)]
         self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
-        self.seg_lr = torch.tensor(lrs, dtype=torch.float64, device=dev)
-        self.seg_wd = torch.tensor(wds, dtype=torch.float64, device=dev)
+        self.seg_lr = torch.tensor([c[0] for c in cfgs], dtype=torch.float64, device=dev)
+        self.seg_wd = torch.tensor([c[1] for c in cfgs], dtype=torch.float64, device=dev)
+        self.seg_clip = torch.tensor([c[2] for c in cfgs], dtype=torch.float64, device=dev) if any(c[2] > 0 for c in cfgs) else None
+
+    def freeze_params_without_grad(self, got_grad: Dict[int, bool]):
+        """Parameters that never receive a gradient (e.g. GILRLayer.layer_norm, constructed but unused) keep
+        `.grad is None` in the reference, so torch.optim.AdamW skips them -- no weight decay either."""
+        frozen = {id(p) for p in self.arena.params if not got_grad.get(id(p), False)}
+        if frozen != self._frozen:
+            self._frozen = frozen
+            self._build_segments()
+            return True
+        return False
 
     def zero_grad(self):
         self.arena.zero_grad()
 
-    def step(self, tau: Optional[float] = None, clip_value: float = 0.0):
+    def step(self, tau: Optional[float] = None):
         tgt = self.target.flat if (self.target is not None and tau is not None) else None
+        gn = None
+        if self.max_norm is not None:
+            N.call("rorl_sumsq", N.ptr(self.arena.grad), self.arena.numel, N.ptr(self.gnorm_sq), N.ptr(self._work), N.stream())
+            gn = self.gnorm_sq
         N.call("rorl_adamw_polyak", N.ptr(self.arena.flat), N.ptr(self.arena.grad), N.ptr(self.m), N.ptr(self.v),
-               N.ptr(tgt), N.ptr(self.seg_end), N.ptr(self.seg_lr), N.ptr(self.seg_wd), len(self.param_groups),
-               self.arena.numel, 0.9, 0.999, 1e-8, float(tau if tau is not None else 1.0), N.ptr(self.step_count),
-               float(clip_value), N.stream())
+               N.ptr(tgt), N.ptr(self.seg_end), N.ptr(self.seg_lr), N.ptr(self.seg_wd), N.ptr(self.seg_clip),
+               len(self.param_groups), self.arena.numel, 0.9, 0.999, 1e-8, float(tau if tau is not None else 1.0),
+               N.ptr(self.step_count), N.ptr(gn), float(self.max_norm or 0.0), N.stream())
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -152,15 +183,13 @@ class FullLengthRNNUpdate:
     """
     base_algorithm = 'sac'
     use_redq = True
+    sep_optim = False           # RESeL per-encoder learning-rate split: only the *_SEP_OPTIM classes (ref: sac.py:81-90 otherwise)
 
     def __init__(self, parameter, policy_args: dict, value_args: dict, max_trajectory_len: int, device=None,
                  dist_group=None):
         hp = dict(DEFAULTS)
         hp.update(parameter if isinstance(parameter, dict) else vars(parameter))
         self.parameter = SimpleNamespace(**hp)
-        for opt in ('policy_max_gradnorm', 'policy_embedding_max_gradnorm', 'value_max_gradnorm', 'value_embedding_max_gradnorm'):
-            if hp.get(opt) is not None:
-                raise NotImplementedError(f'{opt}: gradient clipping is not wired into the fused optimizer yet (all published configs leave it None)')
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = self.sample_device = torch.device(device)
@@ -193,14 +222,14 @@ class FullLengthRNNUpdate:
         self.log_sac_alpha = torch.tensor([a0], dtype=torch.float32, device=self.device, requires_grad=True)
         self.target_entropy = -float(policy_args['action_dim']) * self.parameter.target_entropy_ratio
         self.replay_buffer = NestedMemoryArray(self.parameter.max_buffer_transition_num, max_trajectory_len,
-                                               additional_history_len=self._get_skip_len() - 1, device=self.device)
+                                               additional_history_len=self._get_skip_len(), device=self.device)
         self.Q_guard = QValueGuard(True, True, 1 - 1e-3, device=self.device)
         self.allow_nest_stack = self.allow_nest_stack_trajs()
         self.grad_num = 0
-        self._finalize_models()
         # scratch for the fused reductions
         self._work = torch.zeros(int(N.lib().rorl_loss_work_floats(0)), dtype=torch.float32, device=self.device)
         self._stats = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self._finalize_models()
         self._ensemble_size = int(value_args['uni_model_layer_type'][-1].split('-')[-1])
         self._h2d_stage = None
         self._has_gpt = any('gpt' in lid for net in (self.values[0].embedding_network, self.policy.embedding_network,
@@ -222,12 +251,44 @@ class FullLengthRNNUpdate:
         self.alpha_arena = SimpleNamespace(flat=self.log_sac_alpha.data, grad=torch.zeros_like(self.log_sac_alpha.data),
                                            params=[self.log_sac_alpha], offsets=[0], numel=1, zero_grad=lambda: None)
         p = self.parameter
-        self.optimizer_policy = FusedAdamW(self.policy_arena, prepare_param_list(self.policy, p.rnn_policy_lr, p.policy_l2_norm),
-                                           p.policy_lr, p.policy_l2_norm)
-        self.optimizer_value = FusedAdamW(self.value_arena, prepare_param_list(self.values[0], p.rnn_value_lr, p.value_l2_norm),
-                                          p.value_lr, p.value_l2_norm, target=self.target_arena)
+
+        def groups(model, rnn_lr, l2):
+            # RESeL groups only in the *_SEP_OPTIM classes; otherwise one AdamW over all parameters (ref: sac.py:81-90)
+            return prepare_param_list(model, rnn_lr, l2) if self.sep_optim else [{"params": list(model.parameters(True))}]
+
+        def clip_values(model, bound):
+            """clip_grad_value_ on the embedding network, then the hard-coded 1e-3 on every smamba A_log
+            (ref: sac_full_length_rnn_ensembleQ.py:244-250,279-287)."""
+            if bound is None:
+                return None
+            out = {id(q): float(bound) for q in model.embedding_network.parameters(True)}
+            for layer in model.embedding_network.layer_list:
+                for sub in getattr(layer, 'layers', []):
+                    a_log = getattr(getattr(sub, 'mixer', None), 'A_log', None)
+                    if a_log is None:
+                        break                       # the reference's try/except leaves the layer at the first miss
+                    out[id(a_log)] = min(float(bound), 1e-3)
+            return out
+
+        self.optimizer_policy = FusedAdamW(self.policy_arena, groups(self.policy, p.rnn_policy_lr, p.policy_l2_norm),
+                                           p.policy_lr, p.policy_l2_norm, max_norm=p.policy_max_gradnorm,
+                                           clip_values=clip_values(self.policy, p.policy_embedding_max_gradnorm), work=self._work,
+                                           gnorm_out=self._stats[11:12])
+        self.optimizer_value = FusedAdamW(self.value_arena, groups(self.values[0], p.rnn_value_lr, p.value_l2_norm),
+                                          p.value_lr, p.value_l2_norm, target=self.target_arena, max_norm=p.value_max_gradnorm,
+                                          clip_values=clip_values(self.values[0], p.value_embedding_max_gradnorm), work=self._work,
+                                          gnorm_out=self._stats[10:11])
         # torch.optim.AdamW's default weight_decay (1e-2) applies: the reference passes only lr (ref: sac.py:90)
         self.optimizer_alpha = FusedAdamW(self.alpha_arena, [{"params": [self.log_sac_alpha]}], p.alpha_lr, 1e-2)
+        self._grad_seen = None                         # first update: learn which parameters ever receive a gradient
+        # l2_norm_square() covers the RNNBase modules only (ref: contextual_model.py:227-228): a prefix of each arena
+        self._l2_span = {}
+        for name, model, arena in (('policy', self.policy, self.policy_arena), ('value', self.values[0], self.value_arena)):
+            ids = {id(q) for m in model.contextual_modules.values() if hasattr(m, 'l2_norm_square') for q in m.parameters(True)}
+            flags = [id(q) in ids for q in arena.params]
+            n_in = sum(flags)
+            assert all(flags[:n_in]) and not any(flags[n_in:]), 'RNNBase modules must lead the arena'
+            self._l2_span[name] = arena.offsets[n_in] if n_in < len(arena.params) else arena.numel
         self.value_parameters = list(self.values[0].parameters(True))
         for m in self.values:
             m.train()
@@ -270,6 +331,8 @@ class FullLengthRNNUpdate:
                     skip = max(skip, layer.d_conv)
                 elif 'mamba' in lid:
                     skip = max(skip, layer.mixer.d_conv)
+                elif 'conv1d' in lid:
+                    skip = max(skip, layer.d_conv)
         return skip + 1
 
     def allow_nest_stack_trajs(self):
@@ -311,14 +374,22 @@ class FullLengthRNNUpdate:
 
     # ---- the hot path -----------------------------------------------------------------------------------------------
     def train_one_batch(self, sync: bool = True) -> Dict:
-        """Sample a trajectory batch from the device-resident replay and run one update on it."""
+        """Sample trajectory batches from the device-resident replay and run `utd` updates on them (ref :311-434):
+        every iteration updates the critic; the actor / alpha follow the reference's cadence
+        `grad_num % policy_update_per == 0 and (utd_idx + 1) / utd * policy_utd > policy_update_cnt` (ref :405)."""
         p = self.parameter
-        assert p.utd == 1, 'utd > 1: call train_one_batch repeatedly'
-        # 1. sample (host plan, device gather) ------------------------------------------------------- ref :313-332
-        batch, batch_size, valid_ind, traj_len_array = self.replay_buffer.sample_trajs_device(
-            p.sac_batch_size, None, randomize_mask=p.randomize_mask, valid_number_post_randomized=p.valid_number_post_randomized,
-            equalize_data_of_each_traj=True, random_trunc_traj=p.random_trunc_traj, nest_stack_trajs=self.allow_nest_stack)
-        return self.update_on_batch(batch, batch_size, valid_ind, traj_len_array, sync=sync)
+        out, policy_update_cnt = None, 0
+        for utd_idx in range(p.utd):
+            # 1. sample (host plan, device gather) --------------------------------------------------- ref :313-332
+            batch, batch_size, valid_ind, traj_len_array = self.replay_buffer.sample_trajs_device(
+                p.sac_batch_size, None, randomize_mask=p.randomize_mask, valid_number_post_randomized=p.valid_number_post_randomized,
+                equalize_data_of_each_traj=True, random_trunc_traj=p.random_trunc_traj, nest_stack_trajs=self.allow_nest_stack)
+            did_policy = (self.grad_num % p.policy_update_per == 0) and ((utd_idx + 1) / p.utd * p.policy_utd > policy_update_cnt)
+            out = self.update_on_batch(batch, batch_size, valid_ind, traj_len_array, sync=sync and utd_idx == p.utd - 1,
+                                       did_policy=did_policy, advance=False, policy_logged=policy_update_cnt > 0)
+            policy_update_cnt += int(did_policy)
+        self.grad_num += 1                                  # the caller's `grad_num += 1` (ref: sac.py:359-362)
+        return out
 
     def update_on_host_batch(self, host_batch: torch.Tensor, host_valid: torch.Tensor, batch_size: int,
                              traj_len_array: np.ndarray, sync: bool = True) -> Dict:
@@ -333,7 +404,8 @@ class FullLengthRNNUpdate:
         valid.copy_(host_valid, non_blocking=True)
         return self.update_on_batch(self.replay_buffer.array_to_transition(batch), batch_size, valid, traj_len_array, sync=sync)
 
-    def update_on_batch(self, batch, batch_size, valid_ind, traj_len_array, sync: bool = True) -> Dict:
+    def update_on_batch(self, batch, batch_size, valid_ind, traj_len_array, sync: bool = True, did_policy: Optional[bool] = None,
+                        advance: bool = True, policy_logged: bool = False) -> Dict:
         """One update on a device-resident batch.  Host side: the REDQ subset draw (numpy global RNG, same call
         order as the reference: after the sampler's draws, ref :313 then sac_full_length_rnn_redq.py:28), the
         attention length tables, the policy-update cadence.  Device side: the segments of `_stages`, either launched eagerly
@@ -345,7 +417,8 @@ class FullLengthRNNUpdate:
         B, L = batch.state.shape[0], batch.state.shape[1]
         E = self._ensemble_size
         sel_np = np.random.permutation(E)[:p.redq_m] if self.use_redq else np.arange(E)
-        did_policy = self.grad_num % p.policy_update_per == 0
+        if did_policy is None:
+            did_policy = self.grad_num % p.policy_update_per == 0 and p.policy_utd > 0
         # a fresh pinned staging tensor per step: the host runs ahead of the stream, and the caching host allocator does
         # not hand the block out again before the asynchronous copy that reads it has completed
         sel_pinned = torch.from_numpy(np.asarray(sel_np, dtype=np.int32)).pin_memory()
@@ -395,23 +468,37 @@ class FullLengthRNNUpdate:
                     if len(self._graphs) >= 8:                          # bounded: drop the oldest key
                         self._graphs.pop(next(iter(self._graphs)))
                     self._graphs[key] = 'seen'
+                self._arm_grad_detection()
                 for stage, comm in self._stages(graph_mode=False):
                     stage(ctx)
                     if comm is not None:
                         comm()
-        self.grad_num += 1
+        if advance:
+            self.grad_num += 1
         # logged scalars: one device vector, one read-back ------------------------------------------------------ ref :435-467
         out = {'real_batch_size': batch_size, 'real_batch_traj_num': B, 'policy_updated': did_policy}
         if not sync:
             out['stats_device'] = self._stats
             return out
-        s = self._stats.tolist()
+        stats = self._stats
+        if self.dist_group is not None:          # per-rank partial sums (already divided by the global n_valid) -> global
+            import torch.distributed as dist
+            stats = self._stats.clone()
+            dist.all_reduce(stats[2:8], op=dist.ReduceOp.SUM, group=self.dist_group)
+            dist.all_reduce(stats[0:1], op=dist.ReduceOp.MAX, group=self.dist_group)
+        s = stats.tolist()
         g = self.Q_guard.state.tolist()
+        clipping_emb_v = p.value_embedding_max_gradnorm is not None
         out.update({'critic_loss': s[2], 'target_q_max': s[0], 'log_alpha': float(self.log_sac_alpha.item()),
-                    'clip_min': g[0], 'clip_max': g[1], 'value_grad_norm': 0.0,
-                    'average_traj_len': self.replay_buffer.size / max(len(self.replay_buffer), 1)})
-        if did_policy:
-            out.update({'actor_loss': s[4], 'log_prob': s[5], 'policy_grad_norm': 0})
+                    'clip_min': g[0], 'clip_max': g[1],
+                    'value_grad_norm': (math.sqrt(s[10]) if (p.value_max_gradnorm is not None and not clipping_emb_v) else 0.0),
+                    'q1_l2_norm_square': s[8],
+                    'average_traj_len': self.replay_buffer.size / max(len(self.replay_buffer), 1),
+                    'amp_scalar_pi': 0, 'amp_scalar_q': 0})
+        if did_policy or policy_logged:
+            clipping_emb_p = p.policy_embedding_max_gradnorm is not None
+            out.update({'actor_loss': s[4], 'log_prob': s[5], 'policy_l2_norm_square': s[9],
+                        'policy_grad_norm': (math.sqrt(s[11]) if (p.policy_max_gradnorm is not None and not clipping_emb_p) else 0)})
             if not p.no_alpha_auto_tune:
                 out['alpha_loss'] = s[6]
         return out
@@ -477,13 +564,17 @@ class FullLengthRNNUpdate:
         d_start = rnn_start[:, 1:] - rnn_start[:, :-1]
         total_start = rnn_start.clone()
         total_start[:, :-1] = torch.where(d_start == -1, torch.zeros_like(d_start), total_start[:, :-1])
-        mk = lambda model: model.make_init_state(B, device=dev)
-        c['policy_hidden'], target_policy_hidden = mk(self.policy), mk(self.policy)
+        if p.randomize_first_hidden:                          # ref :345-351: random carried state, shared by both policy passes
+            mk = lambda model: model.make_rnd_init_state(B, device=dev)
+            c['policy_hidden'] = target_policy_hidden = mk(self.policy)
+        else:
+            mk = lambda model: model.make_init_state(B, device=dev)
+            c['policy_hidden'], target_policy_hidden = mk(self.policy), mk(self.policy)
         target_hidden, c['value_hidden'] = mk(self.target_values[0]), mk(self.values[0])
         for h in (target_policy_hidden, target_hidden):
             h.set_rnn_start(total_start), h.set_mask(total_valid), h.set_attention_concat_mask(tgt_att)
-        for h in (c['value_hidden'], c['policy_hidden']):
-            h.set_rnn_start(rnn_start), h.set_mask(valid_ind), h.set_attention_concat_mask(att)
+        c['value_hidden'].set_rnn_start(rnn_start), c['value_hidden'].set_mask(valid_ind), c['value_hidden'].set_attention_concat_mask(att)
+        c['side'] = (rnn_start, valid_ind, att)              # the policy hidden gets the unshifted side-band after the target pass (ref :398-403)
         # 3. target Q (no grad) ------------------------------------------------------------------------------- ref :83-103
         self.policy.eval()
         with torch.no_grad():
@@ -525,10 +616,14 @@ class FullLengthRNNUpdate:
         batch, mask_c = c['batch'], c['mask_c']
         n_valid = self._stats[1:2]
         state, last_state, last_action, reward_input = batch.state, batch.last_state, batch.last_action, batch.reward_input
+        self._freeze_no_grad(self.optimizer_value)
         self.optimizer_value.step(tau=p.sac_tau)   # + Polyak (ref :395)
+        N.call("rorl_sumsq", N.ptr(self.value_arena.flat), self._l2_span['value'], N.ptr(self._stats[8:9]), N.ptr(self._work), N.stream())
         for v in self.values:
             v.eval()
         self.policy.train()
+        rs, vi, at = c['side']
+        c['policy_hidden'].set_rnn_start(rs), c['policy_hidden'].set_mask(vi), c['policy_hidden'].set_attention_concat_mask(at)
         # 5. actor + alpha ---------------------------------------------------------------------------------------- ref :116-132,405-432
         if not c['did_policy']:
             return
@@ -566,10 +661,31 @@ class FullLengthRNNUpdate:
     def _stage_policy_step(self, c):
         if not c['did_policy']:
             return
+        self._freeze_no_grad(self.optimizer_policy)
         self.optimizer_policy.step()
+        N.call("rorl_sumsq", N.ptr(self.policy_arena.flat), self._l2_span['policy'], N.ptr(self._stats[9:10]), N.ptr(self._work), N.stream())
         if not self.parameter.no_alpha_auto_tune:
             self.optimizer_alpha.step()
             self.log_sac_alpha.data.clamp_(max=1.0)
+
+    def _arm_grad_detection(self):
+        """First update with weight decay on: record which parameters receive a gradient at all (hooks fire on
+        accumulation), so that the fused optimizer can skip the others as torch.optim.AdamW skips `.grad is None`."""
+        p = self.parameter
+        if self._grad_seen is not None or not (p.policy_l2_norm > 0 or p.value_l2_norm > 0):
+            return
+        self._grad_seen = {}
+        self._grad_hooks = [q.register_post_accumulate_grad_hook(lambda t: self._grad_seen.__setitem__(id(t), True))
+                            for q in self.policy_arena.params + self.value_arena.params]
+
+    def _freeze_no_grad(self, opt):
+        if getattr(self, '_grad_hooks', None) is None:
+            return
+        opt.freeze_params_without_grad(self._grad_seen)
+        if opt is self.optimizer_policy:                   # both models have been through their first backward
+            for h in self._grad_hooks:
+                h.remove()
+            self._grad_hooks = None
 
     def _sync_guard_and_count(self):
         """Data-parallel: make n_valid and the guard state identical on every rank."""

@@ -5,4 +5,4 @@ from .td3_full_length_rnn_redq import TD3FullLengthRNNREDQ
 
 
 class TD3FullLengthRNNREDQ_SEP_OPTIM(TD3FullLengthRNNREDQ):
-    pass
+    sep_optim = True

@@ -81,6 +81,6 @@ int rorl_traj_gather(const float* ring, int64_t F, const int64_t* plan, int64_t 
     RORL_RETURN_LAUNCH();
 }
 
-int rorl_abi_version(void) { return 2; }   // 2: h0 argument of rorl_selscan_fwd / _bwd, new reduce / lru_fused / conv1d entry points
+int rorl_abi_version(void) { return 3; }   // 3: per-segment / global-norm gradient clipping in rorl_adamw_polyak
 
 }  // extern "C"

@@ -303,16 +303,40 @@ UPDATE_CASES = {
     "sac_gru": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2),
     "td3_gilr": dict(algo="td3", enc="gilr", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1),
     "td3_lru": dict(algo="td3", enc="lru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1),
+    # the plain (non-REDQ, non-SEP_OPTIM) classes: min over all 8 members for target and actor, ONE AdamW group per
+    # model (ref: sac.py:81-90); the TD3 one takes the target action from the frozen target policy.  The TD3 case also
+    # carries weight decay: gilr's unused layer_norm keeps .grad None, so torch.optim.AdamW must not decay it.
+    "sac_ensembleq": dict(algo="sac", cls="SACFullLengthRNNEnsembleQ", enc="lru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2),
+    "td3_ensembleq": dict(algo="td3", cls="TD3FullLengthRNNEnsembleQ", enc="gilr", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2,
+                          hp=dict(policy_l2_norm=1e-2, value_l2_norm=1e-2)),
+    "sac_ensembleq_sep": dict(algo="sac", cls="SACFullLengthRNNENSEMBLEQ_SEP_OPTIM", enc="gilr", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1),
+    # mid-size: every projection is wide enough (K >= 32) for the tensor-core GEMM path
+    "sac_smamba_mid": dict(algo="sac", enc="smamba_s16_c4_b1_nln", hidden=64, emb=32, lens=[40, 33, 25, 37], S=5, A=3, calls=1),
+    "td3_gilr_mid": dict(algo="td3", enc="gilr", hidden=64, emb=32, lens=[40, 33, 25, 37], S=5, A=3, calls=1),
+    # conv1d encoder with nest-stacked trajectories: isolation between neighbours rests on skip_len = d_conv + 1 blanks
+    "sac_conv1d": dict(algo="sac", enc="conv1d_4", hidden=16, lens=[5, 3, 6, 4, 9, 7], S=3, A=2, calls=1, max_len=20),
+    # gradient clipping (ref: sac_full_length_rnn_ensembleQ.py:239-250,274-287): global norm only / norm + value (+ A_log 1e-3)
+    "sac_gru_clipnorm": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1,
+                             hp=dict(policy_max_gradnorm=0.05, value_max_gradnorm=0.5)),
+    "sac_smamba_clipval": dict(algo="sac", enc="smamba_s16_c4_b2_nln", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1,
+                               hp=dict(policy_max_gradnorm=0.05, value_max_gradnorm=0.5, policy_embedding_max_gradnorm=2e-3,
+                                       value_embedding_max_gradnorm=2e-2)),
+    # utd = 2 with one policy update per call (ref :311,405)
+    "sac_gru_utd2": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2, hp=dict(utd=2, policy_utd=1)),
+    # random carried state shared by the target-policy and actor passes (ref :345-351); the draws are recorded (gru: the one
+    # encoder without reset flags, so the carried state actually reaches the outputs)
+    "sac_gru_rndhidden": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1, hp=dict(randomize_first_hidden=True)),
 }
 
 
 def model_kwargs(c, value):
     H = c["hidden"]
-    return dict(state_dim=c["S"], action_dim=c["A"], embedding_size=8, embedding_hidden=[H, H],
+    E = c.get("emb", 8)
+    return dict(state_dim=c["S"], action_dim=c["A"], embedding_size=E, embedding_hidden=[H, H],
                 embedding_activations=['elu', 'elu', 'linear'], embedding_layer_type=['fc', c["enc"], 'fc'],
                 uni_model_hidden=[H, H], uni_model_activations=['elu', 'elu', 'linear'],
                 uni_model_layer_type=(['efc-8'] * 3 if value else ['fc'] * 3), fix_rnn_length=0,
-                uni_model_input_mapping_dim=8, reward_input=False, last_action_input=True, last_state_input=True,
+                uni_model_input_mapping_dim=E, reward_input=False, last_action_input=True, last_state_input=True,
                 separate_encoder=True)
 
 
@@ -324,10 +348,15 @@ HP = dict(utd=1, policy_utd=1, randomize_mask=False, valid_number_post_randomize
           value_l2_norm=0.0, sample_std=0.1, target_entropy_ratio=1.0)
 
 
-def gen_updates():
+def gen_updates(only=None):
     install_algo_stubs()
     from offpolicy_rnn.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM, prepare_param_list
     from offpolicy_rnn.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
+    from offpolicy_rnn.algorithm.sac_full_length_rnn_ensembleQ import SACFullLengthRNNEnsembleQ
+    from offpolicy_rnn.algorithm.td3_full_length_rnn_ensembleQ import TD3FullLengthRNNEnsembleQ
+    from offpolicy_rnn.algorithm.sac_full_length_rnn_ensembleQ_sep_optim import SACFullLengthRNNENSEMBLEQ_SEP_OPTIM
+    classes = {c.__name__: c for c in (SACFullLengthRNNREDQ_SEP_OPTIM, TD3FullLengthRNNREDQ_SEP_OPTIM, SACFullLengthRNNEnsembleQ,
+                                       TD3FullLengthRNNEnsembleQ, SACFullLengthRNNENSEMBLEQ_SEP_OPTIM)}
     from offpolicy_rnn.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
     from offpolicy_rnn.buffers.transition_buffer.replay_memory import Transition
     from offpolicy_rnn.policy_value_models.make_models import make_policy_model, make_value_model
@@ -335,11 +364,16 @@ def gen_updates():
     from offpolicy_rnn.utility.timer import Timer
 
     for tag, c in UPDATE_CASES.items():
+        if only and tag not in only:
+            continue
         torch.manual_seed(5)
         np.random.seed(5)
-        cls = SACFullLengthRNNREDQ_SEP_OPTIM if c["algo"] == "sac" else TD3FullLengthRNNREDQ_SEP_OPTIM
+        cls_name = c.get("cls") or ("SACFullLengthRNNREDQ_SEP_OPTIM" if c["algo"] == "sac" else "TD3FullLengthRNNREDQ_SEP_OPTIM")
+        cls = classes[cls_name]
+        sep = cls_name.endswith("SEP_OPTIM")
         A = object.__new__(cls)
         hp = dict(HP, sac_batch_size=sum(c["lens"]) - 1)
+        hp.update(c.get("hp", {}))
         if c["algo"] == "td3":
             hp["no_alpha_auto_tune"] = True
         A.parameter = types.SimpleNamespace(**hp)
@@ -373,15 +407,22 @@ def gen_updates():
         A.target_policy = make_policy_model(pk, c["algo"], False)
         A.target_policy.copy_weight_from(A.policy, tau=0.0)
         A.optim_class = torch.optim.AdamW
-        A.optimizer_policy = torch.optim.AdamW(prepare_param_list(A.policy, hp["rnn_policy_lr"], 0.0), lr=hp["policy_lr"], weight_decay=0.0)
-        A.optimizer_value = torch.optim.AdamW(prepare_param_list(A.values[0], hp["rnn_value_lr"], 0.0), lr=hp["value_lr"], weight_decay=0.0)
+        if sep:     # ref: sac_full_length_rnn_redq_sep_optim.py:85-92
+            A.optimizer_policy = torch.optim.AdamW(prepare_param_list(A.policy, hp["rnn_policy_lr"], hp["policy_l2_norm"]),
+                                                   lr=hp["policy_lr"], weight_decay=hp["policy_l2_norm"])
+            A.optimizer_value = torch.optim.AdamW(prepare_param_list(A.values[0], hp["rnn_value_lr"], hp["value_l2_norm"]),
+                                                  lr=hp["value_lr"], weight_decay=hp["value_l2_norm"])
+        else:       # ref: sac.py:81-90
+            A.optimizer_policy = torch.optim.AdamW(A.policy.parameters(True), lr=hp["policy_lr"], weight_decay=hp["policy_l2_norm"])
+            A.optimizer_value = torch.optim.AdamW([p for v in A.values for p in v.parameters(True)], lr=hp["value_lr"],
+                                                  weight_decay=hp["value_l2_norm"])
         A.value_parameters = [p for v in A.values for p in v.parameters(True)]
         A.value_embedding_parameters = [p for v in A.values for p in v.embedding_network.parameters(True)]
         A.optimizer_alpha = torch.optim.AdamW([A.log_sac_alpha], lr=hp["alpha_lr"])
         A.grad_num = 0
         A.allow_nest_stack = cls.allow_nest_stack_trajs(A)
         skip = cls._get_skip_len(A)
-        A.replay_buffer = NestedMemoryArray(1000, max(c["lens"]), additional_history_len=skip - 1)
+        A.replay_buffer = NestedMemoryArray(1000, c.get("max_len", max(c["lens"])), additional_history_len=skip)   # ref :41
         fill_buffer(A.replay_buffer, Transition, np.random.RandomState(9), c["lens"], c["S"], c["A"])
 
         arrs = {}
@@ -395,9 +436,19 @@ def gen_updates():
             noises.append(out.detach().clone())
             return out
 
+        hdraws = []
+        orig_randn = torch.rand
+
+        def rec_randn(*a, **k):
+            out = orig_randn(*a, **k)
+            hdraws.append(out.detach().clone())
+            return out
+
         np.random.seed(21)
         torch.manual_seed(22)
         torch.randn_like = rec_randn_like
+        if hp["randomize_first_hidden"]:
+            torch.rand = rec_randn
         try:
             for call in range(c["calls"]):
                 snap = {}
@@ -429,10 +480,13 @@ def gen_updates():
                 arrs[f"c{call}/log_alpha"] = A.log_sac_alpha.detach().clone().numpy()
         finally:
             torch.randn_like = orig_randn_like
+            torch.rand = orig_randn
         for i, nz in enumerate(noises):
             arrs[f"noise/{i}"] = nz.numpy()
-        cfg = dict(case=c, hp=hp, policy_kwargs=pk, value_kwargs=vk, skip=skip, allow_nest_stack=bool(A.allow_nest_stack),
-                   n_noise=len(noises), np_seed_fill=9, np_seed_run=21)
+        for i, nz in enumerate(hdraws):
+            arrs[f"hdraw/{i}"] = nz.numpy()
+        cfg = dict(case=c, hp=hp, cls=cls_name, policy_kwargs=pk, value_kwargs=vk, skip=skip, allow_nest_stack=bool(A.allow_nest_stack),
+                   n_noise=len(noises), n_hdraw=len(hdraws), np_seed_fill=9, np_seed_run=21)
         save(f"update_{tag}.npz", cfg=np.array(json.dumps(cfg)), **arrs)
 
 
@@ -446,5 +500,5 @@ if __name__ == "__main__":
         gen_steps()
     if "sampler" in which:
         gen_sampler([w[len("sampler_"):] for w in which if w.startswith("sampler_")] or None)
-    if "updates" in which:
-        gen_updates()
+    if "updates" in which or any(w.startswith("update_") for w in which):
+        gen_updates([w[len("update_"):] for w in which if w.startswith("update_")] or None)

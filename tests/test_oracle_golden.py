@@ -151,10 +151,14 @@ def run_oracle_update(tag):
     c, hp = cfg["case"], cfg["hp"]
     pol = nested_sd(g, "init/policy/")
     val = nested_sd(g, "init/value/")
-    buf = OS.RefNestedReplay(1000, max(c["lens"]), additional_history_len=cfg["skip"] - 1)
+    buf = OS.RefNestedReplay(1000, c.get("max_len", max(c["lens"])), additional_history_len=cfg["skip"])   # ref: sac_full_length_rnn_ensembleQ.py:41
     _fill(buf, np.random.RandomState(cfg["np_seed_fill"]), c["lens"], c["S"], c["A"])
     noises = [T(g[f"noise/{i}"]) for i in range(cfg["n_noise"])]
     it = iter(noises)
+    hit = iter([T(g[f"hdraw/{i}"]) for i in range(cfg.get("n_hdraw", 0))])
+
+    def hidden_fn(spec, batch):          # the reference's torch.rand draws, one per recurrent layer of the embedding network
+        return {i: next(hit) * 2 - 1 for i, t in enumerate(spec.emb_types) if OM.is_rnn(t)}
 
     def noise_fn(shape):
         n = next(it)
@@ -163,18 +167,24 @@ def run_oracle_update(tag):
 
     pk = dict(cfg["policy_kwargs"])
     vk = dict(cfg["value_kwargs"])
-    upd = OU.RefUpdate(pol, val, OM.ModelSpec(**pk), OM.ModelSpec(**vk), hp, buf, noise_fn, algo=c["algo"], redq=True,
-                       allow_nest_stack=cfg["allow_nest_stack"])
+    cls = cfg.get("cls", "REDQ_SEP_OPTIM")
+    upd = OU.RefUpdate(pol, val, OM.ModelSpec(**pk), OM.ModelSpec(**vk), hp, buf, noise_fn, algo=c["algo"], redq="REDQ" in cls,
+                       allow_nest_stack=cfg["allow_nest_stack"], sep_optim=cls.endswith("SEP_OPTIM"), hidden_fn=hidden_fn)
     np.random.seed(cfg["np_seed_run"])
     return g, cfg, upd
 
 
-@pytest.mark.parametrize("tag", ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru"])
+UPDATE_TAGS = ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru", "sac_ensembleq", "td3_ensembleq", "sac_ensembleq_sep", "sac_smamba_mid",
+               "td3_gilr_mid", "sac_conv1d", "sac_gru_clipnorm", "sac_smamba_clipval", "sac_gru_utd2", "sac_gru_rndhidden"]
+
+
+@pytest.mark.parametrize("tag", UPDATE_TAGS)
 def test_full_update(tag):
     g, cfg, upd = run_oracle_update(tag)
     for call in range(cfg["case"]["calls"]):
         log = upd.train_one_batch()
-        for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "log_alpha", "target_q_max", "clip_min", "clip_max"):
+        for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "log_alpha", "target_q_max", "clip_min", "clip_max",
+                  "q1_l2_norm_square", "policy_l2_norm_square", "value_grad_norm", "policy_grad_norm"):
             key = f"c{call}/log/{k}"
             if key in g and k in log:
                 ref = float(g[key])

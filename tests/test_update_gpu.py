@@ -26,16 +26,24 @@ def fill_buffer(buf, Transition, rng, lens, S, A):
             last_s, last_a, last_r, s = s, a, np.array([[r]]), ns
 
 
+ALG_NAMES = {"SACFullLengthRNNREDQ_SEP_OPTIM": "sac_rnn_full_horizon_redQ_sep_optim",
+             "TD3FullLengthRNNREDQ_SEP_OPTIM": "td3_rnn_full_horizon_redQ_sep_optim",
+             "SACFullLengthRNNEnsembleQ": "sac_rnn_full_horizon_ensembleQ",
+             "TD3FullLengthRNNEnsembleQ": "td3_rnn_full_horizon_ensembleQ",
+             "SACFullLengthRNNENSEMBLEQ_SEP_OPTIM": "sac_rnn_full_horizon_ensemble_q_sep_optim"}
+
+
 def build(tag):
-    from rorl_b200.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM
-    from rorl_b200.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
+    from rorl_b200.utility.alg_init import alg_class
     from rorl_b200.buffers.transition_buffer.replay_memory import Transition
     g = load_npz(f"update_{tag}.npz")
     cfg = cfg_of(g)
     c, hp = cfg["case"], cfg["hp"]
-    cls = SACFullLengthRNNREDQ_SEP_OPTIM if c["algo"] == "sac" else TD3FullLengthRNNREDQ_SEP_OPTIM
+    cls = alg_class(ALG_NAMES[cfg["cls"]])                 # the reference's alg_name switch (ref: utility/alg_init.py:16-47)
+    assert cls.__name__ == cfg["cls"]
     pk = {k: v for k, v in cfg["policy_kwargs"].items() if k != "sample_std"}
-    alg = cls(dict(hp, max_buffer_transition_num=1000), pk, cfg["value_kwargs"], max(c["lens"]), device=torch.device("cuda:0"))
+    alg = cls(dict(hp, max_buffer_transition_num=1000), pk, cfg["value_kwargs"], c.get("max_len", max(c["lens"])),
+              device=torch.device("cuda:0"))
     assert alg._get_skip_len() == cfg["skip"]
     assert alg.allow_nest_stack == cfg["allow_nest_stack"]
     alg.load_models(nested_sd(g, "init/policy/", "cuda"), nested_sd(g, "init/value/", "cuda"))
@@ -49,25 +57,59 @@ def build(tag):
 
     alg.policy.noise_fn = noise_fn
     alg.target_policy.noise_fn = noise_fn
+    if cfg.get("n_hdraw", 0):            # the reference's torch.rand draws of make_rnd_init_state, in call order
+        hdraws = iter([T(g[f"hdraw/{i}"], "cuda") for i in range(cfg["n_hdraw"])])
+        from rorl_b200.models import RNNHidden as RH
+        RH.torch = _TorchWithRand(hdraws)
     np.random.seed(cfg["np_seed_run"])
     return g, cfg, alg
+
+
+class _TorchWithRand:
+    """`torch` as seen by models/RNNHidden.py with `rand` replaced by the recorded draws."""
+
+    def __init__(self, draws):
+        self._draws = draws
+
+    def rand(self, shape, device=None, **kw):
+        d = next(self._draws)
+        assert tuple(d.shape) == tuple(shape), (d.shape, shape)
+        return d.to(device)
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
 
 
 def module_params(model):
     return {k: dict(m.named_parameters()) for k, m in model.contextual_modules.items()}
 
 
-@pytest.mark.parametrize("tag", ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru"])
+UPDATE_TAGS = ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru", "sac_ensembleq", "td3_ensembleq", "sac_ensembleq_sep", "sac_smamba_mid",
+               "td3_gilr_mid", "sac_conv1d", "sac_gru_clipnorm", "sac_smamba_clipval", "sac_gru_utd2", "sac_gru_rndhidden"]
+
+
+@pytest.mark.parametrize("tag", UPDATE_TAGS)
 def test_update_matches_reference(tag):
+    try:
+        _run_update_matches_reference(tag)
+    finally:
+        from rorl_b200.models import RNNHidden as RH
+        RH.torch = torch
+
+
+def _run_update_matches_reference(tag):
     g, cfg, alg = build(tag)
     for call in range(cfg["case"]["calls"]):
         log = alg.train_one_batch()
         # gradients left in the arenas: critic grads (value), actor grads (policy)
         vg = {k: {n: p.grad for n, p in m.items()} for k, m in module_params(alg.values[0]).items()}
         pg = {k: {n: p.grad for n, p in m.items()} for k, m in module_params(alg.policy).items()}
-        for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "log_alpha", "target_q_max", "clip_min", "clip_max"):
+        for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "log_alpha", "target_q_max", "clip_min", "clip_max",
+                  "q1_l2_norm_square", "policy_l2_norm_square", "value_grad_norm", "policy_grad_norm", "amp_scalar_pi", "amp_scalar_q",
+                  "average_traj_len", "real_batch_traj_num"):
             key = f"c{call}/log/{k}"
-            if key in g and k in log:
+            if key in g:
+                assert k in log, f"the reference's return dict has {k!r} (ref: sac_full_length_rnn_ensembleQ.py:435-467)"
                 ref = float(g[key])
                 assert abs(log[k] - ref) <= TOL * max(1.0, abs(ref)), (k, log[k], ref)
         assert log["real_batch_size"] == int(g[f"c{call}/log/real_batch_size"])
@@ -156,7 +198,7 @@ def test_update_vs_oracle_wide(enc, algo):
     pol_sd, val_sd = cpu_sd(alg.policy), cpu_sd(alg.values[0])
     fill_buffer(alg.replay_buffer, Transition, np.random.RandomState(4), lens, S, A)
     skip = alg._get_skip_len()
-    obuf = OS.RefNestedReplay(1000, max(lens), additional_history_len=skip - 1)
+    obuf = OS.RefNestedReplay(1000, max(lens), additional_history_len=skip)
     fill_buffer(obuf, OS.Transition, np.random.RandomState(4), lens, S, A)
     gen = torch.Generator().manual_seed(8)
     drawn = []
