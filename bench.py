@@ -17,9 +17,15 @@ Metric: trajectory-steps/s = valid transitions updated on per second, whole job.
            pinned host batch is copied H2D and the logged scalars are read back D2H, inside the timed region.
   roofline: the selective-scan kernel (forward or backward, whichever takes the larger share), timed alone
            with CUDA events on its launch stream at the workload's shape.
-  cpu_baseline: the oracle's CPU port of the reference update with the GRU encoder (the reference's own
-           CPU-runnable config) on the same 32x1000 shape, on this box's host cores.
-`--impl reference` times the oracle port (CPU, all host threads) on a bounded sample of the same config.
+  cpu_baseline: the reference's OWN `train_one_batch` (unmodified code staged under oracle/_ref by oracle/make_ref.py;
+           kind "reference"; the oracle port, kind "port", only if that copy is missing) with the GRU encoder -- the
+           reference's CPU-runnable configuration -- on the same 32x1000 shape and on config 1's 8x200 shape, on this
+           box's host cores.
+  strong_scaling: the BASELINE config-5 job (256 trajectories x 1000 steps GLOBAL, 256/N per GPU) timed the same way.
+`--impl reference` times the reference's own CPU implementation of THIS arm's configuration (same encoder, 32 rows,
+same widths; on CPU its smamba layer walks `Mamba.step` once per time step) on a bounded sample: every trajectory is
+cut to RORL_REF_TLEN (default 100) of its 1000 steps -- the per-step Python loop is linear in the trajectory length,
+so steps/s of the sample is steps/s of the workload, while the row count (what the loop amortises over) is the real 32.
 """
 import argparse
 import json
@@ -35,6 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 S_DIM, A_DIM, T_LEN, N_TRAJ = 9, 6, 1000, 32
+STRONG_TRAJ = 256
 ENCODER = os.environ.get("RORL_BENCH_ENCODER", "smamba_s32_c16_b2_nln")
 ALGO = os.environ.get("RORL_BENCH_ALGO", "sac")
 METRIC = "sac_update_trajectory_steps_per_s"
@@ -76,6 +83,15 @@ def template_transition():
     return Transition(state=z((1, S_DIM)), last_state=z((1, S_DIM)), last_action=z((1, A_DIM)), action=z((1, A_DIM)),
                       next_state=z((1, S_DIM)), reward=0.0, logp=None, mask=1, done=False, timeout=False, start=True,
                       reward_input=z((1, 1)))
+
+
+def workload_config(world):
+    """`config` of the JSON line -- one function for both arms, so the reference arm reports the configuration it ran."""
+    return {"workload": f"{ALGO.upper()} update, {ENCODER} encoder, {N_TRAJ} trajectories x {T_LEN} steps per GPU "
+                        f"(obs {S_DIM}, act {A_DIM}, efc-8 twin-Q head, REDQ m=2, RESeL lr split)",
+            "global_trajectories": N_TRAJ * world, "valid_steps_per_update": N_TRAJ * T_LEN * world,
+            "parallelism": f"dp{world} (trajectory-sharded, NCCL grad all-reduce)" if world > 1 else "single GPU",
+            "l2": "working set per step (activations > 1 GB) exceeds the 126 MB L2; no flush needed"}
 
 
 class ClockSampler(threading.Thread):
@@ -188,6 +204,25 @@ def run_ours(args):
            "h2d_bytes_per_step": int(host_batch.numel() * 4 + host_valid.numel() * 4),
            "d2h_bytes_per_step": int(alg._stats.numel() * 4 + alg.Q_guard.state.numel() * 8 + 4), "ms_per_step": ms_e2e}
 
+    # ---- strong-scaling leg (BASELINE config 5): 256 trajectories GLOBAL, 256 / N per GPU ------------------------------
+    strong = None
+    if not args.no_strong and STRONG_TRAJ % world == 0:
+        n_local = STRONG_TRAJ // world
+        hp_s = dict(HP, sac_batch_size=n_local * T_LEN - 1, max_buffer_transition_num=n_local * T_LEN + 8)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        alg_s = cls(hp_s, model_kwargs(ENCODER, False), model_kwargs(ENCODER, True), T_LEN, device=dev, dist_group=group)
+        alg_s.replay_buffer._init_memory_buffer(template_transition())
+        rng = np.random.RandomState(2000 + rank)
+        for _ in range(n_local):
+            alg_s.replay_buffer.push_trajectory_array(synth_trajectory(rng))
+        step_s = lambda: alg_s.train_one_batch(sync=False)
+        for _ in range(3):
+            out_s = step_s()
+        k_s = max(3, args.steps // 4)
+        ms_s = timed(step_s, k_s) / k_s
+        strong = {"scaling": "strong", "global_trajectories": STRONG_TRAJ, "trajectories_per_gpu": n_local, "steps": k_s,
+                  "ms_per_step": ms_s, "value": out_s["real_batch_size"] * world / (ms_s * 1e-3), "unit": "trajectory-steps/s"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -195,13 +230,13 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{ALGO.upper()} update, {ENCODER} encoder, {N_TRAJ} trajectories x {T_LEN} steps per GPU "
-                                   f"(obs {S_DIM}, act {A_DIM}, efc-8 twin-Q head, REDQ m=2, RESeL lr split)",
-                       "global_trajectories": N_TRAJ * world, "valid_steps_per_update": valid_steps * world,
-                       "parallelism": f"dp{world} (trajectory-sharded, NCCL grad all-reduce)" if world > 1 else "single GPU",
-                       "l2": "working set per step (activations > 1 GB) exceeds the 126 MB L2; no flush needed"},
+            "config": workload_config(world),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches)}
-    line["roofline"] = scan_roofline(alg, dev, ms_per_step)
+    assert valid_steps == N_TRAJ * T_LEN
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if ENCODER.startswith("smamba"):
+        line["roofline"] = scan_roofline(alg, dev, ms_per_step)
     line["roofline_gemm"] = gemm_roofline(dev)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(encoder="gru", n_traj=N_TRAJ, updates=2, warm=1)
@@ -211,8 +246,9 @@ def run_ours(args):
 
 
 def scan_roofline(alg, dev, ms_per_step):
-    """Time the selective-scan kernels alone at the workload shape [B=32, L=1018, D=512, N=32] with CUDA events on
-    the launch stream.  Operands (4 x 66.7 MB) exceed L2, so consecutive launches do not hit in cache."""
+    """Time the selective-scan kernels alone at the workload shape [B=32, L=1019, D=512, N=32] (1000 steps + the replay's
+    skip_step = d_conv + 2 blanks + 1, ref: nested_replay_memory.py:23,179) with CUDA events on the launch stream.
+    Operands (4 x 66.8 MB) exceed L2, so consecutive launches do not hit in cache."""
     import torch
     import rorl_b200.kernels as K
     peaks = {}
@@ -221,7 +257,7 @@ def scan_roofline(alg, dev, ms_per_step):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    B, L, D, Ns = N_TRAJ, T_LEN + 18, 512, 32
+    B, L, D, Ns = N_TRAJ, T_LEN + 19, 512, 32
     g = torch.Generator(device=dev).manual_seed(0)
     rn = lambda *s: torch.randn(*s, device=dev, generator=g)
     u, delta, z = rn(B, L, D).requires_grad_(), (0.5 * rn(B, L, D) - 1).requires_grad_(), rn(B, L, D).requires_grad_()
@@ -275,7 +311,7 @@ def scan_roofline(alg, dev, ms_per_step):
 
 def gemm_roofline(dev):
     """Second roofline object, for the kernel with the largest share of the step (the tcgen05 3xTF32 GEMM, ~44 %):
-    the in_proj-half shape [32576, 256] x [512, 256]^T timed alone with CUDA events.  `achieved` counts the useful
+    the in_proj-half shape [32608, 256] x [512, 256]^T timed alone with CUDA events.  `achieved` counts the useful
     fp32 FLOPs (2 M N K); the kernel issues three TF32 passes for them.  `peak` is the measured dense bf16 rate of
     MEASURED_PEAKS.json; the TF32 pipe runs at half of it."""
     import torch
@@ -285,7 +321,7 @@ def gemm_roofline(dev):
     except Exception:
         peaks = {}
     peak = float(peaks.get("bf16_tflops", 1590.0))
-    M, Nn, Kk = N_TRAJ * (T_LEN + 18), 512, 256
+    M, Nn, Kk = N_TRAJ * (T_LEN + 19), 512, 256
     g = torch.Generator(device=dev).manual_seed(1)
     a = torch.randn(M, Kk, device=dev, generator=g)
     w = torch.randn(Nn, Kk, device=dev, generator=g)
@@ -349,57 +385,110 @@ def _oracle_update_runner(encoder, n_traj, algo, OM, OS, OU, make_policy_model, 
     return upd, n_traj * T_LEN
 
 
-def cpu_baseline(encoder, n_traj, updates, warm):
+def reference_update_runner(encoder, n_traj, algo="sac", s_dim=None, a_dim=None, t_len=None, t_cut=None):
+    """The UNMODIFIED reference's algorithm object on CPU (oracle/refload.py harness over /root/reference or the staged
+    oracle/_ref copy), replay filled through its own `mem_push` with `n_traj` synthetic trajectories of `t_cut or t_len`
+    steps.  Returns (object with .train_one_batch(), valid steps per update) or None if the reference is not available."""
+    from oracle import refload
+    if not refload.available():
+        return None
     import torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    upd, valid = oracle_update_runner(encoder, n_traj)
+    refload.load_reference(gpu_semantics=False)       # the reference as it runs on a CPU-only machine
+    refload.install_algo_stubs()
+    from offpolicy_rnn.buffers.transition_buffer.replay_memory import Transition
+    global S_DIM, A_DIM, T_LEN
+    saved = (S_DIM, A_DIM, T_LEN)
+    S_DIM, A_DIM, T_LEN = s_dim or S_DIM, a_dim or A_DIM, t_len or T_LEN
+    try:
+        torch.manual_seed(0)
+        np.random.seed(0)
+        steps = t_cut or T_LEN
+        hp = dict(refload.REF_HP, sac_batch_size=n_traj * steps - 1, max_buffer_transition_num=n_traj * steps + 8)
+        cls = "SACFullLengthRNNREDQ_SEP_OPTIM" if algo == "sac" else "TD3FullLengthRNNREDQ_SEP_OPTIM"
+        A = refload.build_algorithm(cls, hp, model_kwargs(encoder, False), model_kwargs(encoder, True), T_LEN, A_DIM)
+        rng = np.random.RandomState(1000)
+        S, Ad = S_DIM, A_DIM
+        for _ in range(n_traj):
+            rows = synth_trajectory(rng, T_LEN)[:steps]
+            for t in range(steps):
+                r = rows[t]
+                last = t == steps - 1
+                A.replay_buffer.mem_push(Transition(
+                    state=r[None, 0:S], last_state=r[None, S:2 * S], last_action=r[None, 2 * S:2 * S + Ad],
+                    action=r[None, 2 * S + Ad:2 * S + 2 * Ad], next_state=r[None, 2 * S + 2 * Ad:3 * S + 2 * Ad],
+                    reward=float(r[3 * S + 2 * Ad]), logp=None, mask=1, done=last, timeout=last, start=(t == 0),
+                    reward_input=r[None, 3 * S + 2 * Ad + 4:3 * S + 2 * Ad + 5]))
+
+        class Runner:
+            def train_one_batch(self_inner):
+                out = A.train_one_batch()
+                A.grad_num += 1
+                return out
+        return Runner(), n_traj * steps
+    finally:
+        S_DIM, A_DIM, T_LEN = saved
+
+
+def _time_updates(upd, updates, warm):
     for _ in range(warm):
         upd.train_one_batch()
     t0 = time.perf_counter()
     for _ in range(updates):
         upd.train_one_batch()
-    dt = (time.perf_counter() - t0) / updates
-    out = {"value": valid / dt, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
-           "sample": f"{updates} timed SAC updates (after {warm} warm-up) of the oracle CPU port with the {encoder} encoder on "
+    return (time.perf_counter() - t0) / updates
+
+
+def cpu_baseline(encoder, n_traj, updates, warm):
+    """The reference's CPU path (GRU encoder, north_star) on this box's host cores: the reference's own code when the
+    staged copy is present (kind "reference"), else the oracle port (kind "port")."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    built = reference_update_runner(encoder, n_traj)
+    kind = "reference" if built is not None else "port"
+    upd, valid = built if built is not None else oracle_update_runner(encoder, n_traj)
+    what = "the reference's own train_one_batch (SACFullLengthRNNREDQ_SEP_OPTIM, unmodified code from oracle/_ref)" \
+        if kind == "reference" else "the oracle CPU port"
+    dt = _time_updates(upd, updates, warm)
+    out = {"value": valid / dt, "unit": "trajectory-steps/s", "cores": cores, "kind": kind,
+           "sample": f"{updates} timed SAC updates (after {warm} warm-up) of {what} with the {encoder} encoder on "
                      f"{n_traj} trajectories x {T_LEN} steps, torch CPU ops on {cores} threads", "s_per_update": dt}
     # the reference's own CPU-runnable case (BASELINE.json configs[0]): Pendulum-V shapes, 8 trajectories x 200 steps
-    upd, valid = oracle_update_runner(encoder, 8, s_dim=1, a_dim=1, t_len=200)
-    upd.train_one_batch()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        upd.train_one_batch()
-    dt1 = (time.perf_counter() - t0) / 3
-    out["config1"] = {"value": valid / dt1, "unit": "trajectory-steps/s", "s_per_update": dt1,
+    built = reference_update_runner(encoder, 8, s_dim=1, a_dim=1, t_len=200)
+    upd, valid = built if built is not None else oracle_update_runner(encoder, 8, s_dim=1, a_dim=1, t_len=200)
+    dt1 = _time_updates(upd, 3, 1)
+    out["config1"] = {"value": valid / dt1, "unit": "trajectory-steps/s", "s_per_update": dt1, "kind": kind,
                       "sample": f"3 timed SAC updates (after 1 warm-up), {encoder} encoder, 8 trajectories x 200 steps, obs 1, act 1"}
     return out
 
 
 def run_reference(args):
-    """Reference arm: the oracle's CPU port of the same config (the Python reference itself cannot travel to this
-    box; its selective_scan_cuda binary does not exist anywhere).  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of this arm's configuration (see the module docstring) on
+    all host threads.  Rank 0 only; the other ranks exit without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_traj = int(os.environ.get("RORL_REF_TRAJ", "2"))
-    upd, valid = oracle_update_runner(ENCODER, n_traj, ALGO)
-    for _ in range(args.warmup):
-        upd.train_one_batch()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        upd.train_one_batch()
-    dt = (time.perf_counter() - t0) / args.steps
+    t_cut = int(os.environ.get("RORL_REF_TLEN", "100"))
+    built = reference_update_runner(ENCODER, N_TRAJ, ALGO, t_cut=t_cut)
+    kind = "reference" if built is not None else "port"
+    if built is None:                                   # staged copy missing: time the oracle port on the same sample
+        upd, valid = oracle_update_runner(ENCODER, N_TRAJ, ALGO, t_len=t_cut)
+    else:
+        upd, valid = built
+    dt = _time_updates(upd, args.steps, args.warmup)
     v = valid / dt
-    sample = (f"each step = one full {ALGO.upper()} update of the oracle CPU port ({ENCODER}, GPU-path semantics via "
-              f"selective_scan_ref restated) on {n_traj} trajectories x {T_LEN} steps (bounded sample of the 32 x 1000 workload)")
+    impl = ("the reference's own train_one_batch, unmodified code staged under oracle/_ref, as it runs on a CPU-only machine "
+            "(smamba: per-time-step Mamba.step loop, ref smamba/mamba.py:133-159)") if kind == "reference" else "the oracle CPU port"
+    sample = (f"each step = one full {ALGO.upper()} update of {impl} with the {ENCODER} encoder on {N_TRAJ} trajectories cut to "
+              f"{t_cut} of their {T_LEN} steps ({valid} valid steps; the loop over time is linear in the length, the {N_TRAJ} rows "
+              f"it amortises over are the workload's), {cores} host threads")
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "trajectory-steps/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"{ALGO.upper()} update, {ENCODER} encoder, {N_TRAJ} trajectories x {T_LEN} steps per GPU "
-                                             f"(obs {S_DIM}, act {A_DIM}, efc-8 twin-Q head, REDQ m=2, RESeL lr split)"},
-                      "cpu_baseline": {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample},
+                      "config": workload_config(args.gpus),
+                      "cpu_baseline": {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": kind, "sample": sample},
                       "e2e": {"value": v, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -410,6 +499,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 256-trajectory strong-scaling leg")
     a = ap.parse_args()
     if a.impl == "reference":
         a.steps = a.steps if a.steps is not None else 3

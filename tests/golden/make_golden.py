@@ -20,10 +20,10 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
-from _refload import load_reference, REF_ROOT  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle.refload import REF_HP, build_algorithm, install_algo_stubs, load_reference  # noqa: E402
 
-load_reference()
+load_reference(gpu_semantics=True)
 torch.set_num_threads(4)
 
 
@@ -266,38 +266,6 @@ def gen_sampler(only=None):
 # ------------------------------------------------------------------------------------------------
 # full update (App. D harness)
 # ------------------------------------------------------------------------------------------------
-def install_algo_stubs():
-    gym = types.ModuleType("gym")
-    gym.Env = object
-    gym.Space = object
-    gym.Wrapper = object
-    spaces = types.ModuleType("gym.spaces")
-    spaces.Box = type("Box", (), {})
-    spaces.Discrete = type("Discrete", (), {})
-    gym.spaces = spaces
-    wr = types.ModuleType("gym.wrappers")
-    wr.RescaleAction = object
-    gym.wrappers = wr
-    sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.wrappers": wr})
-    sl = sys.modules["smart_logger"]
-    sl.Logger = object
-    sl.experiment_config = types.SimpleNamespace()
-    sl.init_config = lambda *a, **k: None
-    pt = types.ModuleType("smart_logger.parameter")
-    ptt = types.ModuleType("smart_logger.parameter.ParameterTemplate")
-    ptt.ParameterTemplate = object
-    pt.ParameterTemplate = ptt
-    sys.modules.update({"smart_logger.parameter": pt, "smart_logger.parameter.ParameterTemplate": ptt})
-    envs = types.ModuleType("envs")
-    mpe = types.ModuleType("envs.make_pomdp_env")
-    mpe.make_pomdp_env = lambda *a, **k: None
-    pc = types.ModuleType("envs.pomdp_config")
-    pc.env_config = {}
-    sys.modules.update({"envs": envs, "envs.make_pomdp_env": mpe, "envs.pomdp_config": pc})
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
-
-
 UPDATE_CASES = {
     "sac_smamba": dict(algo="sac", enc="smamba_s16_c4_b2_nln", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2),
     "sac_gru": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2),
@@ -340,28 +308,12 @@ def model_kwargs(c, value):
                 separate_encoder=True)
 
 
-HP = dict(utd=1, policy_utd=1, randomize_mask=False, valid_number_post_randomized=0, random_trunc_traj=False,
-          randomize_first_hidden=False, gamma=0.99, sac_tau=0.995, policy_update_per=1, no_alpha_auto_tune=False,
-          policy_max_gradnorm=None, policy_embedding_max_gradnorm=None, value_max_gradnorm=None,
-          value_embedding_max_gradnorm=None, redq_m=2, target_action_noise_std=0.04, target_action_noise_clip=0.12,
-          policy_lr=3e-4, value_lr=1e-3, rnn_policy_lr=1e-5, rnn_value_lr=1e-5, alpha_lr=1e-4, policy_l2_norm=0.0,
-          value_l2_norm=0.0, sample_std=0.1, target_entropy_ratio=1.0)
+HP = REF_HP
 
 
 def gen_updates(only=None):
     install_algo_stubs()
-    from offpolicy_rnn.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM, prepare_param_list
-    from offpolicy_rnn.algorithm.td3_full_length_rnn_redq_sep_optim import TD3FullLengthRNNREDQ_SEP_OPTIM
-    from offpolicy_rnn.algorithm.sac_full_length_rnn_ensembleQ import SACFullLengthRNNEnsembleQ
-    from offpolicy_rnn.algorithm.td3_full_length_rnn_ensembleQ import TD3FullLengthRNNEnsembleQ
-    from offpolicy_rnn.algorithm.sac_full_length_rnn_ensembleQ_sep_optim import SACFullLengthRNNENSEMBLEQ_SEP_OPTIM
-    classes = {c.__name__: c for c in (SACFullLengthRNNREDQ_SEP_OPTIM, TD3FullLengthRNNREDQ_SEP_OPTIM, SACFullLengthRNNEnsembleQ,
-                                       TD3FullLengthRNNEnsembleQ, SACFullLengthRNNENSEMBLEQ_SEP_OPTIM)}
-    from offpolicy_rnn.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray
     from offpolicy_rnn.buffers.transition_buffer.replay_memory import Transition
-    from offpolicy_rnn.policy_value_models.make_models import make_policy_model, make_value_model
-    from offpolicy_rnn.utility.q_value_guard import QValueGuard
-    from offpolicy_rnn.utility.timer import Timer
 
     for tag, c in UPDATE_CASES.items():
         if only and tag not in only:
@@ -369,60 +321,12 @@ def gen_updates(only=None):
         torch.manual_seed(5)
         np.random.seed(5)
         cls_name = c.get("cls") or ("SACFullLengthRNNREDQ_SEP_OPTIM" if c["algo"] == "sac" else "TD3FullLengthRNNREDQ_SEP_OPTIM")
-        cls = classes[cls_name]
-        sep = cls_name.endswith("SEP_OPTIM")
-        A = object.__new__(cls)
-        hp = dict(HP, sac_batch_size=sum(c["lens"]) - 1)
+        hp = dict(HP, sac_batch_size=sum(c["lens"]) - 1, max_buffer_transition_num=1000)
         hp.update(c.get("hp", {}))
-        if c["algo"] == "td3":
-            hp["no_alpha_auto_tune"] = True
-        A.parameter = types.SimpleNamespace(**hp)
-        A.timer = Timer()
-        A.device = A.sample_device = torch.device("cpu")
-        A.discrete_env = False
-        A.base_algorithm = c["algo"]
-        A.logger = lambda *a, **k: None
         pk, vk = model_kwargs(c, False), model_kwargs(c, True)
-        if c["algo"] == "td3":
-            pk = dict(pk, sample_std=hp["sample_std"])
-        A.policy = make_policy_model(pk, c["algo"], False)
-        A.values = [make_value_model(vk, c["algo"], False)]
-        A.target_values = [make_value_model(vk, c["algo"], False)]
-        for m in [A.policy] + A.values:
-            with torch.no_grad():
-                for p in m.parameters():
-                    if p.dim() == 1 or p.abs().max() == 0:
-                        p.add_(0.05 * torch.randn_like(p))
-        A._value_update(tau=0.0)
-        A.log_sac_alpha = torch.zeros(1, requires_grad=True)
-        A.target_entropy = -float(c["A"]) * hp["target_entropy_ratio"]
-        for net in (A.values[0].embedding_network.layer_list + A.target_values[0].embedding_network.layer_list
-                    + A.values[0].uni_network.layer_list + A.target_values[0].uni_network.layer_list):
-            if hasattr(net, 'desire_ndim'):
-                net.desire_ndim = 4
-            if hasattr(net, 'in_proj') and hasattr(net.in_proj, 'desire_ndim'):
-                net.in_proj.desire_ndim = 4
-        A.amp_scalar = A.amp_scalar_critic = None
-        A.Q_guard = QValueGuard(True, True, 1 - 1e-3)
-        A.target_policy = make_policy_model(pk, c["algo"], False)
-        A.target_policy.copy_weight_from(A.policy, tau=0.0)
-        A.optim_class = torch.optim.AdamW
-        if sep:     # ref: sac_full_length_rnn_redq_sep_optim.py:85-92
-            A.optimizer_policy = torch.optim.AdamW(prepare_param_list(A.policy, hp["rnn_policy_lr"], hp["policy_l2_norm"]),
-                                                   lr=hp["policy_lr"], weight_decay=hp["policy_l2_norm"])
-            A.optimizer_value = torch.optim.AdamW(prepare_param_list(A.values[0], hp["rnn_value_lr"], hp["value_l2_norm"]),
-                                                  lr=hp["value_lr"], weight_decay=hp["value_l2_norm"])
-        else:       # ref: sac.py:81-90
-            A.optimizer_policy = torch.optim.AdamW(A.policy.parameters(True), lr=hp["policy_lr"], weight_decay=hp["policy_l2_norm"])
-            A.optimizer_value = torch.optim.AdamW([p for v in A.values for p in v.parameters(True)], lr=hp["value_lr"],
-                                                  weight_decay=hp["value_l2_norm"])
-        A.value_parameters = [p for v in A.values for p in v.parameters(True)]
-        A.value_embedding_parameters = [p for v in A.values for p in v.embedding_network.parameters(True)]
-        A.optimizer_alpha = torch.optim.AdamW([A.log_sac_alpha], lr=hp["alpha_lr"])
-        A.grad_num = 0
-        A.allow_nest_stack = cls.allow_nest_stack_trajs(A)
-        skip = cls._get_skip_len(A)
-        A.replay_buffer = NestedMemoryArray(1000, c.get("max_len", max(c["lens"])), additional_history_len=skip)   # ref :41
+        A = build_algorithm(cls_name, hp, pk, vk, c.get("max_len", max(c["lens"])), c["A"], perturb=0.05)
+        hp, pk = vars(A.parameter), A.policy_args
+        skip = type(A)._get_skip_len(A)
         fill_buffer(A.replay_buffer, Transition, np.random.RandomState(9), c["lens"], c["S"], c["A"])
 
         arrs = {}
