@@ -281,6 +281,10 @@ class FullLengthRNNUpdate:
         # torch.optim.AdamW's default weight_decay (1e-2) applies: the reference passes only lr (ref: sac.py:90)
         self.optimizer_alpha = FusedAdamW(self.alpha_arena, [{"params": [self.log_sac_alpha]}], p.alpha_lr, 1e-2)
         self._grad_seen = None                         # first update: learn which parameters ever receive a gradient
+        for h in (getattr(self, '_grad_hooks', None) or []):
+            h.remove()
+        self._grad_hooks = None
+        self._opt_steps = {'value': 0, 'policy': 0}    # completed optimizer steps (GradScaler growth emulation, see _amp_scale)
         # l2_norm_square() covers the RNNBase modules only (ref: contextual_model.py:227-228): a prefix of each arena
         self._l2_span = {}
         for name, model, arena in (('policy', self.policy, self.policy_arena), ('value', self.values[0], self.value_arena)):
@@ -475,6 +479,8 @@ class FullLengthRNNUpdate:
                         comm()
         if advance:
             self.grad_num += 1
+        self._opt_steps['value'] += 1
+        self._opt_steps['policy'] += int(did_policy)
         # logged scalars: one device vector, one read-back ------------------------------------------------------ ref :435-467
         out = {'real_batch_size': batch_size, 'real_batch_traj_num': B, 'policy_updated': did_policy}
         if not sync:
@@ -494,7 +500,7 @@ class FullLengthRNNUpdate:
                     'value_grad_norm': (math.sqrt(s[10]) if (p.value_max_gradnorm is not None and not clipping_emb_v) else 0.0),
                     'q1_l2_norm_square': s[8],
                     'average_traj_len': self.replay_buffer.size / max(len(self.replay_buffer), 1),
-                    'amp_scalar_pi': 0, 'amp_scalar_q': 0})
+                    'amp_scalar_pi': self._amp_scale('policy'), 'amp_scalar_q': self._amp_scale('value')})
         if did_policy or policy_logged:
             clipping_emb_p = p.policy_embedding_max_gradnorm is not None
             out.update({'actor_loss': s[4], 'log_prob': s[5], 'policy_l2_norm_square': s[9],
@@ -502,6 +508,15 @@ class FullLengthRNNUpdate:
             if not p.no_alpha_auto_tune:
                 out['alpha_loss'] = s[6]
         return out
+
+    def _amp_scale(self, which: str) -> float:
+        """The reference wraps both optimizers in a GradScaler when any `gpt` layer is present (ref :34-40,234-258) and
+        logs its scale.  Its autocast region is bf16, whose exponent range is fp32's: scaling the loss by a power of two
+        and un-scaling the gradients is exact and never overflows where fp32 would not, so no scaling is applied here;
+        the logged value follows GradScaler's schedule (65536, doubled every 2000 un-skipped steps)."""
+        if not self._has_gpt:
+            return 0
+        return 65536.0 * 2.0 ** (self._opt_steps[which] // 2000)
 
     def _graph_allowed(self) -> bool:
         """CUDA-graph replay needs a launch sequence that depends on nothing the host decides per step: the cgpt

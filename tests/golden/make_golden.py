@@ -196,6 +196,40 @@ def gen_steps():
             save(f"step_{tag}.npz", layer_id=np.array(lid), **arrs)
     finally:
         smamba.Mamba.forward = patched
+    gen_steps_linear()
+
+
+def gen_steps_linear():
+    """Rollout step path (L == 1 calls with the hidden carried between them) of the gilr / lru / gru / gilr_lstm / conv1d
+    encoders: the UNMODIFIED reference on CPU (scan_cpu / complex_scan_cpu / torch.nn.GRU), incl. a mid-sequence reset
+    (ref: gilr/gilr.py:44-67, lru/lru.py:70-174, rnn_base.py:424-454).  SURVEY.md 8 f2."""
+    from offpolicy_rnn.models.rnn_base import RNNBase
+    for lid in ("gilr", "lru", "gru", "gilr_lstm", "conv1d_4"):
+        torch.manual_seed(13)
+        net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
+        with torch.no_grad():
+            for p in net.parameters():
+                if p.dim() == 1 or p.abs().max() == 0:
+                    p.add_(0.1 * torch.randn_like(p))
+        B, L = 3, 9
+        x = torch.randn(B, L, 12)
+        start = torch.zeros(B, L, 1)
+        start[1, 4] = 1                       # an episode boundary in the middle of the rollout (row 1)
+        hid = net.make_init_state(B)
+        hid[0] = 0.3 * torch.randn_like(hid[0])
+        h_in = hid[0].clone()
+        ys, h = [], hid
+        with torch.no_grad():
+            for t in range(L):
+                if lid != "gru":
+                    h.set_rnn_start(start[:, t:t + 1])
+                    h.set_mask(torch.ones(B, 1, 1))
+                y, h, _ = net.meta_forward(x[:, t:t + 1], h)
+                ys.append(y)
+        arrs = {"x": x, "start": start, "h_in": h_in, "y": torch.cat(ys, dim=1), "h_out": h[0]}
+        for n, p in net.named_parameters():
+            arrs["p/" + n] = p
+        save(f"step_{lid.split('_')[0] if lid.startswith('conv1d') else lid}.npz", layer_id=np.array(lid), **arrs)
 
 
 # ------------------------------------------------------------------------------------------------

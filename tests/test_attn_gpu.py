@@ -136,3 +136,61 @@ def test_cgpt_kv_cache_decode_matches_full_forward():
     err = float((y_dec - y_full).abs().max() / y_full.abs().max())
     print(f"kv-cache decode vs full forward: max-norm relative error {err:.2e}")
     assert err < 1e-2
+
+
+def _fixture(name):
+    import os
+    from helpers import GOLDEN, load_npz
+    if not os.path.exists(os.path.join(GOLDEN, name)):
+        pytest.skip(f"{name}: generated on the GPU box by tests/golden/make_golden_gpu.py (needs flash-attn), not present")
+    return load_npz(name)
+
+
+@pytest.mark.parametrize("tag", ["cgpt_ln", "cgpt_rms"])
+def test_cgpt_layer_matches_reference(tag):
+    """The cgpt encoder against the UNMODIFIED reference's TransformerDecoder run with flash-attn on a B200
+    (tests/golden/layer_cgpt_*.npz, tests/golden/make_golden_gpu.py): forward, input gradient, every parameter gradient.
+    Tolerance 1e-2 (bf16 attention region, BASELINE.json)."""
+    from helpers import T
+    from rorl_b200.models.rnn_base import RNNBase
+    g = _fixture(f"layer_{tag}.npz")
+    lid = str(g["layer_id"])
+    net = RNNBase(12, 8, [128, 128], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
+    net.load_state_dict({k[2:]: T(v) for k, v in g.items() if k.startswith("p/")})
+    net.cuda().train()
+    x = T(g["x"], "cuda", grad=True)
+    seq = g["seqlens"]
+    s_dev = torch.from_numpy(seq).to(torch.int32).cuda()
+    s_dev._host = seq
+    hid = net.make_init_state(x.shape[0], x.device)
+    hid.set_attention_concat_mask(s_dev)
+    y, _, _ = net.meta_forward(x, hid)
+    assert_close(y, g["y"], TOL, "y")
+    params = dict(net.named_parameters())
+    names = [k[2:] for k in g if k.startswith("g/")]
+    gs = torch.autograd.grad(y, [x] + [params[n] for n in names], T(g["dy"], "cuda"))
+    assert_close(gs[0], g["dx"], TOL, "dx")
+    worst = 0.0
+    for n, got in zip(names, gs[1:]):
+        worst = max(worst, assert_close(got, g["g/" + n], 2e-2, n))
+    print(f"{tag}: worst parameter-gradient error vs the reference on flash-attn {worst:.2e}")
+
+
+def test_cgpt_kv_cache_matches_reference():
+    """Rollout path against the reference decoding one token at a time with flash-attn's kv-cache (step_cgpt.npz)."""
+    from helpers import T
+    from rorl_b200.models.rnn_base import RNNBase
+    g = _fixture("step_cgpt.npz")
+    net = RNNBase(10, 6, [128, 128], ['elu', 'elu', 'linear'], ['fc', str(g["layer_id"]), 'fc'])
+    net.load_state_dict({k[2:]: T(v) for k, v in g.items() if k.startswith("p/")})
+    net.cuda().eval()
+    x = T(g["x"], "cuda")
+    with torch.no_grad():
+        hid = net.make_init_state(x.shape[0], x.device)
+        ys = []
+        for t in range(x.shape[1]):
+            y, hid, _ = net.meta_forward(x[:, t:t + 1], hid)
+            ys.append(y)
+        y_full, _, _ = net.meta_forward(x, net.make_init_state(x.shape[0], x.device))
+    assert_close(torch.cat(ys, dim=1), g["y_steps"], TOL, "decoded steps")
+    assert_close(y_full, g["y_full"], TOL, "full forward")

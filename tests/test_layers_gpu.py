@@ -64,6 +64,32 @@ def test_smamba_rollout_step_golden(tag):
     assert_close(h[0], g["h_out"], TOL, "h_out")
 
 
+@pytest.mark.parametrize("tag", ["gilr", "lru", "gru", "gilr_lstm", "conv1d"])
+def test_linear_rollout_step_golden(tag):
+    """L == 1 rollout calls with the hidden carried between them (and a mid-rollout reset) against the UNMODIFIED
+    reference's CPU path for the same loop (tests/golden/step_{gilr,lru,gru,gilr_lstm,conv1d}.npz).  SURVEY.md 8 f2."""
+    from rorl_b200.models.rnn_base import RNNBase
+    g = load_npz(f"step_{tag}.npz")
+    lid = str(g["layer_id"])
+    net = RNNBase(12, 8, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'fc'])
+    net.load_state_dict({k[2:]: T(v) for k, v in g.items() if k.startswith("p/")})
+    net.cuda()
+    x, start = T(g["x"], "cuda"), T(g["start"], "cuda")
+    h = net.make_init_state(x.shape[0], x.device)
+    h[0] = T(g["h_in"], "cuda")
+    ys = []
+    with torch.no_grad():
+        for t in range(x.shape[1]):
+            if lid != "gru":
+                h.set_rnn_start(start[:, t:t + 1])
+                h.set_mask(torch.ones(x.shape[0], 1, 1, device="cuda"))
+            y, h, _ = net.meta_forward(x[:, t:t + 1], h)
+            ys.append(y)
+    assert_close(torch.cat(ys, dim=1), g["y"], TOL, "y")
+    assert tuple(h[0].shape) == g["h_out"].shape
+    assert_close(h[0], g["h_out"], TOL, "h_out")
+
+
 @pytest.mark.parametrize("lid,width", [("gilr", 64), ("lru", 64), ("gru", 64), ("mamba_s16_c4", 64), ("mamba_s32_c16_noff", 32),
                                        ("gilr_lstm", 64), ("conv1d_8", 64)])
 def test_carried_state_composition(lid, width):

@@ -97,7 +97,18 @@ def test_update_matches_reference(tag):
         RH.torch = torch
 
 
-def _run_update_matches_reference(tag):
+def test_update_cgpt_matches_reference():
+    """SAC update with a cgpt encoder against the UNMODIFIED reference run with flash-attn + GradScaler on a B200
+    (tests/golden/update_sac_cgpt.npz from tests/golden/make_golden_gpu.py).  bf16 attention region: 1e-2."""
+    import os
+    from helpers import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "update_sac_cgpt.npz")):
+        pytest.skip("update_sac_cgpt.npz: generated on the GPU box by tests/golden/make_golden_gpu.py, not present")
+    _run_update_matches_reference("sac_cgpt", tol=1e-2)
+
+
+def _run_update_matches_reference(tag, tol=TOL):
+    TOL = tol
     g, cfg, alg = build(tag)
     for call in range(cfg["case"]["calls"]):
         log = alg.train_one_batch()
@@ -121,13 +132,29 @@ def _run_update_matches_reference(tag):
             if k.startswith(f"c{call}/pgrad/"):
                 mod, name = k[len(f"c{call}/pgrad/"):].split("/", 1)
                 worst = max(worst, assert_close(pg[mod][name], v, TOL, k))
-        for which, model in (("policy", alg.policy), ("value", alg.values[0]), ("target", alg.target_values[0])):
+        for which, model, gk in (("policy", alg.policy, "pgrad"), ("value", alg.values[0], "vgrad"), ("target", alg.target_values[0], "vgrad")):
             sd = model.state_dict()
             for k, v in g.items():
                 pre = f"c{call}/{which}/"
                 if k.startswith(pre):
                     mod, name = k[len(pre):].split("/", 1)
-                    worst = max(worst, assert_close(sd[mod][name], v, TOL, k))
+                    gref = g.get(f"c{call}/{gk}/{mod}/{name}")
+                    if tol <= 1e-3 or gref is None:
+                        worst = max(worst, assert_close(sd[mod][name], v, TOL, k))
+                        continue
+                    # bf16 attention region (tol 1e-2): AdamW's first steps are lr * sign-like, so an entry whose reference
+                    # gradient lies inside the gradient tolerance band (|g| < tol * max|g|) may legitimately step the other
+                    # way -- bounded by one flipped step per update; every entry outside the band must match to tol.
+                    lr = max(cfg["hp"]["value_lr"], cfg["hp"]["policy_lr"])
+                    zone = torch.from_numpy(np.abs(gref) < max(1e-6, tol * np.abs(gref).max()))
+                    diff = (sd[mod][name].cpu() - torch.from_numpy(v)).abs()
+                    scale = float(np.abs(v).max()) + 1e-30
+                    if (~zone).any():
+                        bound = tol * scale + 0.05 * lr * (call + 1)
+                        assert float(diff[~zone].max()) <= bound, f"{k}: |diff| {float(diff[~zone].max()):.3e} > {bound:.3e}"
+                        worst = max(worst, float(diff[~zone].max()) / scale)
+                    if zone.any():
+                        assert float(diff[zone].max()) <= 2.2 * lr * (call + 1), f"{k}: in-band entry moved {float(diff[zone].max()):.3e}"
         assert abs(alg.log_sac_alpha.item() - float(g[f"c{call}/log_alpha"][0])) < 1e-6
         print(f"{tag} call {call}: worst relative error {worst:.2e}")
 

@@ -76,7 +76,7 @@ def rec(name, t, nbytes=None, flops=None, note=""):
 
 
 def bench_gilr():
-    B, L, C = 32, 1002, 256
+    B, L, C = 32, 1003, 256
     uv, uf, dh = rn(B, L, C), rn(B, L, C), rn(B, L, C)
     start = torch.zeros(B, L, device=dev); start[:, 0] = 1
     h = torch.empty_like(uv)
@@ -97,7 +97,7 @@ def bench_gilr():
 
 
 def bench_lru():
-    B, L, C = 32, 1002, 256
+    B, L, C = 32, 1003, 256
     vr, vi, fr, fi = rn(B, L, C), rn(B, L, C), 0.9 * torch.rand(B, L, C, device=dev), 0.1 * rn(B, L, C)
     hr, hi = torch.empty_like(vr), torch.empty_like(vr)
     rec("lru_scan_fwd", timeit(lambda: N.call("rorl_lru_scan_fwd", N.ptr(vr), N.ptr(vi), N.ptr(fr), N.ptr(fi), None, None,
@@ -111,7 +111,7 @@ def bench_lru():
 
 
 def bench_lru_fused():
-    B, L, C = 32, 1002, 256
+    B, L, C = 32, 1003, 256
     u_re, u_im = rn(B, L, C).requires_grad_(), rn(B, L, C).requires_grad_()
     lam_re, lam_im, gamma = (0.6 * torch.rand(C, device=dev)).requires_grad_(), (0.6 * torch.rand(C, device=dev)).requires_grad_(), (0.5 + torch.rand(C, device=dev)).requires_grad_()
     start = torch.zeros(B, L, device=dev); start[:, 0] = 1
@@ -124,12 +124,12 @@ def bench_lru_fused():
 
 
 def bench_selscan():
-    B, L, D, Ns = 32, 1018, 512, 32
+    B, L, D, Ns = 32, 1019, 512, 32
     u, delta, z = rn(B, L, D).requires_grad_(), (0.5 * rn(B, L, D) - 1).requires_grad_(), rn(B, L, D).requires_grad_()
     Bm, Cm = rn(B, L, Ns).requires_grad_(), rn(B, L, Ns).requires_grad_()
     A = (-torch.exp(0.3 * rn(D, Ns))).requires_grad_()
     Dk, bias = rn(D).requires_grad_(), rn(D).requires_grad_()
-    start = torch.zeros(B, L, device=dev); start[:, :18] = 1
+    start = torch.zeros(B, L, device=dev); start[:, :19] = 1
     dy = rn(B, L, D)
     with torch.no_grad():
         t_fwd = timeit(lambda: K.selective_scan_tm(u, delta, A, Bm, Cm, Dk, z, bias, start, True))
@@ -144,7 +144,7 @@ def bench_selscan():
 
 
 def bench_conv():
-    B, L, D, Kc = 32, 1018, 512, 16
+    B, L, D, Kc = 32, 1019, 512, 16
     x, w, b = rn(B, L, D).requires_grad_(), rn(D, 1, Kc).requires_grad_(), rn(D).requires_grad_()
     mask = torch.ones(B, L, device=dev)
     dy = rn(B, L, D)
@@ -156,7 +156,7 @@ def bench_conv():
 
 
 def bench_addnorm():
-    rows, C = 32 * 1018, 256
+    rows, C = 32 * 1019, 256
     x, r, w, b = rn(rows, C).requires_grad_(), rn(rows, C).requires_grad_(), rn(C).requires_grad_(), rn(C).requires_grad_()
     dy = rn(rows, C)
     with torch.no_grad():
@@ -168,7 +168,7 @@ def bench_addnorm():
 
 def bench_gru():
     from rorl_b200.models.gru.gru import GRULayer
-    B, L, H = 32, 1002, 256
+    B, L, H = 32, 1003, 256
     gi, w, bh = rn(B, L, 3 * H), 0.06 * rn(3 * H, H), rn(3 * H)
     out, hl, save = torch.empty(B, L, H, device=dev), torch.empty(B, H, device=dev), torch.empty(B, L, 4 * H, device=dev)
     t = timeit(lambda: N.call("rorl_gru_fwd", N.ptr(gi), N.ptr(w), N.ptr(bh), None, N.ptr(out), N.ptr(save), N.ptr(hl), B, L, H, N.stream()), n=10)
@@ -193,7 +193,7 @@ def bench_gru():
 
 
 def bench_gemm():
-    M = 32 * 1018
+    M = 32 * 1019
     for (n, k, g, tag) in [(256, 256, 1, "fc 256x256"), (1024, 256, 1, "in_proj"), (256, 512, 1, "out_proj"), (256, 384, 8, "efc-8 L1 (shared x)"),
                            (256, 256, 8, "efc-8 L2")]:
         a = rn(M, k) if (g == 1 or k == 384) else rn(g, M, k)
@@ -217,15 +217,15 @@ def bench_gemm():
     # weight gradient
     gq, xq = rn(M, 256), rn(M, 256)
     t = timeit(lambda: K.gemm_nt(gq, xq))
-    rec("gemm_nt 256x256 R=32576 passes=3", t, flops=3 * 2.0 * M * 256 * 256, nbytes=4 * (gq.numel() + xq.numel()))
+    rec("gemm_nt 256x256 R=32608 passes=3", t, flops=3 * 2.0 * M * 256 * 256, nbytes=4 * (gq.numel() + xq.numel()))
     c = torch.empty(M, 256, device=dev)
     a2, w2 = rn(M, 256), rn(256, 256)
     t = timeit(lambda: torch.mm(a2, w2, out=c))
-    rec("cublas sgemm 32576x256x256 (library, for scale)", t, flops=2.0 * M * 256 * 256)
+    rec("cublas sgemm 32608x256x256 (library, for scale)", t, flops=2.0 * M * 256 * 256)
 
 
 def bench_reduce():
-    M = 32 * 1018
+    M = 32 * 1019
     for n in (128, 256, 1024):
         x = rn(M, n)
         t = timeit(lambda: K.colsum(x))
@@ -234,7 +234,7 @@ def bench_reduce():
         rec(f"aten sum(0) [{M},{n}] (library, for scale)", t, 4 * M * n)
     dy, y = rn(8, M, 256), rn(8, M, 256)
     t = timeit(lambda: K.elu_bwd_colsum(dy, y))
-    rec("elu_bwd_colsum [8,32576,256]", t, 12 * dy.numel())
+    rec("elu_bwd_colsum [8,32608,256]", t, 12 * dy.numel())
     t = timeit(lambda: torch.ops.aten.elu_backward(dy, 1.0, 1.0, 1.0, True, y).sum(1))
     rec("aten elu_backward + sum (library, for scale)", t, 12 * dy.numel())
     for n, k in ((128, 9), (512, 16)):
@@ -245,7 +245,88 @@ def bench_reduce():
         rec(f"cublas wgrad N={n} K={k} (library, for scale)", t, 4 * M * (n + k))
 
 
-ALL = {"reduce": bench_reduce, "gilr": bench_gilr, "lru": bench_lru, "lru_fused": bench_lru_fused, "selscan": bench_selscan, "conv": bench_conv, "addnorm": bench_addnorm,
+def bench_attn():
+    """cgpt attention at the config-4 shape (32 rows, each a 1-token + a 1002-token sequence, 8 heads x 64) next to the
+    kernel the reference calls on the same box: flash-attn 2's varlen kernel (FA2 `mma.sync` build for sm_100)."""
+    import math
+    import numpy as np
+    H, hd, B = 8, 64, 32
+    lens, starts, pos = [], [], 0
+    for _ in range(B):
+        for n in (1, 1002):
+            starts.append(pos); lens.append(n); pos += n
+    T = pos
+    qkv = rn(T, 3, H, hd).requires_grad_()
+    dout = rn(T, H * hd)
+    slopes = torch.tensor([2 ** (-(i + 1)) for i in range(H)], dtype=torch.float32, device=dev)
+    scale = 1.0 / math.sqrt(hd)
+    tiles, gmap = (t.to(dev) for t in K.attention_tiles(starts, lens))
+    fl_f = sum(4.0 * n * (n + 1) / 2 * hd for n in lens) * H          # causal QK^T + PV
+    with torch.no_grad():
+        t_f = timeit(lambda: K.attn_varlen_alibi(qkv, tiles, gmap, slopes, scale))
+    t_fb = timeit(lambda: torch.autograd.grad(K.attn_varlen_alibi(qkv, tiles, gmap, slopes, scale), qkv, dout), n=10)
+    rec("attn_fwd (ours: prep + tcgen05 kernel, fp32 in/out)", t_f, flops=fl_f)
+    rec("attn_fwd+bwd (ours)", t_fb, flops=3.5 * fl_f)
+    try:
+        import flash_attn as fa
+        cu = torch.tensor(np.concatenate(([0], np.cumsum(lens))), dtype=torch.int32, device=dev)
+        a = qkv.detach().to(torch.bfloat16).requires_grad_()
+        do16 = dout.view(T, H, hd).to(torch.bfloat16)
+        with torch.no_grad():
+            t_f = timeit(lambda: fa.flash_attn_varlen_qkvpacked_func(a, cu, max(lens), 0.0, softmax_scale=scale, causal=True, alibi_slopes=slopes))
+        t_fb = timeit(lambda: torch.autograd.grad(fa.flash_attn_varlen_qkvpacked_func(a, cu, max(lens), 0.0, softmax_scale=scale, causal=True,
+                                                                                      alibi_slopes=slopes), a, do16), n=10)
+        rec("flash-attn 2 varlen fwd (library, same box, bf16 in/out)", t_f, flops=fl_f, note=f"flash_attn {fa.__version__}")
+        rec("flash-attn 2 varlen fwd+bwd (library, same box)", t_fb, flops=3.5 * fl_f)
+        # like for like with the reference's call site: the fp32 -> bf16 casts autocast inserts around the kernel
+        q32 = qkv.detach().clone().requires_grad_()
+        t_fb = timeit(lambda: torch.autograd.grad(fa.flash_attn_varlen_qkvpacked_func(q32.to(torch.bfloat16), cu, max(lens), 0.0, softmax_scale=scale,
+                                                  causal=True, alibi_slopes=slopes).float(), q32, dout.view(T, H, hd)), n=10)
+        rec("flash-attn 2 varlen fwd+bwd incl. fp32<->bf16 casts (library, same box)", t_fb, flops=3.5 * fl_f)
+    except Exception as e:  # pragma: no cover
+        print("flash-attn unavailable:", e)
+
+
+def bench_refs():
+    """The reference's own in-tree Triton scans (K6 / K7) on the same box, imported UNMODIFIED from oracle/_ref
+    (ref: gilr/scan_triton/real_rnn_tie_input_gate.py:170-264, lru/scan_triton/complex_rnn.py:174-244)."""
+    sys.path.insert(0, ROOT)
+    from oracle import refload
+    if not refload.available():
+        print("reference not staged (oracle/make_ref.py)")
+        return
+    refload.load_reference()
+    B, L, C = 32, 1003, 256
+    try:
+        from offpolicy_rnn.models.gilr.scan_triton.real_rnn_tie_input_gate import real_scan_tie_input_gate
+        v, f = rn(B, L, C).requires_grad_(), torch.sigmoid(rn(B, L, C)).requires_grad_()
+        dh = rn(B, L, C)
+        with torch.no_grad():
+            t_f = timeit(lambda: real_scan_tie_input_gate(v, f), n=10)
+        rec("reference Triton gilr scan fwd (K6, same box)", t_f, 12 * B * L * C)
+        # the reference's backward overwrites its saved tensors in place, so time forward + backward together
+        t_fb = timeit(lambda: torch.autograd.grad(real_scan_tie_input_gate(v.clone(), f.clone()), (v, f), dh, allow_unused=True), n=10)
+        rec("reference Triton gilr scan fwd+bwd incl. 2 clones (K6, same box)", t_fb, 36 * B * L * C + 16 * B * L * C)
+    except Exception as e:
+        print("reference gilr Triton scan failed:", repr(e))
+    try:
+        from offpolicy_rnn.models.lru.scan_triton.complex_rnn import complex_scan
+        vr, vi = rn(B, L, C).requires_grad_(), rn(B, L, C).requires_grad_()
+        fr, fi = (0.9 * torch.rand(B, L, C, device=dev)).requires_grad_(), (0.1 * rn(B, L, C)).requires_grad_()
+        h0r, h0i = torch.zeros(B, 1, C, device=dev), torch.zeros(B, 1, C, device=dev)
+        gd = torch.zeros(B, L, 1, device=dev)
+        g1, g2 = rn(B, L, C), rn(B, L, C)
+        with torch.no_grad():
+            t_f = timeit(lambda: complex_scan(vr, vi, fr, fi, h0r, h0i, gd), n=10)
+        rec("reference Triton lru scan fwd (K7, same box)", t_f, 24 * B * L * C)
+        t_fb = timeit(lambda: torch.autograd.grad(complex_scan(vr.clone(), vi.clone(), fr.clone(), fi.clone(), h0r, h0i, gd), (vr, vi, fr, fi), (g1, g2),
+                                                  allow_unused=True), n=10)
+        rec("reference Triton lru scan fwd+bwd incl. 4 clones (K7, same box)", t_fb, (24 + 40 + 32) * B * L * C)
+    except Exception as e:
+        print("reference lru Triton scan failed:", repr(e))
+
+
+ALL = {"attn": bench_attn, "refs": bench_refs, "reduce": bench_reduce, "gilr": bench_gilr, "lru": bench_lru, "lru_fused": bench_lru_fused, "selscan": bench_selscan, "conv": bench_conv, "addnorm": bench_addnorm,
        "gru": bench_gru, "gemm": bench_gemm}
 
 if __name__ == "__main__":
