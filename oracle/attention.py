@@ -6,8 +6,10 @@ ref: offpolicy_rnn/models/flash_attention/TransformerFlashAttention.py:29-121 (R
      requirement.txt:7, unpinned; 2.8.3 in this image).  Its published semantics are restated here:
      score_ij = softmax_scale * q_i . k_j - slope_h * (i - j) for j <= i inside one sequence, softmax over j,
      slopes from get_alibi_slopes (2^(-8 (h+1) / n) for power-of-two n).
-Parity for this piece is pinned on the GPU box against flash-attn itself (tests/test_attn_gpu.py) when it is
-importable there; the oracle alone is "parity unpinned" for the bf16 rounding flash-attn applies internally.
+PINNED: tests/golden/layer_cgpt_{ln,rms}.npz, step_cgpt.npz and update_sac_cgpt.npz are outputs of the UNMODIFIED
+reference (staged copy oracle/_ref) run with flash-attn 2.8.3 on a B200 by tests/golden/make_golden_gpu.py;
+tests/test_oracle_golden.py checks this restatement against them at the bf16 tolerance (1e-2), and
+tests/test_attn_gpu.py checks the CUDA path against the same files and against flash-attn's kernel directly.
 """
 from __future__ import annotations
 

@@ -52,7 +52,8 @@ def gen_layers():
             for p in net.parameters():
                 if p.dim() == 1 or p.abs().max() == 0:
                     p.add_(0.1 * torch.randn_like(p))
-        net.to(dev).train()
+        net.to(dev)
+        net.train()
         B, L = 3, 300
         seq = np.zeros((B, L), dtype=np.int64)
         seq[0, :2] = (200, 100)
@@ -83,7 +84,8 @@ def gen_step():
         for p in net.parameters():
             if p.dim() == 1 or p.abs().max() == 0:
                 p.add_(0.1 * torch.randn_like(p))
-    net.to(dev).eval()
+    net.to(dev)
+    net.eval()
     B, T = 3, 37
     x = torch.randn(B, T, 10).to(dev)
     with torch.no_grad():

@@ -104,6 +104,42 @@ def test_smamba_rollout_step(tag):
     assert_close(h, g["h_out"], TOL, "h_out")
 
 
+@pytest.mark.parametrize("tag", ["cgpt_ln", "cgpt_rms"])
+def test_cgpt_layer_oracle_vs_reference_on_flash_attn(tag):
+    """Pins oracle/attention.py (fp32 restatement of the cgpt decoder) against the UNMODIFIED reference run with
+    flash-attn 2.8.3 in bf16 autocast on a B200 (tests/golden/make_golden_gpu.py).  The reference's attention region
+    computes in bf16, so the two agree to bf16 rounding: 1e-2 (BASELINE.json's tolerance for this path)."""
+    g = load_npz(f"layer_{tag}.npz")
+    lid = str(g["layer_id"])
+    p = {k[2:]: T(v, grad=True) for k, v in g.items() if k.startswith("p/")}
+    x = T(g["x"], grad=True)
+    side = OM.Side(attention_concat_mask=torch.from_numpy(g["seqlens"]).to(torch.int))
+    y = OM.rnn_base(p, ['fc', lid, 'fc'], ['elu', 'elu', 'linear'], x, side)
+    assert_close(y, g["y"], 1e-2, "y")
+    names = [k[2:] for k in g if k.startswith("g/")]
+    gs = torch.autograd.grad(y, [x] + [p[n] for n in names], T(g["dy"]))
+    assert_close(gs[0], g["dx"], 1e-2, "dx")
+    for n, got in zip(names, gs[1:]):
+        assert_close(got, g["g/" + n], 2e-2, n)
+
+
+def test_cgpt_update_oracle_vs_reference_on_flash_attn():
+    """The oracle's full SAC update with a cgpt encoder against the reference's train_one_batch on a B200 with flash-attn
+    and GradScaler (update_sac_cgpt.npz): logged scalars and gradients at the bf16 tolerance."""
+    g, cfg, upd = run_oracle_update("sac_cgpt")
+    log = upd.train_one_batch()
+    for k in ("critic_loss", "actor_loss", "log_prob", "target_q_max", "q1_l2_norm_square"):
+        ref = float(g[f"c0/log/{k}"])
+        assert abs(log[k] - ref) <= 1e-2 * max(1.0, abs(ref)), (k, log[k], ref)
+    for k, v in g.items():
+        if k.startswith("c0/vgrad/"):
+            mod, name = k[len("c0/vgrad/"):].split("/", 1)
+            assert_close(upd.value_grads[mod][name], v, 2e-2, k)
+        if k.startswith("c0/pgrad/"):
+            mod, name = k[len("c0/pgrad/"):].split("/", 1)
+            assert_close(upd.policy_grads[mod][name], v, 2e-2, k)
+
+
 def _fill(buf, rng, lens, S, A):
     for Tn in lens:
         last_s, last_a, last_r = np.zeros((1, S)), np.zeros((1, A)), np.zeros((1, 1))

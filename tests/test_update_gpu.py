@@ -139,18 +139,21 @@ def _run_update_matches_reference(tag, tol=TOL):
                 if k.startswith(pre):
                     mod, name = k[len(pre):].split("/", 1)
                     gref = g.get(f"c{call}/{gk}/{mod}/{name}")
-                    if tol <= 1e-3 or gref is None:
+                    if gref is None:
                         worst = max(worst, assert_close(sd[mod][name], v, TOL, k))
                         continue
-                    # bf16 attention region (tol 1e-2): AdamW's first steps are lr * sign-like, so an entry whose reference
-                    # gradient lies inside the gradient tolerance band (|g| < tol * max|g|) may legitimately step the other
-                    # way -- bounded by one flipped step per update; every entry outside the band must match to tol.
+                    # AdamW's first steps are lr * g / (|g| + eps): sign-like.  An entry whose reference gradient lies inside
+                    # the noise band of the gradient comparison may legitimately step the other way (bounded by one flipped
+                    # step per update); every entry outside the band must match to tol.  Band: fp32 paths -- summation-order
+                    # noise, ~32 ulp of the tensor's largest gradient entry (and Adam's eps regime, 1e-6); bf16 attention
+                    # region -- the gradient tolerance itself.
                     lr = max(cfg["hp"]["value_lr"], cfg["hp"]["policy_lr"])
-                    zone = torch.from_numpy(np.abs(gref) < max(1e-6, tol * np.abs(gref).max()))
+                    band = max(1e-6, (tol if tol > 1e-3 else 4e-6) * float(np.abs(gref).max()))
+                    zone = torch.from_numpy(np.abs(gref) < band)
                     diff = (sd[mod][name].cpu() - torch.from_numpy(v)).abs()
                     scale = float(np.abs(v).max()) + 1e-30
                     if (~zone).any():
-                        bound = tol * scale + 0.05 * lr * (call + 1)
+                        bound = tol * scale + (0.05 if tol > 1e-3 else 0.01) * lr * (call + 1)
                         assert float(diff[~zone].max()) <= bound, f"{k}: |diff| {float(diff[~zone].max()):.3e} > {bound:.3e}"
                         worst = max(worst, float(diff[~zone].max()) / scale)
                     if zone.any():
