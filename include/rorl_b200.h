@@ -217,13 +217,17 @@ int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t 
  *   D[g][M, N] = act(A[g][M, K] * B[g][N, K]^T + bias[g][N]),  g = 0..G-1
  * Both operands K-major (reduction dimension contiguous).  strideA / strideB == 0: operand shared by all g.
  * act: 0 none, 1 ELU (Dpre, may be NULL, receives the pre-activation in D's layout for an exact ELU backward).
- * passes: 3 = 3xTF32 (fp32 parity), 1 = plain TF32.  reduce_g != 0: the G products are
+ * passes: 3 = 3xTF32 (fp32 parity, ~2^-21), 2 = two-term bf16 split, 3 bf16 MMAs (fp32 parity to ~2^-17 at twice
+ * the tensor rate and half the operand bytes), 1 = plain TF32.  reduce_g != 0: the G products are
  * summed into one D[M, N] (data-gradient of an ensemble layer with shared input).
- * K, N, ld*, stride* multiples of 4; bases 16-byte aligned.
+ * K, N, ld*, stride* multiples of 4 (passes == 2: K a multiple of 8); bases 16-byte aligned.
+ * work: device scratch of rorl_gemm_tn_work_bytes(...) bytes, 16-byte aligned (passes == 2: the kernel pre-splits
+ * the B operand -- the weights, re-read by every row tile -- into bf16 hi / lo copies there); NULL otherwise.
  * ---------------------------------------------------------------------------------------------- */
+int64_t rorl_gemm_tn_work_bytes(int64_t N, int64_t K, int64_t G, int64_t strideB, int passes);
 int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
-                 int64_t strideBias, int act, int passes, int reduce_g, cudaStream_t stream);
+                 int64_t strideBias, int act, int passes, int reduce_g, void* work, cudaStream_t stream);
 /* Weight-gradient form: D[s][g][M, N] = sum over the s-th slice of rows r of A[g][r, M]^T B[g][r, N] (both operands
  * row-major with the REDUCTION over rows, i.e. MN-major for the tensor core; no transposed copies).  Split-K over
  * the R rows: splits = rorl_gemm_nt_splits(M, N, R, G); partial s lands at D + s * strideSplit and the caller sums

@@ -499,7 +499,10 @@ def rms_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residua
 # ------------------------------------------------------------------------------------------------
 # tcgen05 GEMM (3xTF32, fp32 parity) behind nn.Linear / EnsembleLinear
 # ------------------------------------------------------------------------------------------------
-GEMM_PASSES = 3          # 3 = fp32-parity split accumulation; 1 = plain TF32 (set by benchmarks only)
+import os as _os
+# 3 = 3xTF32 split accumulation (~2^-21); 2 = two-term bf16 split on kind::f16 (~2^-17, half the tensor time and
+# operand bytes); 1 = plain TF32 (benchmarks only).  RORL_GEMM_PASSES overrides for A/B runs.
+GEMM_PASSES = int(_os.environ.get("RORL_GEMM_PASSES", "3"))
 GEMM_MIN_K = 32
 
 
@@ -527,10 +530,16 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     D = torch.empty((G, M, Nn) if batched_out else (M, Nn), device=A.device, dtype=torch.float32)
     bias_c = None if bias is None else _f32c(bias.reshape(-1, Nn) if batched_out else bias.reshape(Nn))
     pre = torch.empty_like(D) if (want_pre and act) else None
+    passes = int(passes or GEMM_PASSES)
+    if passes == 2 and K % 8:
+        passes = 3                                   # bf16 rows must be 16-byte multiples; such widths are not on the update path
+    strideB = B.stride(0) if B.dim() == 3 else 0
+    wb = int(N.lib().rorl_gemm_tn_work_bytes(Nn, K, G, strideB, passes))
+    work = torch.empty(wb, dtype=torch.uint8, device=A.device) if wb else None
     N.call("rorl_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(bias_c), N.ptr(D), N.ptr(pre), M, Nn, K, G, A.stride(-2), B.stride(-2), Nn,
-           A.stride(0) if A.dim() == 3 else 0, B.stride(0) if B.dim() == 3 else 0, M * Nn if batched_out else 0,
-           Nn if (bias_c is not None and bias_c.dim() == 2) else 0, int(act), int(passes or GEMM_PASSES),
-           int(reduce_g), N.stream())
+           A.stride(0) if A.dim() == 3 else 0, strideB, M * Nn if batched_out else 0,
+           Nn if (bias_c is not None and bias_c.dim() == 2) else 0, int(act), passes,
+           int(reduce_g), N.ptr(work), N.stream())
     return (D, pre) if want_pre else D
 
 

@@ -127,3 +127,37 @@ def test_gemm_tn_bk16_ring(K, M, N, K_):
         NV.lib().rorl_gemm_force_bk(0)
     assert rel_err(D16, ref) < 1e-5
     assert rel_err(D32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (300, 12, 256), (1000, 80, 512), (32608, 256, 384), (4097, 1024, 256),
+                                     (77, 132, 36), (513, 260, 64), (2000, 200, 96), (129, 2048, 384), (255, 256, 40)])
+def test_gemm_tn_bf16_split(K, M, N, K_):
+    """passes = 2: two-term bf16 split (hi*hi + hi*lo + lo*hi on kind::f16).  Error ~2^-17 relative per product,
+    measured against float64; tolerance 3e-5 of max|D| (30x inside the 1e-3 parity budget)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + 7)
+    A = torch.randn(M, K_, device="cuda", generator=g)
+    B = torch.randn(N, K_, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.double() @ B.double().t() + bias.double()
+    D = K.gemm_tn(A, B, bias, passes=2)
+    e = rel_err(D, ref)
+    print(f"M={M} N={N} K={K_}: bf16x3 err {e:.2e}")
+    assert e < 3e-5
+    Delu = K.gemm_tn(A, B, bias, act=1, passes=2)
+    assert rel_err(Delu, torch.nn.functional.elu(ref)) < 3e-5
+
+
+def test_gemm_tn_bf16_split_batched(K):
+    g = torch.Generator(device="cuda").manual_seed(6)
+    E, M, N, K_ = 8, 1500, 256, 384
+    big = torch.randn(M, 2 * K_, device="cuda", generator=g)
+    A = big[:, K_:]
+    W = torch.randn(E, N, K_, device="cuda", generator=g)
+    b = torch.randn(E, N, device="cuda", generator=g)
+    D = K.gemm_tn(A, W, b, passes=2)
+    ref = torch.einsum('mk,enk->emn', A.double(), W.double()) + b.double()[:, None]
+    assert rel_err(D, ref) < 3e-5
+    Ab = torch.randn(E, M, K_, device="cuda", generator=g)
+    D3 = K.gemm_tn(Ab, W, reduce_g=True, passes=2)
+    ref3 = torch.einsum('emk,enk->mn', Ab.double(), W.double())
+    assert rel_err(D3, ref3) < 1e-4

@@ -199,10 +199,10 @@ def bench_gemm():
         a = rn(M, k) if (g == 1 or k == 384) else rn(g, M, k)
         b = rn(n, k) if g == 1 else rn(g, n, k)
         bias = rn(n) if g == 1 else rn(g, n)
-        for passes in (3, 1):
+        for passes in (3, 2, 1):
             t = timeit(lambda: K.gemm_tn(a, b, bias, 1, passes=passes))
             fl = 2.0 * M * n * k * g
-            rec(f"gemm_tn {tag} passes={passes}", t, flops=fl * passes, nbytes=4 * (a.numel() + b.numel() + M * n * g),
+            rec(f"gemm_tn {tag} passes={passes}", t, flops=fl * (3 if passes > 1 else 1), nbytes=4 * (a.numel() + b.numel() + M * n * g),
                 note=f"useful fp32 TFLOP/s {fl / t / 1e12:.1f}")
         for bk in (16,):                 # A/B: 16-wide k-stages (twice as deep a ring)
             N.lib().rorl_gemm_force_bk(bk)
