@@ -382,7 +382,7 @@ struct SelBwdCfg {
     static constexpr int QS = 4 * LPD + 4;                // partial-sum quad stride (4 channels x LPD lanes + skew)
     static constexpr int PROW = QPR * QS;                 // partial-sum row
     static constexpr int PLANE = TC * PROW;               // one plane (sB | sA | y) of per-lane partial sums
-    static constexpr int RED = NMAINW * TC * 2 * N;       // per-warp dB | dC
+    static constexpr int RED = TC * NMAINW * DPW * 2 * N; // per (step, warp, channel-lane): this lane's dB | dC, summed by the helpers
     static constexpr int NHELP = 128;
     static constexpr int NTHREADS = NMAIN + NHELP;
     static constexpr size_t SMEM = sizeof(float) * (NST * STAGE + 3 * PLANE + RED + 2 * DT * (NHELP / QPR)) + 128;
@@ -457,6 +457,10 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
 
     if (tid >= NMAIN) {
         // ------------------------------------------------------------------------------------ helper warps
+        // register re-allocation between the warpgroups (the register file, not the pipes, limits residency here): the
+        // helper warpgroup gives up what it does not need, the two main warpgroups take it (8 x 32 x 208 + 4 x 32 x 80
+        // <= 64 K registers), which keeps the main loop's ~190 live values out of local memory
+        if (NMAIN == 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         const int ht = tid - NMAIN;
         const int myq = ht % QPR;                           // this thread's quad column is fixed (NHELP % QPR == 0)
         const int mycol = d0 + myq * 4;
@@ -582,16 +586,23 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
                     }
                 }
             }
+            // dB_t[n] / dC_t[n]: sum over the CTA's channels.  The main warps leave one row per (step, warp, channel-lane);
+            // the cross-lane / cross-warp sum is done HERE, by warps that otherwise wait for the main warps (the
+            // shuffle reduce-scatter it replaces was ~19 % of the main warps' instructions).
             for (int idx = ht * 4; idx < TC * 2 * N; idx += NHELP * 4) {
                 const int r = idx / (2 * N), t = k * TC + r;
                 if (t < L) {
-                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float* src = s_red + (size_t)r * (NMAINW * DPW * 2 * N) + (idx % (2 * N));
+                    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int w = 0; w < NMAINW; ++w) {
-                        const float4 v = *reinterpret_cast<const float4*>(s_red + w * TC * 2 * N + idx);
-                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    for (int w = 0; w < NMAINW * DPW; w += 2) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(src + w * 2 * N);
+                        const float4 v1 = *reinterpret_cast<const float4*>(src + (w + 1) * 2 * N);
+                        s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+                        s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
                     }
-                    *reinterpret_cast<float4*>(p.dBC_part + (((size_t)blockIdx.x * p.Bsz + b) * L + t) * (2 * N) + (idx % (2 * N))) = sum;
+                    *reinterpret_cast<float4*>(p.dBC_part + (((size_t)blockIdx.x * p.Bsz + b) * L + t) * (2 * N) + (idx % (2 * N))) =
+                        make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
                 }
             }
             __syncwarp();
@@ -622,6 +633,7 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
         // + dl), so that a warp's partial-sum stores stay bank-conflict free; what the channels share is B_t / C_t:
         // one LDS.128 (4 shared-memory wavefronts however much of it is a broadcast) now feeds 8 elements instead
         // of 4 -- ncu had the LSU shared-memory pipe as the busiest unit of this kernel (70 %).
+        if (NMAIN == 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         constexpr int H2 = S / 2, CH = Cfg::CH;
         const int lane = tid & 31, warp = tid >> 5;
         const int dl = lane / LPD, ng = lane % LPD;
@@ -660,15 +672,16 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
             const float* s_dtA = st + 1 * TC * DT;
             const float* s_du = st + 2 * TC * DT;
             const float* s_g = st + 3 * TC * DT;
+            const float* s_dt = st + 4 * TC * DT;            // delta itself (finite at reset steps, where s_dtA holds +inf)
             const float* s_B = st + Cfg::NARR * TC * DT;
             const float* s_C = s_B + TC * N;
             mbar_wait(bar_full(cc % NST), (cc / NST) & 1);
             // ---- phase F: recompute h_t inside the chunk
-            float2 h[CH][H2];
+            float2 h[CH][H2], hent[CH][H2];                 // hent: the state entering the chunk (h_{t-1} of its first step)
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                h[c][0] = f2(hin[c].x, hin[c].y);
-                h[c][1] = f2(hin[c].z, hin[c].w);
+                h[c][0] = hent[c][0] = f2(hin[c].x, hin[c].y);
+                h[c][1] = hent[c][1] = f2(hin[c].z, hin[c].w);
                 hin[c] = ld_ckpt(k - 1, c);                 // prefetch the next chunk's entry state
             }
             float2 hb[CH][TC][H2];
@@ -701,7 +714,7 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
 #pragma unroll                                              // the warp's by the reduce-scatter below
                 for (int c = 0; c < CH; ++c) {
                     const float dtA = s_dtA[i * DT + dloc[c]], du = s_du[i * DT + dloc[c]], g = s_g[i * DT + dloc[c]];
-                    const float dt = (dtA == INFINITY) ? 0.f : dtA;     // at a reset a_t h_{t-1} = 0, so dt is immaterial there
+                    const float dt = s_dt[i * DT + dloc[c]];
                     const float2 g2 = f2(g, g), du2 = f2(du, du), dt2 = f2(dt, dt);
                     float2 sB2 = f2(0.f, 0.f), sA2 = f2(0.f, 0.f), yp2 = f2(0.f, 0.f);
 #pragma unroll
@@ -712,34 +725,23 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
                         dC2[j] = c == 0 ? dc : __fadd2_rn(dC2[j], dc);
                         dB2[j] = c == 0 ? db : __fadd2_rn(dB2[j], db);
                         sB2 = __ffma2_rn(l, Bv[j], sB2);
-                        const float2 ahp = __ffma2_rn(f2(-du, -du), Bv[j], hb[c][i][j]);     // a_t * h_{t-1}
-                        const float2 t1 = __fmul2_rn(l, ahp);
-                        dA[c][j] = __ffma2_rn(t1, dt2, dA[c][j]);
-                        sA2 = __ffma2_rn(t1, A2[c][j], sA2);
                         if (HAS_Z) yp2 = __ffma2_rn(hb[c][i][j], Cv[j], yp2);
                         const float2 e = __fmul2_rn(f2(dtA, dtA), A2[c][j]);
-                        lam[c][j] = __fmul2_rn(f2(ex2f(e.x), ex2f(e.y)), l);
+                        lam[c][j] = __fmul2_rn(f2(ex2f(e.x), ex2f(e.y)), l);           // a_t * lambda_t (0 at a reset step)
+                        // lambda_t * a_t * h_{t-1}: the product with the stored previous state, no h_t - du B_t cancellation
+                        const float2 t1 = __fmul2_rn(lam[c][j], i > 0 ? hb[c][i > 0 ? i - 1 : 0][j] : hent[c][j]);
+                        dA[c][j] = __ffma2_rn(t1, dt2, dA[c][j]);
+                        sA2 = __ffma2_rn(t1, A2[c][j], sA2);
                     }
                     float* pl = s_pl + i * PROW + poff[c];
                     pl[0] = sB2.x + sB2.y;
                     pl[PLANE] = sA2.x + sA2.y;
                     if (HAS_Z) pl[2 * PLANE] = yp2.x + yp2.y;
                 }
-                float dBv[4] = {dB2[0].x, dB2[0].y, dB2[1].x, dB2[1].y}, dCv[4] = {dC2[0].x, dC2[0].y, dC2[1].x, dC2[1].y};
-                int fB, fC;
-                bool wB, wC;
-                const int nB = channel_reduce_scatter4<LPD>(dBv, dl, fB, wB);
-                channel_reduce_scatter4<LPD>(dCv, dl, fC, wC);
-                if (wB) {
-                    float* rr = s_red + ((size_t)warp * TC + i) * (2 * N) + ng * S + fB;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (q < nB) {
-                            rr[q] = dBv[q];
-                            rr[N + q] = dCv[q];
-                        }
-                    }
-                }
+                // this lane's dB | dC (already summed over the thread's channels): one row per (step, warp, channel-lane)
+                float* rr = s_red + ((size_t)(i * NMAINW + warp) * DPW + dl) * (2 * N) + ng * S;
+                *reinterpret_cast<float4*>(rr) = make_float4(dB2[0].x, dB2[0].y, dB2[1].x, dB2[1].y);
+                *reinterpret_cast<float4*>(rr + N) = make_float4(dC2[0].x, dC2[0].y, dC2[1].x, dC2[1].y);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_done);

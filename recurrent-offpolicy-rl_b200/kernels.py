@@ -502,7 +502,7 @@ def rms_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residua
 import os as _os
 # 3 = 3xTF32 split accumulation (~2^-21); 2 = two-term bf16 split on kind::f16 (~2^-17, half the tensor time and
 # operand bytes); 1 = plain TF32 (benchmarks only).  RORL_GEMM_PASSES overrides for A/B runs.
-GEMM_PASSES = int(_os.environ.get("RORL_GEMM_PASSES", "3"))
+GEMM_PASSES = int(_os.environ.get("RORL_GEMM_PASSES", "2"))
 GEMM_MIN_K = 32
 
 
