@@ -356,6 +356,10 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
                    int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
                    int64_t strideBias, int act, int reduce_g, int force_bn, void* bsplit, cudaStream_t stream);
 
+int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda, int64_t ldb,
+                   int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits, int64_t strideSplit,
+                   cudaStream_t stream);
+
 static int g_gemm_dbg = 0;
 static int g_gemm_bn = 0;
 static int g_gemm_bk = 0;
@@ -464,8 +468,9 @@ int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N,
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D)) & 15)
         return RORL_ERR_ALIGN;
     if (passes != 1 && passes != 2 && passes != 3) return RORL_ERR_ARG;
-    if (passes == 2) passes = 3;                 // the weight-gradient form has no bf16-split variant yet: 3xTF32
     if (splits != rorl_gemm_nt_splits(M, N, R, G)) return RORL_ERR_ARG;
+    if (passes == 2)
+        return gemm_nt_bf16x3(A, B, D, M, N, R, G, lda, ldb, ldd, strideA, strideB, strideD, splits, strideSplit, stream);
     CUtensorMap mapA, mapB;
     int rc = make_map(&mapA, A, R, M, lda, strideA ? G : 1, strideA, kGemmBK);
     if (rc) return rc;

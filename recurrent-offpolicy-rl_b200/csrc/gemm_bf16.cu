@@ -31,15 +31,15 @@ constexpr int kBfThreads = 448;
 constexpr int kBfEpiWarps = 8;
 constexpr int kBfStaging = kBfEpiWarps * 32 * 128;
 
-template <int BN>
+template <int BN, bool MN = false>
 struct BfCfg {
     static constexpr int kRawA = kBfBM * kBfBK * 4;               // 16 KiB
-    static constexpr int kRaw = kRawA;                            // the raw ring holds A only
+    static constexpr int kRaw = MN ? kRawA + BN * kBfBK * 4 : kRawA;   // TN: the raw ring holds A only; NT: both operands
     static constexpr int kHalfA = kBfBM * kBfBK * 2;              // one bf16 tile of A (hi or lo): 8 KiB
     static constexpr int kHalfB = BN * kBfBK * 2;
     static constexpr int kSplit = 2 * (kHalfA + kHalfB);          // A_hi | A_lo | B_hi | B_lo
-    static constexpr int kRawStages = BN == 256 ? 3 : 4;
-    static constexpr int kSplitStages = BN == 256 ? 3 : 4;
+    static constexpr int kRawStages = MN ? 3 : (BN == 256 ? 3 : 4);
+    static constexpr int kSplitStages = MN ? 3 : (BN == 256 ? 3 : 4);
     static constexpr int kSmem = kRawStages * kRaw + kSplitStages * kSplit + kBfStaging + 1024 + 256;
 };
 
@@ -50,6 +50,8 @@ struct BfParams {
     int M, N, K, G;
     long long ldd, strideD, strideBias;
     int a_batched, b_batched, act, reduce_g;
+    int splits;                 // NT variant: split-K factor; partial s is written at D + s * strideSplit
+    long long strideSplit;
 };
 
 __device__ __forceinline__ float bf_elu1(float x) {
@@ -73,11 +75,17 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
     two(b.z, b.w, hi.w, lo.w);
 }
 
-template <int BN>
+// MN = false: TN form (both operands K-major; B pre-split, see above).  MN = true: weight-gradient form, both operands
+// row-major with the REDUCTION over rows (MN-major): TMA delivers each operand as 4 boxes of [32 reduction rows][32 MN
+// columns]; the splitters transpose while they split (kind::f16 multiplies K-major operands), writing K-major
+// SWIZZLE_64B bf16 rows (row = MN index, 32 reduction values = 64 B) into the split ring -- a separate buffer, so no
+// in-place hazard and no block barrier, unlike the TF32 form in gemm.cu; split-K partials as there.
+template <int BN, bool MN>
 __global__ void __launch_bounds__(kBfThreads, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
                    const __grid_constant__ CUtensorMap mapBlo, const BfParams p) {
-    using Cfg = BfCfg<BN>;
+    static_assert(!MN || BN == 128, "the weight-gradient form uses 128 x 128 tiles");
+    using Cfg = BfCfg<BN, MN>;
     constexpr int RS = Cfg::kRawStages, SS = Cfg::kSplitStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -98,8 +106,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tilesM = (p.M + kBfBM - 1) / kBfBM, tilesN = (p.N + BN - 1) / BN;
     const int KTg = (p.K + kBfBK - 1) / kBfBK;
-    const int ntiles = tilesM * tilesN * (p.reduce_g ? 1 : p.G);
-    const int KT = p.reduce_g ? KTg * p.G : KTg;
+    const int nsplit = MN ? p.splits : 1;
+    const int ntiles = tilesM * tilesN * (p.reduce_g ? 1 : p.G) * nsplit;
+    const int KTs = (KTg + nsplit - 1) / nsplit;                                  // k-tiles per split (NT variant)
+    const int KT = MN ? KTs : (p.reduce_g ? KTg * p.G : KTg);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < RS; ++s) {
@@ -107,7 +117,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             mbar_init(bar_raw_empty(s), 4);
         }
         for (int s = 0; s < SS; ++s) {
-            mbar_init(bar_split_full(s), 5);                     // 4 splitter warps (A) + the producer's expect_tx (B)
+            mbar_init(bar_split_full(s), MN ? 4 : 5);            // 4 splitter warps (+ the producer's expect_tx for B in the TN form)
             mbar_init(bar_split_empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -135,17 +145,28 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int tn = tile % tilesN, tm = (tile / tilesN) % tilesM;
                 const int g = (tile / (tilesN * tilesM)) % p.G;
+                const int sp = tile / (tilesN * tilesM * p.G);
                 for (int kt = 0; kt < KT; ++kt, ++it) {
                     const int s = it % RS, ss = it % SS;
                     const int gg = p.reduce_g ? kt / KTg : g, kk = p.reduce_g ? kt % KTg : kt;
                     mbar_wait(bar_raw_empty(s), ((it / RS) & 1) ^ 1);
                     mbar_expect_tx(bar_raw_full(s), Cfg::kRaw);
-                    tma_load_3d(base + s * Cfg::kRaw, &mapA, bar_raw_full(s), kk * kBfBK, tm * kBfBM, p.a_batched ? gg : 0);
-                    mbar_wait(bar_split_empty(ss), ((it / SS) & 1) ^ 1);
-                    mbar_expect_tx(bar_split_full(ss), 2 * Cfg::kHalfB);
-                    const uint32_t sb = split_base + ss * Cfg::kSplit + 2 * Cfg::kHalfA;
-                    tma_load_3d(sb, &mapBhi, bar_split_full(ss), kk * kBfBK, tn * BN, p.b_batched ? gg : 0);
-                    tma_load_3d(sb + Cfg::kHalfB, &mapBlo, bar_split_full(ss), kk * kBfBK, tn * BN, p.b_batched ? gg : 0);
+                    if (MN) {
+                        const int r0 = (sp * KTs + kt) * kBfBK;                  // rows beyond the tensor are zero-filled
+                        const uint32_t st = base + s * Cfg::kRaw;
+#pragma unroll
+                        for (int bI = 0; bI < 4; ++bI) {
+                            tma_load_3d(st + bI * 4096, &mapA, bar_raw_full(s), tm * kBfBM + 32 * bI, r0, p.a_batched ? g : 0);
+                            tma_load_3d(st + Cfg::kRawA + bI * 4096, &mapBhi, bar_raw_full(s), tn * BN + 32 * bI, r0, p.b_batched ? g : 0);
+                        }
+                    } else {
+                        tma_load_3d(base + s * Cfg::kRaw, &mapA, bar_raw_full(s), kk * kBfBK, tm * kBfBM, p.a_batched ? gg : 0);
+                        mbar_wait(bar_split_empty(ss), ((it / SS) & 1) ^ 1);
+                        mbar_expect_tx(bar_split_full(ss), 2 * Cfg::kHalfB);
+                        const uint32_t sb = split_base + ss * Cfg::kSplit + 2 * Cfg::kHalfA;
+                        tma_load_3d(sb, &mapBhi, bar_split_full(ss), kk * kBfBK, tn * BN, p.b_batched ? gg : 0);
+                        tma_load_3d(sb + Cfg::kHalfB, &mapBlo, bar_split_full(ss), kk * kBfBK, tn * BN, p.b_batched ? gg : 0);
+                    }
                 }
             }
         }
@@ -194,6 +215,32 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 mbar_wait(bar_split_empty(ss), ((it / SS) & 1) ^ 1);
                 const uint8_t* raw = base_ptr + rs * Cfg::kRaw;
                 uint8_t* sp = split_ptr + ss * Cfg::kSplit;
+                if (MN) {
+                    // thread = (32-column box blk, MN column mn of it = lane): for each of the 4 chunks of 8 reduction rows,
+                    // 8 conflict-free LDS.32 down the column (a warp reads one 128-byte raw row per instruction), split,
+                    // one 16-byte store per half into row blk * 32 + lane of the K-major bf16 tile
+                    const int blk = t >> 5;
+#pragma unroll
+                    for (int op = 0; op < 2; ++op) {
+                        const uint8_t* src = raw + op * Cfg::kRawA + blk * 4096;
+                        const int mn = blk * 32 + lane;
+                        uint8_t* drow = sp + (op ? 2 * Cfg::kHalfA : 0) + mn * 64;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v[8];
+#pragma unroll
+                            for (int rr = 0; rr < 8; ++rr) {
+                                const int r = 8 * j + rr;
+                                v[rr] = *reinterpret_cast<const float*>(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                            }
+                            uint4 hi, lo;
+                            split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+                            uint8_t* dst = drow + ((j ^ ((mn >> 1) & 3)) << 4);
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + (op ? Cfg::kHalfB : Cfg::kHalfA)) = lo;
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int i = 0; i < kBfBM * 4 / 128; ++i) {
                     const int idx = t + 128 * i;
@@ -227,7 +274,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             const int acc = tcount & 1;
             mbar_wait(bar_tfull(acc), (tcount >> 1) & 1);
             tc_fence_after();
-            const long long obase = (long long)g * p.strideD;
+            const int sp = tile / (tilesN * tilesM * p.G);
+            const long long obase = (long long)g * p.strideD + (long long)sp * p.strideSplit;
             const int row0 = tm * kBfBM + q * 32;
             const float* bias = p.bias ? p.bias + (long long)g * p.strideBias : nullptr;
             auto flush = [&](const float4 (&o)[8], float* out, int col0) {
@@ -297,8 +345,9 @@ static int bf_sms() {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BfCfg<128>::kSmem);
-        cudaFuncSetAttribute(gemm_bf16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, BfCfg<256>::kSmem);
+        cudaFuncSetAttribute(gemm_bf16x3_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BfCfg<128>::kSmem);
+        cudaFuncSetAttribute(gemm_bf16x3_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BfCfg<256>::kSmem);
+        cudaFuncSetAttribute(gemm_bf16x3_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BfCfg<128, true>::kSmem);
     }
     return sms;
 }
@@ -366,13 +415,35 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
     p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
     p.ldd = ldd; p.strideD = strideD; p.strideBias = strideBias;
     p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act; p.reduce_g = reduce_g != 0;
+    p.splits = 1; p.strideSplit = 0;
     const int sms = bf_sms();
     const long long tiles = ((M + kBfBM - 1) / kBfBM) * ((N + bn - 1) / bn) * (reduce_g ? 1 : G);
     const int grid = (int)(tiles < sms ? tiles : sms);
     if (wide)
-        gemm_bf16x3_kernel<256><<<grid, kBfThreads, BfCfg<256>::kSmem, stream>>>(mapA, mapBhi, mapBlo, p);
+        gemm_bf16x3_kernel<256, false><<<grid, kBfThreads, BfCfg<256>::kSmem, stream>>>(mapA, mapBhi, mapBlo, p);
     else
-        gemm_bf16x3_kernel<128><<<grid, kBfThreads, BfCfg<128>::kSmem, stream>>>(mapA, mapBhi, mapBlo, p);
+        gemm_bf16x3_kernel<128, false><<<grid, kBfThreads, BfCfg<128>::kSmem, stream>>>(mapA, mapBhi, mapBlo, p);
+    RORL_RETURN_LAUNCH();
+}
+
+// Called from rorl_gemm_nt (gemm.cu) for passes == 2; arguments already validated there.
+int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda, int64_t ldb,
+                   int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits, int64_t strideSplit,
+                   cudaStream_t stream) {
+    CUtensorMap mapA, mapB;
+    int rc = make_map(&mapA, A, R, M, lda, strideA ? G : 1, strideA, kBfBK);
+    if (rc) return rc;
+    rc = make_map(&mapB, B, R, N, ldb, strideB ? G : 1, strideB, kBfBK);
+    if (rc) return rc;
+    BfParams p;
+    p.D = D; p.Dpre = nullptr; p.bias = nullptr; p.M = (int)M; p.N = (int)N; p.K = (int)R; p.G = (int)G;
+    p.ldd = ldd; p.strideD = strideD; p.strideBias = 0;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = 0; p.reduce_g = 0;
+    p.splits = (int)splits; p.strideSplit = strideSplit;
+    const int sms = bf_sms();
+    const long long tiles = ((M + kBfBM - 1) / kBfBM) * ((N + 127) / 128) * G * splits;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gemm_bf16x3_kernel<128, true><<<grid, kBfThreads, BfCfg<128, true>::kSmem, stream>>>(mapA, mapB, mapB, p);
     RORL_RETURN_LAUNCH();
 }
 

@@ -25,14 +25,14 @@ def test_gemm_tn_plain(K, M, N, K_):
     B = torch.randn(N, K_, device="cuda", generator=g)
     bias = torch.randn(N, device="cuda", generator=g)
     ref = A.double() @ B.double().t() + bias.double()
-    D = K.gemm_tn(A, B, bias)
+    D = K.gemm_tn(A, B, bias, passes=3)
     e3 = rel_err(D, ref)
     e_fp32 = rel_err(torch.nn.functional.linear(A, B, bias), ref)
     print(f"M={M} N={N} K={K_}: 3xTF32 err {e3:.2e}, cuBLAS fp32 err {e_fp32:.2e}")
     assert e3 < 1e-5
     D1 = K.gemm_tn(A, B, bias, passes=1)
     assert rel_err(D1, ref) < 5e-3
-    Delu = K.gemm_tn(A, B, bias, act=1)
+    Delu = K.gemm_tn(A, B, bias, act=1, passes=3)
     assert rel_err(Delu, torch.nn.functional.elu(ref)) < 1e-5
 
 
@@ -43,14 +43,14 @@ def test_gemm_tn_strided_and_batched(K):
     A = big[:, K_:]                                   # row-strided column slice
     W = torch.randn(E, N, K_, device="cuda", generator=g)
     b = torch.randn(E, N, device="cuda", generator=g)
-    D = K.gemm_tn(A, W, b)                            # shared A, batched B
+    D = K.gemm_tn(A, W, b, passes=3)                  # shared A, batched B
     ref = torch.einsum('mk,enk->emn', A.double(), W.double()) + b.double()[:, None]
     assert rel_err(D, ref) < 1e-5
     Ab = torch.randn(E, M, K_, device="cuda", generator=g)
-    D2 = K.gemm_tn(Ab, W, b, act=1)
+    D2 = K.gemm_tn(Ab, W, b, act=1, passes=3)
     ref2 = torch.nn.functional.elu(torch.einsum('emk,enk->emn', Ab.double(), W.double()) + b.double()[:, None])
     assert rel_err(D2, ref2) < 1e-5
-    D3 = K.gemm_tn(Ab, W, reduce_g=True)              # sum over members: one K = 8 * 384 reduction
+    D3 = K.gemm_tn(Ab, W, reduce_g=True, passes=3)    # sum over members: one K = 8 * 384 reduction
     ref3 = torch.einsum('emk,enk->mn', Ab.double(), W.double())
     assert rel_err(D3, ref3) < 5e-5
 
@@ -67,9 +67,9 @@ def test_linear_and_ensemble_autograd(K):
     xd, Wd, bd = (t.detach().double().requires_grad_() for t in (x, W, b))
     yr = torch.nn.functional.elu(torch.nn.functional.linear(xd, Wd, bd))
     ref = torch.autograd.grad(yr, (xd, Wd, bd), dy.double())
-    assert rel_err(y, yr) < 1e-5
+    assert rel_err(y, yr) < 3e-5
     for a, r, n in zip(got, ref, "x W b".split()):
-        assert rel_err(a, r) < 5e-5, n
+        assert rel_err(a, r) < 1e-4, n
     # ensemble, shared input then per-member input
     We = (0.1 * torch.randn(E, Kin, Nout, device="cuda", generator=g)).requires_grad_()
     be = torch.randn(E, 1, Nout, device="cuda", generator=g).requires_grad_()
@@ -79,9 +79,9 @@ def test_linear_and_ensemble_autograd(K):
     xd, Wd, bd = (t.detach().double().requires_grad_() for t in (x, We, be))
     yr = torch.nn.functional.elu(torch.einsum('cij,bjk->bcik', xd, Wd) + bd.unsqueeze(1))
     ref = torch.autograd.grad(yr, (xd, Wd, bd), dy1.double())
-    assert rel_err(y1, yr) < 1e-5
+    assert rel_err(y1, yr) < 3e-5
     for a, r, n in zip(got, ref, "x W b".split()):
-        assert rel_err(a, r) < 5e-5, n
+        assert rel_err(a, r) < 1e-4, n
     h = torch.randn(E, B_, L, Kin, device="cuda", generator=g, requires_grad=True)
     y2 = K.ensemble_linear(h, We, be, False, False)
     dy2 = torch.randn_like(y2)
@@ -89,24 +89,26 @@ def test_linear_and_ensemble_autograd(K):
     hd = h.detach().double().requires_grad_()
     yr = torch.einsum('cbij,cjk->cbik', hd, Wd) + bd.unsqueeze(1)
     ref = torch.autograd.grad(yr, (hd, Wd, bd), dy2.double())
-    assert rel_err(y2, yr) < 1e-5
+    assert rel_err(y2, yr) < 3e-5
     for a, r, n in zip(got, ref, "h W b".split()):
-        assert rel_err(a, r) < 5e-5, n
+        assert rel_err(a, r) < 1e-4, n
 
 
 @pytest.mark.parametrize("R,M,N,G", [(128, 128, 128, 1), (1000, 80, 512, 1), (32576, 256, 384, 1), (5000, 384, 256, 8), (333, 12, 260, 2)])
-def test_gemm_nt_weight_gradient_form(K, R, M, N, G):
+@pytest.mark.parametrize("passes", [3, 2])
+def test_gemm_nt_weight_gradient_form(K, R, M, N, G, passes):
     g = torch.Generator(device="cuda").manual_seed(R + M)
     A = torch.randn((G, R, M) if G > 1 else (R, M), device="cuda", generator=g)
     B = torch.randn((G, R, N) if G > 1 else (R, N), device="cuda", generator=g)
-    D = K.gemm_nt(A, B)
+    D = K.gemm_nt(A, B, passes=passes)
     ref = A.double().transpose(-1, -2) @ B.double()
     e = rel_err(D, ref)
-    print(f"NT R={R} M={M} N={N} G={G}: 3xTF32 err {e:.2e}")
-    assert e < 2e-5
+    print(f"NT R={R} M={M} N={N} G={G}: passes={passes} err {e:.2e}")
+    tol = 2e-5 if passes == 3 else 5e-5
+    assert e < tol
     if G > 1:       # shared A (first efc layer: one input, E output gradients)
-        D2 = K.gemm_nt(A[0], B)
-        assert rel_err(D2, A[0].double().t() @ B.double()) < 2e-5
+        D2 = K.gemm_nt(A[0], B, passes=passes)
+        assert rel_err(D2, A[0].double().t() @ B.double()) < tol
 
 
 @pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (1000, 80, 512), (32576, 256, 384), (4097, 1024, 256), (77, 132, 36), (513, 260, 48)])
@@ -120,9 +122,9 @@ def test_gemm_tn_bk16_ring(K, M, N, K_):
     ref = A.double() @ B.double().t() + bias.double()
     try:
         NV.lib().rorl_gemm_force_bk(16)
-        D16 = K.gemm_tn(A, B, bias)
+        D16 = K.gemm_tn(A, B, bias, passes=3)
         NV.lib().rorl_gemm_force_bk(32)
-        D32 = K.gemm_tn(A, B, bias)
+        D32 = K.gemm_tn(A, B, bias, passes=3)
     finally:
         NV.lib().rorl_gemm_force_bk(0)
     assert rel_err(D16, ref) < 1e-5

@@ -216,8 +216,13 @@ def bench_gemm():
             rec(f"gemm_tn {tag} passes=3 BN=128 (A/B)", t, flops=fl * 3, note=f"useful fp32 TFLOP/s {fl / t / 1e12:.1f}")
     # weight gradient
     gq, xq = rn(M, 256), rn(M, 256)
-    t = timeit(lambda: K.gemm_nt(gq, xq))
-    rec("gemm_nt 256x256 R=32608 passes=3", t, flops=3 * 2.0 * M * 256 * 256, nbytes=4 * (gq.numel() + xq.numel()))
+    for passes in (3, 2):
+        t = timeit(lambda: K.gemm_nt(gq, xq, passes=passes))
+        rec(f"gemm_nt 256x256 R=32608 passes={passes}", t, flops=3 * 2.0 * M * 256 * 256, nbytes=4 * (gq.numel() + xq.numel()))
+    g8, x8 = rn(8, M, 256), rn(8, M, 256)
+    for passes in (3, 2):
+        t = timeit(lambda: K.gemm_nt(x8, g8, passes=passes))
+        rec(f"gemm_nt efc-8 L2 dW 8x[256x256] R=32608 passes={passes}", t, flops=3 * 2.0 * M * 256 * 256 * 8, nbytes=4 * (g8.numel() + x8.numel()))
     c = torch.empty(M, 256, device=dev)
     a2, w2 = rn(M, 256), rn(256, 256)
     t = timeit(lambda: torch.mm(a2, w2, out=c))
