@@ -238,6 +238,21 @@ int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N,
                  int64_t strideSplit, int passes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Output layer of the ensemble-Q head (`efc-E` with out_dim = 1) and its backward fused with the ELU backward and
+ * bias gradient of the layer below.  Replaces EnsembleLinear's bmm [E, M, K] x [E, K, 1] and, in the backward, the
+ * outer-product bmm + elu_backward + reductions (ref: offpolicy_rnn/models/ensemble_linear_model.py:36-49,
+ * contextual_model.py:97-116).  K in {128, 256, 384, 512}; y, g [E, M, K] contiguous; w [E, K]; b [E] or NULL.
+ *   rorl_efc_dot_fwd : q[e, m] = sum_k y[e, m, k] w[e, k] + b[e]
+ *   rorl_efc_head_bwd: g = dq w elu'(y) (elu != 0: y is an ELU OUTPUT; else g = dq w);
+ *                      part [E][nblk][2K + 4] = per-CTA partials of (dw[e, k] = sum_m dq y | sum_m g[e, m, k] |
+ *                      db[e] = sum_m dq, 0, 0, 0), nblk = rorl_efc_head_nblk(); the caller sums over nblk.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_efc_head_nblk(void);
+int rorl_efc_dot_fwd(const float* y, const float* w, const float* b, float* q, int64_t E, int64_t M, int64_t K, cudaStream_t stream);
+int rorl_efc_head_bwd(const float* dq, const float* y, const float* w, float* g, float* part, int64_t E, int64_t M, int64_t K,
+                      int elu, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GRU recurrence as a persistent thread-block-cluster kernel (W_hh resident in registers across a
  * cluster of H / 64 CTAs, h_t exchanged through distributed shared memory each step).
  * Replaces the recurrent part of torch.nn.GRU(input, H, batch_first=True) on the `gru` encoder path

@@ -648,6 +648,59 @@ class EnsembleLinearTC(Function):
         return dx, dw, db, None, None
 
 
+class EnsembleHiddenToScalar(Function):
+    """The last two layers of the ensemble-Q head as one autograd node:
+        y = ELU(x[e] W2[e] + b2[e])   (tensor-core GEMM, bias + ELU in its epilogue)
+        q[e] = y[e] . w3[e] + b3[e]   (rorl_efc_dot_fwd: one read of y instead of a bmm GEMV per member)
+    backward: g = dq w3 elu'(y), dW3, db3 and db2 in ONE pass over y (rorl_efc_head_bwd) -- the reference's graph has an
+    outer-product bmm, elu_backward and three reductions there -- then the two GEMMs of the hidden layer.
+    x [E, ..., in]; W2 [E, in, K]; b2 [E, 1, K]; W3 [E, K, 1]; b3 [E, 1, 1] (the reference's EnsembleLinear layout)."""
+
+    @staticmethod
+    def forward(ctx, x, W2, b2, W3, b3):
+        E, Kin, Kh = W2.shape
+        xs = _mat(x.reshape(E, -1, Kin))
+        M = xs.shape[1]
+        y = gemm_tn(xs, W2.transpose(1, 2).contiguous(), None if b2 is None else b2.reshape(E, Kh), 1)      # [E, M, Kh]
+        w3 = _f32c(W3.reshape(E, Kh))
+        q = torch.empty((E, M), device=x.device, dtype=torch.float32)
+        N.call("rorl_efc_dot_fwd", N.ptr(y), N.ptr(w3), N.ptr(None if b3 is None else _f32c(b3.reshape(E))), N.ptr(q), E, M, Kh, N.stream())
+        ctx.save_for_backward(xs, W2, y, w3)
+        ctx.xshape, ctx.has_b2, ctx.has_b3 = x.shape, b2 is not None, b3 is not None
+        return q.view(E, *x.shape[1:-1], 1)
+
+    @staticmethod
+    def backward(ctx, dq):
+        xs, W2, y, w3 = ctx.saved_tensors
+        E, M, Kh = y.shape
+        dq = _f32c(dq.reshape(E, M))
+        nblk = N.lib().rorl_efc_head_nblk()
+        g = torch.empty_like(y)
+        part = torch.empty((E, nblk, 2 * Kh + 4), device=y.device, dtype=torch.float32)
+        N.call("rorl_efc_head_bwd", N.ptr(dq), N.ptr(y), N.ptr(w3), N.ptr(g), N.ptr(part), E, M, Kh, 1, N.stream())
+        need = ctx.needs_input_grad
+        dx = dW2 = db2 = dW3 = db3 = None
+        if any(need[1:]):
+            sums = colsum(part)                                                   # [E, 2 Kh + 4]
+            if need[3]:
+                dW3 = sums[:, :Kh].reshape(E, Kh, 1)
+            if ctx.has_b2 and need[2]:
+                db2 = sums[:, Kh:2 * Kh].reshape(E, 1, Kh)
+            if ctx.has_b3 and need[4]:
+                db3 = sums[:, 2 * Kh].reshape(E, 1, 1)
+        if need[0]:
+            dx = gemm_tn(g, W2).view(ctx.xshape)                                  # W2 [E, in, K] is K-major for this product
+        if need[1]:
+            dW2 = gemm_nt(xs, g) if _gemm_nt_ok(W2.shape[1], Kh, M) else torch.matmul(xs.transpose(-1, -2), g)
+        return dx, dW2, db2, dW3, db3
+
+
+def ensemble_hidden_to_scalar_ok(x, W2, W3):
+    E, Kin, Kh = W2.shape
+    return (x.is_cuda and x.dtype == torch.float32 and Kh in (128, 256, 384, 512) and tuple(W3.shape) == (E, Kh, 1)
+            and x.shape[0] == E and _gemm_ok(x.numel() // Kin // E, Kh, Kin))
+
+
 def ensemble_linear(x, weight, bias, elu, shared):
     E, Kin, Nout = weight.shape
     M = x.numel() // Kin // (1 if shared else E)

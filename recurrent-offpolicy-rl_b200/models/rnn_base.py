@@ -16,6 +16,7 @@ from typing import Dict, List, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
+from .. import kernels as K
 from .RNNHidden import RNNHidden
 from .ensemble_linear_model import EnsembleLinear
 from .linear import Linear
@@ -247,6 +248,7 @@ class RNNBase(nn.Module):
         out_state = RNNHidden(self.rnn_num, self.rnn_layer_type, device=x.device, batch_first=False)
         full = RNNHidden(self.rnn_num, self.rnn_layer_type, device=x.device, batch_first=True) if require_full_hidden else None
         k = 0
+        fused_tail = self._fused_tail(x)
         for ind, layer in enumerate(self.layer_list):
             lid = self.layer_type[ind]
             if check_is_rnn(lid):
@@ -277,6 +279,12 @@ class RNNBase(nn.Module):
                 if require_full_hidden:
                     full.append(x)
             else:
+                if ind == fused_tail and K.ensemble_hidden_to_scalar_ok(x, layer.weight, self.layer_list[ind + 1].weight):
+                    # efc-E (ELU) -> efc-E (out_dim 1): the ensemble-Q head's last two layers as one fused node
+                    nxt = self.layer_list[ind + 1]
+                    x = K.EnsembleHiddenToScalar.apply(x, layer.weight, layer.bias if layer.use_bias else None,
+                                                       nxt.weight, nxt.bias if nxt.use_bias else None)
+                    break
                 if isinstance(self.activation_list[ind], nn.ELU):
                     x = layer(x, fuse_elu=True)          # bias + ELU in the GEMM epilogue
                     continue
@@ -293,6 +301,21 @@ class RNNBase(nn.Module):
         if x_dim == 2 and self.rnn_num > 0:
             x = x.squeeze(0)
         return x, out_state, full
+
+    def _fused_tail(self, x) -> int:
+        """Index of the layer at which the fused `efc (ELU) -> efc (out 1, linear)` tail starts, or -1.  The tail needs
+        a per-member [E, ..., C] input (what an earlier efc layer leaves), so a network whose FIRST layer would be the
+        tail's hidden layer is not fused."""
+        n = len(self.layer_list)
+        if n < 3 or not x.is_cuda:
+            return -1
+        a, b = self.layer_list[n - 2], self.layer_list[n - 1]
+        if not (isinstance(a, EnsembleLinear) and isinstance(b, EnsembleLinear) and isinstance(self.activation_list[n - 2], nn.ELU)
+                and isinstance(self.activation_list[n - 1], nn.Identity) and isinstance(self.layer_list[n - 3], EnsembleLinear)):
+            return -1
+        if a.desire_ndim not in (None, x.dim() + 1) or b.weight.shape[-1] != 1 or a.weight.shape[-1] not in (128, 256, 384, 512):
+            return -1
+        return n - 2
 
     # ---- soft update / persistence (ref: rnn_base.py:475-532) -------------------------------------------------
     @staticmethod

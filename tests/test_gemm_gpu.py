@@ -163,3 +163,28 @@ def test_gemm_tn_bf16_split_batched(K):
     D3 = K.gemm_tn(Ab, W, reduce_g=True, passes=2)
     ref3 = torch.einsum('emk,enk->mn', Ab.double(), W.double())
     assert rel_err(D3, ref3) < 1e-4
+
+
+@pytest.mark.parametrize("Kh,M", [(256, 1000), (128, 37), (384, 513), (512, 130)])
+def test_ensemble_hidden_to_scalar(K, Kh, M):
+    """Fused `efc (ELU) -> efc (out 1)` tail of the ensemble-Q head vs the same two layers in float64."""
+    g = torch.Generator(device="cuda").manual_seed(Kh + M)
+    E, Kin = 8, 96
+    x = torch.randn(E, 3, M, Kin, device="cuda", generator=g, requires_grad=True)
+    W2 = (0.2 * torch.randn(E, Kin, Kh, device="cuda", generator=g)).requires_grad_()
+    b2 = torch.randn(E, 1, Kh, device="cuda", generator=g).requires_grad_()
+    W3 = (0.2 * torch.randn(E, Kh, 1, device="cuda", generator=g)).requires_grad_()
+    b3 = torch.randn(E, 1, 1, device="cuda", generator=g).requires_grad_()
+    assert K.ensemble_hidden_to_scalar_ok(x, W2, W3)
+    q = K.EnsembleHiddenToScalar.apply(x, W2, b2, W3, b3)
+    dq = torch.randn_like(q)
+    got = torch.autograd.grad(q, (x, W2, b2, W3, b3), dq)
+    xd, W2d, b2d, W3d, b3d = (t.detach().double().requires_grad_() for t in (x, W2, b2, W3, b3))
+    y = torch.nn.functional.elu(torch.einsum('ebmi,eik->ebmk', xd, W2d) + b2d.unsqueeze(1))
+    qr = torch.einsum('ebmk,eko->ebmo', y, W3d) + b3d.unsqueeze(1)
+    ref = torch.autograd.grad(qr, (xd, W2d, b2d, W3d, b3d), dq.double())
+    assert q.shape == qr.shape
+    assert rel_err(q, qr) < 3e-5
+    for a, r, n in zip(got, ref, "x W2 b2 W3 b3".split()):
+        assert a.shape == r.shape, n
+        assert rel_err(a, r) < 1e-4, n
