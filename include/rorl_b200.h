@@ -334,9 +334,10 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
 int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
                         int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
                         cudaStream_t stream);
-/* y[m, n] = bias[n] + sum_k x[m, k] W[n, k] for K <= 16, N % 4 == 0 (bias may be NULL): forward of the same projections */
+/* y[m, n] = act(bias[n] + sum_k x[m, k] W[n, k]) for K <= 16, N % 4 == 0 (bias may be NULL; elu != 0: ELU): forward of
+ * the same projections; ldy lets several of them write side by side into one [M, sum N] buffer (no concatenation). */
 int rorl_skinny_linear(const float* x, const float* W, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                       int64_t ldx, int64_t ldy, cudaStream_t stream);
+                       int64_t ldx, int64_t ldy, int elu, cudaStream_t stream);
 int64_t rorl_skinny_wgrad_work_floats(int64_t M, int64_t N, int64_t K);
 int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, int64_t M, int64_t N, int64_t K,
                       int64_t ldg, int64_t ldx, cudaStream_t stream);

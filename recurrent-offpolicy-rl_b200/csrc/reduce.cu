@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
 template <int KP>
 __global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                             const float* __restrict__ bias, float* __restrict__ y, int64_t M,
-                                                            int64_t N, int K, int64_t ldx, int64_t ldy, int rows_per_block) {
+                                                            int64_t N, int K, int64_t ldx, int64_t ldy, int rows_per_block, int elu) {
     __shared__ __align__(16) float s_x[kSkinnyRows * KP];
     const int64_t n0 = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 4;
     const bool act = n0 < N;
@@ -204,6 +204,10 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restr
                         o[j] = fmaf(xv.z, w[j][k4 + 2], o[j]);
                         o[j] = fmaf(xv.w, w[j][k4 + 3], o[j]);
                     }
+                }
+                if (elu) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : ex2f(o[j] * kLog2e) - 1.0f;
                 }
                 *reinterpret_cast<float4*>(y + (mb + r) * ldy + n0) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -307,7 +311,7 @@ int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, in
 }
 
 int rorl_skinny_linear(const float* x, const float* W, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                       int64_t ldx, int64_t ldy, cudaStream_t stream) {
+                       int64_t ldx, int64_t ldy, int elu, cudaStream_t stream) {
     if (!x || !W || !y) return RORL_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
     if (N % 4 || ldy % 4 || !a16(y)) return RORL_ERR_ALIGN;
@@ -326,10 +330,10 @@ int rorl_skinny_linear(const float* x, const float* W, const float* bias, float*
     const int KP = (int)((K + 3) / 4 * 4);
     dim3 grid((unsigned)nblk, (unsigned)chunks);
     switch (KP) {
-        case 4: skinny_linear_kernel<4><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
-        case 8: skinny_linear_kernel<8><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
-        case 12: skinny_linear_kernel<12><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
-        default: skinny_linear_kernel<16><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb); break;
+        case 4: skinny_linear_kernel<4><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
+        case 8: skinny_linear_kernel<8><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
+        case 12: skinny_linear_kernel<12><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
+        default: skinny_linear_kernel<16><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
     }
     RORL_RETURN_LAUNCH();
 }

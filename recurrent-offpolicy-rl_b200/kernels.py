@@ -113,7 +113,7 @@ class LinearSkinny(Function):
         if Nn % 4 == 0 and x2.stride(-1) == 1 and x.dtype == torch.float32:
             y = torch.empty((x2.shape[0], Nn), device=x.device, dtype=torch.float32)
             N.call("rorl_skinny_linear", N.ptr(x2), N.ptr(_f32c(weight)), N.ptr(None if bias is None else _f32c(bias)), N.ptr(y),
-                   x2.shape[0], Nn, K, x2.stride(0), Nn, N.stream())
+                   x2.shape[0], Nn, K, x2.stride(0), Nn, 0, N.stream())
             return y.view(*x.shape[:-1], Nn)
         return torch.nn.functional.linear(x, weight, bias)
 
@@ -127,12 +127,81 @@ class LinearSkinny(Function):
             x2 = x2.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = (g @ weight).view(x.shape)
+            # [M, N] x [N, K <= 16]: the tensor-core kernel with a 16-wide output runs at the rate g is read
+            dx = (gemm_tn(g, weight.t().contiguous()) if _gemm_ok(g.shape[0], K, Nn) else g @ weight).view(x.shape)
         if ctx.needs_input_grad[1]:
             dw = skinny_wgrad(g, x2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(g)
         return dx, dw, db
+
+
+class SkinnyEncoders(Function):
+    """cat_i(x_i W_i^T + b_i) [+ ELU] for narrow inputs (K_i <= 16): the separate 128-d input encoders of the policy /
+    value models and the value's (state, action) mapping (ref: contextual_sac_policy_single_head.py:81-90,
+    contextual_sac_value.py:90-109).  Every projection writes its column block of ONE [M, sum N_i] buffer (no torch.cat,
+    and in the backward no slice copies: weight / bias gradients read the column blocks of dy in place); the optional
+    ELU runs in the projection kernel and its backward is fused with the bias gradients.
+    apply(elu, n, x_1..x_n, W_1..W_n, b_1..b_n)."""
+
+    @staticmethod
+    def forward(ctx, elu, n, *args):
+        xs, Ws, bs = args[:n], args[n:2 * n], args[2 * n:3 * n]
+        lead = xs[0].shape[:-1]
+        M = xs[0].numel() // xs[0].shape[-1]
+        widths = [int(W.shape[0]) for W in Ws]
+        total = sum(widths)
+        out = torch.empty((M, total), device=xs[0].device, dtype=torch.float32)
+        x2s, off = [], 0
+        for x, W, b, w in zip(xs, Ws, bs, widths):
+            x2 = x.reshape(M, x.shape[-1])
+            if x2.dtype != torch.float32 or x2.stride(-1) != 1:
+                x2 = x2.float().contiguous()
+            N.call("rorl_skinny_linear", N.ptr(x2), N.ptr(_f32c(W)), N.ptr(None if b is None else _f32c(b)), N.ptr(out[:, off:]),
+                   M, w, x2.shape[1], x2.stride(0), total, int(bool(elu)), N.stream())
+            x2s.append(x2)
+            off += w
+        ctx.save_for_backward(*x2s, *Ws, *([out] if elu else []))
+        ctx.n, ctx.elu, ctx.widths, ctx.xshapes, ctx.has_bias = n, bool(elu), widths, [x.shape for x in xs], [b is not None for b in bs]
+        return out.view(*lead, total)
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, widths = ctx.n, ctx.widths
+        saved = ctx.saved_tensors
+        x2s, Ws = saved[:n], saved[n:2 * n]
+        total = sum(widths)
+        g = dy.reshape(-1, total)
+        if g.dtype != torch.float32 or g.stride(-1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
+            g = g.float().contiguous()
+        db_all = None
+        if ctx.elu:
+            g, db_all = elu_bwd_colsum(g if g.is_contiguous() else g.contiguous(), saved[2 * n])
+        elif any(ctx.has_bias[i] and ctx.needs_input_grad[2 + 2 * n + i] for i in range(n)):
+            db_all = colsum(g)
+        dxs, dWs, dbs, off = [], [], [], 0
+        for i in range(n):
+            gi = g[:, off:off + widths[i]]
+            dx = dW = db = None
+            if ctx.needs_input_grad[2 + i]:
+                dx = (gi @ Ws[i]).view(ctx.xshapes[i])
+            if ctx.needs_input_grad[2 + n + i]:
+                dW = skinny_wgrad(gi, x2s[i])
+            if ctx.has_bias[i] and ctx.needs_input_grad[2 + 2 * n + i]:
+                db = db_all[off:off + widths[i]]
+            dxs.append(dx), dWs.append(dW), dbs.append(db)
+            off += widths[i]
+        return (None, None, *dxs, *dWs, *dbs)
+
+
+def skinny_encoders_ok(xs, Ws) -> bool:
+    M = xs[0].numel() // xs[0].shape[-1]
+    return (all(x.is_cuda and x.dtype == torch.float32 and x.shape[:-1] == xs[0].shape[:-1] for x in xs) and M >= 1
+            and all(W.shape[1] <= 16 and W.shape[0] % 4 == 0 for W in Ws))
+
+
+def skinny_encoders(xs, Ws, bs, elu=False):
+    return SkinnyEncoders.apply(elu, len(xs), *xs, *Ws, *bs)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from .. import kernels as K
 from ..models.contextual_model import ContextualModel
 from ..models.linear import Linear
 from ..models.RNNHidden import RNNHidden
@@ -49,14 +50,18 @@ class _InputEncoders:
                     self.contextual_register_rnn_base_module(mod, name)
 
     def get_embedding_input(self, state, lst_state, lst_action, reward) -> torch.Tensor:
-        parts = [self.state_encoder(state)]
+        pairs = [(self.state_encoder, state)]
         if self.last_state_input:
-            parts.append(self.last_obs_encoder(lst_state))
+            pairs.append((self.last_obs_encoder, lst_state))
         if self.last_action_input:
-            parts.append(self.last_act_encoder(lst_action))
+            pairs.append((self.last_act_encoder, lst_action))
         if self.reward_input:
-            parts.append(self.reward_encoder(reward))
-        return torch.cat(parts, dim=-1)
+            pairs.append((self.reward_encoder, reward))
+        if self.separate_encoder:
+            xs, Ws, bs = [x for _, x in pairs], [m.weight for m, _ in pairs], [m.bias for m, _ in pairs]
+            if K.skinny_encoders_ok(xs, Ws):          # every encoder writes its column block of one buffer: no cat
+                return K.skinny_encoders(xs, Ws, bs)
+        return torch.cat([m(x) for m, x in pairs], dim=-1)
 
 
 class ContextualSACPolicySingleHead(ContextualModel, _InputEncoders):

@@ -10,6 +10,7 @@ from typing import Optional
 
 import torch
 
+from .. import kernels as K
 from ..models.contextual_model import ContextualModel
 from ..models.linear import Linear
 from ..models.RNNHidden import RNNHidden
@@ -52,6 +53,11 @@ class ContextualSACValue(ContextualModel, _InputEncoders):
         self.state_dim, self.action_dim = state_dim, action_dim
 
     def state_action(self, state, action):
+        if self.separate_encoder and isinstance(self.state_input_encoder, Linear):
+            xs, mods = [state, action], [self.state_input_encoder, self.action_input_encoder]
+            act = self.uni_model_input_mapping_activation_func
+            if K.skinny_encoders_ok(xs, [m.weight for m in mods]) and isinstance(act, (torch.nn.ELU, torch.nn.Identity)):
+                return K.skinny_encoders(xs, [m.weight for m in mods], [m.bias for m in mods], elu=isinstance(act, torch.nn.ELU))
         sa = torch.cat((self.state_input_encoder(state), self.action_input_encoder(action)), dim=-1)
         return self.uni_model_input_mapping_activation_func(sa) if self.separate_encoder else sa
 

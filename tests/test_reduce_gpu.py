@@ -75,3 +75,29 @@ def test_linear_skinny_autograd(K):
     ref = torch.autograd.grad(torch.nn.functional.linear(xd, Wd, bd), (xd, Wd, bd), dy.double())
     for a, r, n in zip(got, ref, "x W b".split()):
         assert rel_err(a, r) < 1e-5, n
+
+
+@pytest.mark.parametrize("elu,M", [(False, 32 * 1019), (True, 32 * 1019), (True, 77)])
+def test_skinny_encoders_write_one_buffer(elu, M):
+    """cat_i(x_i W_i^T + b_i) [+ ELU] with every projection writing its column block of one buffer, against torch."""
+    import rorl_b200.kernels as K
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    dims = (9, 9, 6)
+    xs = [torch.randn(M, k, device="cuda", generator=gen, requires_grad=(i == 2)) for i, k in enumerate(dims)]
+    Ws = [torch.randn(128, k, device="cuda", generator=gen, requires_grad=True) for k in dims]
+    bs = [torch.randn(128, device="cuda", generator=gen, requires_grad=True) for _ in dims]
+    assert K.skinny_encoders_ok(xs, Ws)
+    y = K.skinny_encoders(xs, Ws, bs, elu=elu)
+    dy = torch.randn(M, 384, device="cuda", generator=gen)
+    got = torch.autograd.grad(y, [xs[2]] + Ws + bs, dy)
+    xd = [x.detach().double().requires_grad_(i == 2) for i, x in enumerate(xs)]
+    Wd = [w.detach().double().requires_grad_() for w in Ws]
+    bd = [b.detach().double().requires_grad_() for b in bs]
+    yr = torch.cat([torch.nn.functional.linear(a, w, b) for a, w, b in zip(xd, Wd, bd)], dim=-1)
+    if elu:
+        yr = torch.nn.functional.elu(yr)
+    ref = torch.autograd.grad(yr, [xd[2]] + Wd + bd, dy.double())
+    assert rel_err(y, yr) < 1e-5
+    for a, r in zip(got, ref):
+        assert a.shape == r.shape
+        assert rel_err(a, r) < 1e-4
