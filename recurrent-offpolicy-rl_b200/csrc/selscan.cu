@@ -87,7 +87,7 @@ struct SelFwdCfg {
     static constexpr int QPR = DT / 4;                    // float4 quads per tile row
     static constexpr int TC = 2 * RORL_SEL_S;             // steps per tile
     static constexpr int NST = 4;                         // raw stages in flight
-    static constexpr int STAGE = TC * (4 * DT + 2 * N);   // u->skip, delta->dtA, z->silu(z), du, B, C
+    static constexpr int STAGE = TC * (4 * DT + 2 * N) + TC * QPR;   // u->skip, delta->dtA, z->silu(z), du, B, C, reset flag per quad-row
     static constexpr int PROW = DT * LPD + DT;            // partial-sum row: [DT/4 quads][2 pairs][LPD][2] + 4 floats of skew per quad
     static constexpr int PART = TC * PROW;                // (the skew makes the helpers' LDS.128 of a quad bank-conflict free)
     static constexpr int NHELP = 128;                     // helper threads
@@ -137,6 +137,11 @@ __global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(
                     cp_async16(st + r * DT + q * 4, p.u + row * p.ld_u + (ok ? col : 0), ok);
                     cp_async16(st + TC * DT + r * DT + q * 4, p.delta + row * p.ld_delta + (ok ? col : 0), ok);
                     if (HAS_Z) cp_async16(st + 2 * TC * DT + r * DT + q * 4, p.z + row * p.ld_z + (ok ? col : 0), ok);
+                    // the row's reset flag travels with the tile, one private copy per quad-row so that the thread that
+                    // transforms it is the thread whose wait_group covers it (ncu: the helpers spent 40 % of their time on
+                    // the L2 latency of reading it in the transform, the scan warps a quarter of theirs waiting for them)
+                    const bool okf = p.start != nullptr && t < L;
+                    cp_async4(st + TC * (4 * DT + 2 * N) + idx, p.start + row0 + (okf ? t : 0), okf);
                 }
                 for (int idx = ht; idx < TC * N / 4; idx += NHELP) {
                     const int r = idx / (N / 4), q = idx % (N / 4), t = tile * TC + r;
@@ -148,22 +153,23 @@ __global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(
             }
             cp_async_commit();
         };
+        // loop-invariant per thread: its quad column (NHELP % QPR == 0), hence its slice of delta_bias and D
+        const int hq = ht % QPR, hcol = d0 + hq * 4;
+        float4 hbias = make_float4(0.f, 0.f, 0.f, 0.f), hD4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dbias && hcol < p.D) hbias = __ldg(reinterpret_cast<const float4*>(p.dbias + hcol));
+        if (p.Dskip && hcol < p.D) hD4 = __ldg(reinterpret_cast<const float4*>(p.Dskip + hcol));
         // per-(t, d) transform of the elements this thread staged itself (visible to it after wait_group)
         auto transform = [&](int tile) {
             float* st = smem + (tile % NST) * STAGE;
             for (int idx = ht; idx < TC * QPR; idx += NHELP) {
-                const int r = idx / QPR, q = idx % QPR, t = tile * TC + r, col = d0 + q * 4;
-                // reset flag first: its (L2) latency overlaps the arithmetic below
-                const float rs = (p.start != nullptr && t < L) ? __ldg(p.start + row0 + t) : 0.f;
+                const int r = idx / QPR, q = idx % QPR, t = tile * TC + r;
+                const float rs = st[TC * (4 * DT + 2 * N) + idx];
                 float4* pu = reinterpret_cast<float4*>(st + r * DT + q * 4);
                 float4* pd = reinterpret_cast<float4*>(st + TC * DT + r * DT + q * 4);
                 float4* pz = reinterpret_cast<float4*>(st + 2 * TC * DT + r * DT + q * 4);
                 float4 x = *pd;
                 const float4 uu = *pu;
-                if (p.dbias && col < p.D) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.dbias + col));
-                    x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                }
+                x.x += hbias.x; x.y += hbias.y; x.z += hbias.z; x.w += hbias.w;
                 if (SOFTPLUS) {
                     x.x = softplusf_fast(x.x); x.y = softplusf_fast(x.y);
                     x.z = softplusf_fast(x.z); x.w = softplusf_fast(x.w);
@@ -178,8 +184,7 @@ __global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(
                     gz = make_float4(zz.x * sigmoidf_fast(zz.x), zz.y * sigmoidf_fast(zz.y), zz.z * sigmoidf_fast(zz.z),
                                      zz.w * sigmoidf_fast(zz.w));
                 }
-                float4 D4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.Dskip && col < p.D) D4 = __ldg(reinterpret_cast<const float4*>(p.Dskip + col));
+                const float4 D4 = hD4;
                 *pz = gz;
                 *pu = make_float4(D4.x * uu.x * gz.x, D4.y * uu.y * gz.y, D4.z * uu.z * gz.z, D4.w * uu.w * gz.w);
                 // reset: the scan multiplies this slot by A * log2(e) < 0, so +inf gives a = ex2(-inf) = 0
@@ -378,7 +383,7 @@ struct SelBwdCfg {
     static constexpr int TC = kCkptEvery;                 // steps per chunk
     static constexpr int NST = 3;                         // stages in flight
     static constexpr int NARR = 7;                        // u | dtA | du | g | dt | softplus' | dz coefficient
-    static constexpr int STAGE = TC * (NARR * DT + 2 * N);
+    static constexpr int STAGE = TC * (NARR * DT + 2 * N) + TC * QPR;   // + one reset flag per quad-row (see the forward)
     static constexpr int QS = 4 * LPD + 4;                // partial-sum quad stride (4 channels x LPD lanes + skew)
     static constexpr int PROW = QPR * QS;                 // partial-sum row
     static constexpr int PLANE = TC * PROW;               // one plane (sB | sA | y) of per-lane partial sums
@@ -482,6 +487,8 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
                     cp_async16(st + 4 * TC * DT + r * DT + myq * 4, p.delta + row * p.ld_delta + col, ok);
                     cp_async16(st + 3 * TC * DT + r * DT + myq * 4, p.dy + row * p.ld_dy + col, ok);
                     if (HAS_Z) cp_async16(st + 6 * TC * DT + r * DT + myq * 4, p.z + row * p.ld_z + col, ok);
+                    const bool okf = p.start != nullptr && t < L;
+                    cp_async4(st + TC * (Cfg::NARR * DT + 2 * N) + idx, p.start + row0 + (okf ? t : 0), okf);
                 }
                 for (int idx = ht; idx < TC * N / 4; idx += NHELP) {
                     const int r = idx / (N / 4), q = idx % (N / 4), t = k * TC + r;
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
             float* st = smem + (c % NST) * STAGE;
             for (int idx = ht; idx < TC * QPR; idx += NHELP) {
                 const int r = idx / QPR, t = k * TC + r, o = r * DT + myq * 4;
-                const float rs = (p.start != nullptr && t < L) ? __ldg(p.start + row0 + t) : 0.f;
+                const float rs = st[TC * (Cfg::NARR * DT + 2 * N) + idx];
                 const float4 uu = *reinterpret_cast<const float4*>(st + o);
                 float4 x = *reinterpret_cast<const float4*>(st + 4 * TC * DT + o);
                 const float4 dyv = *reinterpret_cast<const float4*>(st + 3 * TC * DT + o);

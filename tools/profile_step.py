@@ -1,12 +1,22 @@
-"""Diagnostic: torch.profiler table of one update (which ATen ops still run next to the rorl kernels)."""
-import os, sys
+"""Diagnostic: kernel-level table of ONE eager update (torch.profiler device events, aggregated by kernel name), and
+the ATen ops behind the non-rorl kernels.  RORL_BENCH_ENCODER / RORL_BENCH_ALGO select the configuration."""
+import collections
+import os
+import re
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import numpy as np
+import torch
+
 import bench as Bn
-from rorl_b200.algorithm.sac_full_length_rnn_redq_sep_optim import SACFullLengthRNNREDQ_SEP_OPTIM
-torch.manual_seed(0); np.random.seed(0)
+from rorl_b200.utility.alg_init import alg_class
+
+torch.manual_seed(0)
+np.random.seed(0)
 dev = torch.device("cuda:0")
-alg = SACFullLengthRNNREDQ_SEP_OPTIM(dict(Bn.HP), Bn.model_kwargs(Bn.ENCODER, False), Bn.model_kwargs(Bn.ENCODER, True), Bn.T_LEN, device=dev)
+cls = alg_class("sac_rnn_full_horizon_redQ_sep_optim" if Bn.ALGO == "sac" else "td3_rnn_full_horizon_redQ_sep_optim")
+alg = cls(dict(Bn.HP, use_cuda_graph=False), Bn.model_kwargs(Bn.ENCODER, False), Bn.model_kwargs(Bn.ENCODER, True), Bn.T_LEN, device=dev)
 alg.replay_buffer._init_memory_buffer(Bn.template_transition())
 rng = np.random.RandomState(1000)
 for _ in range(Bn.N_TRAJ):
@@ -14,8 +24,20 @@ for _ in range(Bn.N_TRAJ):
 for _ in range(3):
     alg.train_one_batch(sync=False)
 torch.cuda.synchronize()
-from torch.profiler import profile, ProfilerActivity
+from torch.profiler import ProfilerActivity, profile
+
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     alg.train_one_batch(sync=False)
     torch.cuda.synchronize()
-print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=110, max_name_column_width=45, max_shapes_column_width=70))
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if str(e.device_type).endswith("CUDA"):
+        name = re.sub(r"<.*", "", e.name.replace("void ", "")).strip()[:64]
+        agg[name][0] += 1
+        agg[name][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+tot = sum(v[1] for v in agg.values())
+print(f"one eager update: {sum(v[0] for v in agg.values())} device launches, {tot / 1e3:.2f} ms of device time")
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+    print(f"{100 * t / tot:6.2f}% {t:9.1f} us {n:4d}  {k}")
+print()
+print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=70, max_name_column_width=40, max_shapes_column_width=60))
