@@ -113,7 +113,15 @@ class BucketedGradSync:
 
 
 def sync_count_and_guard(n_valid: torch.Tensor, guard_min: torch.Tensor, guard_max: torch.Tensor, group=None):
-    """Make the valid-step count (SUM) and the guard bounds (MIN / MAX) global, in place."""
-    dist.all_reduce(n_valid, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(guard_min, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(guard_max, op=dist.ReduceOp.MAX, group=group)
+    """Make the valid-step count (SUM) and the guard bounds (MIN / MAX) global, in place -- with ONE collective: every
+    rank contributes (n_valid, min, max) to an all-gather of 3 doubles and reduces the gathered table locally (three
+    separate all-reduces cost three NCCL launch latencies for 20 bytes)."""
+    world = dist.get_world_size(group)
+    mine = torch.stack((n_valid.reshape(()).to(torch.float64), guard_min.reshape(()).to(torch.float64),
+                        guard_max.reshape(()).to(torch.float64)))
+    rows = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(rows, mine, group=group)
+    table = torch.stack(rows)
+    n_valid.copy_(table[:, 0].sum().to(n_valid.dtype).reshape(n_valid.shape))
+    guard_min.copy_(table[:, 1].min().to(guard_min.dtype).reshape(guard_min.shape))
+    guard_max.copy_(table[:, 2].max().to(guard_max.dtype).reshape(guard_max.shape))

@@ -67,7 +67,9 @@ def prepare_param_list(model, rnn_lr, l2_norm):
 class FlatArena:
     """All parameters of one model re-homed as views of one flat fp32 buffer (plus flat grad / Adam moments)."""
 
-    def __init__(self, model, device):
+    def __init__(self, model, device, grad_tail: int = 0):
+        """`grad_tail` extra floats at the end of the gradient buffer (not of the parameters): a slot that rides along
+        in the arena's data-parallel all-reduce (the policy arena carries the log-alpha gradient there)."""
         params = [p for p in model.parameters(True)]
         seen, uniq = set(), []
         for p in params:
@@ -81,7 +83,9 @@ class FlatArena:
             n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned inside the arena
         self.numel = n
         self.flat = torch.zeros(n, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grad_full = torch.zeros(n + grad_tail, dtype=torch.float32, device=device)
+        self.grad = self.grad_full[:n]
+        self.tail = self.grad_full[n:]
         with torch.no_grad():
             for p, off in zip(uniq, self.offsets):
                 self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
@@ -95,7 +99,7 @@ class FlatArena:
         raise KeyError
 
     def zero_grad(self):
-        self.grad.zero_()
+        self.grad_full.zero_()
         for p, off in zip(self.params, self.offsets):     # autograd may have swapped .grad out; put the view back
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
                 p.grad = self.grad[off:off + p.numel()].view(p.shape)
@@ -245,11 +249,13 @@ class FullLengthRNNUpdate:
         self._graphs, self._graph_pool = {}, None       # captured graphs point into the old arenas
         self._value_update(tau=0.0)
         self.target_policy.copy_weight_from(self.policy, tau=0.0)
-        self.policy_arena = FlatArena(self.policy, self.device)
+        self.policy_arena = FlatArena(self.policy, self.device, grad_tail=4)
         self.value_arena = FlatArena(self.values[0], self.device)
         self.target_arena = FlatArena(self.target_values[0], self.device)
-        self.alpha_arena = SimpleNamespace(flat=self.log_sac_alpha.data, grad=torch.zeros_like(self.log_sac_alpha.data),
+        # the log-alpha gradient lives in the tail slot of the policy gradient arena: one all-reduce carries both
+        self.alpha_arena = SimpleNamespace(flat=self.log_sac_alpha.data, grad=self.policy_arena.tail[:1],
                                            params=[self.log_sac_alpha], offsets=[0], numel=1, zero_grad=lambda: None)
+        self._guard_init_synced = False
         p = self.parameter
 
         def groups(model, rnn_lr, l2):
@@ -367,6 +373,13 @@ class FullLengthRNNUpdate:
         y = torch.empty_like(r_c)
         N.call("rorl_target_minq", N.ptr(qn), N.ptr(sel), int(sel.numel()), E, M, N.ptr(lp), N.ptr(self.log_sac_alpha.data),
                N.ptr(m), N.ptr(self.Q_guard.state), N.ptr(self._work), N.stream())
+        if self.dist_group is not None and not self._guard_init_synced:
+            # very first call (always launched eagerly): the guard bounds were just initialised from THIS rank's rows;
+            # make them the global extrema before the clamp / update uses them (ref: q_value_guard.py:22-27)
+            import torch.distributed as dist
+            dist.all_reduce(self.Q_guard.state[0:1], op=dist.ReduceOp.MIN, group=self.dist_group)
+            dist.all_reduce(self.Q_guard.state[1:2], op=dist.ReduceOp.MAX, group=self.dist_group)
+            self._guard_init_synced = True
         N.call("rorl_target_finish", N.ptr(m), N.ptr(r_c), N.ptr(d_c), N.ptr(t_c), N.ptr(m_c), float(self.parameter.gamma),
                N.ptr(y), N.ptr(self.Q_guard.state), N.ptr(self._stats), N.ptr(self._work), M, N.stream())
         return y
@@ -555,9 +568,7 @@ class FullLengthRNNUpdate:
             self._allreduce(self.value_arena.grad)
 
         def x_policy():
-            self._allreduce(self.policy_arena.grad)
-            if not self.parameter.no_alpha_auto_tune:
-                self._allreduce(self.alpha_arena.grad)
+            self._allreduce(self.policy_arena.grad_full)      # policy gradients + the log-alpha gradient in the tail slot
 
         return [(s_target, x_count if dist else None),
                 (s_critic, x_value if (dist and not overlap) else None),

@@ -116,7 +116,7 @@ def test_update_stage_schedule_places_the_exchanges():
     class Stub:
         parameter = SimpleNamespace(no_alpha_auto_tune=False)
         value_arena = SimpleNamespace(grad="value_grad")
-        policy_arena = SimpleNamespace(grad="policy_grad")
+        policy_arena = SimpleNamespace(grad="policy_grad", grad_full="policy_grad_full")
         alpha_arena = SimpleNamespace(grad="alpha_grad")
 
         def __init__(self, group):
@@ -141,4 +141,4 @@ def test_update_stage_schedule_places_the_exchanges():
     assert exchanges(None, False) == [(), (), (), ()]
     assert exchanges(None, True) == [(), (), (), ()]
     assert exchanges("g", False) == [("count",), (), (), ()]
-    assert exchanges("g", True) == [("count",), ("value_grad",), ("policy_grad", "alpha_grad"), ()]
+    assert exchanges("g", True) == [("count",), ("value_grad",), ("policy_grad_full",), ()]
