@@ -291,16 +291,20 @@ int rorl_gru_bwd(const float* dout, const float* dh_last, const float* w_hh, con
  * Forward: O fp32 with row stride ld_o, written at OUTPUT rows (columns h*64 .. h*64+63 of head h; other rows are
  * not touched), lse [H, Tp] (log2 domain, attention space) for the backward (may be NULL).
  * Backward: dq, dk, dv fp32 with row stride ld_d, written at OUTPUT rows.
+ * dropout_p > 0: attention-probability dropout (flash-attn's dropout_p; ref TransformerFlashAttention.py:65-70):
+ * keep bits come from a counter hash of (seed[0] (device int64), salt, head, query token, key token); the backward
+ * must be given the same (dropout_p, seed value, salt) as its forward.  dropout_p == 0: seed may be NULL.
  * ---------------------------------------------------------------------------------------------- */
 int rorl_attn_prep(const float* src, int64_t ld_tok, int64_t nsec, int64_t H, int64_t T, int64_t Tp, const int32_t* gmap,
                    void* rm_bf16, void* tr_bf16, const float* o, int64_t ld_o, float* Dout, cudaStream_t stream);
 int rorl_attn_fwd(const void* q_rm, const void* k_rm, const void* v_tr, const int32_t* tiles, int64_t ntiles,
                   const float* slopes, float softmax_scale, float* O, int64_t ld_o, float* lse, int64_t H, int64_t T,
-                  int64_t Tp, cudaStream_t stream);
+                  int64_t Tp, float dropout_p, const int64_t* seed, int64_t salt, cudaStream_t stream);
 int rorl_attn_bwd(const void* q_rm, const void* k_rm, const void* v_rm, const void* do_rm, const void* q_tr,
                   const void* k_tr, const void* do_tr, const float* lse, const float* D, const int32_t* tiles,
                   int64_t ntiles, const float* slopes, float softmax_scale, float* dq, float* dk, float* dv,
-                  int64_t ld_d, int64_t H, int64_t T, int64_t Tp, cudaStream_t stream);
+                  int64_t ld_d, int64_t H, int64_t T, int64_t Tp, float dropout_p, const int64_t* seed, int64_t salt,
+                  cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Trajectory gather: builds the padded, nest-stacked [rows, Lmax, F] fp32 batch of

@@ -532,10 +532,10 @@ class FullLengthRNNUpdate:
         return 65536.0 * 2.0 ** (self._opt_steps[which] // 2000)
 
     def _graph_allowed(self) -> bool:
-        """CUDA-graph replay needs a launch sequence that depends on nothing the host decides per step: the cgpt
-        encoder builds its attention work list on the host from the length table, and an injected `noise_fn`
-        (parity tests) returns a different tensor per call."""
-        if not self.use_cuda_graph or self._has_gpt:
+        """CUDA-graph replay needs a launch sequence that depends on nothing the host decides per step: an injected
+        `noise_fn` (parity tests) returns a different tensor per call.  (The cgpt encoder's attention work list depends
+        on the length table only, which is part of the graph key; it is cached on the device by the first, eager, call.)"""
+        if not self.use_cuda_graph:
             return False
         ok = lambda fn: fn is torch.randn_like or getattr(fn, 'graph_safe', False)   # device-only, same launches every call
         return all(ok(getattr(m, 'noise_fn', torch.randn_like)) for m in (self.policy, self.target_policy))

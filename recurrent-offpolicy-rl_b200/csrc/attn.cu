@@ -96,7 +96,31 @@ struct AttnParams {
     // backward
     const float* lse_in; const float* D;
     float* out1; float* out2; long long ld_out;
+    // dropout: keep if 16 random bits >= drop_thr (= round(p * 65536)); survivors are scaled by drop_scale = 1 / (1 - p)
+    const long long* seed_ptr; uint32_t salt; uint32_t drop_thr; float drop_scale;
 };
+
+// Attention-probability dropout (flash-attn's `dropout_p`, active in training mode; ref:
+// TransformerFlashAttention.py:65-70 builds MHA(dropout=p)): P_d = P * keep / (1 - p) before the P.V product.  The keep
+// bit of (head, query, key) is a counter-based hash of the pair's ABSOLUTE token indices, the per-call seed (a device
+// scalar, so captured graphs draw fresh masks on every replay) and the head, evaluated identically in the forward and
+// in both backward kernels.  16 random bits per element (two elements per 32-bit hash).  flash-attn's own Philox
+// stream cannot be reproduced outside its kernels, so parity for p > 0 is statistical; the mask
+// function is restated in tests/test_attn_gpu.py to check the kernels against an explicit-mask reference.
+__device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t drop_head_seed(const long long* seed_ptr, uint32_t salt, int h) {
+    const unsigned long long s = (unsigned long long)seed_ptr[0] * 0x9E3779B97F4A7C15ull;
+    return drop_mix32((uint32_t)(s >> 32) ^ (uint32_t)s ^ salt ^ ((uint32_t)h * 0x85ebca6bu));
+}
+// keep factor of (query token qa, key token ka), absolute indices in attention token space
+__device__ __forceinline__ float drop_factor(uint32_t hseed, int qa, int ka, int halfT, uint32_t thr, float inv_keep) {
+    const uint32_t r = drop_mix32(hseed + (uint32_t)qa * (uint32_t)halfT + (uint32_t)(ka >> 1));
+    const uint32_t u16 = (ka & 1) ? (r >> 16) : (r & 0xFFFFu);
+    return u16 >= thr ? inv_keep : 0.f;
+}
 
 constexpr int kAttnThreads = 160;
 
@@ -105,6 +129,7 @@ constexpr int kAttnThreads = 160;
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kFwdSmem = 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*Vt*/ + 32768 /*P*/ + 1024 /*align*/ + 128 /*barriers*/;
 
+template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
@@ -187,6 +212,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         const int i = qt * 128 + r;                       // query index inside the sequence
         const float c2 = p.slopes[h] * kLog2e;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const uint32_t hseed = DROP ? drop_head_seed(p.seed_ptr, p.salt, h) : 0u;
+        const int halfT = (p.Tp + 1) >> 1;
         float m = -1e30f, l = 0.f, inv_l = 0.f;
         for (int n = 0; n < total; ++n) {
             const int kt = n % nk, nb = n - nk;
@@ -219,8 +246,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
                 } else {
                     uint32_t pk[16];
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj)
-                        pk[jj] = pack_bf16(ex2f(s2[2 * jj] - m) * inv_l, ex2f(s2[2 * jj + 1] - m) * inv_l);
+                    for (int jj = 0; jj < 16; ++jj) {
+                        float p0 = ex2f(s2[2 * jj] - m) * inv_l, p1 = ex2f(s2[2 * jj + 1] - m) * inv_l;
+                        if (DROP) {
+                            p0 *= drop_factor(hseed, tok0 + i, tok0 + j0 + 2 * jj, halfT, p.drop_thr, p.drop_scale);
+                            p1 *= drop_factor(hseed, tok0 + i, tok0 + j0 + 2 * jj + 1, halfT, p.drop_thr, p.drop_scale);
+                        }
+                        pk[jj] = pack_bf16(p0, p1);
+                    }
                     uint8_t* blk = sP_ptr + (c >> 1) * 16384;
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -269,7 +302,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 constexpr int kBwdSmem = 2 * 16384 /*R, RG*/ + 2 * 32768 /*stages*/ + 2 * 16384 /*P, dS*/ + 1024 /*lse, D of the columns*/ +
                          1024 /*align*/ + 128 /*barriers*/;
 
-template <bool KSIDE>
+template <bool KSIDE, bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapRG,
                 const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapCG,
@@ -362,6 +395,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant_
         const float c2 = p.slopes[h] * kLog2e;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         float lse_r = 0.f, D_r = 0.f;
+        const uint32_t hseed = DROP ? drop_head_seed(p.seed_ptr, p.salt, h) : 0u;
+        const int halfT = (p.Tp + 1) >> 1;
         if (!KSIDE && ri < len) {
             lse_r = p.lse_in[(size_t)h * p.Tp + tok0 + ri];
             D_r = p.D[(size_t)h * p.Tp + tok0 + ri];
@@ -400,8 +435,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant_
                         const float s2 = fmaf(__uint_as_float(xs[jj + e]), p.c1, -c2 * (float)(qi - kj));
                         const bool dead = kj > qi || qi >= len;
                         const float pe = dead ? 0.f : ex2f(s2 - lse_q);
-                        pv[e] = pe;
-                        dv[e] = pe * (__uint_as_float(xd[jj + e]) - D_q) * p.scale;
+                        const float mk = DROP ? drop_factor(hseed, tok0 + qi, tok0 + kj, halfT, p.drop_thr, p.drop_scale) : 1.f;
+                        pv[e] = pe * mk;                                               // dropped probabilities (for dV)
+                        dv[e] = pe * (__uint_as_float(xd[jj + e]) * mk - D_q) * p.scale;   // dS = P (dP_d M / (1-p) - D)
                     }
                     pk_p[jj >> 1] = pack_bf16(pv[0], pv[1]);
                     pk_d[jj >> 1] = pack_bf16(dv[0], dv[1]);
@@ -472,9 +508,12 @@ static int map_tr(CUtensorMap* m, const void* ptr, int H, int Tp) {
 static void attn_attrs() {
     static bool once = false;
     if (!once) {
-        cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
-        cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-        cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+        cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+        cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+        cudaFuncSetAttribute(attn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+        cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+        cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+        cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
         once = true;
     }
 }
@@ -498,8 +537,9 @@ int rorl_attn_prep(const float* src, int64_t ld_tok, int64_t nsec, int64_t H, in
 
 int rorl_attn_fwd(const void* q_rm, const void* k_rm, const void* v_tr, const int32_t* tiles, int64_t ntiles,
                   const float* slopes, float softmax_scale, float* O, int64_t ld_o, float* lse, int64_t H, int64_t T,
-                  int64_t Tp, cudaStream_t stream) {
+                  int64_t Tp, float dropout_p, const int64_t* seed, int64_t salt, cudaStream_t stream) {
     if (!q_rm || !k_rm || !v_tr || !tiles || !slopes || !O) return RORL_ERR_ARG;
+    if (dropout_p < 0.f || dropout_p >= 1.f || (dropout_p > 0.f && !seed)) return RORL_ERR_ARG;
     if (ntiles <= 0 || H <= 0 || T <= 0 || Tp % 64 || ld_o % 4) return RORL_ERR_SHAPE;
     CUtensorMap mQ, mK, mVt;
     int rc = map_rm(&mQ, q_rm, (int)H, (int)T, 128);
@@ -511,16 +551,24 @@ int rorl_attn_fwd(const void* q_rm, const void* k_rm, const void* v_tr, const in
     p.tiles = reinterpret_cast<const int4*>(tiles); p.slopes = slopes; p.c1 = softmax_scale * kLog2e; p.scale = softmax_scale;
     p.H = (int)H; p.T = (int)T; p.Tp = (int)Tp; p.O = O; p.ld_o = ld_o; p.lse = lse;
     dim3 grid((unsigned)ntiles, (unsigned)H);
-    attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, stream>>>(mQ, mK, mVt, p);
+    if (dropout_p > 0.f) {
+        p.seed_ptr = reinterpret_cast<const long long*>(seed); p.salt = (uint32_t)salt;
+        p.drop_thr = (uint32_t)(dropout_p * 65536.0f + 0.5f); p.drop_scale = 1.0f / (1.0f - dropout_p);
+        attn_fwd_kernel<true><<<grid, kAttnThreads, kFwdSmem, stream>>>(mQ, mK, mVt, p);
+    } else {
+        attn_fwd_kernel<false><<<grid, kAttnThreads, kFwdSmem, stream>>>(mQ, mK, mVt, p);
+    }
     RORL_RETURN_LAUNCH();
 }
 
 int rorl_attn_bwd(const void* q_rm, const void* k_rm, const void* v_rm, const void* do_rm, const void* q_tr,
                   const void* k_tr, const void* do_tr, const float* lse, const float* D, const int32_t* tiles,
                   int64_t ntiles, const float* slopes, float softmax_scale, float* dq, float* dk, float* dv,
-                  int64_t ld_d, int64_t H, int64_t T, int64_t Tp, cudaStream_t stream) {
+                  int64_t ld_d, int64_t H, int64_t T, int64_t Tp, float dropout_p, const int64_t* seed, int64_t salt,
+                  cudaStream_t stream) {
     if (!q_rm || !k_rm || !v_rm || !do_rm || !q_tr || !k_tr || !do_tr || !lse || !D || !tiles || !slopes || !dq || !dk || !dv)
         return RORL_ERR_ARG;
+    if (dropout_p < 0.f || dropout_p >= 1.f || (dropout_p > 0.f && !seed)) return RORL_ERR_ARG;
     if (ntiles <= 0 || H <= 0 || T <= 0 || Tp % 64 || ld_d % 4) return RORL_ERR_SHAPE;
     CUtensorMap mQ128, mK128, mV128, mdO128, mQ64, mK64, mV64, mdO64, mQt, mKt, mdOt;
     int rc = map_rm(&mQ128, q_rm, (int)H, (int)T, 128);
@@ -540,12 +588,19 @@ int rorl_attn_bwd(const void* q_rm, const void* k_rm, const void* v_rm, const vo
     p.tiles = reinterpret_cast<const int4*>(tiles); p.slopes = slopes; p.c1 = softmax_scale * kLog2e; p.scale = softmax_scale;
     p.H = (int)H; p.T = (int)T; p.Tp = (int)Tp; p.lse_in = lse; p.D = D; p.ld_out = ld_d;
     dim3 grid((unsigned)ntiles, (unsigned)H);
+    const bool drop = dropout_p > 0.f;
+    if (drop) {
+        p.seed_ptr = reinterpret_cast<const long long*>(seed); p.salt = (uint32_t)salt;
+        p.drop_thr = (uint32_t)(dropout_p * 65536.0f + 0.5f); p.drop_scale = 1.0f / (1.0f - dropout_p);
+    }
     p.out1 = dq; p.out2 = nullptr;
-    attn_bwd_kernel<false><<<grid, kAttnThreads, kBwdSmem, stream>>>(mQ128, mdO128, mK64, mV64, mKt, mKt, p);
+    if (drop) attn_bwd_kernel<false, true><<<grid, kAttnThreads, kBwdSmem, stream>>>(mQ128, mdO128, mK64, mV64, mKt, mKt, p);
+    else attn_bwd_kernel<false, false><<<grid, kAttnThreads, kBwdSmem, stream>>>(mQ128, mdO128, mK64, mV64, mKt, mKt, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return 1000 + (int)e;
     p.out1 = dk; p.out2 = dv;
-    attn_bwd_kernel<true><<<grid, kAttnThreads, kBwdSmem, stream>>>(mK128, mV128, mQ64, mdO64, mQt, mdOt, p);
+    if (drop) attn_bwd_kernel<true, true><<<grid, kAttnThreads, kBwdSmem, stream>>>(mK128, mV128, mQ64, mdO64, mQt, mdOt, p);
+    else attn_bwd_kernel<true, false><<<grid, kAttnThreads, kBwdSmem, stream>>>(mK128, mV128, mQ64, mdO64, mQt, mdOt, p);
     RORL_RETURN_LAUNCH();
 }
 

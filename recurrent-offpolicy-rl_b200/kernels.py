@@ -783,10 +783,12 @@ def ensemble_linear(x, weight, bias, elu, shared):
 # ------------------------------------------------------------------------------------------------
 class AttnVarlen(Function):
     """out[T, H*64] = attention(qkv[T, 3, H, 64]) per sequence.  `tiles` int32 [ntiles, 4] and `gmap` int32 [Ta] on the
-    device come from attention_tiles (see include/rorl_b200.h for the two token spaces); slopes [H] fp32."""
+    device come from attention_tiles (see include/rorl_b200.h for the two token spaces); slopes [H] fp32.
+    dropout_p > 0: attention-probability dropout with the keep mask hashed from (`seed` device int64 [1], `salt`, head,
+    query, key); the backward regenerates the same mask."""
 
     @staticmethod
-    def forward(ctx, qkv, tiles, gmap, slopes, softmax_scale):
+    def forward(ctx, qkv, tiles, gmap, slopes, softmax_scale, dropout_p=0.0, seed=None, salt=0):
         T, three, H, hd = qkv.shape
         assert three == 3 and hd == 64, "the tcgen05 attention kernel is built for head dimension 64"
         qkv = _f32c(qkv)
@@ -799,15 +801,17 @@ class AttnVarlen(Function):
         N.call("rorl_attn_prep", N.ptr(qkv), 3 * H * 64, 3, H, Ta, Tp, N.ptr(gmap), N.ptr(rm), N.ptr(tr), None, 0, None, N.stream())
         out = torch.zeros((T, H * 64), device=dev, dtype=torch.float32)        # rows outside every sequence stay 0
         lse = torch.zeros((H, Tp), device=dev, dtype=torch.float32) if need_grad else None
+        dropout_p = float(dropout_p)
         N.call("rorl_attn_fwd", N.ptr(rm[0]), N.ptr(rm[1]), N.ptr(tr[2]), N.ptr(tiles), tiles.shape[0], N.ptr(slopes),
-               float(softmax_scale), N.ptr(out), H * 64, N.ptr(lse), H, Ta, Tp, N.stream())
-        ctx.save_for_backward(rm, tr, out, lse, tiles, gmap, slopes)
-        ctx.scale, ctx.dims = float(softmax_scale), (T, H, Ta, Tp)
+               float(softmax_scale), N.ptr(out), H * 64, N.ptr(lse), H, Ta, Tp, dropout_p, N.ptr(seed if dropout_p > 0 else None),
+               int(salt), N.stream())
+        ctx.save_for_backward(rm, tr, out, lse, tiles, gmap, slopes, seed if dropout_p > 0 else None)
+        ctx.scale, ctx.dims, ctx.drop = float(softmax_scale), (T, H, Ta, Tp), (dropout_p, int(salt))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        rm, tr, out, lse, tiles, gmap, slopes = ctx.saved_tensors
+        rm, tr, out, lse, tiles, gmap, slopes, seed = ctx.saved_tensors
         T, H, Ta, Tp = ctx.dims
         dev = out.device
         dout = _f32c(dout)
@@ -819,12 +823,44 @@ class AttnVarlen(Function):
         dqkv = torch.zeros((T, 3, H, 64), device=dev, dtype=torch.float32)
         N.call("rorl_attn_bwd", N.ptr(rm[0]), N.ptr(rm[1]), N.ptr(rm[2]), N.ptr(do_rm), N.ptr(tr[0]), N.ptr(tr[1]), N.ptr(do_tr),
                N.ptr(lse), N.ptr(D), N.ptr(tiles), tiles.shape[0], N.ptr(slopes), ctx.scale, N.ptr(dqkv[:, 0]), N.ptr(dqkv[:, 1]),
-               N.ptr(dqkv[:, 2]), 3 * H * 64, H, Ta, Tp, N.stream())
-        return dqkv, None, None, None, None
+               N.ptr(dqkv[:, 2]), 3 * H * 64, H, Ta, Tp, ctx.drop[0], N.ptr(seed), ctx.drop[1], N.stream())
+        return dqkv, None, None, None, None, None, None, None
 
 
-def attn_varlen_alibi(qkv, tiles, gmap, slopes, softmax_scale):
-    return AttnVarlen.apply(qkv, tiles, gmap, slopes, softmax_scale)
+def attn_varlen_alibi(qkv, tiles, gmap, slopes, softmax_scale, dropout_p=0.0, seed=None, salt=0):
+    return AttnVarlen.apply(qkv, tiles, gmap, slopes, softmax_scale, dropout_p, seed, salt)
+
+
+def attention_dropout_mask(seed_value: int, salt: int, H: int, Ta: int, Tp: int, dropout_p: float, device="cpu"):
+    """Host / torch restatement of the kernels' keep-mask hash (csrc/attn.cu drop_factor): [H, Ta, Ta] float factors
+    (0 or 1 / (1 - p)) for (head, query token, key token) in attention token space.  Test infrastructure for the
+    explicit-mask parity check; small Ta only."""
+    M32 = 0xFFFFFFFF
+
+    def mix32(x):
+        x = x ^ (x >> 16)
+        x = (x * 0x7feb352d) & M32
+        x = x ^ (x >> 15)
+        x = (x * 0x846ca68b) & M32
+        return x ^ (x >> 16)
+    s = (int(seed_value) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    base = ((s >> 32) ^ (s & M32) ^ (int(salt) & M32)) & M32
+    halfT = (Tp + 1) >> 1
+    thr = int(dropout_p * 65536.0 + 0.5)
+    q = torch.arange(Ta, dtype=torch.int64, device=device).view(Ta, 1)
+    k = torch.arange(Ta, dtype=torch.int64, device=device).view(1, Ta)
+    out = []
+    for h in range(H):
+        hs = base ^ ((h * 0x85ebca6b) & M32)
+        hseed = hs ^ (hs >> 16)
+        hseed = (hseed * 0x7feb352d) & M32
+        hseed ^= hseed >> 15
+        hseed = (hseed * 0x846ca68b) & M32
+        hseed ^= hseed >> 16
+        r = mix32((hseed + q * halfT + (k >> 1)) & M32)
+        u16 = torch.where((k & 1) == 1, r >> 16, r & 0xFFFF)
+        out.append(torch.where(u16 >= thr, 1.0 / (1.0 - dropout_p), 0.0))
+    return torch.stack(out).to(torch.float32)
 
 
 def attention_tiles(seq_starts, seq_lens):

@@ -13,8 +13,9 @@ What runs where:
 Differences, deliberate: tokens are NOT unpadded / re-padded (ref :104-121): every per-token operation runs on the
 padded [B*L] token axis, the attention kernel walks the sequences through a (start, length) work list, and the
 padding tokens are zeroed once at the end, which is what pad_input produces.  Attention-probability dropout
-(flash-attn's `dropout_p`) is not implemented: with p > 0 in training mode only the three nn.Dropout sites are
-active (the reference's own parity recipe runs cgpt with p0.0).
+(flash-attn's `dropout_p`, training mode) runs inside the attention kernels with a counter-hash keep mask: the
+distribution is flash-attn's (Bernoulli(1 - p) per probability, survivors scaled by 1 / (1 - p)), the random stream
+is not (flash-attn's Philox stream is not reproducible outside its kernels; parity fixtures use p0.0).
 """
 from __future__ import annotations
 
@@ -58,6 +59,7 @@ class LayerNorm(nn.LayerNorm):
 
 class MHA(nn.Module):
     """Self-attention block with flash_attn.modules.mha.MHA's parameter names (fused Wqkv, out_proj)."""
+    _instances = 0
 
     def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0, layer_idx=None):
         super().__init__()
@@ -70,13 +72,24 @@ class MHA(nn.Module):
         self.Wqkv = Linear(embed_dim, 3 * embed_dim)
         self.out_proj = Linear(embed_dim, embed_dim)
         self.register_buffer('alibi_slopes', torch.tensor(get_alibi_slopes(num_heads), dtype=torch.float32), persistent=False)
+        # attention-dropout call counter (device scalar: every call, also one replayed from a CUDA graph, draws a fresh mask)
+        self.register_buffer('_drop_calls', torch.zeros(1, dtype=torch.int64), persistent=False)
+        MHA._instances += 1
+        self._salt = (0x51ED270B * ((layer_idx or 0) + 1) + 0x9E3779B1 * MHA._instances) & 0x7FFFFFFF   # stable across runs
 
     def forward(self, x, tiles):
-        """x: [T, C] tokens; tiles: device (work list, gather map) of the sequences (kernels.attention_tiles)."""
+        """x: [T, C] tokens; tiles: device (work list, gather map) of the sequences (kernels.attention_tiles).
+        In training mode with dropout > 0 the attention probabilities are dropped inside the kernel, as flash-attn does
+        for `MHA(dropout=p)` (ref: TransformerFlashAttention.py:65-70)."""
         T = x.shape[0]
         qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=1)
+        p_drop = self.attn_dropout if self.training else 0.0
+        seed = None
+        if p_drop > 0.0:
+            self._drop_calls += 1
+            seed = self._drop_calls.clone()                  # the backward needs THIS call's value
         o = K.attn_varlen_alibi(qkv.view(T, 3, self.num_heads, self.head_dim), tiles[0], tiles[1], self.alibi_slopes,
-                                1.0 / math.sqrt(self.head_dim))
+                                1.0 / math.sqrt(self.head_dim), p_drop, seed, self._salt)
         return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=1)
 
     def decode_step(self, x, cache):
@@ -161,6 +174,7 @@ class TransformerDecoder(nn.Module):
                                              for i in range(n_layer)])
         self.output_ln = LayerNorm(d_model) if ln else RMSNorm(d_model)
         self.output_fc = Linear(d_model, d_model)
+        self._tiles_cache = {}
 
     def forward(self, x, inference_params=None, seqlens=None):
         """x: [B, L, C].  seqlens: [B, L] lengths of the sequences packed in each row (zeros padded), as the update
@@ -183,15 +197,28 @@ class TransformerDecoder(nn.Module):
             host = getattr(seqlens, '_host', None)
             if host is None:
                 host = seqlens.detach().cpu().numpy()
-        starts, lens, row_tokens = sequences_of(np.asarray(host), L)
-        tiles = tuple(t.to(x.device, non_blocking=True) for t in K.attention_tiles(starts, lens))
+        # the attention work list and the padding mask depend only on the length table: built once per table on the host,
+        # kept on the device (a captured CUDA graph must not contain the pageable host-to-device copies that build them)
+        host = np.ascontiguousarray(np.asarray(host))
+        key = (host.tobytes(), host.shape, L, str(x.device))
+        cached = self._tiles_cache.get(key)
+        if cached is None:
+            starts, lens, row_tokens = sequences_of(host, L)
+            tiles = tuple(t.to(x.device) for t in K.attention_tiles(starts, lens))
+            keep = None
+            if any(n < L for n in row_tokens):                                   # pad_input: padding tokens -> 0
+                keep = torch.zeros((B, L, 1), dtype=torch.float32)
+                for b, n in enumerate(row_tokens):
+                    keep[b, :n] = 1
+                keep = keep.to(x.device)
+            if len(self._tiles_cache) >= 16:
+                self._tiles_cache.pop(next(iter(self._tiles_cache)))
+            cached = self._tiles_cache[key] = (tiles, keep)
+        tiles, keep = cached
         h = x.reshape(B * L, C)
         for layer in self.decoder_layers:
             h = layer(h, tiles)
         h = self.output_fc(self.output_ln(h)).view(B, L, C)
-        if any(n < L for n in row_tokens):                                       # pad_input: padding tokens -> 0
-            keep = torch.zeros((B, L, 1), dtype=h.dtype)
-            for b, n in enumerate(row_tokens):
-                keep[b, :n] = 1
-            h = h * keep.to(x.device, non_blocking=True)
+        if keep is not None:
+            h = h * keep
         return h

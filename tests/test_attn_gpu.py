@@ -194,3 +194,77 @@ def test_cgpt_kv_cache_matches_reference():
         y_full, _, _ = net.meta_forward(x, net.make_init_state(x.shape[0], x.device))
     assert_close(torch.cat(ys, dim=1), g["y_steps"], TOL, "decoded steps")
     assert_close(y_full, g["y_full"], TOL, "full forward")
+
+
+def test_attention_dropout_explicit_mask():
+    """Attention-probability dropout: the kernels' keep mask (a counter hash, restated in kernels.attention_dropout_mask)
+    applied in an fp32 torch attention must reproduce the kernel's output and gradients -- forward and both backward
+    kernels regenerate the same mask.  Also: the keep rate is 1 - p."""
+    import rorl_b200.kernels as K
+    from oracle import attention as OA
+    H, hd, p_drop = 4, 64, 0.25
+    lens, gaps = [100, 37, 130], [0, 0, 3]
+    starts, used = _seqs(lens, gaps)
+    T = used + 5
+    gen = torch.Generator().manual_seed(11)
+    qkv = torch.randn(T, 3, H, hd, generator=gen)
+    dout = torch.randn(T, H * hd, generator=gen)
+    slopes = OA.alibi_slopes(H)
+    scale = 1.0 / math.sqrt(hd)
+    tiles, gmap = K.attention_tiles(starts, lens)
+    Ta = gmap.shape[0]
+    Tp = (Ta + 63) // 64 * 64
+    seed_val, salt = 12345, 777
+    mask = K.attention_dropout_mask(seed_val, salt, H, Ta, Tp, p_drop)           # [H, Ta, Ta]
+    keep_rate = float((mask > 0).float().mean())
+    assert abs(keep_rate - (1 - p_drop)) < 5e-3, keep_rate
+    pos = {}                                                                       # attention-space start of each sequence
+    for row in tiles.tolist():
+        pos[row[3]] = row[0]
+    ref_in = qkv.clone().requires_grad_()
+    ref = torch.zeros(T, H * hd)
+    sl = torch.tensor(slopes).view(H, 1, 1)
+    for s0, n in zip(starts, lens):
+        q, k, v = (ref_in[s0:s0 + n, i].transpose(0, 1) for i in range(3))
+        idx = torch.arange(n)
+        rel = (idx.view(n, 1) - idx.view(1, n)).float()
+        sc = (scale * q @ k.transpose(1, 2) - sl * rel).masked_fill(rel.unsqueeze(0) < 0, float("-inf"))
+        a0 = pos[s0]
+        pd = torch.softmax(sc, dim=-1) * mask[:, a0:a0 + n, a0:a0 + n]
+        ref = ref.index_add(0, torch.arange(s0, s0 + n), (pd @ v).transpose(0, 1).reshape(n, H * hd))
+    inside = torch.zeros(T, 1)
+    for s0, n in zip(starts, lens):
+        inside[s0:s0 + n] = 1
+    (ref * dout * inside).sum().backward()
+    x = qkv.cuda().requires_grad_()
+    seed = torch.tensor([seed_val], dtype=torch.int64, device="cuda")
+    out = K.attn_varlen_alibi(x, tiles.cuda(), gmap.cuda(), torch.tensor(slopes, dtype=torch.float32, device="cuda"), scale, p_drop, seed, salt)
+    (out * (dout * inside).cuda()).sum().backward()
+    assert_close(out, ref, 2e-2, "out with dropout")
+    for i, name in enumerate("qkv"):
+        assert_close(x.grad[:, i], ref_in.grad[:, i], 2e-2, f"d{name} with dropout")
+    # a different seed value gives a different mask; p = 0 ignores the seed
+    out2 = K.attn_varlen_alibi(qkv.cuda(), tiles.cuda(), gmap.cuda(), torch.tensor(slopes, dtype=torch.float32, device="cuda"), scale,
+                               p_drop, seed + 1, salt)
+    assert float((out2 - out).abs().max()) > 1e-3
+
+
+def test_cgpt_dropout_active_only_in_training():
+    """cgpt_*_p0.1: train() draws a fresh attention / residual dropout mask per call, eval() is deterministic and equals
+    the p0.0 network (ref: TransformerFlashAttention.py:57,65-70,83-84)."""
+    from rorl_b200.models.rnn_base import RNNBase
+    torch.manual_seed(4)
+    net = RNNBase(10, 6, [128, 128], ['elu', 'elu', 'linear'], ['fc', 'cgpt_h2_l2_p0.1_ml512', 'fc']).cuda()
+    ref = RNNBase(10, 6, [128, 128], ['elu', 'elu', 'linear'], ['fc', 'cgpt_h2_l2_p0.0_ml512', 'fc']).cuda()
+    ref.load_state_dict(net.state_dict())
+    x = torch.randn(2, 200, 10, device="cuda")
+    net.eval(); ref.eval()
+    with torch.no_grad():
+        a, _, _ = net.meta_forward(x, net.make_init_state(2, x.device))
+        b, _, _ = ref.meta_forward(x, ref.make_init_state(2, x.device))
+        assert torch.equal(a, b)
+        net.train()
+        c, _, _ = net.meta_forward(x, net.make_init_state(2, x.device))
+        d, _, _ = net.meta_forward(x, net.make_init_state(2, x.device))
+    assert float((c - a).abs().max()) > 1e-4 and float((c - d).abs().max()) > 1e-4
+    assert float((c - a).abs().mean() / a.abs().mean()) < 0.5          # a perturbation, not garbage
