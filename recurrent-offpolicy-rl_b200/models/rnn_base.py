@@ -21,7 +21,10 @@ from .RNNHidden import RNNHidden
 from .ensemble_linear_model import EnsembleLinear
 from .linear import Linear
 from .gilr.gilr import GILRLayer
+from .gilr.egilr import EnsembleGILRLayer
 from .lru.lru import LRULayer
+from .lru.elru import EnsembleLRULayer
+from .conv1d.econv1d import EConv1d
 from .smamba.mamba import BlockList as MambaBlockList
 from .s6.mamba import MambaResidualBlock
 from .conv1d.conv1d import Conv1d
@@ -101,9 +104,20 @@ def parse_layer_id(layer_id: str) -> Tuple[str, Dict]:
         return layer_id, {}
     if layer_id.startswith('conv1d'):                          # ref: rnn_base.py:227-234
         return 'conv1d', {'d_conv': int(layer_id.split('_')[-1]) if '_' in layer_id else 4}
+    # ensemble encoders: one independent encoder per ensemble member, output [E, B, L, C]  (ref: rnn_base.py:110-117,235-244)
+    if layer_id.startswith('e') and layer_id[1:].split('-')[0] in ('lru', 'gilr_lstm'):
+        return 'elru', {'ensemble': int(layer_id.split('-')[-1])}      # `egilr_lstm-E` builds EnsembleLRULayer too (ref :110-113)
+    if layer_id.startswith('egilr'):
+        return 'egilr', {'ensemble': int(layer_id.split('-')[-1])}
+    if layer_id.startswith('econv1d'):
+        name, ens = layer_id.split('-')
+        return 'econv1d', {'ensemble': int(ens), 'd_conv': int(name.split('_')[-1]) if '_' in name else 4}
+    if layer_id == 'cgru':
+        raise NotImplementedError("'cgru' is listed among the reference's recurrent type names (ref: rnn_base.py:70) but has no "
+                                  "constructor there (its layer_dict has no such key, ref :55-69): it cannot be built in the reference either")
     raise NotImplementedError(
         f'layer type {layer_id!r} is outside the update hot path this package covers '
-        f'(fc, efc-E, gru, lru, gilr, gilr_lstm, conv1d_*, smamba_*, mamba_*, cgpt_*)')
+        f'(fc, efc-E, gru, lru, gilr, gilr_lstm, conv1d_*, smamba_*, mamba_*, cgpt_*, elru-E, egilr-E, egilr_lstm-E, econv1d_*-E)')
 
 
 class RNNBase(nn.Module):
@@ -149,6 +163,16 @@ class RNNBase(nn.Module):
                     blk = Conv1d(width_in, width, d_conv=cfg['d_conv'])
                     self.layer_list.append(blk)
                     self.rnn_hidden_state_input_size.append(blk.desired_hidden_dim)
+                elif kind == 'elru':
+                    self.layer_list.append(EnsembleLRULayer(width_in, width, cfg['ensemble'], batch_first=True))
+                    self.rnn_hidden_state_input_size.append(width * 2 * cfg['ensemble'])
+                elif kind == 'egilr':
+                    self.layer_list.append(EnsembleGILRLayer(width_in, width, cfg['ensemble'], batch_first=True))
+                    self.rnn_hidden_state_input_size.append(width * cfg['ensemble'])
+                elif kind == 'econv1d':
+                    blk = EConv1d(width_in, width, num_ensemble=cfg['ensemble'], d_conv=cfg['d_conv'])
+                    self.layer_list.append(blk)
+                    self.rnn_hidden_state_input_size.append(blk.desired_hidden_dim)
                 elif kind == 'smamba':
                     assert width_in == width, f'mamba_simple require input_dim == output_dim, while got {width_in} and {width}'
                     blk = MambaBlockList(cfg['block_num'], width_in, d_conv=cfg['d_conv'], d_state=cfg['d_state'],
@@ -186,6 +210,14 @@ class RNNBase(nn.Module):
         if getattr(efc, 'bias', None) is not None:
             nn.init.constant_(efc.bias, 0)
 
+    @staticmethod
+    def _xavier_multi(mefc):
+        for i in range(mefc.weight.shape[0]):
+            for j in range(mefc.weight.shape[1]):
+                nn.init.xavier_uniform_(mefc.weight[i, j].transpose(0, 1))
+        if getattr(mefc, 'bias', None) is not None:
+            nn.init.constant_(mefc.bias, 0)
+
     def xavier_initialize_weights(self):
         for m in self.layer_list:
             if isinstance(m, nn.Linear):
@@ -206,7 +238,13 @@ class RNNBase(nn.Module):
                 nn.init.constant_(m.out_proj.bias, 0)
                 self._xavier_efc(m.in_proj)
                 self._xavier_efc(m.middle_proj)
-            elif isinstance(m, (MambaBlockList, MambaResidualBlock, Conv1d)) or (TransformerDecoder is not None and isinstance(m, TransformerDecoder)):
+            elif isinstance(m, EnsembleLRULayer):
+                self._xavier_multi(m.in_proj)
+                self._xavier_multi(m.middle_proj)
+            elif isinstance(m, EnsembleGILRLayer):
+                self._xavier_efc(m.out_proj)
+                self._xavier_multi(m.in_proj)
+            elif isinstance(m, (MambaBlockList, MambaResidualBlock, Conv1d, EConv1d)) or (TransformerDecoder is not None and isinstance(m, TransformerDecoder)):
                 pass
             else:   # GRU and anything else with plain weight/bias tensors
                 for name, param in m.named_parameters():

@@ -154,6 +154,51 @@ def gen_layers(only=None):
         save(f"layer_{tag}.npz", layer_id=np.array(lid), **arrs)
 
 
+ENSEMBLE_LAYER_IDS = {"elru": "elru-3", "econv1d": "econv1d_4-3", "egilr_lstm": "egilr_lstm-3", "elru_h0": "elru-3"}
+
+
+def gen_ensemble_layers():
+    """Ensemble encoder IDs (one independent encoder per ensemble member, output [E, B, L, C]):
+    RNNBase(['fc', <ID>, 'efc-3']) forward + all gradients on the reference's CPU path.  (`egilr-E` cannot run on the
+    reference's CPU path -- its zero hidden has the wrong shape for scan_cpu -- and is generated on the GPU box by
+    make_golden_gpu.py.)"""
+    from offpolicy_rnn.models.rnn_base import RNNBase
+    for tag, lid in ENSEMBLE_LAYER_IDS.items():
+        torch.manual_seed(17)
+        net = RNNBase(12, 2, [16, 16], ['elu', 'elu', 'linear'], ['fc', lid, 'efc-3'])
+        for l in net.layer_list:
+            if hasattr(l, 'desire_ndim'):
+                l.desire_ndim = 4
+        with torch.no_grad():
+            for p in net.parameters():
+                if p.dim() == 1 or p.abs().max() == 0:
+                    p.add_(0.1 * torch.randn_like(p))
+        B, L = 3, 23
+        x = torch.randn(B, L, 12, requires_grad=True)
+        start = torch.zeros(B, L, 1)
+        start[:, 0] = 1
+        start[1, 9] = 1
+        mask = torch.ones(B, L, 1)
+        mask[2, 15:18] = 0
+        hid = net.make_init_state(B)
+        hid.set_rnn_start(start)
+        hid.set_mask(mask)
+        arrs = {}
+        if tag.endswith("_h0"):
+            hid[0] = 0.3 * torch.randn_like(hid[0])
+            arrs["h_in"] = hid[0].clone()
+        y, h_out, _ = net.meta_forward(x, hid)
+        dy = torch.randn_like(y)
+        params = dict(net.named_parameters())
+        grads = torch.autograd.grad(y, [x] + list(params.values()), dy, allow_unused=True)
+        arrs.update({"x": x, "start": start, "mask": mask, "y": y, "dy": dy, "dx": grads[0], "h_out": h_out[0]})
+        for (n, p), gr in zip(params.items(), grads[1:]):
+            arrs["p/" + n] = p
+            if gr is not None:
+                arrs["g/" + n] = gr
+        save(f"layer_{tag}.npz", layer_id=np.array(lid), **arrs)
+
+
 def gen_steps():
     """Rollout step path of the smamba layer: the UNMODIFIED reference on CPU walks Mamba.step() once per time step
     (ref: smamba/mamba.py:133-159,257-305) -- its natural CPU path, no patching (a fresh import would be needed to
@@ -434,6 +479,8 @@ if __name__ == "__main__":
         gen_ops()
     if "layers" in which:
         gen_layers([w[len("layer_"):] for w in which if w.startswith("layer_")] or None)
+    if "layers" in which or "ensemble" in which:
+        gen_ensemble_layers()
     if "steps" in which:
         gen_steps()
     if "sampler" in which:

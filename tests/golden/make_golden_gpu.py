@@ -74,6 +74,43 @@ def gen_layers():
         save(f"layer_{tag}.npz", layer_id=np.array(lid), **arrs)
 
 
+def gen_egilr():
+    """`egilr-3` on the reference's GPU path (Triton scan: width % 256 == 0; its CPU path cannot take the zero hidden)."""
+    from offpolicy_rnn.models.rnn_base import RNNBase
+    lid = "egilr-3"
+    torch.manual_seed(17)
+    net = RNNBase(12, 2, [256, 256], ['elu', 'elu', 'linear'], ['fc', lid, 'efc-3'])
+    for l in net.layer_list:
+        if hasattr(l, 'desire_ndim'):
+            l.desire_ndim = 4
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1 or p.abs().max() == 0:
+                p.add_(0.1 * torch.randn_like(p))
+    net.to(dev)
+    for l in net.layer_list:
+        if hasattr(l, 'to') and hasattr(l, 'device'):
+            l.to(dev)
+    B, L = 3, 23
+    x = torch.randn(B, L, 12).to(dev).requires_grad_()
+    start = torch.zeros(B, L, 1)
+    start[:, 0] = 1
+    start[1, 9] = 1
+    start = start.to(dev)
+    hid = net.make_init_state(B, dev)
+    hid.set_rnn_start(start)
+    y, h_out, _ = net.meta_forward(x, hid)
+    dy = torch.randn_like(y)
+    params = dict(net.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), dy, allow_unused=True)
+    arrs = {"x": x, "start": start, "mask": torch.ones(B, L, 1), "y": y, "dy": dy, "dx": grads[0], "h_out": h_out[0]}
+    for (n, p), gr in zip(params.items(), grads[1:]):
+        arrs["p/" + n] = p
+        if gr is not None:
+            arrs["g/" + n] = gr
+    save("layer_egilr.npz", layer_id=np.array(lid), **arrs)
+
+
 def gen_step():
     """Rollout: one token per call against the kv-cache (ref: rnn_base.py:437-452; flash-attn MHA inference path)."""
     from offpolicy_rnn.models.rnn_base import RNNBase
@@ -190,7 +227,7 @@ def gen_update():
 
 
 if __name__ == "__main__":
-    for fn in (gen_layers, gen_step, gen_update):
+    for fn in (gen_layers, gen_egilr, gen_step, gen_update):
         try:
             fn()
         except Exception as e:      # keep going: each fixture is independent

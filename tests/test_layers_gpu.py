@@ -41,6 +41,45 @@ def test_layer_golden(tag):
         assert_close(got, g["g/" + n], TOL, n)
 
 
+@pytest.mark.parametrize("tag", ["elru", "econv1d", "egilr_lstm", "elru_h0", "egilr"])
+def test_ensemble_layer_golden(tag):
+    """Ensemble encoder IDs (`elru-E`, `egilr-E`, `egilr_lstm-E`, `econv1d_K-E`: one independent encoder per member,
+    output [E, B, L, C]) against the UNMODIFIED reference: RNNBase(['fc', ID, 'efc-3']) forward, returned hidden, input
+    and parameter gradients (tests/golden/layer_e*.npz; `egilr` comes from the reference's Triton path on the GPU box)."""
+    import os
+    from helpers import GOLDEN
+    from rorl_b200.models.rnn_base import RNNBase
+    if not os.path.exists(os.path.join(GOLDEN, f"layer_{tag}.npz")):
+        pytest.skip(f"layer_{tag}.npz is generated on the GPU box (tests/golden/make_golden_gpu.py)")
+    g = load_npz(f"layer_{tag}.npz")
+    lid = str(g["layer_id"])
+    width = g["p/layer_list.0.weight"].shape[0]
+    net = RNNBase(12, 2, [width, width], ['elu', 'elu', 'linear'], ['fc', lid, 'efc-3'])
+    for l in net.layer_list:
+        if hasattr(l, 'desire_ndim'):
+            l.desire_ndim = 4
+    missing, unexpected = net.load_state_dict({k[2:]: T(v) for k, v in g.items() if k.startswith("p/")}, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    net.cuda()
+    x = T(g["x"], "cuda", grad=True)
+    hid = net.make_init_state(x.shape[0], x.device)
+    hid.set_rnn_start(T(g["start"], "cuda"))
+    hid.set_mask(T(g["mask"], "cuda"))
+    if "h_in" in g:
+        hid[0] = T(g["h_in"], "cuda")
+    y, h_out, _ = net.meta_forward(x, hid)
+    assert tuple(y.shape) == g["y"].shape
+    assert_close(y, g["y"], TOL, "y")
+    assert tuple(h_out[0].shape) == g["h_out"].shape
+    assert_close(h_out[0], g["h_out"], TOL, "h_out")
+    params = dict(net.named_parameters())
+    names = [k[2:] for k in g if k.startswith("g/")]
+    gs = torch.autograd.grad(y, [x] + [params[n] for n in names], T(g["dy"], "cuda"))
+    assert_close(gs[0], g["dx"], TOL, "dx")
+    for n, got in zip(names, gs[1:]):
+        assert_close(got, g["g/" + n], TOL, n)
+
+
 @pytest.mark.parametrize("tag", ["smamba_rms", "smamba_ln16"])
 def test_smamba_rollout_step_golden(tag):
     """The L == 1 rollout path (conv window roll + one step of the scan kernel with the carried SSM state) against the
