@@ -372,3 +372,23 @@ def value_forward(sd, spec: ModelSpec, state, lst_state, lst_action, action, sid
     q, emb = contextual_forward(sd, spec, embedding_input(sd, spec, state, lst_state, lst_action, reward), sa, side,
                                 detach_embedding, desire_ndim=4)
     return q, emb
+
+
+def policy_forward_discrete(sd, spec: ModelSpec, state, lst_state, lst_action, side, reward=None):
+    """Categorical policy: softmax of the head output mixed with a 0.01 floor, renormalised; returns (mode, emb, log_probs).
+    ref: contextual_sac_discrete_policy.py:88-118"""
+    out, emb = contextual_forward(sd, spec, embedding_input(sd, spec, state, lst_state, lst_action, reward), state, side, False)
+    probs = (out - out.max(dim=-1, keepdim=True).values).exp()
+    probs = probs / probs.sum(dim=-1, keepdim=True)
+    probs = probs + 0.01
+    probs = probs / probs.sum(dim=-1, keepdim=True)
+    return probs.argmax(dim=-1, keepdim=True), emb, torch.log(probs)
+
+
+def value_forward_discrete(sd, spec: ModelSpec, state, lst_state, lst_action, side, reward=None, detach_embedding=False):
+    """One Q per action from act(Linear(state)) and the embedding; the action argument of the reference's forward is
+    ignored there.  ref: contextual_sac_discrete_value.py:98-126"""
+    lin = lambda name, x: F.linear(x, sd[name]['weight'], sd[name]['bias'])
+    se = ACT[spec.map_act](lin('state_input_encoder_q', state))
+    return contextual_forward(sd, spec, embedding_input(sd, spec, state, lst_state, lst_action, reward), se, side,
+                              detach_embedding, desire_ndim=4)

@@ -122,7 +122,7 @@ def algo_class(cls_name):
     return getattr(importlib.import_module("offpolicy_rnn.algorithm." + mods[cls_name]), cls_name)
 
 
-def build_algorithm(cls_name, hp, policy_kwargs, value_kwargs, max_traj_len, act_dim, device="cpu", perturb=0.0):
+def build_algorithm(cls_name, hp, policy_kwargs, value_kwargs, max_traj_len, act_dim, device="cpu", perturb=0.0, discrete=False):
     """The reference algorithm object, constructed without its environment / logger (`object.__new__` + exactly the
     attributes SAC.__init__ and the subclass __init__s set; ref: algorithm/sac.py:34-127,
     sac_full_length_rnn_ensembleQ.py:17-55, sac_full_length_rnn_redq_sep_optim.py:81-102).  `hp` must already hold
@@ -138,21 +138,21 @@ def build_algorithm(cls_name, hp, policy_kwargs, value_kwargs, max_traj_len, act
     sep = cls_name.endswith("SEP_OPTIM")
     A = object.__new__(cls)
     hp = dict(hp)
-    if algo == "td3":
+    if algo == "td3" or discrete:                      # ref: sac.py:72-74, td3_full_length_rnn_ensembleQ.py:21
         hp["no_alpha_auto_tune"] = True
     A.parameter = types.SimpleNamespace(**hp)
     A.timer = Timer()
     A.device = A.sample_device = torch.device(device)
-    A.discrete_env = False
+    A.discrete_env = bool(discrete)
     A.base_algorithm = algo
     A.logger = lambda *a, **k: None
     pk = dict(policy_kwargs)
     if algo == "td3":
         pk["sample_std"] = hp["sample_std"]
     A.policy_args, A.value_args = pk, dict(value_kwargs)
-    A.policy = make_policy_model(pk, algo, False)
-    A.values = [make_value_model(value_kwargs, algo, False)]
-    A.target_values = [make_value_model(value_kwargs, algo, False)]
+    A.policy = make_policy_model(pk, algo, discrete)
+    A.values = [make_value_model(value_kwargs, algo, discrete)]
+    A.target_values = [make_value_model(value_kwargs, algo, discrete)]
     for m in [A.policy] + A.values + A.target_values:
         m.to(A.device)
     if perturb:
@@ -162,8 +162,10 @@ def build_algorithm(cls_name, hp, policy_kwargs, value_kwargs, max_traj_len, act
                     if p.dim() == 1 or p.abs().max() == 0:
                         p.add_(perturb * torch.randn_like(p))
     A._value_update(tau=0.0)
-    A.log_sac_alpha = torch.zeros(1, requires_grad=True, device=A.device)
-    A.target_entropy = -float(act_dim) * hp["target_entropy_ratio"]
+    import math
+    a0 = math.log(hp.get("sac_alpha", 1.0)) if hp.get("no_alpha_auto_tune") else 0.0                       # ref: sac.py:75-78
+    A.log_sac_alpha = torch.full((1,), a0, requires_grad=True, device=A.device)
+    A.target_entropy = hp["target_entropy_ratio"] if discrete else -float(act_dim) * hp["target_entropy_ratio"]   # ref: sac.py:80
     for net in (A.values[0].embedding_network.layer_list + A.target_values[0].embedding_network.layer_list
                 + A.values[0].uni_network.layer_list + A.target_values[0].uni_network.layer_list):
         if hasattr(net, 'desire_ndim'):
@@ -174,8 +176,8 @@ def build_algorithm(cls_name, hp, policy_kwargs, value_kwargs, max_traj_len, act
     if cls._get_whether_require_amp(A):
         from torch.cuda.amp import GradScaler
         A.amp_scalar, A.amp_scalar_critic = GradScaler(), GradScaler()
-    A.Q_guard = QValueGuard(True, True, 1 - 1e-3)
-    A.target_policy = make_policy_model(pk, algo, False)
+    A.Q_guard = QValueGuard(True, True, 1.0 if discrete else 1 - 1e-3)                                      # ref: sac_full_length_rnn_ensembleQ.py:43-46
+    A.target_policy = make_policy_model(pk, algo, discrete)
     A.target_policy.to(A.device)
     A.target_policy.copy_weight_from(A.policy, tau=0.0)
     A.target_policy.eval()

@@ -45,7 +45,7 @@ class RefUpdate:
 
     def __init__(self, policy_sd, value_sd, policy_spec: M.ModelSpec, value_spec: M.ModelSpec, hp, replay,
                  noise_fn: Callable, algo='sac', redq=True, allow_nest_stack=True, module_order=None, sep_optim=True,
-                 hidden_fn: Callable = None):
+                 hidden_fn: Callable = None, discrete=False):
         self.hp = hp
         self.algo, self.redq = algo, redq
         self.pspec, self.vspec = policy_spec, value_spec
@@ -53,15 +53,19 @@ class RefUpdate:
         self.value = clone_sd(value_sd, True)
         self.target = clone_sd(value_sd, False)
         self.target_policy = clone_sd(policy_sd, False)
-        self.log_alpha = torch.zeros(1, requires_grad=True)
-        self.target_entropy = -float(policy_spec.action_dim) * hp.get('target_entropy_ratio', 1.0)
+        import math
+        self.discrete = discrete
+        fixed_alpha = discrete or algo == 'td3' or hp.get('no_alpha_auto_tune', False)      # ref: sac.py:72-78
+        self.log_alpha = torch.full((1,), math.log(hp.get('sac_alpha', 1.0)) if fixed_alpha else 0.0, requires_grad=True)
+        self.target_entropy = (hp.get('target_entropy_ratio', 1.0) if discrete
+                               else -float(policy_spec.action_dim) * hp.get('target_entropy_ratio', 1.0))
         self.opt_pi = torch.optim.AdamW(param_groups(self.policy, hp['rnn_policy_lr'], hp.get('policy_l2_norm', 0.0), sep_optim),
                                         lr=hp['policy_lr'], weight_decay=hp.get('policy_l2_norm', 0.0))
         self.opt_q = torch.optim.AdamW(param_groups(self.value, hp['rnn_value_lr'], hp.get('value_l2_norm', 0.0), sep_optim),
                                        lr=hp['value_lr'], weight_decay=hp.get('value_l2_norm', 0.0))
         self.hidden_fn = hidden_fn
         self.opt_alpha = torch.optim.AdamW([self.log_alpha], lr=hp['alpha_lr'])
-        self.guard = QValueGuard(decay_ratio=1 - 1e-3)
+        self.guard = QValueGuard(decay_ratio=1.0 if discrete else 1 - 1e-3)       # ref: sac_full_length_rnn_ensembleQ.py:43-46
         self.replay = replay
         self.noise_fn = noise_fn
         self.allow_nest_stack = allow_nest_stack
@@ -69,6 +73,59 @@ class RefUpdate:
 
     def _mask_mean(self, data, mask, n):
         return (data * mask).sum() / n
+
+    def _one_update_discrete(self, did_policy, state, last_state, action, last_action, next_state, done, mask, reward, reward_input,
+                             side_t, side_qt, side, side_pi, alpha, total):
+        """Discrete action space.  ref: sac_full_length_rnn_ensembleQ.py:134-185 (+ REDQ: sac_full_length_rnn_redq.py:52-88);
+        alpha is fixed (sac.py:72-74), so no alpha step."""
+        hp = self.hp
+        A = self.pspec.action_dim
+        onehot = torch.nn.functional.one_hot(action.squeeze(-1).long(), num_classes=A).float()
+        with torch.no_grad():
+            lst_a = onehot if self.redq else action
+            _, _, logp_next = M.policy_forward_discrete(self.policy, self.pspec, next_state, state, lst_a, side_t, reward)
+            q_next, _ = M.value_forward_discrete(self.target, self.vspec, next_state, state, onehot, side_qt, reward)
+            if self.redq:
+                idx = np.random.permutation(q_next.shape[0])[:hp['redq_m']]
+                q_next = q_next[idx, :]
+            m = ((q_next.min(dim=0).values - alpha * logp_next) * logp_next.exp()).sum(dim=-1, keepdim=True)
+            target_q = reward + (1 - done) * hp['gamma'] * self.guard.clamp(m)
+        self.guard.update(target_q * mask)
+        n_valid = mask.sum()
+        q, _ = M.value_forward_discrete(self.value, self.vspec, state, last_state, last_action, side, reward_input)
+        q_sel = q.gather(-1, action.long().unsqueeze(0).expand(q.shape[0], *action.shape))
+        q_loss = sum(self._mask_mean((q_sel[i] - target_q).pow(2), mask, n_valid) for i in range(q_sel.shape[0]))
+        self.opt_q.zero_grad()
+        q_loss.backward()
+        q_norm = self._clip(self.value, hp.get('value_max_gradnorm'), hp.get('value_embedding_max_gradnorm'))
+        self.value_grads = {k: {n: (t.grad.clone() if t.grad is not None else None) for n, t in v.items()} for k, v in self.value.items()}
+        self.opt_q.step()
+        tau = hp['sac_tau']
+        with torch.no_grad():
+            for k in self.value:
+                for n in self.value[k]:
+                    tp = self.target[k][n]
+                    tp.copy_(tp * tau + (1 - tau) * self.value[k][n])
+        out = {'critic_loss': q_loss.item(), 'target_q_max': target_q.abs().max().item(), 'real_batch_size': total, 'value_grad_norm': q_norm}
+        if did_policy:
+            _, _, logp = M.policy_forward_discrete(self.policy, self.pspec, state, last_state, last_action, side_pi, reward_input)
+            qp, _ = M.value_forward_discrete(self.value, self.vspec, state, last_state, last_action, side, reward_input, detach_embedding=True)
+            agg = qp.mean(dim=0) if self.redq else qp.min(dim=0).values
+            actor_loss = self._mask_mean((((alpha * logp) - agg) * logp.exp()).sum(dim=-1, keepdim=True), mask, n_valid)
+            self.opt_pi.zero_grad()
+            actor_loss.backward()
+            out['policy_grad_norm'] = self._clip(self.policy, hp.get('policy_max_gradnorm'), hp.get('policy_embedding_max_gradnorm'))
+            self.policy_grads = {k: {n: (t.grad.clone() if t.grad is not None else None) for n, t in v.items()} for k, v in self.policy.items()}
+            self.opt_pi.step()
+            out['actor_loss'] = actor_loss.item()
+            out['log_prob'] = self._mask_mean((logp * logp.exp()).sum(dim=-1, keepdim=True), mask, n_valid).item()
+            out['policy_l2_norm_square'] = sum(float((t.detach() ** 2).sum()) for k in ('embedding_model', 'universal_model', 'uni_input_mapping_network')
+                                               if k in self.policy for t in self.policy[k].values())
+        out['log_alpha'] = self.log_alpha.item()
+        out['clip_min'], out['clip_max'] = self.guard.min, self.guard.max
+        out['q1_l2_norm_square'] = sum(float((t.detach() ** 2).sum()) for k in ('embedding_model', 'universal_model', 'uni_input_mapping_network')
+                                       if k in self.value for t in self.value[k].values())
+        return out
 
     def _clip(self, sd, max_norm, emb_clip):
         """ref: sac_full_length_rnn_ensembleQ.py:239-250,274-287 -- global-norm clip, then value clip on the embedding
@@ -122,6 +179,9 @@ class RefUpdate:
         side = M.Side(rnn_start, valid_ind, att, h0=h0_q)
         side_pi = M.Side(rnn_start, valid_ind, att, h0=h0_pi)
         td3 = self.algo == 'td3'
+        if self.discrete:
+            return self._one_update_discrete(did_policy, state, last_state, action, last_action, next_state, done, mask, reward,
+                                             reward_input, side_t, side_qt, side, side_pi, alpha, total)
         # ---- target (no grad) -------------------------------------------------------------- :83-103
         with torch.no_grad():
             pol_t = self.policy if (self.redq or not td3) else self.target_policy

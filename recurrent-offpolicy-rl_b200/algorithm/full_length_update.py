@@ -190,7 +190,7 @@ class FullLengthRNNUpdate:
     sep_optim = False           # RESeL per-encoder learning-rate split: only the *_SEP_OPTIM classes (ref: sac.py:81-90 otherwise)
 
     def __init__(self, parameter, policy_args: dict, value_args: dict, max_trajectory_len: int, device=None,
-                 dist_group=None):
+                 dist_group=None, discrete_env: bool = False):
         hp = dict(DEFAULTS)
         hp.update(parameter if isinstance(parameter, dict) else vars(parameter))
         self.parameter = SimpleNamespace(**hp)
@@ -199,9 +199,13 @@ class FullLengthRNNUpdate:
         self.device = self.sample_device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('the update hot path runs on sm_100a kernels only; no CPU path exists')
-        self.discrete_env = False
+        self.discrete_env = bool(discrete_env)
         self.dist_group = dist_group
         td3 = self.base_algorithm == 'td3'
+        if self.discrete_env:
+            # ref: sac.py:72-74 (discrete action space: fixed alpha), sac_full_length_rnn_ensembleQ.py:43-44 (guard decay 1)
+            assert not td3, 'the TD3 classes have no discrete-action variant in the reference'
+            self.parameter.no_alpha_auto_tune = True
         if td3:
             self.parameter.no_alpha_auto_tune = True
             policy_args = dict(policy_args, sample_std=self.parameter.sample_std)
@@ -210,10 +214,10 @@ class FullLengthRNNUpdate:
         for item in value_args['uni_model_layer_type']:
             assert item.startswith('e')
         # models (ref: sac.py:61-70) --------------------------------------------------------------------------
-        self.policy = make_policy_model(policy_args, self.base_algorithm, False)
-        self.values = [make_value_model(value_args, self.base_algorithm, False)]
-        self.target_values = [make_value_model(value_args, self.base_algorithm, False)]
-        self.target_policy = make_policy_model(policy_args, self.base_algorithm, False)
+        self.policy = make_policy_model(policy_args, self.base_algorithm, self.discrete_env)
+        self.values = [make_value_model(value_args, self.base_algorithm, self.discrete_env)]
+        self.target_values = [make_value_model(value_args, self.base_algorithm, self.discrete_env)]
+        self.target_policy = make_policy_model(policy_args, self.base_algorithm, self.discrete_env)
         for m in [self.policy, self.target_policy] + self.values + self.target_values:
             m.to(self.device)
         for net in (self.values[0].embedding_network.layer_list + self.target_values[0].embedding_network.layer_list
@@ -224,10 +228,11 @@ class FullLengthRNNUpdate:
                 net.in_proj.desire_ndim = 4
         a0 = math.log(self.parameter.sac_alpha) if self.parameter.no_alpha_auto_tune else 0.0
         self.log_sac_alpha = torch.tensor([a0], dtype=torch.float32, device=self.device, requires_grad=True)
-        self.target_entropy = -float(policy_args['action_dim']) * self.parameter.target_entropy_ratio
+        self.target_entropy = (self.parameter.target_entropy_ratio if self.discrete_env            # ref: sac.py:80
+                               else -float(policy_args['action_dim']) * self.parameter.target_entropy_ratio)
         self.replay_buffer = NestedMemoryArray(self.parameter.max_buffer_transition_num, max_trajectory_len,
                                                additional_history_len=self._get_skip_len(), device=self.device)
-        self.Q_guard = QValueGuard(True, True, 1 - 1e-3, device=self.device)
+        self.Q_guard = QValueGuard(True, True, 1.0 if self.discrete_env else 1 - 1e-3, device=self.device)
         self.allow_nest_stack = self.allow_nest_stack_trajs()
         self.grad_num = 0
         # scratch for the fused reductions
@@ -535,7 +540,7 @@ class FullLengthRNNUpdate:
         """CUDA-graph replay needs a launch sequence that depends on nothing the host decides per step: an injected
         `noise_fn` (parity tests) returns a different tensor per call.  (The cgpt encoder's attention work list depends
         on the length table only, which is part of the graph key; it is cached on the device by the first, eager, call.)"""
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or self.discrete_env:
             return False
         ok = lambda fn: fn is torch.randn_like or getattr(fn, 'graph_safe', False)   # device-only, same launches every call
         return all(ok(getattr(m, 'noise_fn', torch.randn_like)) for m in (self.policy, self.target_policy))
@@ -603,6 +608,9 @@ class FullLengthRNNUpdate:
         c['side'] = (rnn_start, valid_ind, att)              # the policy hidden gets the unshifted side-band after the target pass (ref :398-403)
         # 3. target Q (no grad) ------------------------------------------------------------------------------- ref :83-103
         self.policy.eval()
+        if self.discrete_env:
+            self._stage_target_discrete(c, target_policy_hidden, target_hidden)
+            return
         with torch.no_grad():
             pol_t = self.target_policy if (td3 and not self.use_redq) else self.policy
             a_mean, _, a_next, logp_next, _, _ = pol_t.forward(next_state, state, action, target_policy_hidden, reward)
@@ -614,6 +622,24 @@ class FullLengthRNNUpdate:
             c['target_Q'] = self._target_Q(q_next, sel, logp_next, reward, done, timeout, mask)
         self.last_target_Q = c['target_Q']
 
+    def _stage_target_discrete(self, c, target_policy_hidden, target_hidden):
+        """Discrete actions: y = r + (1 - done) gamma clamp(sum_a pi(a|s') (min_sel Q'(s', a) - alpha log pi(a|s')))
+        (ref: sac_full_length_rnn_ensembleQ.py:134-151; REDQ subset + one-hot last action: sac_full_length_rnn_redq.py:52-72).
+        The expectation over actions is formed with torch ops on [B, L, A] tensors; clamp / guard / statistics run on the
+        same fused kernels as the continuous path (the per-step scalar enters as a one-member `q`)."""
+        batch, sel = c['batch'], c['sel']
+        with torch.no_grad():
+            onehot = self.policy.action2onehot(batch.action.long())
+            lst_a = onehot if self.use_redq else batch.action                       # ref :141 (base class passes the raw index)
+            _, _, a_next, logp_next, _, _ = self.policy.forward(batch.next_state, batch.state, lst_a, target_policy_hidden, batch.reward)
+            q_next = self.target_values[0].forward(batch.next_state, batch.state, onehot, a_next, target_hidden, batch.reward)[0]
+            q_min = q_next.index_select(0, sel.long()).min(dim=0).values              # [B, L, A]
+            alpha = self.log_sac_alpha.data.exp()
+            m = ((q_min - alpha * logp_next) * logp_next.exp()).sum(dim=-1, keepdim=True)
+            one = torch.zeros(1, dtype=torch.int32, device=self.device)
+            c['target_Q'] = self._target_Q(m.reshape(1, *m.shape), one, None, batch.reward, batch.done, batch.timeout, batch.mask)
+        self.last_target_Q = c['target_Q']
+
     def _stage_critic(self, c, overlap):
         # 4. critic ------------------------------------------------------------------------------------------------ ref :105-114,261-295
         batch = c['batch']
@@ -622,6 +648,8 @@ class FullLengthRNNUpdate:
         for v in self.values:
             v.train()
         q = self.values[0].forward(batch.state, batch.last_state, batch.last_action, batch.action, c['value_hidden'], batch.reward_input)[0]
+        if self.discrete_env:                                         # Q of the action taken (ref :153-163)
+            q = q.gather(-1, batch.action.long().unsqueeze(0).expand(q.shape[0], *batch.action.shape))
         E, M = q.shape[0], q[0].numel()
         dq = torch.empty((E, M), dtype=torch.float32, device=dev)
         qc, tq_c, mask_c = q.contiguous(), c['target_Q'].contiguous(), batch.mask.contiguous()
@@ -653,6 +681,9 @@ class FullLengthRNNUpdate:
         # 5. actor + alpha ---------------------------------------------------------------------------------------- ref :116-132,405-432
         if not c['did_policy']:
             return
+        if self.discrete_env:
+            self._actor_discrete(c, overlap)
+            return
         for w in self.value_arena.params:
             w.requires_grad_(False)
         try:
@@ -683,6 +714,36 @@ class FullLengthRNNUpdate:
             self.alpha_arena.grad.copy_(self._stats[7:8])
             if overlap:
                 self._allreduce(self.alpha_arena.grad)
+
+    def _actor_discrete(self, c, overlap):
+        """Discrete actor: L = sum_mask sum_a pi(a|s) (alpha log pi(a|s) - agg_e Q_e(s, a)) / n_valid, agg = min (ensembleQ)
+        or mean (REDQ) (ref: sac_full_length_rnn_ensembleQ.py:165-179, sac_full_length_rnn_redq.py:74-88); alpha is fixed
+        for discrete action spaces (ref: sac.py:72-74).  torch autograd over [B, L, A] tensors."""
+        batch = c['batch']
+        n_valid = self._stats[1:2]
+        for w in self.value_arena.params:
+            w.requires_grad_(False)
+        try:
+            _, _, a_samp, logp, _, _ = self.policy.forward(batch.state, batch.last_state, batch.last_action, c['policy_hidden'], batch.reward_input)
+            qp = self.values[0].forward(batch.state, batch.last_state, batch.last_action, a_samp, c['value_hidden'], batch.reward_input,
+                                        detach_embedding=True)[0]
+        finally:
+            for w in self.value_arena.params:
+                w.requires_grad_(True)
+        agg = qp.mean(dim=0) if self.use_redq else qp.min(dim=0).values
+        alpha = self.log_sac_alpha.data.exp()
+        probs = logp.exp()
+        per_step = ((alpha * logp - agg) * probs).sum(dim=-1, keepdim=True)
+        actor_loss = (per_step * batch.mask).sum() / n_valid
+        self.optimizer_policy.zero_grad()
+        if overlap:
+            self._sync_policy.begin()
+        actor_loss.backward()
+        if overlap:
+            self._sync_policy.finish()
+        with torch.no_grad():
+            self._stats[4:5].copy_(actor_loss.detach().reshape(1))
+            self._stats[5:6].copy_((((logp * probs).sum(dim=-1, keepdim=True) * batch.mask).sum() / n_valid).reshape(1))
 
     def _stage_policy_step(self, c):
         if not c['did_policy']:

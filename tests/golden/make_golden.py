@@ -280,6 +280,24 @@ def gen_steps_linear():
 # ------------------------------------------------------------------------------------------------
 # sampler
 # ------------------------------------------------------------------------------------------------
+def fill_buffer_discrete(buf, Transition, rng, lens, S, A):
+    """Discrete action space: `action` is the index [1, 1], `last_action` its one-hot [1, A] (what the last-action encoder
+    of the discrete models takes, ref: contextual_sac_discrete_policy.py:35-36)."""
+    for T in lens:
+        last_s, last_a, last_r = np.zeros((1, S)), np.zeros((1, A)), np.zeros((1, 1))
+        s = rng.standard_normal((1, S))
+        for t in range(T):
+            ai = int(rng.randint(A))
+            ns = rng.standard_normal((1, S))
+            r = float(rng.standard_normal())
+            done = t == T - 1
+            buf.mem_push(Transition(state=s, last_state=last_s, last_action=last_a, action=np.array([[float(ai)]]), next_state=ns, reward=r,
+                                    logp=None, mask=1, done=done, timeout=done, start=(t == 0), reward_input=last_r))
+            last_a = np.zeros((1, A))
+            last_a[0, ai] = 1.0
+            last_s, last_r, s = s, np.array([[r]]), ns
+
+
 def fill_buffer(buf, Transition, rng, lens, S, A):
     """Synthetic trajectories in the shape SAC.train() pushes them (ref: algorithm/sac.py:337-351)."""
     for T in lens:
@@ -372,6 +390,9 @@ UPDATE_CASES = {
     "sac_gru_utd2": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=2, hp=dict(utd=2, policy_utd=1)),
     # random carried state shared by the target-policy and actor passes (ref :345-351); the draws are recorded (gru: the one
     # encoder without reset flags, so the carried state actually reaches the outputs)
+    # discrete action space: categorical policy, one Q per action, expectation over actions in target
+    # and actor, fixed alpha (ref: sac_full_length_rnn_ensembleQ.py:134-185, sac_full_length_rnn_redq.py:52-88, sac.py:72-74)
+    "sac_discrete": dict(algo="sac", enc="gilr", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=4, calls=2, discrete=True, hp=dict(sac_alpha=0.2)),
     "sac_gru_rndhidden": dict(algo="sac", enc="gru", hidden=16, lens=[14, 9, 20, 6, 11], S=3, A=2, calls=1, hp=dict(randomize_first_hidden=True)),
 }
 
@@ -403,10 +424,10 @@ def gen_updates(only=None):
         hp = dict(HP, sac_batch_size=sum(c["lens"]) - 1, max_buffer_transition_num=1000)
         hp.update(c.get("hp", {}))
         pk, vk = model_kwargs(c, False), model_kwargs(c, True)
-        A = build_algorithm(cls_name, hp, pk, vk, c.get("max_len", max(c["lens"])), c["A"], perturb=0.05)
+        A = build_algorithm(cls_name, hp, pk, vk, c.get("max_len", max(c["lens"])), c["A"], perturb=0.05, discrete=c.get("discrete", False))
         hp, pk = vars(A.parameter), A.policy_args
         skip = type(A)._get_skip_len(A)
-        fill_buffer(A.replay_buffer, Transition, np.random.RandomState(9), c["lens"], c["S"], c["A"])
+        (fill_buffer_discrete if c.get("discrete") else fill_buffer)(A.replay_buffer, Transition, np.random.RandomState(9), c["lens"], c["S"], c["A"])
 
         arrs = {}
         arrs.update(flat_sd(A.policy.state_dict(), "init/policy/"))

@@ -140,6 +140,22 @@ def test_cgpt_update_oracle_vs_reference_on_flash_attn():
             assert_close(upd.policy_grads[mod][name], v, 2e-2, k)
 
 
+def _fill_discrete(buf, rng, lens, S, A):
+    for Tn in lens:
+        last_s, last_a, last_r = np.zeros((1, S)), np.zeros((1, A)), np.zeros((1, 1))
+        s = rng.standard_normal((1, S))
+        for t in range(Tn):
+            ai = int(rng.randint(A))
+            ns = rng.standard_normal((1, S))
+            r = float(rng.standard_normal())
+            done = t == Tn - 1
+            buf.mem_push(OS.Transition(state=s, last_state=last_s, last_action=last_a, action=np.array([[float(ai)]]), next_state=ns, reward=r,
+                                       logp=None, mask=1, done=done, timeout=done, start=(t == 0), reward_input=last_r))
+            last_a = np.zeros((1, A))
+            last_a[0, ai] = 1.0
+            last_s, last_r, s = s, np.array([[r]]), ns
+
+
 def _fill(buf, rng, lens, S, A):
     for Tn in lens:
         last_s, last_a, last_r = np.zeros((1, S)), np.zeros((1, A)), np.zeros((1, 1))
@@ -188,7 +204,7 @@ def run_oracle_update(tag):
     pol = nested_sd(g, "init/policy/")
     val = nested_sd(g, "init/value/")
     buf = OS.RefNestedReplay(1000, c.get("max_len", max(c["lens"])), additional_history_len=cfg["skip"])   # ref: sac_full_length_rnn_ensembleQ.py:41
-    _fill(buf, np.random.RandomState(cfg["np_seed_fill"]), c["lens"], c["S"], c["A"])
+    (_fill_discrete if c.get("discrete") else _fill)(buf, np.random.RandomState(cfg["np_seed_fill"]), c["lens"], c["S"], c["A"])
     noises = [T(g[f"noise/{i}"]) for i in range(cfg["n_noise"])]
     it = iter(noises)
     hit = iter([T(g[f"hdraw/{i}"]) for i in range(cfg.get("n_hdraw", 0))])
@@ -205,13 +221,14 @@ def run_oracle_update(tag):
     vk = dict(cfg["value_kwargs"])
     cls = cfg.get("cls", "REDQ_SEP_OPTIM")
     upd = OU.RefUpdate(pol, val, OM.ModelSpec(**pk), OM.ModelSpec(**vk), hp, buf, noise_fn, algo=c["algo"], redq="REDQ" in cls,
-                       allow_nest_stack=cfg["allow_nest_stack"], sep_optim=cls.endswith("SEP_OPTIM"), hidden_fn=hidden_fn)
+                       allow_nest_stack=cfg["allow_nest_stack"], sep_optim=cls.endswith("SEP_OPTIM"), hidden_fn=hidden_fn,
+                       discrete=bool(c.get("discrete", False)))
     np.random.seed(cfg["np_seed_run"])
     return g, cfg, upd
 
 
 UPDATE_TAGS = ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru", "sac_ensembleq", "td3_ensembleq", "sac_ensembleq_sep", "sac_smamba_mid",
-               "td3_gilr_mid", "sac_conv1d", "sac_gru_clipnorm", "sac_smamba_clipval", "sac_gru_utd2", "sac_gru_rndhidden"]
+               "td3_gilr_mid", "sac_conv1d", "sac_gru_clipnorm", "sac_smamba_clipval", "sac_gru_utd2", "sac_gru_rndhidden", "sac_discrete"]
 
 
 @pytest.mark.parametrize("tag", UPDATE_TAGS)

@@ -33,6 +33,22 @@ ALG_NAMES = {"SACFullLengthRNNREDQ_SEP_OPTIM": "sac_rnn_full_horizon_redQ_sep_op
              "SACFullLengthRNNENSEMBLEQ_SEP_OPTIM": "sac_rnn_full_horizon_ensemble_q_sep_optim"}
 
 
+def fill_buffer_discrete(buf, Transition, rng, lens, S, A):
+    for Tn in lens:
+        last_s, last_a, last_r = np.zeros((1, S)), np.zeros((1, A)), np.zeros((1, 1))
+        s = rng.standard_normal((1, S))
+        for t in range(Tn):
+            ai = int(rng.randint(A))
+            ns = rng.standard_normal((1, S))
+            r = float(rng.standard_normal())
+            done = t == Tn - 1
+            buf.mem_push(Transition(state=s, last_state=last_s, last_action=last_a, action=np.array([[float(ai)]]), next_state=ns, reward=r,
+                                    logp=None, mask=1, done=done, timeout=done, start=(t == 0), reward_input=last_r))
+            last_a = np.zeros((1, A))
+            last_a[0, ai] = 1.0
+            last_s, last_r, s = s, np.array([[r]]), ns
+
+
 def build(tag):
     from rorl_b200.utility.alg_init import alg_class
     from rorl_b200.buffers.transition_buffer.replay_memory import Transition
@@ -43,11 +59,12 @@ def build(tag):
     assert cls.__name__ == cfg["cls"]
     pk = {k: v for k, v in cfg["policy_kwargs"].items() if k != "sample_std"}
     alg = cls(dict(hp, max_buffer_transition_num=1000), pk, cfg["value_kwargs"], c.get("max_len", max(c["lens"])),
-              device=torch.device("cuda:0"))
+              device=torch.device("cuda:0"), discrete_env=bool(c.get("discrete", False)))
     assert alg._get_skip_len() == cfg["skip"]
     assert alg.allow_nest_stack == cfg["allow_nest_stack"]
     alg.load_models(nested_sd(g, "init/policy/", "cuda"), nested_sd(g, "init/value/", "cuda"))
-    fill_buffer(alg.replay_buffer, Transition, np.random.RandomState(cfg["np_seed_fill"]), c["lens"], c["S"], c["A"])
+    (fill_buffer_discrete if c.get("discrete") else fill_buffer)(alg.replay_buffer, Transition, np.random.RandomState(cfg["np_seed_fill"]),
+                                                                c["lens"], c["S"], c["A"])
     noises = iter([T(g[f"noise/{i}"], "cuda") for i in range(cfg["n_noise"])])
 
     def noise_fn(like):
@@ -85,7 +102,7 @@ def module_params(model):
 
 
 UPDATE_TAGS = ["sac_smamba", "sac_gru", "td3_gilr", "td3_lru", "sac_ensembleq", "td3_ensembleq", "sac_ensembleq_sep", "sac_smamba_mid",
-               "td3_gilr_mid", "sac_conv1d", "sac_gru_clipnorm", "sac_smamba_clipval", "sac_gru_utd2", "sac_gru_rndhidden"]
+               "td3_gilr_mid", "sac_conv1d", "sac_gru_clipnorm", "sac_smamba_clipval", "sac_gru_utd2", "sac_gru_rndhidden", "sac_discrete"]
 
 
 @pytest.mark.parametrize("tag", UPDATE_TAGS)
