@@ -333,11 +333,15 @@ int rorl_traj_gather(const float* ring, int64_t F, const int64_t* plan, int64_t 
  * N % 4 == 0 and 16-byte aligned rows for the column sums; `work` holds rorl_*_work_floats() floats.
  * ---------------------------------------------------------------------------------------------- */
 int64_t rorl_colsum_work_floats(int64_t G, int64_t M, int64_t N);
+/* tickets: device int32[rorl_colsum_tickets()] zero-initialised ONCE by the caller (the kernels re-arm them): with it the
+ * per-CTA partial rows are folded by the last CTA to finish, in a fixed order (deterministic), in the SAME launch; NULL:
+ * a second tiny launch does the fold.  One ticket array must not be shared by launches that can run concurrently. */
+int rorl_colsum_tickets(void);
 int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, int64_t N, int64_t ldx, int64_t gsx,
-                cudaStream_t stream);
+                int32_t* tickets, cudaStream_t stream);
 int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
                         int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
-                        cudaStream_t stream);
+                        int32_t* tickets, cudaStream_t stream);
 /* y[m, n] = act(bias[n] + sum_k x[m, k] W[n, k]) for K <= 16, N % 4 == 0 (bias may be NULL; elu != 0: ELU): forward of
  * the same projections; ldy lets several of them write side by side into one [M, sum N] buffer (no concatenation). */
 int rorl_skinny_linear(const float* x, const float* W, const float* bias, float* y, int64_t M, int64_t N, int64_t K,

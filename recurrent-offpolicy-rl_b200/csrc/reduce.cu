@@ -19,14 +19,17 @@ namespace rorl {
 constexpr int kRedThreads = 256;
 constexpr int kRedMaxQuads = 256;      // column quads (float4) handled by one CTA in x
 constexpr int kRedMaxBlocks = 592;     // 4 x 148 row blocks
+constexpr int kRedTickets = 4096;      // ticket slots a caller provides for the single-launch form (one per column chunk x group)
 
 // grid: (row blocks, column chunks of 4 * kRedMaxQuads).  thread = (row lane, column quad).
 template <bool ELU>
 __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                              float* __restrict__ g, float* __restrict__ partial,
                                                              int64_t M, int64_t N, int64_t ldx, int64_t ldy, int64_t ldg,
-                                                             int64_t gsx, int64_t gsy, int64_t gsg, int rows_per_block) {
+                                                             int64_t gsx, int64_t gsy, int64_t gsg, int rows_per_block,
+                                                             float* __restrict__ out, int* __restrict__ tickets) {
     __shared__ float4 s_acc[kRedThreads];
+    __shared__ int s_last;
     x += (int64_t)blockIdx.z * gsx;                                        // group (ensemble member)
     if (ELU) { y += (int64_t)blockIdx.z * gsy; g += (int64_t)blockIdx.z * gsg; }
     partial += (int64_t)blockIdx.z * gridDim.x * N;
@@ -83,6 +86,35 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __rest
         }
         *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * N + (q0 + q) * 4) = acc;
     }
+    if (tickets == nullptr || gridDim.x == 1) return;
+    // Single-launch form: the LAST CTA of this (column chunk, group) to publish its partial row folds all rows, in a
+    // fixed order that does not depend on which CTA that is (deterministic), and re-arms the ticket.  (The separate
+    // second-stage launch this replaces cost ~5 us of launch latency for a few kilobytes, ~60 times per update.)
+    __threadfence();
+    __syncthreads();
+    int* ticket = tickets + blockIdx.z * gridDim.y + blockIdx.y;
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes) {
+        for (int bI = rl; bI < (int)gridDim.x; bI += lanes) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)bI * N + (q0 + q) * 4));
+            tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+        }
+    }
+    __syncthreads();
+    s_acc[threadIdx.x] = tot;
+    __syncthreads();
+    if (rl == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            const float4 v = s_acc[l * nq + q];
+            tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + (int64_t)blockIdx.z * N + (q0 + q) * 4) = tot;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 // out[n] = sum_b partial[b, n]: a CTA owns 32 column quads, 8 lanes split the nblk partial rows, shared-memory combine
@@ -234,13 +266,15 @@ static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) ==
 
 extern "C" {
 
+int rorl_colsum_tickets(void) { return kRedTickets; }
+
 int64_t rorl_colsum_work_floats(int64_t G, int64_t M, int64_t N) {
     int rpb;
     return G * (int64_t)red_blocks(M, &rpb) * N;
 }
 
 int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, int64_t N, int64_t ldx, int64_t gsx,
-                cudaStream_t stream) {
+                int32_t* tickets, cudaStream_t stream) {
     if (!x || !out || !work) return RORL_ERR_ARG;
     if (M <= 0 || N <= 0 || G <= 0 || G > 65535) return RORL_ERR_SHAPE;
     if (N % 4 || ldx % 4 || gsx % 4 || !a16(x) || !a16(out) || !a16(work)) return RORL_ERR_ALIGN;
@@ -249,8 +283,10 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
     if (chunks > 65535) return RORL_ERR_SHAPE;
     const int nblk = red_blocks(M, &rpb, G, chunks);
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
-    colsum_kernel<false><<<grid, kRedThreads, 0, stream>>>(x, nullptr, nullptr, nblk == 1 ? out : work, M, N, ldx, 0, 0, gsx, 0, 0, rpb);
-    if (nblk > 1) {
+    if (tickets && (int64_t)chunks * G > kRedTickets) tickets = nullptr;
+    colsum_kernel<false><<<grid, kRedThreads, 0, stream>>>(x, nullptr, nullptr, nblk == 1 ? out : work, M, N, ldx, 0, 0, gsx, 0, 0, rpb,
+                                                           out, tickets);
+    if (nblk > 1 && !tickets) {
         dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
     }
@@ -259,7 +295,7 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
 
 int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
                         int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
-                        cudaStream_t stream) {
+                        int32_t* tickets, cudaStream_t stream) {
     if (!dy || !y || !g || !out || !work) return RORL_ERR_ARG;
     if (M <= 0 || N <= 0 || G <= 0 || G > 65535) return RORL_ERR_SHAPE;
     if (N % 4 || ld_dy % 4 || ld_y % 4 || ld_g % 4 || gs_dy % 4 || gs_y % 4 || gs_g % 4 || !a16(dy) || !a16(y) || !a16(g) ||
@@ -270,8 +306,10 @@ int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, f
     if (chunks > 65535) return RORL_ERR_SHAPE;
     const int nblk = red_blocks(M, &rpb, G, chunks);
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
-    colsum_kernel<true><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb);
-    if (nblk > 1) {
+    if (tickets && (int64_t)chunks * G > kRedTickets) tickets = nullptr;
+    colsum_kernel<true><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb,
+                                                          out, tickets);
+    if (nblk > 1 && !tickets) {
         dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
     }

@@ -50,6 +50,20 @@ def _red_ok(t: torch.Tensor, n: int) -> bool:
     return t.is_cuda and t.dtype == torch.float32 and n % 4 == 0 and t.data_ptr() % 16 == 0
 
 
+_TICKETS = {}
+
+
+def _tickets(device) -> torch.Tensor:
+    """Persistent zero-initialised ticket slots for the single-launch reductions (the kernels re-arm them).  One array
+    per device: every reduction of the update runs on the one compute stream (forward, autograd backward and CUDA-graph
+    replays alike), so no two launches that share it can overlap."""
+    key = device.index
+    t = _TICKETS.get(key)
+    if t is None:
+        t = _TICKETS[key] = torch.zeros(int(N.lib().rorl_colsum_tickets()), dtype=torch.int32, device=device)
+    return t
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     """[M, N] -> [N] or [G, M, N] -> [G, N]: sum over the row axis (bias gradients)."""
     G = x.shape[0] if x.dim() == 3 else 1
@@ -58,7 +72,8 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
         return x.sum(-2)
     out = torch.empty((G, Nn) if x.dim() == 3 else (Nn,), device=x.device, dtype=torch.float32)
     work = torch.empty(int(N.lib().rorl_colsum_work_floats(G, M, Nn)), device=x.device, dtype=torch.float32)
-    N.call("rorl_colsum", N.ptr(x), N.ptr(out), N.ptr(work), G, M, Nn, x.stride(-2), x.stride(0) if x.dim() == 3 else 0, N.stream())
+    N.call("rorl_colsum", N.ptr(x), N.ptr(out), N.ptr(work), G, M, Nn, x.stride(-2), x.stride(0) if x.dim() == 3 else 0,
+           N.ptr(_tickets(x.device)), N.stream())
     return out
 
 
@@ -84,7 +99,7 @@ def elu_bwd_colsum(dy: torch.Tensor, y: torch.Tensor):
     out = torch.empty((G, Nn) if dy.dim() == 3 else (Nn,), device=dy.device, dtype=torch.float32)
     work = torch.empty(int(N.lib().rorl_colsum_work_floats(G, M, Nn)), device=dy.device, dtype=torch.float32)
     N.call("rorl_elu_bwd_colsum", N.ptr(dy), N.ptr(y), N.ptr(g), N.ptr(out), N.ptr(work), G, M, Nn, Nn, Nn, Nn, M * Nn, M * Nn,
-           M * Nn, N.stream())
+           M * Nn, N.ptr(_tickets(dy.device)), N.stream())
     return g, out
 
 
