@@ -494,8 +494,106 @@ def gen_updates(only=None):
         save(f"update_{tag}.npz", cfg=np.array(json.dumps(cfg)), **arrs)
 
 
+# ------------------------------------------------------------------------------------------------
+# full size (BASELINE.json config 2: 32 trajectories x 1000 steps, width 256) -- scalars only
+# ------------------------------------------------------------------------------------------------
+FULLSIZE_BIG = 16384          # parameters with at least this many elements are regenerated from their name (helpers.det_uniform)
+
+
+def gen_full_size(tags=None):
+    """The reference's own train_one_batch at the benchmark shape.  Inputs are reproducible without being stored: the
+    replay rows come from bench.synth_trajectory(RandomState(1000)), every large weight matrix is helpers.det_uniform(name)
+    scaled to the reference initialiser's range, the Gaussian draws are helpers.det_normal(i).  The fixture keeps the
+    small parameters, the per-parameter ranges, the returned log and one gradient norm per parameter."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import det_normal, det_uniform
+    import bench
+    install_algo_stubs()
+    from offpolicy_rnn.buffers.transition_buffer.replay_memory import Transition
+    cases = {"sac_smamba": dict(algo="sac", enc="smamba_s32_c16_b2_nln", n_traj=32, t_len=1000),
+             "td3_gilr": dict(algo="td3", enc="gilr", n_traj=32, t_len=1000)}
+    for tag, c in cases.items():
+        if tags and tag not in tags:
+            continue
+        torch.manual_seed(5)
+        np.random.seed(5)
+        S, Ad, n_traj, t_len = bench.S_DIM, bench.A_DIM, c["n_traj"], c["t_len"]
+        cls_name = "SACFullLengthRNNREDQ_SEP_OPTIM" if c["algo"] == "sac" else "TD3FullLengthRNNREDQ_SEP_OPTIM"
+        hp = dict(REF_HP, sac_batch_size=n_traj * t_len - 1, max_buffer_transition_num=n_traj * t_len + 8)
+        pk, vk = bench.model_kwargs(c["enc"], False), bench.model_kwargs(c["enc"], True)
+        A = build_algorithm(cls_name, hp, pk, vk, t_len, Ad, perturb=0.05)
+        hp, pk = vars(A.parameter), A.policy_args
+        arrs, bounds = {}, {}
+        with torch.no_grad():
+            for side, model in (("policy", A.policy), ("value", A.values[0])):
+                for mod, m in model.contextual_modules.items():
+                    for n, p in m.named_parameters():
+                        key = f"{side}/{mod}/{n}"
+                        if p.numel() >= FULLSIZE_BIG:
+                            bounds[key] = float(p.abs().max())
+                            p.copy_(torch.from_numpy(det_uniform(key, p.shape, bounds[key])))
+                        else:
+                            arrs["init/" + key] = p.detach().clone().numpy()
+        A._value_update(tau=0.0)
+        A.target_policy.copy_weight_from(A.policy, tau=0.0)
+        rng = np.random.RandomState(1000)
+        for _ in range(n_traj):
+            rows = bench.synth_trajectory(rng, t_len)
+            for t in range(t_len):
+                r = rows[t]
+                last = t == t_len - 1
+                A.replay_buffer.mem_push(Transition(
+                    state=r[None, 0:S], last_state=r[None, S:2 * S], last_action=r[None, 2 * S:2 * S + Ad],
+                    action=r[None, 2 * S + Ad:2 * S + 2 * Ad], next_state=r[None, 2 * S + 2 * Ad:3 * S + 2 * Ad],
+                    reward=float(r[3 * S + 2 * Ad]), logp=None, mask=1, done=last, timeout=last, start=(t == 0),
+                    reward_input=r[None, 3 * S + 2 * Ad + 4:3 * S + 2 * Ad + 5]))
+        draws = [0]
+        orig_randn_like = torch.randn_like
+
+        def det_randn_like(t, *a, **k):
+            out = torch.from_numpy(det_normal(draws[0], t.shape)).to(t.dtype)
+            draws[0] += 1
+            return out
+
+        np.random.seed(21)
+        torch.randn_like = det_randn_like
+        vnorm = {}
+        orig_step = A.optimizer_value.step
+
+        def step_and_snap(*a, **k):
+            for mod, m in A.values[0].contextual_modules.items():
+                for n, p in m.named_parameters():
+                    if p.grad is not None:
+                        vnorm[f"{mod}/{n}"] = float(p.grad.double().norm())
+            return orig_step(*a, **k)
+
+        A.optimizer_value.step = step_and_snap
+        try:
+            import time
+            t0 = time.time()
+            log = A.train_one_batch()
+            print(tag, "reference update took", round(time.time() - t0, 1), "s")
+        finally:
+            torch.randn_like = orig_randn_like
+            A.optimizer_value.step = orig_step
+        for k, v in log.items():
+            arrs[f"log/{k}"] = np.array(float(v[0] if isinstance(v, tuple) else v))
+        for k, v in vnorm.items():
+            arrs[f"vgnorm/{k}"] = np.array(v)
+        for mod, m in A.policy.contextual_modules.items():
+            for n, p in m.named_parameters():
+                if p.grad is not None:
+                    arrs[f"pgnorm/{mod}/{n}"] = np.array(float(p.grad.double().norm()))
+        arrs["log_alpha"] = A.log_sac_alpha.detach().clone().numpy()
+        cfg = dict(case=c, hp=hp, cls=cls_name, policy_kwargs=pk, value_kwargs=vk, bounds=bounds, n_draws=draws[0],
+                   np_seed_run=21, traj_seed=1000, S=S, A=Ad)
+        save(f"fullsize_{tag}.npz", cfg=np.array(json.dumps(cfg)), **arrs)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ops", "layers", "steps", "sampler", "updates"]
+    if "fullsize" in which or any(w.startswith("fullsize_") for w in which):
+        gen_full_size([w[len("fullsize_"):] for w in which if w.startswith("fullsize_")] or None)
     if "ops" in which:
         gen_ops()
     if "layers" in which:

@@ -47,3 +47,16 @@ def nested_sd(arrs, prefix, device="cpu", grad=False):
 
 def cfg_of(arrs):
     return json.loads(str(arrs["cfg"]))
+
+
+def det_uniform(name, shape, bound):
+    """Machine-independent stand-in for a large weight matrix: uniform(-bound, bound) from numpy's MT19937 seeded by the
+    parameter name.  Lets a full-size fixture (tests/golden/fullsize_*.npz) hold scalars only."""
+    import zlib
+    rng = np.random.RandomState(zlib.crc32(name.encode()))
+    return ((rng.random_sample(tuple(shape)) * 2.0 - 1.0) * bound).astype(np.float32)
+
+
+def det_normal(index, shape):
+    """The index-th Gaussian draw of a full-size fixture run (replaces torch.randn_like on both sides)."""
+    return np.random.RandomState(70000 + index).standard_normal(tuple(shape)).astype(np.float32)

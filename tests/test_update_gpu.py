@@ -179,6 +179,73 @@ def _run_update_matches_reference(tag, tol=TOL):
         print(f"{tag} call {call}: worst relative error {worst:.2e}")
 
 
+@pytest.mark.parametrize("tag", ["td3_gilr", "sac_smamba"])
+def test_update_full_size_matches_reference(tag):
+    """BASELINE.json config 2 at its real size -- 32 trajectories x 1000 steps, width 256, the benchmark's encoder -- against
+    the UNMODIFIED reference's train_one_batch run on CPU at the same size (tests/golden/fullsize_*.npz, written by
+    tests/golden/make_golden.py `fullsize`): every returned scalar and the gradient norm of every parameter to 1e-3.
+    The inputs are regenerated from seeds on both sides (helpers.det_uniform / det_normal, bench.synth_trajectory);
+    the fixture holds the small parameters and the results only."""
+    import os
+    import bench
+    from helpers import GOLDEN, det_normal, det_uniform
+    from rorl_b200.utility.alg_init import alg_class
+    if not os.path.exists(os.path.join(GOLDEN, f"fullsize_{tag}.npz")):
+        pytest.skip(f"fullsize_{tag}.npz not generated")
+    g = load_npz(f"fullsize_{tag}.npz")
+    cfg = cfg_of(g)
+    c, hp = cfg["case"], cfg["hp"]
+    cls = alg_class(ALG_NAMES[cfg["cls"]])
+    pk = {k: v for k, v in cfg["policy_kwargs"].items() if k != "sample_std"}
+    alg = cls(hp, pk, cfg["value_kwargs"], c["t_len"], device=torch.device("cuda:0"))
+    sds = {}
+    for side, model in (("policy", alg.policy), ("value", alg.values[0])):
+        sd = {}
+        for mod, m in model.contextual_modules.items():
+            for n, p in m.named_parameters():
+                key = f"{side}/{mod}/{n}"
+                val = det_uniform(key, p.shape, cfg["bounds"][key]) if key in cfg["bounds"] else g["init/" + key]
+                assert tuple(val.shape) == tuple(p.shape), key
+                sd.setdefault(mod, {})[n] = T(val, "cuda")
+        sds[side] = sd
+    alg.load_models(sds["policy"], sds["value"])
+    rng = np.random.RandomState(cfg["traj_seed"])
+    alg.replay_buffer._init_memory_buffer(bench.template_transition())
+    for _ in range(c["n_traj"]):
+        alg.replay_buffer.push_trajectory_array(bench.synth_trajectory(rng, c["t_len"]))
+    draws = [0]
+
+    def noise_fn(like):
+        out = T(det_normal(draws[0], like.shape), "cuda")
+        draws[0] += 1
+        return out
+
+    alg.policy.noise_fn = noise_fn
+    alg.target_policy.noise_fn = noise_fn
+    np.random.seed(cfg["np_seed_run"])
+    log = alg.train_one_batch()
+    assert draws[0] == cfg["n_draws"]
+    worst = 0.0
+    for k in ("critic_loss", "actor_loss", "alpha_loss", "log_prob", "log_alpha", "target_q_max", "clip_min", "clip_max",
+              "q1_l2_norm_square", "policy_l2_norm_square", "average_traj_len", "real_batch_traj_num", "real_batch_size"):
+        if f"log/{k}" in g:
+            ref = float(g[f"log/{k}"])
+            err = abs(float(log[k]) - ref) / max(1.0, abs(ref))
+            assert err <= TOL, (k, log[k], ref)
+            worst = max(worst, err)
+    for pre, model in (("vgnorm/", alg.values[0]), ("pgnorm/", alg.policy)):
+        params = module_params(model)
+        top = max(float(v) for k, v in g.items() if k.startswith(pre))
+        for k, v in g.items():
+            if k.startswith(pre):
+                mod, name = k[len(pre):].split("/", 1)
+                got = float(params[mod][name].grad.double().norm())
+                err = abs(got - float(v)) / max(float(v), 1e-3 * top)
+                assert err <= TOL, (k, got, float(v))
+                worst = max(worst, err)
+    print(f"fullsize {tag}: worst relative error {worst:.2e}")
+
+
 def test_sampler_device_bit_exact():
     """Device gather == reference sample_trajs bit for bit (after the fp32 cast n2t applies)."""
     from rorl_b200.buffers.transition_buffer.nested_replay_memory import NestedMemoryArray

@@ -41,3 +41,22 @@ for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{100 * t / tot:6.2f}% {t:9.1f} us {n:4d}  {k}")
 print()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=70, max_name_column_width=40, max_shapes_column_width=60))
+
+# who launches the non-rorl kernels: innermost CPU op -> chain of its parents (up to 4), with input shapes
+chains = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    ks = [k for k in getattr(e, "kernels", []) if not k.name.startswith("void rorl::") and not k.name.startswith("rorl::")]
+    if not ks or str(e.device_type).endswith("CUDA"):
+        continue
+    if any(getattr(c, "kernels", []) for c in (e.cpu_children or [])):
+        continue                                   # not the innermost launcher
+    chain, p = [e.name], e.cpu_parent
+    while p is not None and len(chain) < 4:
+        chain.append(p.name)
+        p = p.cpu_parent
+    key = " <- ".join(chain) + "  " + str(e.input_shapes)[:70]
+    chains[key][0] += len(ks)
+    chains[key][1] += sum(k.duration for k in ks)
+print("\nnon-rorl launches by launching op:")
+for k, (n, t) in sorted(chains.items(), key=lambda kv: -kv[1][1])[:70]:
+    print(f"{t:8.1f} us {n:4d}  {k}")
