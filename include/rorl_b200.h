@@ -223,11 +223,13 @@ int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t 
  * K, N, ld*, stride* multiples of 4 (passes == 2: K a multiple of 8); bases 16-byte aligned.
  * work: device scratch of rorl_gemm_tn_work_bytes(...) bytes, 16-byte aligned (passes == 2: the kernel pre-splits
  * the B operand -- the weights, re-read by every row tile -- into bf16 hi / lo copies there); NULL otherwise.
+ * transb != 0 (passes == 2 only): B is stored [K, N] with row stride ldb -- nn.Linear's weight as its input-gradient
+ * GEMM needs it, EnsembleLinear's [E, in, out] weight as its forward needs it -- and the pre-split transposes it.
  * ---------------------------------------------------------------------------------------------- */
 int64_t rorl_gemm_tn_work_bytes(int64_t N, int64_t K, int64_t G, int64_t strideB, int passes);
 int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
-                 int64_t strideBias, int act, int passes, int reduce_g, void* work, cudaStream_t stream);
+                 int64_t strideBias, int act, int passes, int reduce_g, int transb, void* work, cudaStream_t stream);
 /* Weight-gradient form: D[s][g][M, N] = sum over the s-th slice of rows r of A[g][r, M]^T B[g][r, N] (both operands
  * row-major with the REDUCTION over rows, i.e. MN-major for the tensor core; no transposed copies).  Split-K over
  * the R rows: splits = rorl_gemm_nt_splits(M, N, R, G); partial s lands at D + s * strideSplit and the caller sums
@@ -343,12 +345,17 @@ int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, f
                         int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
                         int32_t* tickets, cudaStream_t stream);
 /* y[m, n] = act(bias[n] + sum_k x[m, k] W[n, k]) for K <= 16, N % 4 == 0 (bias may be NULL; elu != 0: ELU): forward of
- * the same projections; ldy lets several of them write side by side into one [M, sum N] buffer (no concatenation). */
+ * the same projections; ldy lets several of them write side by side into one [M, sum N] buffer (no concatenation).
+ * Row m of x is read at x + (m / seg_rows) * seg_stride + (m % seg_rows) * ldx, so that a [B, L, K] slice of the
+ * sampled batch tensor (ref: the column / time slices of sac_full_length_rnn_ensembleQ.py:318-343) is used in place;
+ * seg_rows = M, seg_stride = 0 for a plain [M, K] operand.  rorl_skinny_wgrad addresses x the same way.
+ * rorl_skinny_dgrad: dx[m, k] = sum_n g[m, n] W[n, k] (dx contiguous [M, K]; N <= 1024). */
 int rorl_skinny_linear(const float* x, const float* W, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                       int64_t ldx, int64_t ldy, int elu, cudaStream_t stream);
+                       int64_t ldx, int64_t seg_rows, int64_t seg_stride, int64_t ldy, int elu, cudaStream_t stream);
 int64_t rorl_skinny_wgrad_work_floats(int64_t M, int64_t N, int64_t K);
 int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, int64_t M, int64_t N, int64_t K,
-                      int64_t ldg, int64_t ldx, cudaStream_t stream);
+                      int64_t ldg, int64_t ldx, int64_t seg_rows, int64_t seg_stride, cudaStream_t stream);
+int rorl_skinny_dgrad(const float* g, const float* W, float* dx, int64_t M, int64_t N, int64_t K, int64_t ldg, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

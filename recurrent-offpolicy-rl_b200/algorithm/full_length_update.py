@@ -98,11 +98,35 @@ class FlatArena:
                 return off
         raise KeyError
 
-    def zero_grad(self):
+    def _views(self):
+        if getattr(self, '_view_cache', None) is None:
+            self._view_cache = [self.grad[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets)]
+        return self._view_cache
+
+    def zero_grad(self, detach: bool = False):
+        """detach=False: `.grad` stays the arena view and autograd accumulates into it (one add_ launch per parameter; what
+        the bucketed data-parallel hooks need).  detach=True: `.grad` is dropped so that autograd keeps each produced
+        gradient by reference, and `collect()` moves them all into the arena with one multi-tensor copy."""
         self.grad_full.zero_()
-        for p, off in zip(self.params, self.offsets):     # autograd may have swapped .grad out; put the view back
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
-                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+        if detach:
+            for p in self.params:
+                p.grad = None
+            return
+        for p, v in zip(self.params, self._views()):      # autograd may have swapped .grad out; put the view back
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def collect(self):
+        """After a backward run with zero_grad(detach=True): gather the gradients into the (zeroed) arena, re-point `.grad`."""
+        srcs, dsts = [], []
+        for p, v in zip(self.params, self._views()):
+            g = p.grad
+            if g is not None and g.data_ptr() != v.data_ptr():
+                srcs.append(g if g.shape == v.shape else g.reshape(v.shape))
+                dsts.append(v)
+            p.grad = v
+        if srcs:
+            torch._foreach_copy_(dsts, srcs)
 
 
 class FusedAdamW:
@@ -160,8 +184,8 @@ class FusedAdamW:
             return True
         return False
 
-    def zero_grad(self):
-        self.arena.zero_grad()
+    def zero_grad(self, detach: bool = False):
+        self.arena.zero_grad(detach)
 
     def step(self, tau: Optional[float] = None):
         tgt = self.target.flat if (self.target is not None and tau is not None) else None
@@ -655,12 +679,14 @@ class FullLengthRNNUpdate:
         qc, tq_c, mask_c = q.contiguous(), c['target_Q'].contiguous(), batch.mask.contiguous()
         N.call("rorl_q_loss_fwd_bwd", N.ptr(qc), N.ptr(tq_c), N.ptr(mask_c), N.ptr(n_valid),
                N.ptr(self._stats[2:3]), N.ptr(dq), N.ptr(self._work), E, M, N.stream())
-        self.optimizer_value.zero_grad()
+        self.optimizer_value.zero_grad(detach=not overlap)
         if overlap:
             self._sync_value.begin()
         qc.backward(dq.view_as(qc))
         if overlap:
             self._sync_value.finish()
+        else:
+            self.value_arena.collect()
         c['mask_c'] = mask_c
 
     def _stage_value_step_and_actor(self, c, overlap):
@@ -701,7 +727,7 @@ class FullLengthRNNUpdate:
         N.call("rorl_actor_loss_fwd_bwd", N.ptr(qpc), N.ptr(logp_c), N.ptr(mask_c), N.ptr(n_valid),
                N.ptr(self.log_sac_alpha.data), float(self.target_entropy), 1 if self.use_redq else 0,
                N.ptr(self._stats[4:8]), N.ptr(dqp), N.ptr(dlogp), N.ptr(self._work), E, M, N.stream())
-        self.optimizer_policy.zero_grad()
+        self.optimizer_policy.zero_grad(detach=not overlap)
         if overlap:
             self._sync_policy.begin()
         if td3:
@@ -710,6 +736,8 @@ class FullLengthRNNUpdate:
             torch.autograd.backward([qpc, logp_c], [dqp.view_as(qpc), dlogp.view_as(logp_c)])
         if overlap:
             self._sync_policy.finish()
+        else:
+            self.policy_arena.collect()
         if not p.no_alpha_auto_tune:
             self.alpha_arena.grad.copy_(self._stats[7:8])
             if overlap:
@@ -735,12 +763,14 @@ class FullLengthRNNUpdate:
         probs = logp.exp()
         per_step = ((alpha * logp - agg) * probs).sum(dim=-1, keepdim=True)
         actor_loss = (per_step * batch.mask).sum() / n_valid
-        self.optimizer_policy.zero_grad()
+        self.optimizer_policy.zero_grad(detach=not overlap)
         if overlap:
             self._sync_policy.begin()
         actor_loss.backward()
         if overlap:
             self._sync_policy.finish()
+        else:
+            self.policy_arena.collect()
         with torch.no_grad():
             self._stats[4:5].copy_(actor_loss.detach().reshape(1))
             self._stats[5:6].copy_((((logp * probs).sum(dim=-1, keepdim=True) * batch.mask).sum() / n_valid).reshape(1))

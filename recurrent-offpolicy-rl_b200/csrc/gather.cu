@@ -81,6 +81,6 @@ int rorl_traj_gather(const float* ring, int64_t F, const int64_t* plan, int64_t 
     RORL_RETURN_LAUNCH();
 }
 
-int rorl_abi_version(void) { return 4; }   // 4: rorl_gemm_tn takes a workspace (bf16-split form), gradient clipping in rorl_adamw_polyak
+int rorl_abi_version(void) { return 5; }   // 5: rorl_gemm_tn transb, segmented addressing in the skinny projections, rorl_skinny_dgrad
 
 }  // extern "C"

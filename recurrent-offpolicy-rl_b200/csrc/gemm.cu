@@ -354,7 +354,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 // gemm_bf16.cu: the two-term bf16 split ("bf16x3", passes == 2)
 int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                    int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
-                   int64_t strideBias, int act, int reduce_g, int force_bn, void* bsplit, cudaStream_t stream);
+                   int64_t strideBias, int act, int reduce_g, int transb, int force_bn, void* bsplit, cudaStream_t stream);
 
 int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda, int64_t ldb,
                    int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits, int64_t strideSplit,
@@ -391,8 +391,9 @@ extern "C" {
 // 3xTF32, 1 = single TF32.  Requirements: K % 4 == 0, N % 4 == 0, lda/ldb/ldd % 4 == 0, 16-byte aligned bases.
 int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
-                 int64_t strideBias, int act, int passes, int reduce_g, void* work, cudaStream_t stream) {
+                 int64_t strideBias, int act, int passes, int reduce_g, int transb, void* work, cudaStream_t stream) {
     if (!A || !B || !D) return RORL_ERR_ARG;
+    if (transb && passes != 2) return RORL_ERR_ARG;              // only the pre-splitting form re-lays B out
     if (M <= 0 || N <= 0 || K <= 0 || G <= 0) return RORL_ERR_SHAPE;
     if (K % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideBias % 4)
         return RORL_ERR_ALIGN;
@@ -403,7 +404,7 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     if (reduce_g && (!strideA || !strideB)) return RORL_ERR_ARG;
     if (passes == 2)
         return gemm_tn_bf16x3(A, B, bias, D, Dpre, M, N, K, G, lda, ldb, ldd, strideA, strideB, strideD, strideBias, act, reduce_g,
-                              g_gemm_bn, work, stream);
+                              transb, g_gemm_bn, work, stream);
     CUtensorMap mapA, mapB;
     const bool wide = N > kGemmBN && g_gemm_bn != 128;            // N > 128: 128 x 256 tiles (see GemmCfg)
     const int bn = wide ? 256 : kGemmBN;

@@ -372,6 +372,30 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     }
 }
 
+// the same from the TRANSPOSED source: fp32 [G][K rows, N cols] (row stride ld) -> bf16 hi / lo [G][N, K].  nn.Linear's
+// input-gradient GEMM multiplies by W, not W^T; the K-major copy the MMA wants is made here instead of by an ATen transposition.
+__global__ void __launch_bounds__(256) split_bf16_t_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo, int N, int K, long long ld, long long gs) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    w += (long long)blockIdx.z * gs;
+    const long long obase = (long long)blockIdx.z * N * K;
+    for (int j = ty; j < 32; j += 8) {
+        const int k = k0 + j, n = n0 + tx;
+        tile[j][tx] = (k < K && n < N) ? __ldg(w + (long long)k * ld + n) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int n = n0 + j, k = k0 + tx;
+        if (n < N && k < K) {
+            const float x = tile[tx][j];
+            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+            hi[obase + (long long)n * K + k] = h;
+            lo[obase + (long long)n * K + k] = __float2bfloat16_rn(x - __bfloat162float(h));
+        }
+    }
+}
+
 // 3-D map over a contiguous bf16 [batch][rows][cols] tensor: box = 32 cols (64 B) x box_rows x 1, SWIZZLE_64B
 static int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long batch, int box_rows) {
     EncodeTiledFn enc = get_encode();
@@ -387,16 +411,20 @@ static int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long
 }
 
 // Called from rorl_gemm_tn_ws (gemm.cu) for passes == 2; arguments already validated there.  `bsplit`: 2 * GB * N * K
-// bf16 (GB = G if B is batched, else 1) of caller-provided scratch, filled here with B's hi | lo halves.
+// bf16 (GB = G if B is batched, else 1) of caller-provided scratch, filled here with B's hi | lo halves.  transb: B is
+// stored [K, N] (row stride ldb) and is transposed by the splitting pass.
 int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                    int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
-                   int64_t strideBias, int act, int reduce_g, int force_bn, void* bsplit, cudaStream_t stream) {
+                   int64_t strideBias, int act, int reduce_g, int transb, int force_bn, void* bsplit, cudaStream_t stream) {
     if (!bsplit || (reinterpret_cast<uintptr_t>(bsplit) & 15)) return RORL_ERR_WORKSPACE;
     if (K % 8) return RORL_ERR_ALIGN;                            // bf16 rows must be 16-byte multiples for the tensor map
     const int64_t GB = strideB ? G : 1;
     __nv_bfloat16* bhi = reinterpret_cast<__nv_bfloat16*>(bsplit);
     __nv_bfloat16* blo = bhi + GB * N * K;
-    {
+    if (transb) {
+        dim3 grid((unsigned)((N + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)GB);
+        split_bf16_t_kernel<<<grid, 256, 0, stream>>>(B, bhi, blo, (int)N, (int)K, ldb, strideB);
+    } else {
         const long long total4 = (long long)GB * N * K / 4;
         long long nb = (total4 + 255) / 256;
         if (nb > 148 * 4) nb = 148 * 4;

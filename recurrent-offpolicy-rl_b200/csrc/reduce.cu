@@ -27,14 +27,14 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __rest
                                                              float* __restrict__ g, float* __restrict__ partial,
                                                              int64_t M, int64_t N, int64_t ldx, int64_t ldy, int64_t ldg,
                                                              int64_t gsx, int64_t gsy, int64_t gsg, int rows_per_block,
-                                                             float* __restrict__ out, int* __restrict__ tickets) {
+                                                             float* __restrict__ out, int* __restrict__ tickets, int chunk_quads) {
     __shared__ float4 s_acc[kRedThreads];
     __shared__ int s_last;
     x += (int64_t)blockIdx.z * gsx;                                        // group (ensemble member)
     if (ELU) { y += (int64_t)blockIdx.z * gsy; g += (int64_t)blockIdx.z * gsg; }
     partial += (int64_t)blockIdx.z * gridDim.x * N;
-    const int64_t q0 = (int64_t)blockIdx.y * kRedMaxQuads;
-    const int nq = (int)min((int64_t)kRedMaxQuads, N / 4 - q0);          // quads in this chunk
+    const int64_t q0 = (int64_t)blockIdx.y * chunk_quads;
+    const int nq = (int)min((int64_t)chunk_quads, N / 4 - q0);           // quads in this chunk
     const int lanes = kRedThreads / nq;                                    // row lanes (>= 1)
     const int q = threadIdx.x % nq, rl = threadIdx.x / nq;
     const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
@@ -49,23 +49,24 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __rest
             v.w *= o.w > 0.f ? 1.f : o.w + 1.f;
         };
         int64_t m = m0 + rl;
-        // four rows per iteration: all loads are issued before the first use (memory-level parallelism; a one-row
-        // loop left each thread with a single 16-byte load in flight and ran at a quarter of the HBM rate)
-        for (; m + 3 * (int64_t)lanes < m1; m += 4 * (int64_t)lanes) {
-            float4 v[4], o[4];
+        // U rows per iteration: all loads are issued before the first use (memory-level parallelism; a one-row loop left
+        // each thread with a single 16-byte load in flight and ran at a quarter of the HBM rate)
+        constexpr int U = ELU ? 4 : 8;
+        for (; m + (U - 1) * (int64_t)lanes < m1; m += U * (int64_t)lanes) {
+            float4 v[U], o[ELU ? U : 1];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(x + (m + u * lanes) * ldx + col));
+            for (int u = 0; u < U; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(x + (m + u * lanes) * ldx + col));
             if (ELU) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) o[u] = __ldcs(reinterpret_cast<const float4*>(y + (m + u * lanes) * ldy + col));
+                for (int u = 0; u < U; ++u) o[u] = __ldcs(reinterpret_cast<const float4*>(y + (m + u * lanes) * ldy + col));
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     elu_grad(v[u], o[u]);
                     *reinterpret_cast<float4*>(g + (m + u * lanes) * ldg + col) = v[u];
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            for (int u = 0; u < U; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
         }
         for (; m < m1; m += lanes) {
             float4 v = __ldcs(reinterpret_cast<const float4*>(x + m * ldx + col));
@@ -99,8 +100,17 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __rest
     __threadfence();
     float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
     if (rl < lanes) {
-        for (int bI = rl; bI < (int)gridDim.x; bI += lanes) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)bI * N + (q0 + q) * 4));
+        const float* pp = partial + (q0 + q) * 4;
+        int bI = rl;
+        for (; bI + 7 * lanes < (int)gridDim.x; bI += 8 * lanes) {          // 8 partial rows in flight: this is the latency tail
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(pp + (int64_t)(bI + u * lanes) * N));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { tot.x += v[u].x; tot.y += v[u].y; tot.z += v[u].z; tot.w += v[u].w; }
+        }
+        for (; bI < (int)gridDim.x; bI += lanes) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(pp + (int64_t)bI * N));
             tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
         }
     }
@@ -152,7 +162,8 @@ constexpr int kSkinnyRows = 64;
 template <int KP>        // K padded to a multiple of 4, <= 16
 __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ x,
                                                                    float* __restrict__ partial, int64_t M, int64_t N, int K,
-                                                                   int64_t ldg, int64_t ldx, int rows_per_block) {
+                                                                   int64_t ldg, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                                                                   int rows_per_block) {
     __shared__ __align__(16) float s_x[kSkinnyRows * KP];
     const int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
@@ -165,7 +176,8 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
         __syncthreads();
         for (int i = threadIdx.x; i < kSkinnyRows * KP; i += blockDim.x) {
             const int r = i / KP, k = i % KP;
-            s_x[i] = (r < rows && k < K) ? __ldg(x + (mb + r) * ldx + k) : 0.f;
+            const int64_t m = mb + r;
+            s_x[i] = (r < rows && k < K) ? __ldg(x + (m / seg_rows) * seg_stride + (m % seg_rows) * ldx + k) : 0.f;
         }
         __syncthreads();
         if (n < N) {
@@ -197,14 +209,20 @@ __global__ void __launch_bounds__(kRedThreads) skinny_wgrad_kernel(const float* 
 
 // y[m, n] = bias[n] + sum_k x[m, k] W[n, k], K <= 16: the forward of the narrow-input projections.  thread = 4 output
 // columns with their W rows in registers; x rows are staged in shared memory and read back as broadcasts; the only
-// real traffic is the coalesced float4 store of y (HBM-bound on the output).
+// real traffic is the coalesced float4 store of y (HBM-bound on the output).  128-thread CTAs: `ct` threads across the
+// columns (N / 4 rounded up to a warp) times 128 / ct row lanes that take alternate rows of the staged block, so that a
+// 128-wide output still runs four warps per CTA (one-warp CTAs left the SMs at 3 warps each: 16 us for 16.7 MB).
+// Row m of x is at x + (m / seg_rows) * seg_stride + (m % seg_rows) * ldx: a [B, L, K] slice of a wider / longer
+// batch tensor is read in place (no contiguous copy).
 template <int KP>
 __global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                             const float* __restrict__ bias, float* __restrict__ y, int64_t M,
-                                                            int64_t N, int K, int64_t ldx, int64_t ldy, int rows_per_block, int elu) {
+                                                            int64_t N, int K, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                                                            int64_t ldy, int rows_per_block, int elu, int ct) {
     __shared__ __align__(16) float s_x[kSkinnyRows * KP];
-    const int64_t n0 = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 4;
-    const bool act = n0 < N;
+    const int cx = threadIdx.x % ct, rl = threadIdx.x / ct, RL = 128 / ct;
+    const int64_t n0 = ((int64_t)blockIdx.y * ct + cx) * 4;
+    const bool act = n0 < N && rl < RL;
     float w[4][KP], b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -217,14 +235,15 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restr
     for (int64_t mb = m0; mb < m1; mb += kSkinnyRows) {
         const int rows = (int)min((int64_t)kSkinnyRows, m1 - mb);
         __syncthreads();
-        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += blockDim.x) {
+        for (int i = threadIdx.x; i < kSkinnyRows * KP; i += 128) {
             const int r = i / KP, k = i % KP;
-            s_x[i] = (r < rows && k < K) ? __ldg(x + (mb + r) * ldx + k) : 0.f;
+            const int64_t m = mb + r;
+            s_x[i] = (r < rows && k < K) ? __ldg(x + (m / seg_rows) * seg_stride + (m % seg_rows) * ldx + k) : 0.f;
         }
         __syncthreads();
         if (act) {
 #pragma unroll 2
-            for (int r = 0; r < rows; ++r) {
+            for (int r = rl; r < rows; r += RL) {
                 float o[4] = {b4[0], b4[1], b4[2], b4[3]};
 #pragma unroll
                 for (int k4 = 0; k4 < KP; k4 += 4) {
@@ -247,6 +266,41 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(const float* __restr
     }
 }
 
+// dx[m, k] = sum_n g[m, n] W[n, k], K <= 16: the data gradient of the same projections (the actor's path into the
+// critic's action encoder).  One warp per row: lane l takes columns l, l + 32, ... of g (coalesced) against W staged
+// in shared memory, K-wide partials combined by shuffles, lanes 0..K-1 store.
+template <int KP>
+__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ W,
+                                                           float* __restrict__ dx, int64_t M, int N, int K, int64_t ldg) {
+    extern __shared__ float s_w[];                         // [N][KP]
+    for (int i = threadIdx.x; i < N * KP; i += 256) {
+        const int n = i / KP, k = i % KP;
+        s_w[i] = k < K ? __ldg(W + (int64_t)n * K + k) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarp = (int64_t)gridDim.x * 8;
+    for (int64_t m = warp; m < M; m += nwarp) {
+        float acc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+        for (int n = lane; n < N; n += 32) {
+            const float gv = __ldg(g + m * ldg + n);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[k] = fmaf(gv, s_w[n * KP + k], acc[k]);
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            float v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == k) mine = v;
+        }
+        if (lane < K) dx[m * K + lane] = mine;
+    }
+}
+
 static inline int red_blocks(int64_t M, int* rows_per_block, int64_t G = 1, int64_t chunks = 1) {
     int nblk = (int)((M + 63) / 64);                     // at least 64 rows per block
     int cap = (int)(kRedMaxBlocks / (G * chunks));       // about 4 CTAs per SM over the whole grid
@@ -256,6 +310,28 @@ static inline int red_blocks(int64_t M, int* rows_per_block, int64_t G = 1, int6
     const int rpb = (int)((M + nblk - 1) / nblk);
     *rows_per_block = rpb;
     return (int)((M + rpb - 1) / rpb);
+}
+
+// Grid of the column sums.  Single-launch (ticket) form: 128-column chunks and about two CTAs per SM over the whole
+// grid -- the last CTA's fold over the row blocks is a latency chain (row blocks / row lanes dependent-free loads), so
+// few, long row blocks and many row lanes (256 / 32 quads = 8) keep it to a few microseconds.  Two-launch form: wide
+// chunks, about four CTAs per SM.
+static inline void colsum_geometry(int64_t G, int64_t M, int64_t N, bool tickets, int* chunk_quads, int* chunks, int* nblk, int* rpb,
+                                   int target = 296) {
+    const int64_t quads = N / 4;
+    *chunk_quads = (tickets && quads > 32) ? 32 : (int)(quads < kRedMaxQuads ? (quads > 0 ? quads : 1) : kRedMaxQuads);
+    *chunks = (int)((quads + *chunk_quads - 1) / *chunk_quads);
+    if (tickets) {
+        int nb = (int)((M + 63) / 64);
+        int cap = (int)(target / (G * *chunks));
+        if (cap < 1) cap = 1;
+        if (nb > cap) nb = cap;
+        const int r = (int)((M + nb - 1) / nb);
+        *rpb = r;
+        *nblk = (int)((M + r - 1) / r);
+    } else {
+        *nblk = red_blocks(M, rpb, G, *chunks);
+    }
 }
 
 }  // namespace rorl
@@ -278,14 +354,16 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
     if (!x || !out || !work) return RORL_ERR_ARG;
     if (M <= 0 || N <= 0 || G <= 0 || G > 65535) return RORL_ERR_SHAPE;
     if (N % 4 || ldx % 4 || gsx % 4 || !a16(x) || !a16(out) || !a16(work)) return RORL_ERR_ALIGN;
-    int rpb;
-    const int chunks = (int)((N / 4 + kRedMaxQuads - 1) / kRedMaxQuads);
+    int rpb, cq, chunks, nblk;
+    colsum_geometry(G, M, N, tickets != nullptr, &cq, &chunks, &nblk, &rpb);
+    if (tickets && (int64_t)chunks * G > kRedTickets) {
+        tickets = nullptr;
+        colsum_geometry(G, M, N, false, &cq, &chunks, &nblk, &rpb);
+    }
     if (chunks > 65535) return RORL_ERR_SHAPE;
-    const int nblk = red_blocks(M, &rpb, G, chunks);
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
-    if (tickets && (int64_t)chunks * G > kRedTickets) tickets = nullptr;
     colsum_kernel<false><<<grid, kRedThreads, 0, stream>>>(x, nullptr, nullptr, nblk == 1 ? out : work, M, N, ldx, 0, 0, gsx, 0, 0, rpb,
-                                                           out, tickets);
+                                                           out, tickets, cq);
     if (nblk > 1 && !tickets) {
         dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
@@ -301,14 +379,16 @@ int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, f
     if (N % 4 || ld_dy % 4 || ld_y % 4 || ld_g % 4 || gs_dy % 4 || gs_y % 4 || gs_g % 4 || !a16(dy) || !a16(y) || !a16(g) ||
         !a16(out) || !a16(work))
         return RORL_ERR_ALIGN;
-    int rpb;
-    const int chunks = (int)((N / 4 + kRedMaxQuads - 1) / kRedMaxQuads);
+    int rpb, cq, chunks, nblk;
+    colsum_geometry(G, M, N, tickets != nullptr, &cq, &chunks, &nblk, &rpb, 592);   // three streams per element: bandwidth, not the fold
+    if (tickets && (int64_t)chunks * G > kRedTickets) {
+        tickets = nullptr;
+        colsum_geometry(G, M, N, false, &cq, &chunks, &nblk, &rpb);
+    }
     if (chunks > 65535) return RORL_ERR_SHAPE;
-    const int nblk = red_blocks(M, &rpb, G, chunks);
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
-    if (tickets && (int64_t)chunks * G > kRedTickets) tickets = nullptr;
     colsum_kernel<true><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb,
-                                                          out, tickets);
+                                                          out, tickets, cq);
     if (nblk > 1 && !tickets) {
         dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
@@ -323,9 +403,9 @@ int64_t rorl_skinny_wgrad_work_floats(int64_t M, int64_t N, int64_t K) {
 }
 
 int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, int64_t M, int64_t N, int64_t K,
-                      int64_t ldg, int64_t ldx, cudaStream_t stream) {
+                      int64_t ldg, int64_t ldx, int64_t seg_rows, int64_t seg_stride, cudaStream_t stream) {
     if (!g || !x || !dW || !work) return RORL_ERR_ARG;
-    if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
+    if (M <= 0 || N <= 0 || K <= 0 || K > 16 || seg_rows <= 0) return RORL_ERR_SHAPE;
     if (!a16(work) || !a16(dW)) return RORL_ERR_ALIGN;
     int rpb;
     int threads = (int)((N + 31) / 32 * 32);                // one thread per output column
@@ -336,10 +416,10 @@ int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, in
     dim3 grid((unsigned)nblk, (unsigned)chunks);
     float* dst = nblk == 1 ? dW : work;
     switch (KP) {
-        case 4: skinny_wgrad_kernel<4><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
-        case 8: skinny_wgrad_kernel<8><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
-        case 12: skinny_wgrad_kernel<12><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
-        default: skinny_wgrad_kernel<16><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, rpb); break;
+        case 4: skinny_wgrad_kernel<4><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, seg_rows, seg_stride, rpb); break;
+        case 8: skinny_wgrad_kernel<8><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, seg_rows, seg_stride, rpb); break;
+        case 12: skinny_wgrad_kernel<12><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, seg_rows, seg_stride, rpb); break;
+        default: skinny_wgrad_kernel<16><<<grid, threads, 0, stream>>>(g, x, dst, M, N, (int)K, ldg, ldx, seg_rows, seg_stride, rpb); break;
     }
     if (nblk > 1) {
         dim3 g2((unsigned)((N * KP / 4 + 31) / 32), 1u);
@@ -349,29 +429,42 @@ int rorl_skinny_wgrad(const float* g, const float* x, float* dW, float* work, in
 }
 
 int rorl_skinny_linear(const float* x, const float* W, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                       int64_t ldx, int64_t ldy, int elu, cudaStream_t stream) {
+                       int64_t ldx, int64_t seg_rows, int64_t seg_stride, int64_t ldy, int elu, cudaStream_t stream) {
     if (!x || !W || !y) return RORL_ERR_ARG;
-    if (M <= 0 || N <= 0 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
+    if (M <= 0 || N <= 0 || K <= 0 || K > 16 || seg_rows <= 0) return RORL_ERR_SHAPE;
     if (N % 4 || ldy % 4 || !a16(y)) return RORL_ERR_ALIGN;
-    // one thread per 4 output columns: narrow outputs (N = 128) get 32-thread CTAs instead of 128-thread CTAs that
-    // are three quarters idle, and proportionally more of them (more row blocks)
-    int threads = (int)((N / 4 + 31) / 32 * 32);
-    if (threads > 128) threads = 128;
-    const int chunks = (int)((N / 4 + threads - 1) / threads);
-    int rpb;
+    int ct = (int)((N / 4 + 31) / 32 * 32);                 // threads across the columns; 128 / ct row lanes (see the kernel)
+    if (ct > 128) ct = 128;
+    const int chunks = (int)((N / 4 + ct - 1) / ct);
     int nblk = (int)((M + kSkinnyRows - 1) / kSkinnyRows);
-    const int cap = 148 * 8 * (128 / threads) / (chunks > 0 ? chunks : 1);
+    const int cap = 148 * 8 / (chunks > 0 ? chunks : 1);
     if (nblk > cap) nblk = cap > 0 ? cap : 1;
-    rpb = (int)((M + nblk - 1) / nblk);
+    int rpb = (int)((M + nblk - 1) / nblk);
     rpb = (rpb + kSkinnyRows - 1) / kSkinnyRows * kSkinnyRows;
     nblk = (int)((M + rpb - 1) / rpb);
     const int KP = (int)((K + 3) / 4 * 4);
     dim3 grid((unsigned)nblk, (unsigned)chunks);
     switch (KP) {
-        case 4: skinny_linear_kernel<4><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
-        case 8: skinny_linear_kernel<8><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
-        case 12: skinny_linear_kernel<12><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
-        default: skinny_linear_kernel<16><<<grid, threads, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, ldy, rpb, elu); break;
+        case 4: skinny_linear_kernel<4><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, seg_rows, seg_stride, ldy, rpb, elu, ct); break;
+        case 8: skinny_linear_kernel<8><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, seg_rows, seg_stride, ldy, rpb, elu, ct); break;
+        case 12: skinny_linear_kernel<12><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, seg_rows, seg_stride, ldy, rpb, elu, ct); break;
+        default: skinny_linear_kernel<16><<<grid, 128, 0, stream>>>(x, W, bias, y, M, N, (int)K, ldx, seg_rows, seg_stride, ldy, rpb, elu, ct); break;
+    }
+    RORL_RETURN_LAUNCH();
+}
+
+int rorl_skinny_dgrad(const float* g, const float* W, float* dx, int64_t M, int64_t N, int64_t K, int64_t ldg, cudaStream_t stream) {
+    if (!g || !W || !dx) return RORL_ERR_ARG;
+    if (M <= 0 || N <= 0 || N > 1024 || K <= 0 || K > 16) return RORL_ERR_SHAPE;
+    const int KP = (int)((K + 3) / 4 * 4);
+    int64_t nb = (M + 7) / 8;
+    if (nb > 148 * 8) nb = 148 * 8;
+    const size_t smem = (size_t)N * KP * sizeof(float);
+    switch (KP) {
+        case 4: skinny_dgrad_kernel<4><<<(unsigned)nb, 256, smem, stream>>>(g, W, dx, M, (int)N, (int)K, ldg); break;
+        case 8: skinny_dgrad_kernel<8><<<(unsigned)nb, 256, smem, stream>>>(g, W, dx, M, (int)N, (int)K, ldg); break;
+        case 12: skinny_dgrad_kernel<12><<<(unsigned)nb, 256, smem, stream>>>(g, W, dx, M, (int)N, (int)K, ldg); break;
+        default: skinny_dgrad_kernel<16><<<(unsigned)nb, 256, smem, stream>>>(g, W, dx, M, (int)N, (int)K, ldg); break;
     }
     RORL_RETURN_LAUNCH();
 }

@@ -103,15 +103,39 @@ def elu_bwd_colsum(dy: torch.Tensor, y: torch.Tensor):
     return g, out
 
 
+def _rows_in_place(x: torch.Tensor):
+    """A narrow operand [..., K] as the skinny kernels address it: (tensor, ldx, seg_rows, seg_stride) with row m at
+    base + (m // seg_rows) * seg_stride + (m % seg_rows) * ldx.  [M, K] and [B, L, K] slices of a wider / longer tensor
+    (the column and time slices of the sampled batch) are used where they lie; anything else is made contiguous."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.dim() == 3 and x.stride(-1) == 1:
+        return x, x.stride(1), x.shape[1], x.stride(0)
+    if x.dim() == 2 and x.stride(-1) == 1:
+        return x, x.stride(0), x.shape[0], 0
+    x = x.reshape(-1, x.shape[-1]).contiguous()
+    return x, x.stride(0), x.shape[0], 0
+
+
 def skinny_wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW [N, K] = g[M, N]^T x[M, K] for K <= 16 (unit inner strides, any row stride)."""
+    """dW [N, K] = g[M, N]^T x[M, K] for K <= 16 (g: unit inner stride, any row stride; x: see _rows_in_place)."""
     M, Nn = g.shape
-    K = x.shape[1]
+    K = x.shape[-1]
     KP = (K + 3) // 4 * 4
+    x, ldx, seg_rows, seg_stride = _rows_in_place(x)
     dW = torch.empty((Nn, KP), device=g.device, dtype=torch.float32)       # K padded to a multiple of 4 (zero columns)
     work = torch.empty(int(N.lib().rorl_skinny_wgrad_work_floats(M, Nn, K)), device=g.device, dtype=torch.float32)
-    N.call("rorl_skinny_wgrad", N.ptr(g), N.ptr(x), N.ptr(dW), N.ptr(work), M, Nn, K, g.stride(0), x.stride(0), N.stream())
+    N.call("rorl_skinny_wgrad", N.ptr(g), N.ptr(x), N.ptr(dW), N.ptr(work), M, Nn, K, g.stride(0), ldx, seg_rows, seg_stride, N.stream())
     return dW[:, :K]
+
+
+def skinny_dgrad(g: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """dx [M, K] = g[M, N] W[N, K] for K <= 16."""
+    M, Nn = g.shape
+    K = weight.shape[1]
+    dx = torch.empty((M, K), device=g.device, dtype=torch.float32)
+    N.call("rorl_skinny_dgrad", N.ptr(g), N.ptr(_f32c(weight)), N.ptr(dx), M, Nn, K, g.stride(0), N.stream())
+    return dx
 
 
 class LinearSkinny(Function):
@@ -124,11 +148,12 @@ class LinearSkinny(Function):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         Nn, K = weight.shape
-        x2 = x.reshape(-1, K)
-        if Nn % 4 == 0 and x2.stride(-1) == 1 and x.dtype == torch.float32:
-            y = torch.empty((x2.shape[0], Nn), device=x.device, dtype=torch.float32)
-            N.call("rorl_skinny_linear", N.ptr(x2), N.ptr(_f32c(weight)), N.ptr(None if bias is None else _f32c(bias)), N.ptr(y),
-                   x2.shape[0], Nn, K, x2.stride(0), Nn, 0, N.stream())
+        if Nn % 4 == 0 and x.dtype == torch.float32:
+            M = x.numel() // K
+            xr, ldx, seg_rows, seg_stride = _rows_in_place(x)
+            y = torch.empty((M, Nn), device=x.device, dtype=torch.float32)
+            N.call("rorl_skinny_linear", N.ptr(xr), N.ptr(_f32c(weight)), N.ptr(None if bias is None else _f32c(bias)), N.ptr(y),
+                   M, Nn, K, ldx, seg_rows, seg_stride, Nn, 0, N.stream())
             return y.view(*x.shape[:-1], Nn)
         return torch.nn.functional.linear(x, weight, bias)
 
@@ -137,15 +162,12 @@ class LinearSkinny(Function):
         x, weight = ctx.saved_tensors
         Nn, K = weight.shape
         g = _f32c(dy.reshape(-1, Nn))
-        x2 = x.reshape(-1, K)
-        if x2.stride(-1) != 1:
-            x2 = x2.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # [M, N] x [N, K <= 16]: the tensor-core kernel with a 16-wide output runs at the rate g is read
-            dx = (gemm_tn(g, weight.t().contiguous()) if _gemm_ok(g.shape[0], K, Nn) else g @ weight).view(x.shape)
+            dx = (gemm_tn(g, weight, transb=True) if _gemm_ok(g.shape[0], K, Nn) else skinny_dgrad(g, weight)).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw = skinny_wgrad(g, x2)
+            dw = skinny_wgrad(g, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(g)
         return dx, dw, db
@@ -169,12 +191,10 @@ class SkinnyEncoders(Function):
         out = torch.empty((M, total), device=xs[0].device, dtype=torch.float32)
         x2s, off = [], 0
         for x, W, b, w in zip(xs, Ws, bs, widths):
-            x2 = x.reshape(M, x.shape[-1])
-            if x2.dtype != torch.float32 or x2.stride(-1) != 1:
-                x2 = x2.float().contiguous()
-            N.call("rorl_skinny_linear", N.ptr(x2), N.ptr(_f32c(W)), N.ptr(None if b is None else _f32c(b)), N.ptr(out[:, off:]),
-                   M, w, x2.shape[1], x2.stride(0), total, int(bool(elu)), N.stream())
-            x2s.append(x2)
+            xr, ldx, seg_rows, seg_stride = _rows_in_place(x)
+            N.call("rorl_skinny_linear", N.ptr(xr), N.ptr(_f32c(W)), N.ptr(None if b is None else _f32c(b)), N.ptr(out[:, off:]),
+                   M, w, x.shape[-1], ldx, seg_rows, seg_stride, total, int(bool(elu)), N.stream())
+            x2s.append(xr)
             off += w
         ctx.save_for_backward(*x2s, *Ws, *([out] if elu else []))
         ctx.n, ctx.elu, ctx.widths, ctx.xshapes, ctx.has_bias = n, bool(elu), widths, [x.shape for x in xs], [b is not None for b in bs]
@@ -199,7 +219,7 @@ class SkinnyEncoders(Function):
             gi = g[:, off:off + widths[i]]
             dx = dW = db = None
             if ctx.needs_input_grad[2 + i]:
-                dx = (gi @ Ws[i]).view(ctx.xshapes[i])
+                dx = skinny_dgrad(gi, Ws[i]).view(ctx.xshapes[i])
             if ctx.needs_input_grad[2 + n + i]:
                 dW = skinny_wgrad(gi, x2s[i])
             if ctx.has_bias[i] and ctx.needs_input_grad[2 + 2 * n + i]:
@@ -602,19 +622,22 @@ def _mat(t: torch.Tensor) -> torch.Tensor:
     return t if ok else t.contiguous()
 
 
-def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int = None, want_pre: bool = False):
+def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int = None, want_pre: bool = False, transb: bool = False):
     """D[g] = act(A[g] @ B[g]^T + bias[g]).  A [M, K] or [G, M, K]; B [N, K] or [G, N, K]; bias [N] or [G, N].
+    transb: B is handed over as [K, N] / [G, K, N] (D = A @ B) and transposed by the kernel's own pre-split pass.
     Returns [M, N] (no batched operand, or reduce_g) or [G, M, N]."""
+    passes = int(passes or GEMM_PASSES)
+    if transb and (passes != 2 or A.shape[-1] % 8):
+        B, transb = B.transpose(-1, -2).contiguous(), False
     A, B = _mat(A), _mat(B)
     G = max(A.shape[0] if A.dim() == 3 else 1, B.shape[0] if B.dim() == 3 else 1)
     M, K = A.shape[-2], A.shape[-1]
-    Nn = B.shape[-2]
-    assert B.shape[-1] == K
+    Nn = B.shape[-1] if transb else B.shape[-2]
+    assert (B.shape[-2] if transb else B.shape[-1]) == K
     batched_out = (A.dim() == 3 or B.dim() == 3) and not reduce_g
     D = torch.empty((G, M, Nn) if batched_out else (M, Nn), device=A.device, dtype=torch.float32)
     bias_c = None if bias is None else _f32c(bias.reshape(-1, Nn) if batched_out else bias.reshape(Nn))
     pre = torch.empty_like(D) if (want_pre and act) else None
-    passes = int(passes or GEMM_PASSES)
     if passes == 2 and K % 8:
         passes = 3                                   # bf16 rows must be 16-byte multiples; such widths are not on the update path
     strideB = B.stride(0) if B.dim() == 3 else 0
@@ -623,7 +646,7 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     N.call("rorl_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(bias_c), N.ptr(D), N.ptr(pre), M, Nn, K, G, A.stride(-2), B.stride(-2), Nn,
            A.stride(0) if A.dim() == 3 else 0, strideB, M * Nn if batched_out else 0,
            Nn if (bias_c is not None and bias_c.dim() == 2) else 0, int(act), passes,
-           int(reduce_g), N.ptr(work), N.stream())
+           int(reduce_g), int(transb), N.ptr(work), N.stream())
     return (D, pre) if want_pre else D
 
 
@@ -678,7 +701,7 @@ class LinearTC(Function):
         if not want_db:
             db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm_tn(g, weight.t().contiguous(), passes=ctx.passes).view(ctx.xshape)
+            dx = gemm_tn(g, weight, passes=ctx.passes, transb=True).view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             dw = gemm_nt(g, xs, passes=ctx.passes) if _gemm_nt_ok(Nn, xs.shape[1], xs.shape[0]) else g.t() @ xs
         return dx, dw, db, None, None
@@ -705,9 +728,8 @@ class EnsembleLinearTC(Function):
     def forward(ctx, x, weight, bias, elu, shared):
         E, Kin, Nout = weight.shape
         xs = _mat(x.reshape(-1, Kin) if shared else x.reshape(E, -1, Kin))
-        wt = weight.transpose(1, 2).contiguous()                  # [E, out, in]: K-major B operand
         b2 = None if bias is None else bias.reshape(E, Nout)
-        y = gemm_tn(xs, wt, b2, 1 if elu else 0)
+        y = gemm_tn(xs, weight, b2, 1 if elu else 0, transb=True)      # weight [E, in, out]: transposed by the kernel's pre-split
         ctx.save_for_backward(xs, weight, y if elu else None)
         ctx.elu, ctx.has_bias, ctx.shared, ctx.xshape = elu, bias is not None, shared, x.shape
         lead = x.shape[:-1] if shared else x.shape[1:-1]
@@ -745,7 +767,7 @@ class EnsembleHiddenToScalar(Function):
         E, Kin, Kh = W2.shape
         xs = _mat(x.reshape(E, -1, Kin))
         M = xs.shape[1]
-        y = gemm_tn(xs, W2.transpose(1, 2).contiguous(), None if b2 is None else b2.reshape(E, Kh), 1)      # [E, M, Kh]
+        y = gemm_tn(xs, W2, None if b2 is None else b2.reshape(E, Kh), 1, transb=True)      # [E, M, Kh]
         w3 = _f32c(W3.reshape(E, Kh))
         q = torch.empty((E, M), device=x.device, dtype=torch.float32)
         N.call("rorl_efc_dot_fwd", N.ptr(y), N.ptr(w3), N.ptr(None if b3 is None else _f32c(b3.reshape(E))), N.ptr(q), E, M, Kh, N.stream())

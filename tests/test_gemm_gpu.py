@@ -165,6 +165,23 @@ def test_gemm_tn_bf16_split_batched(K):
     assert rel_err(D3, ref3) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K_,G", [(1000, 512, 256, 1), (700, 16, 512, 1), (300, 80, 512, 1), (1500, 256, 384, 8), (129, 36, 40, 3)])
+def test_gemm_tn_transposed_weights(K, M, N, K_, G):
+    """transb: B handed over as [K, N] (nn.Linear's weight for its input-gradient GEMM, EnsembleLinear's [E, in, out]
+    weight for its forward); the kernel's pre-split pass transposes it -- no transposed copy is made by the caller."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K_, device="cuda", generator=g)
+    if G == 1:
+        Bt = torch.randn(K_, N, device="cuda", generator=g)
+        ref = A.double() @ Bt.double()
+    else:
+        Bt = torch.randn(G, K_, N, device="cuda", generator=g)
+        ref = torch.einsum('mk,gkn->gmn', A.double(), Bt.double())
+    D = K.gemm_tn(A, Bt, passes=2, transb=True)
+    assert D.shape == ref.shape
+    assert rel_err(D, ref) < 3e-5
+
+
 @pytest.mark.parametrize("Kh,M", [(256, 1000), (128, 37), (384, 513), (512, 130)])
 def test_ensemble_hidden_to_scalar(K, Kh, M):
     """Fused `efc (ELU) -> efc (out 1)` tail of the ensemble-Q head vs the same two layers in float64."""

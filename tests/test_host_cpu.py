@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert len(protos) >= 25
     missing = [n for n in protos if not hasattr(lib, n)]
     assert not missing, missing
-    assert N.lib().rorl_abi_version() == 4
+    assert N.lib().rorl_abi_version() == 5
     assert N.lib().rorl_selscan_dtile(32) == 64 and N.lib().rorl_selscan_dtile(7) < 0
 
 

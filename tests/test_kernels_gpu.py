@@ -189,20 +189,22 @@ def test_selscan_strided_inputs(K):
 
 
 # ------------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("D,L,masked", [(96, 300, True), (97, 300, True), (96, 131, False), (130, 7, True), (512, 1019, True)])
 @pytest.mark.parametrize("K_", [2, 4, 8, 16])
-def test_conv1d_silu_vs_oracle(K, K_):
+def test_conv1d_silu_vs_oracle(K, K_, D, L, masked):
+    """D even: the channel-pair (f32x2) kernels; D odd: the one-channel kernels; L below / across / many segments."""
     from oracle import ops as O
-    B, L, D = 3, 300, 96
+    B = 3 if D < 512 else 2
     gen = torch.Generator().manual_seed(K_)
     x = torch.randn(B, L, D, generator=gen)
     w, b = 0.3 * torch.randn(D, 1, K_, generator=gen), 0.1 * torch.randn(D, generator=gen)
-    mask = (torch.rand(B, L, 1, generator=gen) > 0.1).float()
+    mask = (torch.rand(B, L, 1, generator=gen) > 0.1).float() if masked else torch.ones(B, L, 1)
     dy = torch.randn(B, L, D, generator=gen)
     cx, cw, cb = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
     ref = O.causal_conv1d_silu(cx.transpose(1, 2), cw, cb, mask.transpose(1, 2)).transpose(1, 2)
     rg = torch.autograd.grad(ref, (cx, cw, cb), dy)
     gx, gw, gb = x.cuda().requires_grad_(), w.cuda().requires_grad_(), b.cuda().requires_grad_()
-    y = K.causal_conv1d_silu(gx, gw, gb, mask.cuda())
+    y = K.causal_conv1d_silu(gx, gw, gb, mask.cuda() if masked else None)
     assert_close(y, ref, TOL, "y")
     gg = torch.autograd.grad(y, (gx, gw, gb), dy.cuda())
     for a, r, n in zip(gg, rg, ("dx", "dw", "db")):

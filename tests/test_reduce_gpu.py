@@ -101,3 +101,44 @@ def test_skinny_encoders_write_one_buffer(elu, M):
     for a, r in zip(got, ref):
         assert a.shape == r.shape
         assert rel_err(a, r) < 1e-4
+
+
+@pytest.mark.parametrize("elu", [False, True])
+def test_skinny_encoders_read_batch_slices_in_place(elu):
+    """The projections' inputs are column AND time slices of one [B, L + 1, C] batch tensor (rows not mergeable into one
+    stride): read where they lie (seg_rows / seg_stride addressing), forward, data gradient, weight and bias gradients."""
+    import rorl_b200.kernels as K
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    B, L = 5, 203
+    batch = torch.randn(B, L + 1, 30, device="cuda", generator=gen)
+    act = torch.randn(B, L, 6, device="cuda", generator=gen, requires_grad=True)
+    xs = [batch[:, 1:, 0:9], batch[:, :-1, 9:18], act]
+    assert not xs[0].is_contiguous() and xs[0].reshape(-1, 9).data_ptr() != xs[0].data_ptr()      # reshape would copy
+    Ws = [torch.randn(128, x.shape[-1], device="cuda", generator=gen, requires_grad=True) for x in xs]
+    bs = [torch.randn(128, device="cuda", generator=gen, requires_grad=True) for _ in xs]
+    y = K.skinny_encoders(xs, Ws, bs, elu=elu)
+    assert y.shape == (B, L, 384)
+    dy = torch.randn(B, L, 384, device="cuda", generator=gen)
+    got = torch.autograd.grad(y, [act] + Ws + bs, dy)
+    xd = [x.detach().double() for x in xs]
+    xd[2].requires_grad_()
+    Wd = [w.detach().double().requires_grad_() for w in Ws]
+    bd = [b.detach().double().requires_grad_() for b in bs]
+    yr = torch.cat([torch.nn.functional.linear(a, w, b) for a, w, b in zip(xd, Wd, bd)], dim=-1)
+    if elu:
+        yr = torch.nn.functional.elu(yr)
+    ref = torch.autograd.grad(yr, [xd[2]] + Wd + bd, dy.double())
+    assert rel_err(y, yr) < 1e-5
+    for a, r in zip(got, ref):
+        assert a.shape == r.shape
+        assert rel_err(a, r) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,Kk", [(1000, 128, 6), (32608, 128, 9), (77, 256, 16), (3, 128, 1)])
+def test_skinny_dgrad(M, N, Kk):
+    import rorl_b200.kernels as K
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    g = torch.randn(M, N + 8, device="cuda", generator=gen)[:, :N]         # row-strided
+    W = torch.randn(N, Kk, device="cuda", generator=gen)
+    got = K.skinny_dgrad(g, W)
+    assert rel_err(got, g.double() @ W.double()) < 1e-5

@@ -231,7 +231,19 @@ def bench_gemm():
 
 def bench_reduce():
     M = 32 * 1019
-    for n in (128, 256, 1024):
+    for shape in ((16, 32 * 1019 * 64), (4, 512 * 256), (32, 512 * 32)):
+        x = rn(*shape)
+        t = timeit(lambda: K.sum_leading(x))
+        rec(f"sum_leading {list(shape)}", t, 4 * x.numel())
+    for n, k in ((128, 9), (128, 6), (512, 16)):
+        x, W, b = rn(M, k), rn(n, k), rn(n)
+        out = torch.empty(M, n, device=dev)
+        t = timeit(lambda: K.skinny_encoders([x], [W], [b]))
+        rec(f"skinny_linear N={n} K={k}", t, 4 * M * (n + k))
+    g6, W6 = rn(M, 128), rn(128, 6)
+    t = timeit(lambda: K.skinny_dgrad(g6, W6))
+    rec("skinny_dgrad N=128 K=6", t, 4 * M * (128 + 6))
+    for n in (128, 256, 512, 1024):
         x = rn(M, n)
         t = timeit(lambda: K.colsum(x))
         rec(f"colsum [{M},{n}]", t, 4 * M * n)
