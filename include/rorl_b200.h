@@ -87,7 +87,7 @@ int rorl_lru_fused_bwd(const float* g_re, const float* g_im, const float* lam_re
  * bwd_recurrence (ref: offpolicy_rnn/models/s6/selective_scan/triton_scan.py:19-72,75-182).
  *
  * Token-major layout: u, delta, z, y: [B, L, D] with row strides ld_*; Bm, Cm: [B, L, N] with row
- * strides ld_B, ld_C; A: [D, N] (already -exp(A_log)); Dskip, delta_bias: [D] or NULL; z may be NULL;
+ * strides ld_B, ld_C; A: [D, N] (-exp(A_log), or A_log itself with flag bit 1); Dskip, delta_bias: [D] or NULL; z may be NULL;
  * start: [B, L] (1 = reset the state before this step) or NULL.  N in {16, 32, 64}; D % 4 == 0.
  * h0 (may be NULL = 0): [B, D, N] state carried into the call (the s6 layer's `initial_state`,
  * ref: offpolicy_rnn/models/s6/selective_scan/cpu_scan.py:52-53); a constant: no gradient is produced for it.
@@ -99,6 +99,9 @@ int rorl_lru_fused_bwd(const float* g_re, const float* g_im, const float* lam_re
  *   dBC_part  [ceil(D / rorl_selscan_dtile(N)), B, L, 2N]  sum over axis 0 -> dB = [..., :N], dC = [..., N:]
  *   dA_part   [B, D, N]   sum over axis 0 -> dA
  *   dD_part   [B, D], dbias_part [B, D]   sum over axis 0 -> dD, d(delta_bias)
+ * `delta_softplus` is a flag word: bit 0 = delta = softplus(delta_raw + delta_bias) (else delta_raw + delta_bias);
+ * bit 1 = `A` points at the PARAMETER A_log and the kernels form A = -exp(A_log) themselves (ref: smamba/mamba.py:215),
+ * in which case dA_part holds partials of d A_log (= dA * A), so that no exp / neg / mul launches surround the scan.
  * ---------------------------------------------------------------------------------------------- */
 int rorl_selscan_dtile(int64_t N);
 int rorl_selscan_ckpt_every(void);
@@ -216,7 +219,9 @@ int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t 
  * ensemble_linear_model.py:36-49; smamba projections, ref: offpolicy_rnn/models/smamba/mamba.py:176,231-233,252).
  *   D[g][M, N] = act(A[g][M, K] * B[g][N, K]^T + bias[g][N]),  g = 0..G-1
  * Both operands K-major (reduction dimension contiguous).  strideA / strideB == 0: operand shared by all g.
- * act: 0 none, 1 ELU (Dpre, may be NULL, receives the pre-activation in D's layout for an exact ELU backward).
+ * act: flag word -- bit 0 (1) ELU (Dpre, may be NULL, receives the pre-activation in D's layout for an exact ELU
+ * backward); bit 2 (4, passes == 2 only) ACCUMULATE: D += result, so that a gradient with two producers (the scan's du
+ * and x_proj's input gradient, ref: smamba/mamba.py:213-233) needs no separate add pass.
  * passes: 3 = 3xTF32 (fp32 parity, ~2^-21), 2 = two-term bf16 split, 3 bf16 MMAs (fp32 parity to ~2^-17 at twice
  * the tensor rate and half the operand bytes), 1 = plain TF32.  reduce_g != 0: the G products are
  * summed into one D[M, N] (data-gradient of an ensemble layer with shared input).
@@ -253,6 +258,22 @@ int rorl_efc_head_nblk(void);
 int rorl_efc_dot_fwd(const float* y, const float* w, const float* b, float* q, int64_t E, int64_t M, int64_t K, cudaStream_t stream);
 int rorl_efc_head_bwd(const float* dq, const float* y, const float* w, float* g, float* part, int64_t E, int64_t M, int64_t K,
                       int elu, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tanh-Gaussian policy head (csrc/head.cu), forward and backward in one kernel each.  Replaces the elementwise graph
+ * of ContextualSACPolicySingleHead.forward after the universal network
+ * (ref: offpolicy_rnn/policy_value_models/contextual_sac_policy_single_head.py:105-123):
+ *   out [M, 2A] (row stride ld_out) = [logstd | mean];  noise [M, A] standard normal draws
+ *   logstd clamped to [min_logstd, max_logstd]; sample = mean + noise * exp(logstd)
+ *   action_mean = tanh(mean), action_sample = tanh(sample)            [M, A]
+ *   log_prob [M] = sum_a N(sample; mean, std) log-density - 2 (log 2 - sample - softplus(-2 sample))
+ * bwd: d_mean / d_sample / d_log_prob may be NULL (treated as zero); d_out [M, 2A] contiguous.
+ * ---------------------------------------------------------------------------------------------- */
+int rorl_tanh_gaussian_fwd(const float* out, const float* noise, float* action_mean, float* action_sample, float* log_prob,
+                           int64_t M, int64_t A, int64_t ld_out, float min_logstd, float max_logstd, cudaStream_t stream);
+int rorl_tanh_gaussian_bwd(const float* out, const float* noise, const float* d_mean, const float* d_sample, const float* d_log_prob,
+                           float* d_out, int64_t M, int64_t A, int64_t ld_out, float min_logstd, float max_logstd,
+                           cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GRU recurrence as a persistent thread-block-cluster kernel (W_hh resident in registers across a
@@ -344,6 +365,10 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
 int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
                         int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
                         int32_t* tickets, cudaStream_t stream);
+/* out[r * out_ld + c] = sum_p part[p][r * C + c]  (part: P planes of contiguous [rows, C]; C, out_ld % 4 == 0): per-tile
+ * partial rows summed straight into a column block of a wider buffer -- the selective scan's dB | dC partials into
+ * their columns of d(x_dbl) (ref: the column slices of smamba/mamba.py:214-222). */
+int rorl_sum_leading_rows(const float* part, float* out, int64_t P, int64_t rows, int64_t C, int64_t out_ld, cudaStream_t stream);
 /* y[m, n] = act(bias[n] + sum_k x[m, k] W[n, k]) for K <= 16, N % 4 == 0 (bias may be NULL; elu != 0: ELU): forward of
  * the same projections; ldy lets several of them write side by side into one [M, sum N] buffer (no concatenation).
  * Row m of x is read at x + (m / seg_rows) * seg_stride + (m % seg_rows) * ldx, so that a [B, L, K] slice of the

@@ -276,6 +276,8 @@ class FullLengthRNNUpdate:
     def _finalize_models(self):
         """(Re)build arenas + optimizers after weights are in place; call again after load_state_dict."""
         self._graphs, self._graph_pool = {}, None       # captured graphs point into the old arenas
+        for m in [self.policy, self.target_policy] + list(self.values) + list(self.target_values):
+            m.need_full_hidden = False                  # the update never reads forward()'s per-layer output record
         self._value_update(tau=0.0)
         self.target_policy.copy_weight_from(self.policy, tau=0.0)
         self.policy_arena = FlatArena(self.policy, self.device, grad_tail=4)
@@ -612,6 +614,10 @@ class FullLengthRNNUpdate:
         state, action, next_state = batch.state, batch.action, batch.next_state
         done, mask, reward, timeout, rnn_start = batch.done, batch.mask, batch.reward, batch.timeout, batch.start
         B = state.shape[0]
+        # the side-band flags are read by every recurrent / conv layer of four forward passes: hand them over contiguous and
+        # in fp32 ONCE here (batch.start is a column slice of the sampled batch; each kernel wrapper would otherwise copy it)
+        rnn_start = rnn_start.float().contiguous()
+        valid_ind = valid_ind.float().contiguous()
         # 2. target-pass side-band ------------------------------------------------------------------------ ref :338-341
         d_valid = valid_ind[:, 1:] - valid_ind[:, :-1]
         total_valid = valid_ind.clone()

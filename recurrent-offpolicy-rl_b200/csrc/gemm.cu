@@ -394,6 +394,7 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
                  int64_t strideBias, int act, int passes, int reduce_g, int transb, void* work, cudaStream_t stream) {
     if (!A || !B || !D) return RORL_ERR_ARG;
     if (transb && passes != 2) return RORL_ERR_ARG;              // only the pre-splitting form re-lays B out
+    if ((act & ~5) || ((act & 4) && passes != 2)) return RORL_ERR_ARG;   // accumulate: bf16-split form only
     if (M <= 0 || N <= 0 || K <= 0 || G <= 0) return RORL_ERR_SHAPE;
     if (K % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideBias % 4)
         return RORL_ERR_ALIGN;

@@ -50,6 +50,7 @@ struct BfParams {
     int M, N, K, G;
     long long ldd, strideD, strideBias;
     int a_batched, b_batched, act, reduce_g;
+    int accum;                  // TN form: D += result (read-modify-write in the epilogue's coalesced row stores)
     int splits;                 // NT variant: split-K factor; partial s is written at D + s * strideSplit
     long long strideSplit;
 };
@@ -278,7 +279,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             const long long obase = (long long)g * p.strideD + (long long)sp * p.strideSplit;
             const int row0 = tm * kBfBM + q * 32;
             const float* bias = p.bias ? p.bias + (long long)g * p.strideBias : nullptr;
-            auto flush = [&](const float4 (&o)[8], float* out, int col0) {
+            auto flush = [&](const float4 (&o)[8], float* out, int col0, bool add) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
@@ -288,8 +289,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     const int rloc = rr * 4 + (lane >> 3), ch = lane & 7;
                     const float4 v = *reinterpret_cast<const float4*>(stg + rloc * 128 + ((ch ^ (rloc & 7)) << 4));
                     const int grow = row0 + rloc, col = col0 + ch * 4;
-                    if (grow < p.M && col < p.N)
-                        *reinterpret_cast<float4*>(out + obase + (long long)grow * p.ldd + col) = v;
+                    if (grow < p.M && col < p.N) {
+                        float4* dst = reinterpret_cast<float4*>(out + obase + (long long)grow * p.ldd + col);
+                        if (add) {
+                            const float4 c = *dst;
+                            dst[0] = make_float4(v.x + c.x, v.y + c.y, v.z + c.z, v.w + c.w);
+                        } else {
+                            *dst = v;
+                        }
+                    }
                 }
                 __syncwarp();
             };
@@ -321,12 +329,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                             o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
                         }
                     }
-                    if (p.Dpre) flush(o, p.Dpre, col0);
+                    if (p.Dpre) flush(o, p.Dpre, col0, false);
                     if (p.act == 1) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { o[j].x = bf_elu1(o[j].x); o[j].y = bf_elu1(o[j].y); o[j].z = bf_elu1(o[j].z); o[j].w = bf_elu1(o[j].w); }
                     }
-                    flush(o, p.D, col0);
+                    flush(o, p.D, col0, p.accum != 0);
                 }
             }
         }
@@ -442,7 +450,7 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
     BfParams p;
     p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
     p.ldd = ldd; p.strideD = strideD; p.strideBias = strideBias;
-    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act; p.reduce_g = reduce_g != 0;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act & 1; p.accum = (act & 4) != 0; p.reduce_g = reduce_g != 0;
     p.splits = 1; p.strideSplit = 0;
     const int sms = bf_sms();
     const long long tiles = ((M + kBfBM - 1) / kBfBM) * ((N + bn - 1) / bn) * (reduce_g ? 1 : G);
@@ -466,7 +474,7 @@ int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t 
     BfParams p;
     p.D = D; p.Dpre = nullptr; p.bias = nullptr; p.M = (int)M; p.N = (int)N; p.K = (int)R; p.G = (int)G;
     p.ldd = ldd; p.strideD = strideD; p.strideBias = 0;
-    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = 0; p.reduce_g = 0;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = 0; p.accum = 0; p.reduce_g = 0;
     p.splits = (int)splits; p.strideSplit = strideSplit;
     const int sms = bf_sms();
     const long long tiles = ((M + kBfBM - 1) / kBfBM) * ((N + 127) / 128) * G * splits;

@@ -301,6 +301,33 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
     }
 }
 
+// out[r * out_ld + c] = sum_p part[p][r * C + c]: per-tile partial rows summed straight into a column block of a wider
+// row-major buffer (the selective scan's dB | dC partials -> their columns of d(x_dbl); no slice-gradient copies)
+__global__ void __launch_bounds__(256) sum_leading_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int P,
+                                                               int64_t rows, int C, int64_t out_ld) {
+    const int cq = C / 4;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * cq) return;
+    const int64_t r = i / cq;
+    const int c = (int)(i % cq) * 4;
+    const float* src = part + r * C + c;
+    const int64_t plane = rows * C;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int pI = 0;
+    for (; pI + 8 <= P; pI += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(src + (pI + u) * plane));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; pI < P; ++pI) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + pI * plane));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + r * out_ld + c) = acc;
+}
+
 static inline int red_blocks(int64_t M, int* rows_per_block, int64_t G = 1, int64_t chunks = 1) {
     int nblk = (int)((M + 63) / 64);                     // at least 64 rows per block
     int cap = (int)(kRedMaxBlocks / (G * chunks));       // about 4 CTAs per SM over the whole grid
@@ -393,6 +420,15 @@ int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, f
         dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
     }
+    RORL_RETURN_LAUNCH();
+}
+
+int rorl_sum_leading_rows(const float* part, float* out, int64_t P, int64_t rows, int64_t C, int64_t out_ld, cudaStream_t stream) {
+    if (!part || !out) return RORL_ERR_ARG;
+    if (P <= 0 || rows <= 0 || C <= 0 || out_ld < C) return RORL_ERR_SHAPE;
+    if (C % 4 || out_ld % 4 || !a16(part) || !a16(out)) return RORL_ERR_ALIGN;
+    const int64_t n = rows * (C / 4);
+    sum_leading_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(part, out, (int)P, rows, (int)C, out_ld);
     RORL_RETURN_LAUNCH();
 }
 

@@ -50,6 +50,7 @@ struct SelFwdParams {
     int L, D;
     int ld_u, ld_delta, ld_z, ld_B, ld_C, ld_y;
     int nckpt;
+    int a_log;                  // A is handed over as A_log (A = -exp(A_log))
     int dbg;
 };
 
@@ -96,6 +97,8 @@ struct SelFwdCfg {
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+// the state matrix as the caller holds it: A itself, or the parameter A_log with A = -exp(A_log) (ref: smamba/mamba.py:215)
+__device__ __forceinline__ float sel_A(float a, int a_log) { return a_log ? -expf(a) : a; }
 
 template <int N, bool HAS_Z, bool SOFTPLUS>
 __global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(const SelFwdParams p) {
@@ -248,7 +251,8 @@ __global__ void __launch_bounds__(SelFwdCfg<N>::NTHREADS, 2) selscan_fwd_kernel(
             const bool ok = d + c < p.D;
 #pragma unroll
             for (int j = 0; j < H2; ++j) {
-                A2[c][j] = ok ? f2(p.A[(size_t)(d + c) * N + ng * S + 2 * j] * kLog2e, p.A[(size_t)(d + c) * N + ng * S + 2 * j + 1] * kLog2e)
+                A2[c][j] = ok ? f2(sel_A(p.A[(size_t)(d + c) * N + ng * S + 2 * j], p.a_log) * kLog2e,
+                                   sel_A(p.A[(size_t)(d + c) * N + ng * S + 2 * j + 1], p.a_log) * kLog2e)
                               : f2(0.f, 0.f);
                 h[c][j] = f2(0.f, 0.f);
                 if (p.h0 != nullptr && ok) {                // carried state entering the call: [B, D, N]
@@ -348,6 +352,7 @@ struct SelBwdParams {
     int L, D, Bsz;
     int ld_u, ld_delta, ld_z, ld_B, ld_C, ld_dy, ld_du, ld_ddelta, ld_dz;
     int nckpt;
+    int a_log;                  // A is handed over as A_log; dA_part then receives d A_log partials
 };
 
 // Backward decomposition (warp specialised like the forward).
@@ -657,7 +662,8 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
             for (int j = 0; j < H2; ++j) {
                 // channels past D: any negative A keeps (+inf) * A = -inf at reset steps (0 would give NaN, and this
                 // thread's zero contributions still enter the cross-channel dB / dC sums)
-                A2[c][j] = dvalid[c] ? f2(p.A[(size_t)d * N + ng * S + 2 * j] * kLog2e, p.A[(size_t)d * N + ng * S + 2 * j + 1] * kLog2e)
+                A2[c][j] = dvalid[c] ? f2(sel_A(p.A[(size_t)d * N + ng * S + 2 * j], p.a_log) * kLog2e,
+                                          sel_A(p.A[(size_t)d * N + ng * S + 2 * j + 1], p.a_log) * kLog2e)
                                      : f2(-1.f, -1.f);
                 dA[c][j] = f2(0.f, 0.f);
                 lam[c][j] = f2(0.f, 0.f);                   // a_{t+1} * lambda_{t+1}
@@ -757,6 +763,10 @@ __global__ void __launch_bounds__(SelBwdCfg<N>::NTHREADS, 1) selscan_bwd_kernel(
         for (int c = 0; c < CH; ++c) {
             if (dvalid[c]) {
                 float* a = p.dA_part + ((size_t)b * p.D + d0 + dloc[c]) * N + ng * S;
+                if (p.a_log) {                               // A = -exp(A_log): d A_log = dA * A (A2 holds A * log2 e)
+#pragma unroll
+                    for (int j = 0; j < H2; ++j) dA[c][j] = __fmul2_rn(dA[c][j], __fmul2_rn(A2[c][j], f2(kLn2, kLn2)));
+                }
                 *reinterpret_cast<float4*>(a) = make_float4(dA[c][0].x, dA[c][0].y, dA[c][1].x, dA[c][1].y);
             }
         }
@@ -849,7 +859,8 @@ int rorl_selscan_fwd(const float* u, const float* delta, const float* A, const f
     p.ld_y = (int)ld_y;
     p.nckpt = (int)(L / kCkptEvery);
     p.dbg = g_sel_dbg;
-    const bool has_z = z != nullptr, sp = delta_softplus != 0;
+    const bool has_z = z != nullptr, sp = (delta_softplus & 1) != 0;
+    p.a_log = (delta_softplus & 2) != 0;
     SEL_DISPATCH(launch_fwd, p, B, stream);
 }
 
@@ -882,7 +893,8 @@ int rorl_selscan_bwd(const float* u, const float* delta, const float* A, const f
     p.ld_u = (int)ld_u; p.ld_delta = (int)ld_delta; p.ld_z = (int)ld_z; p.ld_B = (int)ld_B; p.ld_C = (int)ld_C;
     p.ld_dy = (int)ld_dy; p.ld_du = (int)ld_du; p.ld_ddelta = (int)ld_ddelta; p.ld_dz = (int)ld_dz;
     p.nckpt = (int)(L / kCkptEvery);
-    const bool has_z = z != nullptr, sp = delta_softplus != 0;
+    const bool has_z = z != nullptr, sp = (delta_softplus & 1) != 0;
+    p.a_log = (delta_softplus & 2) != 0;
     SEL_DISPATCH(launch_bwd, p, B, stream);
 }
 

@@ -240,6 +240,46 @@ def skinny_encoders(xs, Ws, bs, elu=False):
 
 
 # ------------------------------------------------------------------------------------------------
+# tanh-Gaussian policy head
+# ------------------------------------------------------------------------------------------------
+class TanhGaussianHead(Function):
+    """(tanh(mean), tanh(sample), log_prob) from the head output [.., 2A] = [logstd | mean] and a standard-normal draw
+    [.., A]: one kernel forward, one backward (csrc/head.cu)."""
+
+    @staticmethod
+    def forward(ctx, out, noise, lo, hi):
+        A = noise.shape[-1]
+        o2 = out.reshape(-1, 2 * A)
+        if o2.dtype != torch.float32 or o2.stride(-1) != 1:
+            o2 = o2.float().contiguous()
+        n2 = _f32c(noise.reshape(-1, A))
+        M = o2.shape[0]
+        am = torch.empty((M, A), device=out.device, dtype=torch.float32)
+        asamp = torch.empty_like(am)
+        lp = torch.empty((M,), device=out.device, dtype=torch.float32)
+        N.call("rorl_tanh_gaussian_fwd", N.ptr(o2), N.ptr(n2), N.ptr(am), N.ptr(asamp), N.ptr(lp), M, A, o2.stride(0),
+               float(lo), float(hi), N.stream())
+        ctx.save_for_backward(o2, n2)
+        ctx.lo, ctx.hi, ctx.oshape = float(lo), float(hi), out.shape
+        lead = out.shape[:-1]
+        return am.view(*lead, A), asamp.view(*lead, A), lp.view(*lead, 1)
+
+    @staticmethod
+    def backward(ctx, d_am, d_as, d_lp):
+        o2, n2 = ctx.saved_tensors
+        M, A = n2.shape
+        d_out = torch.empty((M, 2 * A), device=o2.device, dtype=torch.float32)
+        c = lambda t, w: None if t is None else _f32c(t.reshape(M, w) if w > 1 else t.reshape(M))
+        N.call("rorl_tanh_gaussian_bwd", N.ptr(o2), N.ptr(n2), N.ptr(c(d_am, A)), N.ptr(c(d_as, A)), N.ptr(c(d_lp, 1)), N.ptr(d_out),
+               M, A, o2.stride(0), ctx.lo, ctx.hi, N.stream())
+        return d_out.view(ctx.oshape), None, None, None
+
+
+def tanh_gaussian_head(out, noise, lo, hi):
+    return TanhGaussianHead.apply(out, noise, lo, hi)
+
+
+# ------------------------------------------------------------------------------------------------
 # GILR
 # ------------------------------------------------------------------------------------------------
 class GILRScan(Function):
@@ -426,7 +466,8 @@ class SelectiveScan(Function):
     D / delta_bias [D], start [B, L].  Returns y [B, L, D] (and last_state [B, D, N])."""
 
     @staticmethod
-    def forward(ctx, u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state, h0=None):
+    def forward(ctx, u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state, h0=None, a_log=False):
+        """a_log: `A` is the parameter A_log (A = -exp(A_log) is formed inside the kernels; its gradient is d A_log)."""
         u, delta, Bm, Cm = _rows(u), _rows(delta), _rows(Bm), _rows(Cm)
         z = None if z is None else _rows(z)
         A = _f32c(A)
@@ -446,8 +487,8 @@ class SelectiveScan(Function):
         N.call("rorl_selscan_fwd", N.ptr(u), N.ptr(delta), N.ptr(A), N.ptr(Bm), N.ptr(Cm), N.ptr(Dskip), N.ptr(z),
                N.ptr(delta_bias), N.ptr(start), N.ptr(h0), N.ptr(y), N.ptr(ckpt), N.ptr(last), B, L, D, Ns,
                u.stride(1), delta.stride(1), 0 if z is None else z.stride(1), Bm.stride(1), Cm.stride(1), D,
-               int(bool(delta_softplus)), N.stream())
-        ctx.delta_softplus = bool(delta_softplus)
+               int(bool(delta_softplus)) | (2 if a_log else 0), N.stream())
+        ctx.delta_softplus = int(bool(delta_softplus)) | (2 if a_log else 0)
         ctx.return_last_state = return_last_state
         ctx.save_for_backward(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, ckpt, h0)
         if return_last_state:
@@ -478,12 +519,93 @@ class SelectiveScan(Function):
         dBC = sum_leading(dBC)
         return (du, ddelta, sum_leading(dA), dBC[..., :Ns], dBC[..., Ns:],
                 None if Dskip is None else sum_leading(dD), dz,
-                None if delta_bias is None else sum_leading(dbias), None, None, None, None)
+                None if delta_bias is None else sum_leading(dbias), None, None, None, None, None)
 
 
 def selective_scan_tm(u, delta, A, Bm, Cm, Dskip=None, z=None, delta_bias=None, start=None, delta_softplus=False,
-                      return_last_state=False, h0=None):
-    return SelectiveScan.apply(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state, h0)
+                      return_last_state=False, h0=None, a_log=False):
+    return SelectiveScan.apply(u, delta, A, Bm, Cm, Dskip, z, delta_bias, start, delta_softplus, return_last_state, h0, a_log)
+
+
+class SSMCore(Function):
+    """The data-dependent half of a Mamba block as ONE autograd node (ref: smamba/mamba.py:213-233):
+        x_dbl = xs Wx^T;  delta = x_dbl[:, :R] Wdt^T;  y = selective_scan(xs, delta, -exp(A_log), B = x_dbl[:, R:R+N],
+        C = x_dbl[:, R+N:], D, z, dt_bias, softplus, reset)
+    The scan and dt_proj read their column blocks of x_dbl in place; A = -exp(A_log) is formed inside the scan kernels.
+    In the backward the scan's dB | dC partials are summed straight into their columns of d(x_dbl), dt_proj's input
+    gradient is written into the others by its GEMM, and x_proj's input gradient is ACCUMULATED onto the scan's du in
+    the GEMM epilogue: the slice gradients (zero-fill + copy + add per slice), the [B, L, D] gradient add and the
+    exp / neg / mul launches of the unfused graph do not exist."""
+
+    @staticmethod
+    def forward(ctx, xs, Wx, Wdt, A_log, Dskip, z, dt_bias, start):
+        xs, z = _rows(xs), _rows(z)
+        B, L, Dn = xs.shape
+        R, Ns = Wdt.shape[1], A_log.shape[1]
+        W = R + 2 * Ns
+        M = B * L
+        xs2 = xs.view(M, Dn) if xs.is_contiguous() else xs.as_strided((M, Dn), (xs.stride(1), 1))
+        x_dbl = gemm_tn(xs2, Wx)                                              # [M, R + 2N]
+        Wdt_c, A_c, D_c, b_c = _f32c(Wdt), _f32c(A_log), _f32c(Dskip), _f32c(dt_bias)
+        delta = torch.empty((B, L, Dn), device=xs.device, dtype=torch.float32)
+        N.call("rorl_skinny_linear", N.ptr(x_dbl), N.ptr(Wdt_c), N.ptr(None), N.ptr(delta), M, Dn, R, W, M, 0, Dn, 0, N.stream())
+        start = _flag(start, B, L)
+        y = torch.empty((B, L, Dn), device=xs.device, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad)
+        nck = L // N.lib().rorl_selscan_ckpt_every()
+        ckpt = torch.empty((B, nck, Dn, Ns), device=xs.device, dtype=torch.float32) if (need_grad and nck > 0) else None
+        Bm, Cm = x_dbl[:, R:R + Ns], x_dbl[:, R + Ns:]
+        N.call("rorl_selscan_fwd", N.ptr(xs), N.ptr(delta), N.ptr(A_c), N.ptr(Bm), N.ptr(Cm), N.ptr(D_c), N.ptr(z), N.ptr(b_c),
+               N.ptr(start), N.ptr(None), N.ptr(y), N.ptr(ckpt), N.ptr(None), B, L, Dn, Ns, xs.stride(1), Dn, z.stride(1), W, W, Dn,
+               3, N.stream())
+        ctx.save_for_backward(xs, x_dbl, delta, z, ckpt, Wx, Wdt_c, A_c, D_c, b_c, start)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, x_dbl, delta, z, ckpt, Wx, Wdt, A_log, Dskip, dt_bias, start = ctx.saved_tensors
+        dy = _rows(dy)
+        B, L, Dn = xs.shape
+        R, Ns = Wdt.shape[1], A_log.shape[1]
+        W, M, dev = R + 2 * Ns, B * L, xs.device
+        ntile = (Dn + N.lib().rorl_selscan_dtile(Ns) - 1) // N.lib().rorl_selscan_dtile(Ns)
+        du = torch.empty((B, L, Dn), device=dev, dtype=torch.float32)
+        ddelta, dz = torch.empty_like(du), torch.empty_like(du)
+        dBC = torch.empty((ntile, M, 2 * Ns), device=dev, dtype=torch.float32)
+        dA = torch.empty((B, Dn, Ns), device=dev, dtype=torch.float32)
+        dD = torch.empty((B, Dn), device=dev, dtype=torch.float32)
+        dbias = torch.empty((B, Dn), device=dev, dtype=torch.float32)
+        Bm, Cm = x_dbl[:, R:R + Ns], x_dbl[:, R + Ns:]
+        N.call("rorl_selscan_bwd", N.ptr(xs), N.ptr(delta), N.ptr(A_log), N.ptr(Bm), N.ptr(Cm), N.ptr(Dskip), N.ptr(z),
+               N.ptr(dt_bias), N.ptr(start), N.ptr(None), N.ptr(dy), N.ptr(ckpt), N.ptr(du), N.ptr(ddelta), N.ptr(dz),
+               N.ptr(dBC), N.ptr(dA), N.ptr(dD), N.ptr(dbias), B, L, Dn, Ns, xs.stride(1), Dn, z.stride(1), W, W,
+               dy.stride(1), Dn, Dn, Dn, 3, N.stream())
+        dx_dbl = torch.empty((M, W), device=dev, dtype=torch.float32)
+        N.call("rorl_sum_leading_rows", N.ptr(dBC), N.ptr(dx_dbl[:, R:]), ntile, M, 2 * Ns, W, N.stream())
+        dd2, du2 = ddelta.view(M, Dn), du.view(M, Dn)
+        xs2 = xs.view(M, Dn) if xs.is_contiguous() else xs.as_strided((M, Dn), (xs.stride(1), 1))
+        need = ctx.needs_input_grad
+        if _gemm_ok(M, R, Dn):
+            gemm_tn(dd2, Wdt, transb=True, out=dx_dbl[:, :R])                  # d(x_dbl[:, :R]) = ddelta Wdt
+        else:
+            dx_dbl[:, :R] = skinny_dgrad(dd2, Wdt)
+        dWdt = skinny_wgrad(dd2, x_dbl[:, :R]) if need[2] else None
+        dWx = (gemm_nt(dx_dbl, xs2) if _gemm_nt_ok(W, Dn, M) else dx_dbl.t() @ xs2) if need[1] else None
+        if need[0]:
+            gemm_tn(dx_dbl, Wx, transb=True, out=du2, accumulate=True)        # du += d(x_dbl) Wx
+        return (du if need[0] else None, dWx, dWdt, sum_leading(dA) if need[3] else None, sum_leading(dD) if need[4] else None,
+                dz if need[5] else None, sum_leading(dbias) if need[6] else None, None)
+
+
+def ssm_core_ok(xs, z, Wx, Wdt, A_log) -> bool:
+    Dn, R, Ns = xs.shape[-1], Wdt.shape[1], A_log.shape[1]
+    M = xs.numel() // Dn
+    return (xs.is_cuda and xs.dtype == torch.float32 and xs.dim() == 3 and z is not None and R % 4 == 0 and R <= 16
+            and Ns in (16, 32, 64) and Dn % 4 == 0 and _gemm_ok(M, R + 2 * Ns, Dn) and xs.shape[1] > 1)
+
+
+def ssm_core(xs, Wx, Wdt, A_log, Dskip, z, dt_bias, start):
+    return SSMCore.apply(xs, Wx, Wdt, A_log, Dskip, z, dt_bias, start)
 
 
 def selective_scan_fn(u, delta, A, B, C, start, D=None, z=None, delta_bias=None, delta_softplus=False,
@@ -622,11 +744,17 @@ def _mat(t: torch.Tensor) -> torch.Tensor:
     return t if ok else t.contiguous()
 
 
-def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int = None, want_pre: bool = False, transb: bool = False):
+def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int = None, want_pre: bool = False, transb: bool = False,
+            out: torch.Tensor = None, accumulate: bool = False):
     """D[g] = act(A[g] @ B[g]^T + bias[g]).  A [M, K] or [G, M, K]; B [N, K] or [G, N, K]; bias [N] or [G, N].
     transb: B is handed over as [K, N] / [G, K, N] (D = A @ B) and transposed by the kernel's own pre-split pass.
+    out (unbatched only): a [M, N] destination with unit inner stride and any row stride (a column block of a wider
+    buffer); accumulate: out += result, in the kernel's epilogue.
     Returns [M, N] (no batched operand, or reduce_g) or [G, M, N]."""
     passes = int(passes or GEMM_PASSES)
+    if accumulate and (passes != 2 or A.shape[-1] % 8):          # only the bf16-split kernel has the accumulating epilogue
+        out.add_(gemm_tn(A, B, bias, act, reduce_g, passes, False, transb))
+        return out
     if transb and (passes != 2 or A.shape[-1] % 8):
         B, transb = B.transpose(-1, -2).contiguous(), False
     A, B = _mat(A), _mat(B)
@@ -635,7 +763,13 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     Nn = B.shape[-1] if transb else B.shape[-2]
     assert (B.shape[-2] if transb else B.shape[-1]) == K
     batched_out = (A.dim() == 3 or B.dim() == 3) and not reduce_g
-    D = torch.empty((G, M, Nn) if batched_out else (M, Nn), device=A.device, dtype=torch.float32)
+    if out is not None:
+        assert not batched_out and not want_pre and tuple(out.shape) == (M, Nn) and out.dtype == torch.float32
+        assert out.stride(1) == 1 and out.stride(0) % 4 == 0 and out.data_ptr() % 16 == 0
+        D = out
+    else:
+        D = torch.empty((G, M, Nn) if batched_out else (M, Nn), device=A.device, dtype=torch.float32)
+    ldd = D.stride(-2)
     bias_c = None if bias is None else _f32c(bias.reshape(-1, Nn) if batched_out else bias.reshape(Nn))
     pre = torch.empty_like(D) if (want_pre and act) else None
     if passes == 2 and K % 8:
@@ -643,9 +777,9 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     strideB = B.stride(0) if B.dim() == 3 else 0
     wb = int(N.lib().rorl_gemm_tn_work_bytes(Nn, K, G, strideB, passes))
     work = torch.empty(wb, dtype=torch.uint8, device=A.device) if wb else None
-    N.call("rorl_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(bias_c), N.ptr(D), N.ptr(pre), M, Nn, K, G, A.stride(-2), B.stride(-2), Nn,
+    N.call("rorl_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(bias_c), N.ptr(D), N.ptr(pre), M, Nn, K, G, A.stride(-2), B.stride(-2), ldd,
            A.stride(0) if A.dim() == 3 else 0, strideB, M * Nn if batched_out else 0,
-           Nn if (bias_c is not None and bias_c.dim() == 2) else 0, int(act), passes,
+           Nn if (bias_c is not None and bias_c.dim() == 2) else 0, int(act) | (4 if accumulate else 0), passes,
            int(reduce_g), int(transb), N.ptr(work), N.stream())
     return (D, pre) if want_pre else D
 

@@ -47,6 +47,10 @@ class ContextualModel:
         self.rnn_num = self.embedding_network.rnn_num + self.uni_network.rnn_num
         self.device = torch.device('cpu')
         self.dtype = torch.float32
+        # forward() also returns every recurrent layer's output sequence (`full_rnn_memory`, ref: contextual_model.py:57-116).
+        # A caller that never reads it (the update engine) clears this flag: the record is skipped and the activation that
+        # follows a recurrent layer may then be fused into that layer's last kernel.
+        self.need_full_hidden = True
 
     def contextual_register_rnn_base_module(self, module, module_name: str):
         self.contextual_modules[module_name] = module
@@ -70,18 +74,18 @@ class ContextualModel:
         if detach_embedding:
             emb = emb.detach()
         out, uni_mem, uni_full = self._meta_forward_uni_model(uni_model_input, emb, rnn_memory)
-        return out, emb_mem + uni_mem, emb, emb_full + uni_full
+        return out, emb_mem + uni_mem, emb, (emb_full + uni_full if self.need_full_hidden else None)
 
     def _meta_forward_embedding(self, embedding_input, rnn_memory: Optional[RNNHidden]):
         mem = rnn_memory[:self.embedding_network.rnn_num] if rnn_memory is not None and len(rnn_memory) > 0 else None
-        return self.embedding_network.meta_forward(embedding_input, mem, require_full_hidden=True)
+        return self.embedding_network.meta_forward(embedding_input, mem, require_full_hidden=self.need_full_hidden)
 
     def _meta_forward_uni_model(self, uni_model_input, embedding, rnn_memory: Optional[RNNHidden]):
         uni_model_input = self.uni_input_mapping_network(uni_model_input)
         mem = rnn_memory[self.embedding_network.rnn_num:] if rnn_memory is not None and len(rnn_memory) > 0 else None
         if embedding.dim() - uni_model_input.dim() == 1:
             uni_model_input = uni_model_input.unsqueeze(0).repeat_interleave(repeats=embedding.shape[0], dim=0)
-        return self.uni_network.meta_forward(torch.cat((uni_model_input, embedding), dim=-1), mem, require_full_hidden=True)
+        return self.uni_network.meta_forward(torch.cat((uni_model_input, embedding), dim=-1), mem, require_full_hidden=self.need_full_hidden)
 
     def get_embedding(self, x, rnn_memory):
         return self._meta_forward_embedding(x, rnn_memory)

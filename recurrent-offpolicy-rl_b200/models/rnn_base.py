@@ -296,7 +296,13 @@ class RNNBase(nn.Module):
                 elif 'lru' in lid:
                     x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.grad_detach)
                 elif lid.startswith('smamba'):
-                    x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.mask)
+                    # the full-hidden record takes the layer output BEFORE the activation, so no fusion when it is asked for
+                    fuse = isinstance(self.activation_list[ind], nn.ELU) and x.is_cuda and not require_full_hidden
+                    x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.mask, fuse_elu=fuse)
+                    if fuse:                               # the ELU ran in the layer's last GEMM
+                        k += 1
+                        out_state.append(h)
+                        continue
                 elif lid.startswith('mamba'):
                     x, h = layer(x, h_in, hidden_state.rnn_start, hidden_state.mask, hidden_state.grad_detach)
                 elif 'conv1d' in lid:

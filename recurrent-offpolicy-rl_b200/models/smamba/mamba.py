@@ -89,11 +89,14 @@ class Mamba(nn.Module):
             xs = K.causal_conv1d_silu(xs, self.conv1d.weight, self.conv1d.bias, mask)
         elif mask is not None:
             xs = xs * mask
-        x_dbl = self.x_proj(xs)                                        # [B, L, R + 2N]
-        delta = K.linear(x_dbl[..., :R], self.dt_proj.weight)          # bias + softplus happen in the scan
-        A = -torch.exp(self.A_log.float())
-        y = K.selective_scan_tm(xs, delta, A, x_dbl[..., R:R + N], x_dbl[..., R + N:], self.D.float(), z,
-                                self.dt_proj.bias.float(), rnn_start, True)
+        if K.ssm_core_ok(xs, z, self.x_proj.weight, self.dt_proj.weight, self.A_log):
+            # x_proj + dt_proj + A = -exp(A_log) + scan as one autograd node (no slice / add / exp launches around the scan)
+            y = K.ssm_core(xs, self.x_proj.weight, self.dt_proj.weight, self.A_log, self.D, z, self.dt_proj.bias, rnn_start)
+        else:
+            x_dbl = self.x_proj(xs)                                    # [B, L, R + 2N]
+            delta = K.linear(x_dbl[..., :R], self.dt_proj.weight)      # bias + softplus happen in the scan
+            y = K.selective_scan_tm(xs, delta, self.A_log.float(), x_dbl[..., R:R + N], x_dbl[..., R + N:], self.D.float(), z,
+                                    self.dt_proj.bias.float(), rnn_start, True, a_log=True)
         out = self.out_proj(y)
         if hidden is None:
             hidden = torch.zeros((1, Bsz, self.desired_hidden_dim), device=x.device)
@@ -124,9 +127,8 @@ class Mamba(nn.Module):
             xs = F.silu(xs).unsqueeze(1)                               # [B, 1, D]
         x_dbl = self.x_proj(xs)
         delta = K.linear(x_dbl[..., :R], self.dt_proj.weight)
-        A = -torch.exp(self.A_log.float())
-        y, last = K.selective_scan_tm(xs.contiguous(), delta, A, x_dbl[..., R:R + N], x_dbl[..., R + N:], self.D.float(),
-                                      z, self.dt_proj.bias.float(), None, True, True, ssm_state)
+        y, last = K.selective_scan_tm(xs.contiguous(), delta, self.A_log.float(), x_dbl[..., R:R + N], x_dbl[..., R + N:], self.D.float(),
+                                      z, self.dt_proj.bias.float(), None, True, True, ssm_state, a_log=True)
         out = self.out_proj(y)
         parts = ([conv_state.reshape(1, Bsz, -1)] if self.use_conv else []) + [last.reshape(1, Bsz, -1)]
         return out, torch.cat(parts, dim=-1)
@@ -202,7 +204,9 @@ class BlockList(nn.Module):
             self.norm_f = norm_cls(dim)
         self.apply(partial(_init_weights, n_layer=block_num))
 
-    def forward(self, x, hidden=None, rnn_start=None, mask=None):
+    def forward(self, x, hidden=None, rnn_start=None, mask=None, fuse_elu: bool = False):
+        """fuse_elu: the caller's ELU after this layer (ref: rnn_base.py activation list) runs in the epilogue of the
+        head projection's GEMM; honoured when the head is the plain Linear (not the position-wise FFN)."""
         if hidden is None:
             hidden = torch.zeros((x.shape[0], 1, self.desired_hidden_dim), device=x.device)
         hiddens = torch.chunk(hidden, self.block_num, dim=-1)
@@ -216,4 +220,7 @@ class BlockList(nn.Module):
                                 is_rms_norm=isinstance(self.norm_f, RMSNorm))
         else:
             x = (x + residual) if residual is not None else x
-        return self.head(x), torch.cat(outs, dim=-1)
+        if self.use_ff:
+            y = self.head(x)
+            return (F.elu(y) if fuse_elu else y), torch.cat(outs, dim=-1)
+        return self.head(x, fuse_elu=fuse_elu), torch.cat(outs, dim=-1)

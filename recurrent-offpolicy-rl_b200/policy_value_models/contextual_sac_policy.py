@@ -97,8 +97,13 @@ class ContextualSACPolicySingleHead(ContextualModel, _InputEncoders):
     def forward(self, state, lst_state, lst_action, rnn_memory: Optional[RNNHidden], reward=None, detach_embedding=False):
         emb_in = self.get_embedding_input(state, lst_state, lst_action, reward)
         out, rnn_memory, emb, full = self.meta_forward(emb_in, state, rnn_memory, detach_embedding)
-        logstd, logit = out.chunk(2, dim=-1)
-        action_mean, action_sample, log_prob = self.process_model_out(logit, logstd)
+        if out.is_cuda and out.dtype == torch.float32:
+            # one kernel for the whole head (forward) and one for its backward; the draw stays injectable
+            noise = self.noise_fn(out[..., self.action_dim:]).detach()
+            action_mean, action_sample, log_prob = K.tanh_gaussian_head(out, noise, self.MIN_LOG_STD, self.MAX_LOG_STD)
+        else:
+            logstd, logit = out.chunk(2, dim=-1)
+            action_mean, action_sample, log_prob = self.process_model_out(logit, logstd)
         return action_mean, emb, action_sample, log_prob, rnn_memory, full
 
     def process_model_out(self, logit, logstd):

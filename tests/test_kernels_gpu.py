@@ -346,3 +346,76 @@ def test_lru_fused_matches_materialised_path(K, shape, with_h0):
     got = torch.autograd.grad((hr, hi), gin, (gr.cuda(), gi.cuda()))
     for a, b, n in zip(got, ref, ("du_re", "du_im", "dlam_re", "dlam_im", "dgamma")):
         assert_close(a, b, TOL, n)
+
+
+# ------------------------------------------------------------------------------------------------ tanh-Gaussian head
+@pytest.mark.parametrize("M,A", [(1000, 6), (32 * 1019, 6), (77, 1), (300, 17)])
+def test_tanh_gaussian_head(K, M, A):
+    """One-kernel policy head (csrc/head.cu) against the elementwise torch graph of the reference's process_model_out
+    (ref: contextual_sac_policy_single_head.py:105-123) in float64: outputs and the gradient w.r.t. the head output,
+    with logstd values outside the clamp range (zero gradient there) and large |sample| (softplus tails)."""
+    import numpy as np
+    gen = torch.Generator(device="cuda").manual_seed(A)
+    out = torch.randn(M, 2 * A, device="cuda", generator=gen) * 3.0
+    out[::7, 0] = 5.0                      # above MAX_LOG_STD
+    out[1::7, 0] = -25.0                   # below MIN_LOG_STD
+    out.requires_grad_()
+    noise = torch.randn(M, A, device="cuda", generator=gen)
+    am, asamp, lp = K.tanh_gaussian_head(out, noise, -20.0, 2.0)
+    d_am, d_as, d_lp = (torch.randn_like(t) for t in (am, asamp, lp))
+    got = torch.autograd.grad((am, asamp, lp), out, (d_am, d_as, d_lp))[0]
+    o64 = out.detach().double().requires_grad_()
+    logstd, logit = o64.chunk(2, dim=-1)
+    logstd = torch.clamp(logstd, -20.0, 2.0)
+    sample = logit + noise.double() * logstd.exp()
+    ref_lp = (-0.5 * noise.double().pow(2) - (logstd + 0.5 * np.log(2 * np.pi))).sum(-1, keepdim=True)
+    ref_lp = ref_lp - (2 * (-sample - torch.nn.functional.softplus(-2 * sample) + np.log(2))).sum(-1, keepdim=True)
+    ref = torch.autograd.grad((torch.tanh(logit), torch.tanh(sample), ref_lp), o64, (d_am.double(), d_as.double(), d_lp.double()))[0]
+    assert_close(am, torch.tanh(logit), 1e-6, "action_mean")
+    assert_close(asamp, torch.tanh(sample), 1e-6, "action_sample")
+    assert_close(lp, ref_lp, 1e-6, "log_prob")
+    assert_close(got, ref, 1e-5, "d_out")
+    # only the log-prob gradient (the alpha / entropy path)
+    got2 = torch.autograd.grad(K.tanh_gaussian_head(out, noise, -20.0, 2.0)[2], out, d_lp)[0]
+    ref2 = torch.autograd.grad(ref_lp_of(o64, noise), o64, d_lp.double())[0]
+    assert_close(got2, ref2, 1e-5, "d_out (log_prob only)")
+
+
+def ref_lp_of(o64, noise):
+    import numpy as np
+    logstd, logit = o64.chunk(2, dim=-1)
+    logstd = torch.clamp(logstd, -20.0, 2.0)
+    sample = logit + noise.double() * logstd.exp()
+    lp = (-0.5 * noise.double().pow(2) - (logstd + 0.5 * np.log(2 * np.pi))).sum(-1, keepdim=True)
+    return lp - (2 * (-sample - torch.nn.functional.softplus(-2 * sample) + np.log(2))).sum(-1, keepdim=True)
+
+
+# ------------------------------------------------------------------------------------------------ fused SSM core
+@pytest.mark.parametrize("B,L,Dn,R,Ns", [(3, 203, 128, 4, 16), (4, 1019, 512, 16, 32), (2, 77, 64, 8, 64)])
+def test_ssm_core_matches_unfused_graph(K, B, L, Dn, R, Ns):
+    """x_proj + dt_proj + A = -exp(A_log) + scan as one autograd node against the same computation composed of the
+    separately tested pieces (tensor-core linear, narrow linear, selective_scan_tm on column slices, torch exp): output
+    and every gradient (xs, x_proj / dt_proj weights, A_log, D, z, dt bias)."""
+    gen = torch.Generator(device="cuda").manual_seed(B * L)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=gen)
+    xs, z = rn(B, L, Dn), rn(B, L, Dn)
+    Wx, Wdt = 0.1 * rn(R + 2 * Ns, Dn), 0.3 * rn(Dn, R)
+    A_log = torch.log(torch.arange(1, Ns + 1, device="cuda", dtype=torch.float32).repeat(Dn, 1)) + 0.05 * rn(Dn, Ns)
+    Dk, bias = rn(Dn), 0.5 * rn(Dn)
+    start = torch.zeros(B, L, 1, device="cuda")
+    start[:, 0] = 1
+    start[1, L // 2] = 1
+    dy = rn(B, L, Dn)
+    leaves = [t.clone().requires_grad_() for t in (xs, Wx, Wdt, A_log, Dk, z, bias)]
+    assert K.ssm_core_ok(leaves[0], leaves[5], leaves[1], leaves[2], leaves[3])
+    y = K.ssm_core(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[5], leaves[6], start)
+    got = torch.autograd.grad(y, leaves, dy)
+    ref_leaves = [t.clone().requires_grad_() for t in (xs, Wx, Wdt, A_log, Dk, z, bias)]
+    x_, Wx_, Wdt_, A_, D_, z_, b_ = ref_leaves
+    x_dbl = K.linear(x_, Wx_)
+    delta = K.linear(x_dbl[..., :R], Wdt_)
+    y_ref = K.selective_scan_tm(x_, delta, -torch.exp(A_), x_dbl[..., R:R + Ns], x_dbl[..., R + Ns:], D_, z_, b_, start, True)
+    ref = torch.autograd.grad(y_ref, ref_leaves, dy)
+    assert_close(y, y_ref, 1e-5, "y")
+    for a, r, n in zip(got, ref, ("dxs", "dWx", "dWdt", "dA_log", "dD", "dz", "dbias")):
+        assert_close(a, r, 2e-5, n)
