@@ -548,7 +548,11 @@ class SSMCore(Function):
         x_dbl = gemm_tn(xs2, Wx)                                              # [M, R + 2N]
         Wdt_c, A_c, D_c, b_c = _f32c(Wdt), _f32c(A_log), _f32c(Dskip), _f32c(dt_bias)
         delta = torch.empty((B, L, Dn), device=xs.device, dtype=torch.float32)
-        N.call("rorl_skinny_linear", N.ptr(x_dbl), N.ptr(Wdt_c), N.ptr(None), N.ptr(delta), M, Dn, R, W, M, 0, Dn, 0, N.stream())
+        if R % 8 == 0 and GEMM_PASSES == 2 and not _os.environ.get("RORL_DT_SKINNY"):
+            # K = R = 16: one half-empty k-tile on the tensor-core kernel, which then runs at the rate delta is written
+            gemm_tn(x_dbl[:, :R], Wdt_c, out=delta.view(M, Dn))
+        else:
+            N.call("rorl_skinny_linear", N.ptr(x_dbl), N.ptr(Wdt_c), N.ptr(None), N.ptr(delta), M, Dn, R, W, M, 0, Dn, 0, N.stream())
         start = _flag(start, B, L)
         y = torch.empty((B, L, Dn), device=xs.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad)
