@@ -310,10 +310,10 @@ def scan_roofline(alg, dev, ms_per_step):
 
 
 def gemm_roofline(dev):
-    """Second roofline object, for the kernel with the largest share of the step (the tcgen05 3xTF32 GEMM, ~44 %):
-    the in_proj-half shape [32608, 256] x [512, 256]^T timed alone with CUDA events.  `achieved` counts the useful
-    fp32 FLOPs (2 M N K); the kernel issues three TF32 passes for them.  `peak` is the measured dense bf16 rate of
-    MEASURED_PEAKS.json; the TF32 pipe runs at half of it."""
+    """Second roofline object, for the kernel with the largest share of the step (the tcgen05 GEMM, ~39 %): the
+    in_proj-half shape [32608, 256] x [512, 256]^T timed alone with CUDA events.  `achieved` counts the useful fp32 FLOPs
+    (2 M N K); the kernel issues three bf16 MMAs for them (two-term bf16 split, csrc/gemm_bf16.cu).  `peak` is the
+    measured dense bf16 rate of MEASURED_PEAKS.json."""
     import torch
     import rorl_b200.kernels as K
     try:
@@ -336,11 +336,19 @@ def gemm_roofline(dev):
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 20 * 1e-3
     useful = 2.0 * M * Nn * Kk
-    return {"bound": "tensor", "kernel": "gemm_kernel<TN, BN 256, BK 16> (3xTF32)", "shape": [M, Nn, Kk], "us": t * 1e6,
-            "achieved": useful / t / 1e12, "issued_tf32": 3 * useful / t / 1e12, "peak": peak, "unit": "TFLOP/s",
-            "frac": useful / t / 1e12 / peak, "frac_issued_of_tf32_peak": 3 * useful / t / 1e12 / (peak / 2),
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); TF32 = half" if peaks else "fallback 1590 TFLOP/s bf16",
-            "tensor_pipe_pct_ncu": 44.0, "ncu_source": "profiles/r01i_step_breakdown.md (fc 256x256 shape)"}
+    ncu = {}
+    try:
+        for row in json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json"))):
+            if row["kernel"].startswith("void gemm_bf16x3_kernel<256, 0>") and abs(row.get("us", 0) - 41.0) < 3:
+                ncu = row
+    except Exception:
+        pass
+    return {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<BN 256, TN> (two-term bf16 split: 3 MMAs on kind::f16; includes the B pre-split launch)",
+            "shape": [M, Nn, Kk], "us": t * 1e6, "achieved": useful / t / 1e12, "issued_bf16": 3 * useful / t / 1e12, "peak": peak,
+            "unit": "TFLOP/s", "frac": useful / t / 1e12 / peak, "frac_issued_of_bf16_peak": 3 * useful / t / 1e12 / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 TFLOP/s bf16",
+            "tensor_pipe_pct_ncu": ncu.get("tensor_pipe_cycles_pct"), "l1tex_pct_ncu": ncu.get("l1tex_pct"),
+            "ncu_source": "profiles/r02_ncu_summary.json (same shape, ncu --set full)"}
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -138,9 +138,17 @@ __global__ void __launch_bounds__(kRedThreads) partial_sum_kernel(const float* _
     const int64_t q = (int64_t)blockIdx.x * 32 + ql;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q * 4 < N) {
-#pragma unroll 4
-        for (int b = rl; b < nblk; b += 8) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)b * N + q * 4));
+        const float* pp = partial + q * 4;
+        int b = rl;
+        for (; b + 56 < nblk; b += 64) {                      // eight partial rows in flight per thread: the chain is latency
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(pp + (int64_t)(b + 8 * u) * N));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; b < nblk; b += 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(pp + (int64_t)b * N));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
     }

@@ -60,3 +60,13 @@ for e in prof.events():
 print("\nnon-rorl launches by launching op:")
 for k, (n, t) in sorted(chains.items(), key=lambda kv: -kv[1][1])[:70]:
     print(f"{t:8.1f} us {n:4d}  {k}")
+
+# individual launches in time order with their durations (spot kernels that are slow for their shape)
+if os.environ.get("RORL_PROFILE_LAUNCHES"):
+    evs = [e for e in prof.events() if str(e.device_type).endswith("CUDA")]
+    evs.sort(key=lambda e: e.time_range.start)
+    print("\nlaunch sequence (us):")
+    for e in evs:
+        t = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        name = re.sub(r"\(.*", "", e.name.replace("void ", "")).strip()[:70]
+        print(f"{t:8.1f}  {name}")
