@@ -290,6 +290,9 @@ int rorl_tanh_gaussian_bwd(const float* out, const float* noise, const float* d_
  * caller: dW_hh = [dgi_r, dgi_z, dghn]^T h_{t-1}.
  * ---------------------------------------------------------------------------------------------- */
 int rorl_gru_save_floats_per_step(int64_t H);
+/* Tuning knob (process-wide, read at launch time): SMs the forward recurrence may occupy, default 148.  A caller that
+ * runs two independent recurrences on two streams sets about half for the duration of those launches. Returns the value set. */
+int rorl_gru_set_fwd_sms(int sms);
 int rorl_gru_fwd(const float* gi, const float* w_hh, const float* b_hh, const float* h0, float* out, float* save,
                  float* h_last, int64_t B, int64_t L, int64_t H, cudaStream_t stream);
 int rorl_gru_bwd(const float* dout, const float* dh_last, const float* w_hh, const float* save, const float* out,

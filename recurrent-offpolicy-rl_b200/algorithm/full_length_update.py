@@ -278,6 +278,12 @@ class FullLengthRNNUpdate:
         self._graphs, self._graph_pool = {}, None       # captured graphs point into the old arenas
         for m in [self.policy, self.target_policy] + list(self.values) + list(self.target_values):
             m.need_full_hidden = False                  # the update never reads forward()'s per-layer output record
+        gpt = any(str(t).startswith(('cgpt', 'gpt', 'transformer')) for m in (self.policy, self.values[0])
+                  for t in m.embedding_network.layer_type)
+        side_ok = (self.device.type == 'cuda' and not self.discrete_env and not gpt       # cgpt: device-side dropout counter order
+                   and os.environ.get('RORL_SIDE_STREAM', '1') != '0')
+        self._side_stream = torch.cuda.Stream(device=self.device) if side_ok else None
+        self._has_gru = any(str(t) == 'gru' for m in (self.policy, self.values[0]) for t in m.embedding_network.layer_type)
         self._value_update(tau=0.0)
         self.target_policy.copy_weight_from(self.policy, tau=0.0)
         self.policy_arena = FlatArena(self.policy, self.device, grad_tail=4)
@@ -562,6 +568,31 @@ class FullLengthRNNUpdate:
             return 0
         return 65536.0 * 2.0 ** (self._opt_steps[which] // 2000)
 
+    def _beside(self, fn):
+        """Launch fn() -- a no-grad forward that the caller's next launches do not depend on -- on the side stream, so that
+        it runs BESIDE them; returns a join() that makes the current stream wait for it and hands back fn's result.
+        Used for the two places where the update runs two independent context encoders back to back (target policy ||
+        target value; actor's policy || the critic's encoder under the actor): a 0.86-wave scan grid, a 4-SM GRU
+        recurrence or a short elementwise kernel leaves SMs idle that the other encoder's kernels can use.
+        Works unchanged under CUDA-graph capture (fork / join through events on the capture stream).  No
+        record_stream is needed: the results are consumed on the current stream before the next fork, and every fork
+        starts by making the side stream wait for the current one."""
+        if self._side_stream is None:
+            res = fn()
+            return lambda: res
+        cur = torch.cuda.current_stream(self.device)
+        self._side_stream.wait_stream(cur)
+        if self._has_gru:                          # two recurrences at a time: each takes half the SMs (csrc/gru.cu)
+            N.lib().rorl_gru_set_fwd_sms(72)
+        with torch.cuda.stream(self._side_stream), torch.no_grad():
+            res = fn()
+        def join():
+            cur.wait_stream(self._side_stream)
+            if self._has_gru:
+                N.lib().rorl_gru_set_fwd_sms(148)
+            return res
+        return join
+
     def _graph_allowed(self) -> bool:
         """CUDA-graph replay needs a launch sequence that depends on nothing the host decides per step: an injected
         `noise_fn` (parity tests) returns a different tensor per call.  (The cgpt encoder's attention work list depends
@@ -643,12 +674,14 @@ class FullLengthRNNUpdate:
             return
         with torch.no_grad():
             pol_t = self.target_policy if (td3 and not self.use_redq) else self.policy
+            # the target critic's context encoder does not depend on the action: it runs beside the policy
+            tv_embedded = self._beside(lambda: self.target_values[0].embed(next_state, state, action, target_hidden, reward))
             a_mean, _, a_next, logp_next, _, _ = pol_t.forward(next_state, state, action, target_policy_hidden, reward)
             if td3:
                 noise = pol_t.noise_fn(a_mean) * p.target_action_noise_std
                 a_next = torch.clamp(a_mean + torch.clamp(noise, -p.target_action_noise_clip, p.target_action_noise_clip), -1, 1)
                 logp_next = None
-            q_next = self.target_values[0].forward(next_state, state, action, a_next, target_hidden, reward)[0]
+            q_next = self.target_values[0].forward(next_state, state, action, a_next, target_hidden, reward, embedded=tv_embedded())[0]
             c['target_Q'] = self._target_Q(q_next, sel, logp_next, reward, done, timeout, mask)
         self.last_target_Q = c['target_Q']
 
@@ -719,9 +752,12 @@ class FullLengthRNNUpdate:
         for w in self.value_arena.params:
             w.requires_grad_(False)
         try:
+            # the critic's encoder under the actor is detached and its weights are frozen here: no graph, runs beside the policy
+            v_embedded = self._beside(lambda: self.values[0].embed(state, last_state, last_action, c['value_hidden'], reward_input))
             a_mean, _, a_samp, logp, _, _ = self.policy.forward(state, last_state, last_action, c['policy_hidden'], reward_input)
             a_in = a_mean if td3 else a_samp
-            qp = self.values[0].forward(state, last_state, last_action, a_in, c['value_hidden'], reward_input, detach_embedding=True)[0]
+            qp = self.values[0].forward(state, last_state, last_action, a_in, c['value_hidden'], reward_input, detach_embedding=True,
+                                        embedded=v_embedded())[0]
         finally:
             for w in self.value_arena.params:
                 w.requires_grad_(True)

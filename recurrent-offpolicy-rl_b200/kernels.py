@@ -55,9 +55,8 @@ _TICKETS = {}
 
 def _tickets(device) -> torch.Tensor:
     """Persistent zero-initialised ticket slots for the single-launch reductions (the kernels re-arm them).  One array
-    per device: every reduction of the update runs on the one compute stream (forward, autograd backward and CUDA-graph
-    replays alike), so no two launches that share it can overlap."""
-    key = device.index
+    per (device, stream): launches on one stream are ordered, so no two reductions that share an array can overlap."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     t = _TICKETS.get(key)
     if t is None:
         t = _TICKETS[key] = torch.zeros(int(N.lib().rorl_colsum_tickets()), dtype=torch.int32, device=device)

@@ -67,10 +67,12 @@ class ContextualModel:
         return [p for m in self.contextual_modules.values() if hasattr(m, 'rnn_parameters') for p in m.rnn_parameters(recursive)]
 
     # ---- forward (ref: contextual_model.py:57-116) ---------------------------------------------------------
-    def meta_forward(self, embedding_input, uni_model_input, rnn_memory=None, detach_embedding=False):
+    def meta_forward(self, embedding_input, uni_model_input, rnn_memory=None, detach_embedding=False, embedded=None):
+        """embedded: the result of `_meta_forward_embedding` computed earlier (e.g. on a side stream while another model's
+        encoder runs); `embedding_input` is then ignored."""
         if rnn_memory is None:
             rnn_memory = self.make_init_state(1 if embedding_input.dim() == 2 else embedding_input.shape[0], embedding_input.device)
-        emb, emb_mem, emb_full = self._meta_forward_embedding(embedding_input, rnn_memory)
+        emb, emb_mem, emb_full = embedded if embedded is not None else self._meta_forward_embedding(embedding_input, rnn_memory)
         if detach_embedding:
             emb = emb.detach()
         out, uni_mem, uni_full = self._meta_forward_uni_model(uni_model_input, emb, rnn_memory)

@@ -61,10 +61,19 @@ class ContextualSACValue(ContextualModel, _InputEncoders):
         sa = torch.cat((self.state_input_encoder(state), self.action_input_encoder(action)), dim=-1)
         return self.uni_model_input_mapping_activation_func(sa) if self.separate_encoder else sa
 
-    def forward(self, state, lst_state, lst_action, action, rnn_memory: Optional[RNNHidden], reward, detach_embedding=False):
-        emb_in = self.get_embedding_input(state, lst_state, lst_action, reward)
-        value, rnn_memory, emb, full = self.meta_forward(emb_in, self.state_action(state, action), rnn_memory, detach_embedding)
+    def forward(self, state, lst_state, lst_action, action, rnn_memory: Optional[RNNHidden], reward, detach_embedding=False,
+                embedded=None):
+        """embedded: what `embed(...)` returned for the same (state, lst_state, lst_action, rnn_memory, reward) -- the
+        context encoder does not depend on `action`, so a caller may run it ahead of (or beside) the policy that produces
+        the action."""
+        emb_in = None if embedded is not None else self.get_embedding_input(state, lst_state, lst_action, reward)
+        value, rnn_memory, emb, full = self.meta_forward(emb_in, self.state_action(state, action), rnn_memory, detach_embedding,
+                                                         embedded=embedded)
         return value, emb, rnn_memory, full
+
+    def embed(self, state, lst_state, lst_action, rnn_memory: Optional[RNNHidden], reward):
+        """The context-encoder half of forward(): (embedding, its hidden, its per-layer record)."""
+        return self._meta_forward_embedding(self.get_embedding_input(state, lst_state, lst_action, reward), rnn_memory)
 
     def forward_embedding(self, state, lst_state, lst_action, rnn_memory, reward):
         return self.get_embedding(self.get_embedding_input(state, lst_state, lst_action, reward), rnn_memory)
