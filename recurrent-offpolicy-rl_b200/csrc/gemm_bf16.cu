@@ -27,6 +27,18 @@
 namespace rorl {
 
 constexpr int kBfBM = 128, kBfBK = 32;
+// Weight-gradient (NT) form, two interchangeable operand layouts for the tensor core:
+//   default            the splitters TRANSPOSE while they split (LDS.32 down the columns) into K-major SWIZZLE_64B tiles;
+//   -DRORL_NT_MNMAJOR  no transposition: MN-major SWIZZLE_128B tiles (vectorised LDS.128 / STS.128 splitters, a_major /
+//                      b_major set in the instruction descriptor).  Bit-identical results (tests/test_gemm_gpu.py passes
+//                      with either); measured 246 vs 230 us on the efc-8 dW shape and 33.4 vs 32.6 us on 256 x 256, i.e.
+//                      the splitter's transposition is not what bounds this form -- both operands being split per
+//                      128 x 128 tile is -- so the transposing form stays the default.
+#ifdef RORL_NT_MNMAJOR
+constexpr bool kNtMnMajor = true;
+#else
+constexpr bool kNtMnMajor = false;
+#endif
 constexpr int kBfThreads = 448;
 constexpr int kBfEpiWarps = 8;
 constexpr int kBfStaging = kBfEpiWarps * 32 * 128;
@@ -174,7 +186,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = idesc_bf16(kBfBM, BN);
+            const uint32_t idesc = (MN && kNtMnMajor) ? idesc_bf16_mn(kBfBM, BN) : idesc_bf16(kBfBM, BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
                 const int acc = tcount & 1;
@@ -186,12 +198,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     mbar_wait(bar_split_full(s), (it / SS) & 1);
                     tc_fence_after();
                     const uint32_t st = split_base + s * Cfg::kSplit;
-                    const uint64_t a_hi = make_kmajor_desc_sw64(st), a_lo = make_kmajor_desc_sw64(st + Cfg::kHalfA);
-                    const uint64_t b_hi = make_kmajor_desc_sw64(st + 2 * Cfg::kHalfA);
-                    const uint64_t b_lo = make_kmajor_desc_sw64(st + 2 * Cfg::kHalfA + Cfg::kHalfB);
+                    uint64_t a_hi, a_lo, b_hi, b_lo;
+                    if (MN && kNtMnMajor) {        // MN-major tiles: [64-column group][32 k rows][128 B], groups 4 KiB apart
+                        a_hi = make_mnmajor_desc(st, 4096, 1024); a_lo = make_mnmajor_desc(st + Cfg::kHalfA, 4096, 1024);
+                        b_hi = make_mnmajor_desc(st + 2 * Cfg::kHalfA, 4096, 1024);
+                        b_lo = make_mnmajor_desc(st + 2 * Cfg::kHalfA + Cfg::kHalfB, 4096, 1024);
+                    } else {
+                        a_hi = make_kmajor_desc_sw64(st); a_lo = make_kmajor_desc_sw64(st + Cfg::kHalfA);
+                        b_hi = make_kmajor_desc_sw64(st + 2 * Cfg::kHalfA);
+                        b_lo = make_kmajor_desc_sw64(st + 2 * Cfg::kHalfA + Cfg::kHalfB);
+                    }
 #pragma unroll
                     for (int k = 0; k < kBfBK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 16 * 2 >> 4);        // 32 B per k-step inside the 64-B swizzle row
+                        // K-major: 32 B per k-step inside the 64-B swizzle row; MN-major: 16 k rows = two 1 KiB atoms
+                        const uint64_t adv = (MN && kNtMnMajor) ? (uint64_t)(k * 2048 >> 4) : (uint64_t)(k * 16 * 2 >> 4);
                         const uint32_t first = (kt | k) == 0 ? 0u : 1u;
                         umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, first);
                         umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -216,8 +236,33 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 mbar_wait(bar_split_empty(ss), ((it / SS) & 1) ^ 1);
                 const uint8_t* raw = base_ptr + rs * Cfg::kRaw;
                 uint8_t* sp = split_ptr + ss * Cfg::kSplit;
-                if (MN) {
-                    // thread = (32-column box blk, MN column mn of it = lane): for each of the 4 chunks of 8 reduction rows,
+                if (MN && kNtMnMajor) {
+                    // No transposition: the tensor core takes MN-major operands.  item = (reduction row r, 64-column group g,
+                    // 16-byte output chunk oc = 8 columns): two raw chunks of box 2g + (oc >> 2) become chunk oc of the
+                    // 128-byte bf16 row (g, r), SWIZZLE_128B on both sides.  A quarter-warp covers one output row (8 distinct
+                    // chunks); its second half reads its odd raw chunk first so the two boxes' reads fall in different banks.
+#pragma unroll
+                    for (int op = 0; op < 2; ++op) {
+                        const uint8_t* src = raw + op * Cfg::kRawA;
+                        uint8_t* dhi = sp + (op ? 2 * Cfg::kHalfA : 0);
+                        const int half = op ? Cfg::kHalfB : Cfg::kHalfA;
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int pr = pass * 16 + (t >> 3), oc = t & 7;
+                            const int g = pr & 1, r = pr >> 1;
+                            const int c = 2 * (oc & 3), sw = oc >> 2;
+                            const uint8_t* row = src + (2 * g + sw) * 4096 + r * 128;
+                            const float4 f0 = *reinterpret_cast<const float4*>(row + (((c + sw) ^ (r & 7)) << 4));
+                            const float4 f1 = *reinterpret_cast<const float4*>(row + (((c + 1 - sw) ^ (r & 7)) << 4));
+                            uint4 hi, lo;
+                            split8(sw ? f1 : f0, sw ? f0 : f1, hi, lo);
+                            uint8_t* dst = dhi + g * 4096 + r * 128 + ((oc ^ (r & 7)) << 4);
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + half) = lo;
+                        }
+                    }
+                } else if (MN) {
+                                        // thread = (32-column box blk, MN column mn of it = lane): for each of the 4 chunks of 8 reduction rows,
                     // 8 conflict-free LDS.32 down the column (a warp reads one 128-byte raw row per instruction), split,
                     // one 16-byte store per half into row blk * 32 + lane of the K-major bf16 tile
                     const int blk = t >> 5;

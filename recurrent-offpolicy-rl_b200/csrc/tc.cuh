@@ -43,6 +43,19 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_sw64(uint32_t saddr) {
     return d;
 }
 
+// MN-major, SWIZZLE_128B: rows of 128 B hold 64 consecutive bf16 along M (or N) for ONE k; 8 consecutive k rows form a
+// 1024-byte swizzle atom.  Canonical form (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>, in 16-byte units):
+// ((8, n), (8, k)) : ((1, LBO), (8, SBO)) -- LBO = distance between 64-element MN groups, SBO = between 8-row k groups.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -53,6 +66,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with both operands MN-major (a_major = bit 15, b_major = bit 16)
+__device__ __forceinline__ uint32_t idesc_bf16_mn(int M, int N) { return idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
 // 32 TMEM lanes (this warp's quarter) x 32 consecutive fp32 columns -> 32 registers per lane (lane = row)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
