@@ -223,7 +223,8 @@ int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t 
  * backward); bit 2 (4, passes == 2 only) ACCUMULATE: D += result, so that a gradient with two producers (the scan's du
  * and x_proj's input gradient, ref: smamba/mamba.py:213-233) needs no separate add pass.
  * passes: 3 = 3xTF32 (fp32 parity, ~2^-21), 2 = two-term bf16 split, 3 bf16 MMAs (fp32 parity to ~2^-17 at twice
- * the tensor rate and half the operand bytes), 1 = plain TF32.  reduce_g != 0: the G products are
+ * the tensor rate and half the operand bytes), 1 = plain TF32, 4 = the bf16 kernel's hi * hi term alone (one bf16 MMA per
+ * k-step: what a layer the reference runs under bf16 autocast computes, ref TransformerFlashAttention.py:80-81).  reduce_g != 0: the G products are
  * summed into one D[M, N] (data-gradient of an ensemble layer with shared input).
  * K, N, ld*, stride* multiples of 4 (passes == 2: K a multiple of 8); bases 16-byte aligned.
  * work: device scratch of rorl_gemm_tn_work_bytes(...) bytes, 16-byte aligned (passes == 2: the kernel pre-splits

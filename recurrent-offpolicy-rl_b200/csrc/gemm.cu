@@ -354,11 +354,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 // gemm_bf16.cu: the two-term bf16 split ("bf16x3", passes == 2)
 int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                    int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
-                   int64_t strideBias, int act, int reduce_g, int transb, int force_bn, void* bsplit, cudaStream_t stream);
+                   int64_t strideBias, int act, int reduce_g, int transb, int single, int force_bn, void* bsplit, cudaStream_t stream);
 
 int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda, int64_t ldb,
                    int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits, int64_t strideSplit,
-                   cudaStream_t stream);
+                   int single, cudaStream_t stream);
 
 static int g_gemm_dbg = 0;
 static int g_gemm_bn = 0;
@@ -393,19 +393,20 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
                  int64_t strideBias, int act, int passes, int reduce_g, int transb, void* work, cudaStream_t stream) {
     if (!A || !B || !D) return RORL_ERR_ARG;
-    if (transb && passes != 2) return RORL_ERR_ARG;              // only the pre-splitting form re-lays B out
-    if ((act & ~5) || ((act & 4) && passes != 2)) return RORL_ERR_ARG;   // accumulate: bf16-split form only
+    const bool bf = passes == 2 || passes == 4;                  // the bf16 kernel: two-term split (2) or its hi * hi term alone (4)
+    if (transb && !bf) return RORL_ERR_ARG;                      // only the pre-splitting form re-lays B out
+    if ((act & ~5) || ((act & 4) && !bf)) return RORL_ERR_ARG;   // accumulate: bf16 kernel only
     if (M <= 0 || N <= 0 || K <= 0 || G <= 0) return RORL_ERR_SHAPE;
     if (K % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideBias % 4)
         return RORL_ERR_ALIGN;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D) |
          reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(Dpre)) & 15)
         return RORL_ERR_ALIGN;
-    if (passes != 1 && passes != 2 && passes != 3) return RORL_ERR_ARG;
+    if (passes < 1 || passes > 4) return RORL_ERR_ARG;
     if (reduce_g && (!strideA || !strideB)) return RORL_ERR_ARG;
-    if (passes == 2)
+    if (bf)
         return gemm_tn_bf16x3(A, B, bias, D, Dpre, M, N, K, G, lda, ldb, ldd, strideA, strideB, strideD, strideBias, act, reduce_g,
-                              transb, g_gemm_bn, work, stream);
+                              transb, passes == 4, g_gemm_bn, work, stream);
     CUtensorMap mapA, mapB;
     const bool wide = N > kGemmBN && g_gemm_bn != 128;            // N > 128: 128 x 256 tiles (see GemmCfg)
     const int bn = wide ? 256 : kGemmBN;
@@ -435,7 +436,7 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
 
 // bytes of `work` rorl_gemm_tn needs for passes == 2 (the B operand's bf16 hi | lo copies); 0 for the TF32 forms
 int64_t rorl_gemm_tn_work_bytes(int64_t N, int64_t K, int64_t G, int64_t strideB, int passes) {
-    if (passes != 2) return 0;
+    if (passes != 2 && passes != 4) return 0;
     return 2 * (strideB ? G : 1) * N * K * 2;
 }
 
@@ -469,10 +470,10 @@ int rorl_gemm_nt(const float* A, const float* B, float* D, int64_t M, int64_t N,
         return RORL_ERR_ALIGN;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D)) & 15)
         return RORL_ERR_ALIGN;
-    if (passes != 1 && passes != 2 && passes != 3) return RORL_ERR_ARG;
+    if (passes < 1 || passes > 4) return RORL_ERR_ARG;
     if (splits != rorl_gemm_nt_splits(M, N, R, G)) return RORL_ERR_ARG;
-    if (passes == 2)
-        return gemm_nt_bf16x3(A, B, D, M, N, R, G, lda, ldb, ldd, strideA, strideB, strideD, splits, strideSplit, stream);
+    if (passes == 2 || passes == 4)
+        return gemm_nt_bf16x3(A, B, D, M, N, R, G, lda, ldb, ldd, strideA, strideB, strideD, splits, strideSplit, passes == 4, stream);
     CUtensorMap mapA, mapB;
     int rc = make_map(&mapA, A, R, M, lda, strideA ? G : 1, strideA, kGemmBK);
     if (rc) return rc;

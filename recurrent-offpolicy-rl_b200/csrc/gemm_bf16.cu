@@ -63,6 +63,7 @@ struct BfParams {
     long long ldd, strideD, strideBias;
     int a_batched, b_batched, act, reduce_g;
     int accum;                  // TN form: D += result (read-modify-write in the epilogue's coalesced row stores)
+    int single;                 // hi * hi only: one bf16 MMA per k-step (what a bf16-autocast layer of the reference computes)
     int splits;                 // NT variant: split-K factor; partial s is written at D + s * strideSplit
     long long strideSplit;
 };
@@ -213,9 +214,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                         // K-major: 32 B per k-step inside the 64-B swizzle row; MN-major: 16 k rows = two 1 KiB atoms
                         const uint64_t adv = (MN && kNtMnMajor) ? (uint64_t)(k * 2048 >> 4) : (uint64_t)(k * 16 * 2 >> 4);
                         const uint32_t first = (kt | k) == 0 ? 0u : 1u;
-                        umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, first);
-                        umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-                        umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                        if (!p.single) {
+                            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, first);
+                            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        }
+                        umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, p.single ? first : 1u);
                     }
                     umma_commit(bar_split_empty(s));
                 }
@@ -477,7 +480,7 @@ static int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long
 // stored [K, N] (row stride ldb) and is transposed by the splitting pass.
 int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                    int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
-                   int64_t strideBias, int act, int reduce_g, int transb, int force_bn, void* bsplit, cudaStream_t stream) {
+                   int64_t strideBias, int act, int reduce_g, int transb, int single, int force_bn, void* bsplit, cudaStream_t stream) {
     if (!bsplit || (reinterpret_cast<uintptr_t>(bsplit) & 15)) return RORL_ERR_WORKSPACE;
     if (K % 8) return RORL_ERR_ALIGN;                            // bf16 rows must be 16-byte multiples for the tensor map
     const int64_t GB = strideB ? G : 1;
@@ -504,7 +507,7 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
     BfParams p;
     p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
     p.ldd = ldd; p.strideD = strideD; p.strideBias = strideBias;
-    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act & 1; p.accum = (act & 4) != 0; p.reduce_g = reduce_g != 0;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act & 1; p.accum = (act & 4) != 0; p.reduce_g = reduce_g != 0; p.single = single != 0;
     p.splits = 1; p.strideSplit = 0;
     const int sms = bf_sms();
     const long long tiles = ((M + kBfBM - 1) / kBfBM) * ((N + bn - 1) / bn) * (reduce_g ? 1 : G);
@@ -523,7 +526,7 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
 // Called from rorl_gemm_nt (gemm.cu) for passes == 2; arguments already validated there.
 int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda, int64_t ldb,
                    int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits, int64_t strideSplit,
-                   cudaStream_t stream) {
+                   int single, cudaStream_t stream) {
     CUtensorMap mapA, mapB;
     int rc = make_map(&mapA, A, R, M, lda, strideA ? G : 1, strideA, kBfBK);
     if (rc) return rc;
@@ -532,7 +535,7 @@ int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t 
     BfParams p;
     p.D = D; p.Dpre = nullptr; p.bias = nullptr; p.M = (int)M; p.N = (int)N; p.K = (int)R; p.G = (int)G;
     p.ldd = ldd; p.strideD = strideD; p.strideBias = 0;
-    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = 0; p.accum = 0; p.reduce_g = 0;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = 0; p.accum = 0; p.reduce_g = 0; p.single = single != 0;
     p.splits = (int)splits; p.strideSplit = strideSplit;
     const int sms = bf_sms();
     const long long tiles = ((M + kBfBM - 1) / kBfBM) * ((N + 127) / 128) * G * splits;

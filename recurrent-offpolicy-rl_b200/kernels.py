@@ -755,10 +755,10 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     buffer); accumulate: out += result, in the kernel's epilogue.
     Returns [M, N] (no batched operand, or reduce_g) or [G, M, N]."""
     passes = int(passes or GEMM_PASSES)
-    if accumulate and (passes != 2 or A.shape[-1] % 8):          # only the bf16-split kernel has the accumulating epilogue
+    if accumulate and (passes not in (2, 4) or A.shape[-1] % 8):  # only the bf16 kernel has the accumulating epilogue
         out.add_(gemm_tn(A, B, bias, act, reduce_g, passes, False, transb))
         return out
-    if transb and (passes != 2 or A.shape[-1] % 8):
+    if transb and (passes not in (2, 4) or A.shape[-1] % 8):
         B, transb = B.transpose(-1, -2).contiguous(), False
     A, B = _mat(A), _mat(B)
     G = max(A.shape[0] if A.dim() == 3 else 1, B.shape[0] if B.dim() == 3 else 1)
@@ -775,8 +775,8 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     ldd = D.stride(-2)
     bias_c = None if bias is None else _f32c(bias.reshape(-1, Nn) if batched_out else bias.reshape(Nn))
     pre = torch.empty_like(D) if (want_pre and act) else None
-    if passes == 2 and K % 8:
-        passes = 3                                   # bf16 rows must be 16-byte multiples; such widths are not on the update path
+    if passes in (2, 4) and K % 8:
+        passes = 3 if passes == 2 else 1                                   # bf16 rows must be 16-byte multiples; such widths are not on the update path
     strideB = B.stride(0) if B.dim() == 3 else 0
     wb = int(N.lib().rorl_gemm_tn_work_bytes(Nn, K, G, strideB, passes))
     work = torch.empty(wb, dtype=torch.uint8, device=A.device) if wb else None

@@ -30,6 +30,11 @@ from ... import kernels as K
 from ..linear import Linear
 from ..RNNHidden import InferenceParams  # noqa: F401  (re-exported under the reference's name)
 
+# The reference runs the MHA (Wqkv, attention, out_proj) under torch.cuda.amp.autocast(bfloat16) (ref :80-81): its linears
+# are single bf16 GEMMs.  4 = one bf16 MMA per k-step on the tcgen05 kernel (RORL_MHA_PASSES=1 selects the TF32 form).
+import os as _os
+BF16_AUTOCAST_PASSES = int(_os.environ.get("RORL_MHA_PASSES", "4"))
+
 
 def get_alibi_slopes(nheads: int):
     """Same schedule as flash_attn.modules.mha.get_alibi_slopes (geometric in 2^(-8/n))."""
@@ -82,7 +87,7 @@ class MHA(nn.Module):
         In training mode with dropout > 0 the attention probabilities are dropped inside the kernel, as flash-attn does
         for `MHA(dropout=p)` (ref: TransformerFlashAttention.py:65-70)."""
         T = x.shape[0]
-        qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=1)
+        qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=BF16_AUTOCAST_PASSES)
         p_drop = self.attn_dropout if self.training else 0.0
         seed = None
         if p_drop > 0.0:
@@ -90,7 +95,7 @@ class MHA(nn.Module):
             seed = self._drop_calls.clone()                  # the backward needs THIS call's value
         o = K.attn_varlen_alibi(qkv.view(T, 3, self.num_heads, self.head_dim), tiles[0], tiles[1], self.alibi_slopes,
                                 1.0 / math.sqrt(self.head_dim), p_drop, seed, self._salt)
-        return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=1)
+        return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=BF16_AUTOCAST_PASSES)
 
     def decode_step(self, x, cache):
         """One rollout step with the kv-cache: x [B, 1, C]; `cache` is the layer stack's InferenceParams
@@ -100,7 +105,7 @@ class MHA(nn.Module):
         called from TransformerFlashAttention.py:76-83 and rnn_base.py:437-452.)  Tiny tensors: plain CUDA ops."""
         B = x.shape[0]
         H, hd = self.num_heads, self.head_dim
-        qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=1).view(B, 3, H, hd)
+        qkv = K.linear(x, self.Wqkv.weight, self.Wqkv.bias, passes=BF16_AUTOCAST_PASSES).view(B, 3, H, hd)
         kv = cache.key_value_memory_dict.get(self.layer_idx)
         if kv is None:
             kv = torch.zeros((cache.max_batch_size, cache.max_seqlen, 2, H, hd), device=x.device, dtype=torch.bfloat16)
@@ -116,7 +121,7 @@ class MHA(nn.Module):
         scores = scores - self.alibi_slopes.view(1, H, 1) * dist.view(1, 1, -1)
         p = torch.softmax(scores, dim=-1).to(torch.bfloat16).float()
         o = torch.einsum('bht,bthd->bhd', p, vals).reshape(B, 1, H * hd)
-        return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=1)
+        return K.linear(o, self.out_proj.weight, self.out_proj.bias, passes=BF16_AUTOCAST_PASSES)
 
 
 class PositionWiseFeedForward(nn.Module):

@@ -182,6 +182,23 @@ def test_gemm_tn_transposed_weights(K, M, N, K_, G):
     assert rel_err(D, ref) < 3e-5
 
 
+@pytest.mark.parametrize("M,N,K_", [(1000, 512, 256), (32608, 1536, 512), (300, 80, 64)])
+def test_gemm_bf16_single_pass(K, M, N, K_):
+    """passes = 4: the hi * hi term alone (one bf16 MMA per k-step), for the layers the reference runs under bf16 autocast.
+    Checked against the product of the bf16-ROUNDED operands in float64 (exact up to fp32 accumulation), forward, the
+    transposed-weight form and the weight-gradient form."""
+    g = torch.Generator(device="cuda").manual_seed(M + K_)
+    A = torch.randn(M, K_, device="cuda", generator=g)
+    B = torch.randn(N, K_, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    r = lambda t: t.to(torch.bfloat16).double()
+    ref = r(A) @ r(B).t() + bias.double()
+    assert rel_err(K.gemm_tn(A, B, bias, passes=4), ref) < 2e-5
+    assert rel_err(K.gemm_tn(A, B.t().contiguous(), bias, passes=4, transb=True), ref) < 2e-5
+    G_ = torch.randn(M, N, device="cuda", generator=g)
+    assert rel_err(K.gemm_nt(G_, A, passes=4), r(G_).t() @ r(A)) < 2e-5
+
+
 @pytest.mark.parametrize("Kh,M", [(256, 1000), (128, 37), (384, 513), (512, 130)])
 def test_ensemble_hidden_to_scalar(K, Kh, M):
     """Fused `efc (ELU) -> efc (out 1)` tail of the ensemble-Q head vs the same two layers in float64."""
