@@ -229,10 +229,17 @@ int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t 
  * K, N, ld*, stride* multiples of 4 (passes == 2: K a multiple of 8); bases 16-byte aligned.
  * work: device scratch of rorl_gemm_tn_work_bytes(...) bytes, 16-byte aligned (passes == 2: the kernel pre-splits
  * the B operand -- the weights, re-read by every row tile -- into bf16 hi / lo copies there); NULL otherwise.
- * transb != 0 (passes == 2 only): B is stored [K, N] with row stride ldb -- nn.Linear's weight as its input-gradient
+ * transb is a flag word (passes 2 / 4 only).  Bit 1 (2): `work` ALREADY holds B's split copy -- the caller keeps it up to
+ * date with rorl_split_bf16_multi after every change of the weights -- and the per-call pre-split launch is skipped (an
+ * update issues ~110 GEMMs on weights that change three times).  Bit 0 (1): B is stored [K, N] with row stride ldb -- nn.Linear's weight as its input-gradient
  * GEMM needs it, EnsembleLinear's [E, in, out] weight as its forward needs it -- and the pre-split transposes it.
  * ---------------------------------------------------------------------------------------------- */
 int64_t rorl_gemm_tn_work_bytes(int64_t N, int64_t K, int64_t G, int64_t strideB, int passes);
+/* (Re)build the split copies of many B operands in one launch.  jobs: DEVICE array of njobs records
+ *   struct { const float* src; void* dst; int32_t N, K, G, transposed; int64_t ld, gs; }      (48 bytes each)
+ * src: G groups (group stride gs floats) of [N, K] rows with row stride ld, or -- transposed != 0 -- of [K, N] rows;
+ * dst: rorl_gemm_tn_work_bytes(N, K, G, gs, 2) bytes, the buffer to hand to rorl_gemm_tn as `work` with transb bit 1. */
+int rorl_split_bf16_multi(const void* jobs, int64_t njobs, cudaStream_t stream);
 int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, float* Dpre, int64_t M, int64_t N, int64_t K, int64_t G,
                  int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
                  int64_t strideBias, int act, int passes, int reduce_g, int transb, void* work, cudaStream_t stream);

@@ -293,6 +293,14 @@ class FullLengthRNNUpdate:
         self.alpha_arena = SimpleNamespace(flat=self.log_sac_alpha.data, grad=self.policy_arena.tail[:1],
                                            params=[self.log_sac_alpha], offsets=[0], numel=1, zero_grad=lambda: None)
         self._guard_init_synced = False
+        # bf16 hi | lo copies of the weights as the GEMMs' B operands, kept across the ~110 GEMM calls of an update and rebuilt
+        # by one launch per arena whenever that arena changes (kernels.WeightSplitCache)
+        self._split_cache = None
+        if self.device.type == 'cuda' and os.environ.get('RORL_SPLIT_CACHE', '1') != '0':
+            import rorl_b200.kernels as K
+            self._split_cache = K.WeightSplitCache(self.device)
+            self._split_owner = {name: self._split_cache.add_owner(a.flat) for name, a in
+                                 (('policy', self.policy_arena), ('value', self.value_arena), ('target', self.target_arena))}
         p = self.parameter
 
         def groups(model, rnn_lr, l2):
@@ -508,7 +516,7 @@ class FullLengthRNNUpdate:
                 segments = []
                 for stage, comm in self._stages(graph_mode=True):
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode="thread_local"):
+                    with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode="thread_local"), self._splits_active():
                         stage(ctx)
                     if self._graph_pool is None:
                         self._graph_pool = graph.pool()
@@ -524,9 +532,12 @@ class FullLengthRNNUpdate:
                     self._graphs[key] = 'seen'
                 self._arm_grad_detection()
                 for stage, comm in self._stages(graph_mode=False):
-                    stage(ctx)
+                    with self._splits_active():
+                        stage(ctx)
                     if comm is not None:
                         comm()
+                if self._split_cache is not None:
+                    self._split_cache.prepare()             # job tables of the operands first seen in this call (outside capture)
         if advance:
             self.grad_num += 1
         self._opt_steps['value'] += 1
@@ -567,6 +578,18 @@ class FullLengthRNNUpdate:
         if not self._has_gpt:
             return 0
         return 65536.0 * 2.0 ** (self._opt_steps[which] // 2000)
+
+    def _splits_active(self):
+        import contextlib
+        return self._split_cache.active() if self._split_cache is not None else contextlib.nullcontext()
+
+    def _splits(self, refresh=(), invalidate=()):
+        if self._split_cache is None:
+            return
+        for name in refresh:
+            self._split_cache.refresh(self._split_owner[name])
+        for name in invalidate:
+            self._split_cache.invalidate(self._split_owner[name])
 
     def _beside(self, fn):
         """Launch fn() -- a no-grad forward that the caller's next launches do not depend on -- on the side stream, so that
@@ -645,6 +668,7 @@ class FullLengthRNNUpdate:
         state, action, next_state = batch.state, batch.action, batch.next_state
         done, mask, reward, timeout, rnn_start = batch.done, batch.mask, batch.reward, batch.timeout, batch.start
         B = state.shape[0]
+        self._splits(refresh=('policy', 'value', 'target'))     # weights may have changed since the last update (steps, loads)
         # the side-band flags are read by every recurrent / conv layer of four forward passes: hand them over contiguous and
         # in fp32 ONCE here (batch.start is a column slice of the sampled batch; each kernel wrapper would otherwise copy it)
         rnn_start = rnn_start.float().contiguous()
@@ -737,6 +761,7 @@ class FullLengthRNNUpdate:
         state, last_state, last_action, reward_input = batch.state, batch.last_state, batch.last_action, batch.reward_input
         self._freeze_no_grad(self.optimizer_value)
         self.optimizer_value.step(tau=p.sac_tau)   # + Polyak (ref :395)
+        self._splits(refresh=('value',), invalidate=('target',))
         N.call("rorl_sumsq", N.ptr(self.value_arena.flat), self._l2_span['value'], N.ptr(self._stats[8:9]), N.ptr(self._work), N.stream())
         for v in self.values:
             v.eval()
@@ -822,6 +847,7 @@ class FullLengthRNNUpdate:
             return
         self._freeze_no_grad(self.optimizer_policy)
         self.optimizer_policy.step()
+        self._splits(invalidate=('policy',))
         N.call("rorl_sumsq", N.ptr(self.policy_arena.flat), self._l2_span['policy'], N.ptr(self._stats[9:10]), N.ptr(self._work), N.stream())
         if not self.parameter.no_alpha_auto_tune:
             self.optimizer_alpha.step()

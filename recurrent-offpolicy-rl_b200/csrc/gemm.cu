@@ -356,6 +356,7 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
                    int64_t lda, int64_t ldb, int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD,
                    int64_t strideBias, int act, int reduce_g, int transb, int single, int force_bn, void* bsplit, cudaStream_t stream);
 
+int split_bf16_multi(const void* jobs, int njobs, cudaStream_t stream);
 int gemm_nt_bf16x3(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t R, int64_t G, int64_t lda, int64_t ldb,
                    int64_t ldd, int64_t strideA, int64_t strideB, int64_t strideD, int64_t splits, int64_t strideSplit,
                    int single, cudaStream_t stream);
@@ -394,7 +395,7 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
                  int64_t strideBias, int act, int passes, int reduce_g, int transb, void* work, cudaStream_t stream) {
     if (!A || !B || !D) return RORL_ERR_ARG;
     const bool bf = passes == 2 || passes == 4;                  // the bf16 kernel: two-term split (2) or its hi * hi term alone (4)
-    if (transb && !bf) return RORL_ERR_ARG;                      // only the pre-splitting form re-lays B out
+    if ((transb & ~3) || (transb && !bf)) return RORL_ERR_ARG;   // only the pre-splitting form re-lays B out / takes a kept copy
     if ((act & ~5) || ((act & 4) && !bf)) return RORL_ERR_ARG;   // accumulate: bf16 kernel only
     if (M <= 0 || N <= 0 || K <= 0 || G <= 0) return RORL_ERR_SHAPE;
     if (K % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideBias % 4)
@@ -432,6 +433,15 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     else
         gemm_kernel<false, 128, 32><<<grid, kGemmThreads, GemmCfg<128, 32>::kSmem, stream>>>(mapA, mapB, p);
     RORL_RETURN_LAUNCH();
+}
+
+// B operands whose split copy the CALLER maintains (transb bit 1 of rorl_gemm_tn): (re)build many of them in one launch.
+// `jobs`: device array of njobs records {const float* src; void* dst; int32 N, K, G, transposed; int64 ld, gs} (48 bytes
+// each, natural alignment); job j writes G groups of [N, K] bf16 hi at dst and lo at dst + 2 * G * N * K bytes.
+int rorl_split_bf16_multi(const void* jobs, int64_t njobs, cudaStream_t stream) {
+    if (!jobs && njobs > 0) return RORL_ERR_ARG;
+    if (njobs < 0 || njobs > 65535) return RORL_ERR_SHAPE;
+    return rorl::split_bf16_multi(jobs, (int)njobs, stream);
 }
 
 // bytes of `work` rorl_gemm_tn needs for passes == 2 (the B operand's bf16 hi | lo copies); 0 for the TF32 forms

@@ -461,6 +461,60 @@ __global__ void __launch_bounds__(256) split_bf16_t_kernel(const float* __restri
     }
 }
 
+// Many B operands in one launch: job j = one operand (G groups of [N, K], source either [N, K] rows or, transposed, [K, N]
+// rows with row stride ld) -> its bf16 hi | lo copy in the layout gemm_tn_bf16x3 reads.  grid = (32 x 32 tiles, jobs);
+// the jobs table lives in device memory (it is static: weights sit in fixed arenas, the copies in persistent buffers).
+struct SplitJob {
+    const float* src;
+    __nv_bfloat16* dst;          // hi at dst, lo at dst + G * N * K
+    int N, K, G, transposed;
+    long long ld, gs;
+};
+__global__ void __launch_bounds__(256) split_bf16_multi_kernel(const SplitJob* __restrict__ jobs) {
+    __shared__ float tile[32][33];
+    const SplitJob jb = jobs[blockIdx.y];
+    const int tn = (jb.N + 31) / 32, tk = (jb.K + 31) / 32;
+    const long long ntile = (long long)tn * tk * jb.G;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __nv_bfloat16* hi = jb.dst;
+    __nv_bfloat16* lo = jb.dst + (long long)jb.G * jb.N * jb.K;
+    for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
+        const int g = (int)(t / ((long long)tn * tk));
+        const int rem = (int)(t % ((long long)tn * tk));
+        const int n0 = (rem / tk) * 32, k0 = (rem % tk) * 32;
+        const float* w = jb.src + (long long)g * jb.gs;
+        const long long obase = (long long)g * jb.N * jb.K;
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            // tile[a][b]: a = n - n0, b = k - k0
+            if (jb.transposed) {                   // source rows are k: read along n (contiguous), store transposed
+                const int k = k0 + j, n = n0 + tx;
+                tile[tx][j] = (k < jb.K && n < jb.N) ? __ldg(w + (long long)k * jb.ld + n) : 0.f;
+            } else {
+                const int n = n0 + j, k = k0 + tx;
+                tile[j][tx] = (n < jb.N && k < jb.K) ? __ldg(w + (long long)n * jb.ld + k) : 0.f;
+            }
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int n = n0 + j, k = k0 + tx;
+            if (n < jb.N && k < jb.K) {
+                const float x = tile[j][tx];
+                const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                hi[obase + (long long)n * jb.K + k] = h;
+                lo[obase + (long long)n * jb.K + k] = __float2bfloat16_rn(x - __bfloat162float(h));
+            }
+        }
+    }
+}
+
+int split_bf16_multi(const void* jobs, int njobs, cudaStream_t stream) {
+    if (njobs <= 0) return RORL_OK;
+    dim3 grid(64u, (unsigned)njobs);
+    split_bf16_multi_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const SplitJob*>(jobs));
+    RORL_RETURN_LAUNCH();
+}
+
 // 3-D map over a contiguous bf16 [batch][rows][cols] tensor: box = 32 cols (64 B) x box_rows x 1, SWIZZLE_64B
 static int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long batch, int box_rows) {
     EncodeTiledFn enc = get_encode();
@@ -486,7 +540,9 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
     const int64_t GB = strideB ? G : 1;
     __nv_bfloat16* bhi = reinterpret_cast<__nv_bfloat16*>(bsplit);
     __nv_bfloat16* blo = bhi + GB * N * K;
-    if (transb) {
+    if (transb & 2) {
+        // the caller keeps B's split copy up to date itself (rorl_split_bf16_multi after every weight change): nothing to do
+    } else if (transb & 1) {
         dim3 grid((unsigned)((N + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)GB);
         split_bf16_t_kernel<<<grid, 256, 0, stream>>>(B, bhi, blo, (int)N, (int)K, ldb, strideB);
     } else {

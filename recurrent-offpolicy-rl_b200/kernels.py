@@ -747,6 +747,99 @@ def _mat(t: torch.Tensor) -> torch.Tensor:
     return t if ok else t.contiguous()
 
 
+class WeightSplitCache:
+    """bf16 hi | lo copies of the GEMMs' B operands (the weights) kept across calls.
+
+    rorl_gemm_tn pre-splits its B operand once per call (csrc/gemm_bf16.cu); an update issues ~110 GEMMs on weights that
+    change three times (critic step, actor step, Polyak).  While a cache is active (`with cache.active():`, the update
+    engine only) every B operand that is a view into one of the registered parameter arenas gets a persistent buffer the
+    first time it is seen; `refresh(owner)` rebuilds all buffers of one arena in ONE launch (rorl_split_bf16_multi over a
+    device-resident job table) and the GEMMs then skip their own pre-split launch (transb bit 1).  The owner of the
+    weights calls refresh() after every change; nothing is cached for operands outside the registered arenas.  Tables are
+    uploaded by prepare() outside CUDA-graph capture; refresh() itself only launches."""
+
+    def __init__(self, device):
+        self.device = device
+        self.owners = []            # flat parameter arenas
+        self.entries = {}           # key -> [buffer, owner index, fresh]
+        self._jobs = {}             # owner index -> list of job records
+        self._tables = {}           # owner index -> (device table, njobs)
+        self._dirty = set()
+
+    def add_owner(self, flat: torch.Tensor) -> int:
+        self.owners.append(flat)
+        self._jobs[len(self.owners) - 1] = []
+        return len(self.owners) - 1
+
+    def _owner_of(self, t: torch.Tensor):
+        p = t.data_ptr()
+        for i, flat in enumerate(self.owners):
+            if flat.data_ptr() <= p < flat.data_ptr() + 4 * flat.numel():
+                return i
+        return None
+
+    def lookup(self, B, transb, Nn, K, G, ld, gs):
+        key = (B.data_ptr(), Nn, K, G, ld, gs, bool(transb))
+        e = self.entries.get(key)
+        if e is not None:
+            return e[0] if e[2] else None
+        i = self._owner_of(B)
+        if i is not None and not torch.cuda.is_current_stream_capturing():
+            wb = int(N.lib().rorl_gemm_tn_work_bytes(Nn, K, G, gs, 2))
+            buf = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            self.entries[key] = [buf, i, False]
+            self._jobs[i].append((B.data_ptr(), buf.data_ptr(), Nn, K, G if gs else 1, int(bool(transb)), ld, gs))
+            self._dirty.add(i)
+        return None                 # the caller splits by itself this time
+
+    def prepare(self):
+        """Upload the job tables that gained entries (host -> device copy: call outside graph capture)."""
+        import numpy as np
+        rec = np.dtype([('src', '<u8'), ('dst', '<u8'), ('N', '<i4'), ('K', '<i4'), ('G', '<i4'), ('T', '<i4'), ('ld', '<i8'), ('gs', '<i8')])
+        for i in sorted(self._dirty):
+            arr = np.array(self._jobs[i], dtype=rec)
+            self._tables[i] = (torch.from_numpy(arr.view(np.uint8).copy()).to(self.device), len(self._jobs[i]))
+        self._dirty.clear()
+
+    def refresh(self, i: int):
+        """All cached copies of arena i are rebuilt from the current weights (one launch)."""
+        if i in self._dirty:
+            if torch.cuda.is_current_stream_capturing():
+                self.invalidate(i)             # cannot upload now: those operands fall back to per-call splits
+                return
+            self.prepare()
+        tab = self._tables.get(i)
+        if tab is None:
+            return
+        N.call("rorl_split_bf16_multi", N.ptr(tab[0]), tab[1], N.stream())
+        for e in self.entries.values():
+            if e[1] == i:
+                e[2] = True
+
+    def invalidate(self, i: int):
+        for e in self.entries.values():
+            if e[1] == i:
+                e[2] = False
+
+    def active(self):
+        cache = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                global _ACTIVE_SPLIT_CACHE
+                self_inner.prev = _ACTIVE_SPLIT_CACHE
+                _ACTIVE_SPLIT_CACHE = cache
+
+            def __exit__(self_inner, *exc):
+                global _ACTIVE_SPLIT_CACHE
+                _ACTIVE_SPLIT_CACHE = self_inner.prev
+                return False
+        return _Ctx()
+
+
+_ACTIVE_SPLIT_CACHE = None
+
+
 def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int = None, want_pre: bool = False, transb: bool = False,
             out: torch.Tensor = None, accumulate: bool = False):
     """D[g] = act(A[g] @ B[g]^T + bias[g]).  A [M, K] or [G, M, K]; B [N, K] or [G, N, K]; bias [N] or [G, N].
@@ -778,12 +871,18 @@ def gemm_tn(A, B, bias=None, act: int = 0, reduce_g: bool = False, passes: int =
     if passes in (2, 4) and K % 8:
         passes = 3 if passes == 2 else 1                                   # bf16 rows must be 16-byte multiples; such widths are not on the update path
     strideB = B.stride(0) if B.dim() == 3 else 0
-    wb = int(N.lib().rorl_gemm_tn_work_bytes(Nn, K, G, strideB, passes))
-    work = torch.empty(wb, dtype=torch.uint8, device=A.device) if wb else None
+    work, tflag = None, int(transb)
+    if _ACTIVE_SPLIT_CACHE is not None and passes in (2, 4):
+        work = _ACTIVE_SPLIT_CACHE.lookup(B, transb, Nn, K, G, B.stride(-2), strideB)
+        if work is not None:
+            tflag |= 2                                   # the cache keeps this operand's split copy: no pre-split launch
+    if work is None:
+        wb = int(N.lib().rorl_gemm_tn_work_bytes(Nn, K, G, strideB, passes))
+        work = torch.empty(wb, dtype=torch.uint8, device=A.device) if wb else None
     N.call("rorl_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(bias_c), N.ptr(D), N.ptr(pre), M, Nn, K, G, A.stride(-2), B.stride(-2), ldd,
            A.stride(0) if A.dim() == 3 else 0, strideB, M * Nn if batched_out else 0,
            Nn if (bias_c is not None and bias_c.dim() == 2) else 0, int(act) | (4 if accumulate else 0), passes,
-           int(reduce_g), int(transb), N.ptr(work), N.stream())
+           int(reduce_g), tflag, N.ptr(work), N.stream())
     return (D, pre) if want_pre else D
 
 
