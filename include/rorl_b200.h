@@ -219,8 +219,8 @@ int rorl_sumsq(const float* p, int64_t n, float* out, float* work, cudaStream_t 
  * ensemble_linear_model.py:36-49; smamba projections, ref: offpolicy_rnn/models/smamba/mamba.py:176,231-233,252).
  *   D[g][M, N] = act(A[g][M, K] * B[g][N, K]^T + bias[g][N]),  g = 0..G-1
  * Both operands K-major (reduction dimension contiguous).  strideA / strideB == 0: operand shared by all g.
- * act: flag word -- bit 0 (1) ELU (Dpre, may be NULL, receives the pre-activation in D's layout for an exact ELU
- * backward); bit 2 (4, passes == 2 only) ACCUMULATE: D += result, so that a gradient with two producers (the scan's du
+ * act: flag word -- bits 0-1: 1 = ELU, 2 = exact (erf) GELU (passes 2 / 4; the cgpt FFN, ref TransformerFlashAttention.py:
+ * 43-57); Dpre, may be NULL, receives the pre-activation in D's layout (the GELU backward needs it, rorl_gelu_bwd_colsum); bit 2 (4, passes == 2 only) ACCUMULATE: D += result, so that a gradient with two producers (the scan's du
  * and x_proj's input gradient, ref: smamba/mamba.py:213-233) needs no separate add pass.
  * passes: 3 = 3xTF32 (fp32 parity, ~2^-21), 2 = two-term bf16 split, 3 bf16 MMAs (fp32 parity to ~2^-17 at twice
  * the tensor rate and half the operand bytes), 1 = plain TF32, 4 = the bf16 kernel's hi * hi term alone (one bf16 MMA per
@@ -376,6 +376,10 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
 int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
                         int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
                         int32_t* tickets, cudaStream_t stream);
+/* the same for the exact GELU, from the PRE-activation: gout = dy * (Phi(pre) + pre phi(pre)), out = column sums of gout */
+int rorl_gelu_bwd_colsum(const float* dy, const float* pre, float* g, float* out, float* work, int64_t G, int64_t M,
+                         int64_t N, int64_t ld_dy, int64_t ld_pre, int64_t ld_g, int64_t gs_dy, int64_t gs_pre, int64_t gs_g,
+                         int32_t* tickets, cudaStream_t stream);
 /* out[r * out_ld + c] = sum_p part[p][r * C + c]  (part: P planes of contiguous [rows, C]; C, out_ld % 4 == 0): per-tile
  * partial rows summed straight into a column block of a wider buffer -- the selective scan's dB | dC partials into
  * their columns of d(x_dbl) (ref: the column slices of smamba/mamba.py:214-222). */

@@ -396,7 +396,7 @@ int rorl_gemm_tn(const float* A, const float* B, const float* bias, float* D, fl
     if (!A || !B || !D) return RORL_ERR_ARG;
     const bool bf = passes == 2 || passes == 4;                  // the bf16 kernel: two-term split (2) or its hi * hi term alone (4)
     if ((transb & ~3) || (transb && !bf)) return RORL_ERR_ARG;   // only the pre-splitting form re-lays B out / takes a kept copy
-    if ((act & ~5) || ((act & 4) && !bf)) return RORL_ERR_ARG;   // accumulate: bf16 kernel only
+    if ((act & ~7) || (act & 3) == 3 || ((act & 6) && !bf)) return RORL_ERR_ARG;   // GELU, accumulate: bf16 kernel only
     if (M <= 0 || N <= 0 || K <= 0 || G <= 0) return RORL_ERR_SHAPE;
     if (K % 4 || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || strideA % 4 || strideB % 4 || strideD % 4 || strideBias % 4)
         return RORL_ERR_ALIGN;

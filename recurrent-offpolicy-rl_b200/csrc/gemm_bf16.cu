@@ -68,6 +68,8 @@ struct BfParams {
     long long strideSplit;
 };
 
+// exact GELU (torch.nn.GELU default, erf form): the cgpt FFN's activation (ref: TransformerFlashAttention.py:43-57)
+__device__ __forceinline__ float bf_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float bf_elu1(float x) {
     const float e = ex2f(fminf(x, 0.f) * kLog2e) - 1.0f;
     return x > 0.f ? x : e;
@@ -388,6 +390,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     if (p.act == 1) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { o[j].x = bf_elu1(o[j].x); o[j].y = bf_elu1(o[j].y); o[j].z = bf_elu1(o[j].z); o[j].w = bf_elu1(o[j].w); }
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { o[j].x = bf_gelu(o[j].x); o[j].y = bf_gelu(o[j].y); o[j].z = bf_gelu(o[j].z); o[j].w = bf_gelu(o[j].w); }
                     }
                     flush(o, p.D, col0, p.accum != 0);
                 }
@@ -563,7 +568,7 @@ int gemm_tn_bf16x3(const float* A, const float* B, const float* bias, float* D, 
     BfParams p;
     p.D = D; p.Dpre = Dpre; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G = (int)G;
     p.ldd = ldd; p.strideD = strideD; p.strideBias = strideBias;
-    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act & 1; p.accum = (act & 4) != 0; p.reduce_g = reduce_g != 0; p.single = single != 0;
+    p.a_batched = strideA != 0; p.b_batched = strideB != 0; p.act = act & 3; p.accum = (act & 4) != 0; p.reduce_g = reduce_g != 0; p.single = single != 0;
     p.splits = 1; p.strideSplit = 0;
     const int sms = bf_sms();
     const long long tiles = ((M + kBfBM - 1) / kBfBM) * ((N + bn - 1) / bn) * (reduce_g ? 1 : G);

@@ -22,7 +22,8 @@ constexpr int kRedMaxBlocks = 592;     // 4 x 148 row blocks
 constexpr int kRedTickets = 4096;      // ticket slots a caller provides for the single-launch form (one per column chunk x group)
 
 // grid: (row blocks, column chunks of 4 * kRedMaxQuads).  thread = (row lane, column quad).
-template <bool ELU>
+// ELU: 0 = plain column sum; 1 = ELU backward from the layer OUTPUT y; 2 = exact-GELU backward from the PRE-activation y
+template <int ELU>
 __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                              float* __restrict__ g, float* __restrict__ partial,
                                                              int64_t M, int64_t N, int64_t ldx, int64_t ldy, int64_t ldg,
@@ -43,10 +44,15 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(const float* __rest
     if (rl < lanes) {
         const int64_t col = (q0 + q) * 4;
         auto elu_grad = [&](float4& v, const float4& o) {
-            v.x *= o.x > 0.f ? 1.f : o.x + 1.f;
-            v.y *= o.y > 0.f ? 1.f : o.y + 1.f;
-            v.z *= o.z > 0.f ? 1.f : o.z + 1.f;
-            v.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+            if (ELU == 2) {                        // d/dx [x Phi(x)] = Phi(x) + x phi(x), Phi via erff (torch.nn.GELU default)
+                auto dg = [](float x) { return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x); };
+                v.x *= dg(o.x); v.y *= dg(o.y); v.z *= dg(o.z); v.w *= dg(o.w);
+            } else {
+                v.x *= o.x > 0.f ? 1.f : o.x + 1.f;
+                v.y *= o.y > 0.f ? 1.f : o.y + 1.f;
+                v.z *= o.z > 0.f ? 1.f : o.z + 1.f;
+                v.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+            }
         };
         int64_t m = m0 + rl;
         // U rows per iteration: all loads are issued before the first use (memory-level parallelism; a one-row loop left
@@ -397,7 +403,7 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
     }
     if (chunks > 65535) return RORL_ERR_SHAPE;
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
-    colsum_kernel<false><<<grid, kRedThreads, 0, stream>>>(x, nullptr, nullptr, nblk == 1 ? out : work, M, N, ldx, 0, 0, gsx, 0, 0, rpb,
+    colsum_kernel<0><<<grid, kRedThreads, 0, stream>>>(x, nullptr, nullptr, nblk == 1 ? out : work, M, N, ldx, 0, 0, gsx, 0, 0, rpb,
                                                            out, tickets, cq);
     if (nblk > 1 && !tickets) {
         dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
@@ -406,9 +412,9 @@ int rorl_colsum(const float* x, float* out, float* work, int64_t G, int64_t M, i
     RORL_RETURN_LAUNCH();
 }
 
-int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
-                        int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
-                        int32_t* tickets, cudaStream_t stream) {
+static int act_bwd_colsum(int g_act_mode, const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
+                          int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
+                          int32_t* tickets, cudaStream_t stream) {
     if (!dy || !y || !g || !out || !work) return RORL_ERR_ARG;
     if (M <= 0 || N <= 0 || G <= 0 || G > 65535) return RORL_ERR_SHAPE;
     if (N % 4 || ld_dy % 4 || ld_y % 4 || ld_g % 4 || gs_dy % 4 || gs_y % 4 || gs_g % 4 || !a16(dy) || !a16(y) || !a16(g) ||
@@ -422,8 +428,12 @@ int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, f
     }
     if (chunks > 65535) return RORL_ERR_SHAPE;
     dim3 grid((unsigned)nblk, (unsigned)chunks, (unsigned)G);
-    colsum_kernel<true><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb,
-                                                          out, tickets, cq);
+    if (g_act_mode == 2)
+        colsum_kernel<2><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb,
+                                                           out, tickets, cq);
+    else
+        colsum_kernel<1><<<grid, kRedThreads, 0, stream>>>(dy, y, g, nblk == 1 ? out : work, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, rpb,
+                                                           out, tickets, cq);
     if (nblk > 1 && !tickets) {
         dim3 g2((unsigned)((N / 4 + 31) / 32), (unsigned)G);
         partial_sum_kernel<<<g2, kRedThreads, 0, stream>>>(work, out, nblk, N);
@@ -438,6 +448,18 @@ int rorl_sum_leading_rows(const float* part, float* out, int64_t P, int64_t rows
     const int64_t n = rows * (C / 4);
     sum_leading_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(part, out, (int)P, rows, (int)C, out_ld);
     RORL_RETURN_LAUNCH();
+}
+
+int rorl_elu_bwd_colsum(const float* dy, const float* y, float* g, float* out, float* work, int64_t G, int64_t M,
+                        int64_t N, int64_t ld_dy, int64_t ld_y, int64_t ld_g, int64_t gs_dy, int64_t gs_y, int64_t gs_g,
+                        int32_t* tickets, cudaStream_t stream) {
+    return act_bwd_colsum(1, dy, y, g, out, work, G, M, N, ld_dy, ld_y, ld_g, gs_dy, gs_y, gs_g, tickets, stream);
+}
+
+int rorl_gelu_bwd_colsum(const float* dy, const float* pre, float* g, float* out, float* work, int64_t G, int64_t M,
+                         int64_t N, int64_t ld_dy, int64_t ld_pre, int64_t ld_g, int64_t gs_dy, int64_t gs_pre, int64_t gs_g,
+                         int32_t* tickets, cudaStream_t stream) {
+    return act_bwd_colsum(2, dy, pre, g, out, work, G, M, N, ld_dy, ld_pre, ld_g, gs_dy, gs_pre, gs_g, tickets, stream);
 }
 
 int64_t rorl_skinny_wgrad_work_floats(int64_t M, int64_t N, int64_t K) {

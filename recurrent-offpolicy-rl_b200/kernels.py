@@ -86,18 +86,24 @@ def sum_leading(t: torch.Tensor) -> torch.Tensor:
     return colsum(t.view(t.shape[0], n)).view(t.shape[1:])
 
 
-def elu_bwd_colsum(dy: torch.Tensor, y: torch.Tensor):
+def gelu_bwd_colsum(dy: torch.Tensor, pre: torch.Tensor):
+    """Exact-GELU backward from the PRE-activation fused with the bias gradient (same contract as elu_bwd_colsum)."""
+    return elu_bwd_colsum(dy, pre, _entry="rorl_gelu_bwd_colsum")
+
+
+def elu_bwd_colsum(dy: torch.Tensor, y: torch.Tensor, _entry: str = "rorl_elu_bwd_colsum"):
     """ELU backward from the layer output fused with the bias gradient: dy, y [M, N] or [G, M, N] contiguous ->
     (g = dy * elu'(y), g.sum(rows))."""
     G = dy.shape[0] if dy.dim() == 3 else 1
     M, Nn = dy.shape[-2], dy.shape[-1]
     if not (_red_ok(dy, Nn) and _red_ok(y, Nn) and dy.is_contiguous() and y.is_contiguous()):
-        g = torch.ops.aten.elu_backward(dy, 1.0, 1.0, 1.0, True, y)
+        g = (torch.ops.aten.gelu_backward(dy, y, approximate='none') if _entry == "rorl_gelu_bwd_colsum"
+             else torch.ops.aten.elu_backward(dy, 1.0, 1.0, 1.0, True, y))
         return g, g.sum(-2)
     g = torch.empty_like(dy)
     out = torch.empty((G, Nn) if dy.dim() == 3 else (Nn,), device=dy.device, dtype=torch.float32)
     work = torch.empty(int(N.lib().rorl_colsum_work_floats(G, M, Nn)), device=dy.device, dtype=torch.float32)
-    N.call("rorl_elu_bwd_colsum", N.ptr(dy), N.ptr(y), N.ptr(g), N.ptr(out), N.ptr(work), G, M, Nn, Nn, Nn, Nn, M * Nn, M * Nn,
+    N.call(_entry, N.ptr(dy), N.ptr(y), N.ptr(g), N.ptr(out), N.ptr(work), G, M, Nn, Nn, Nn, Nn, M * Nn, M * Nn,
            M * Nn, N.ptr(_tickets(dy.device)), N.stream())
     return g, out
 
@@ -914,13 +920,21 @@ class LinearTC(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, elu, passes=None):
+        """elu: False / True, or 2 = exact GELU in the epilogue (bf16 kernel; the pre-activation is kept for its backward)."""
         K, Nn = weight.shape[1], weight.shape[0]
         xs = _mat(x.reshape(-1, K))
         ctx.passes = passes
-        y = gemm_tn(xs, weight, bias, 1 if elu else 0, passes=passes)
-        # ELU backward from the OUTPUT (elu' = y + 1 for y <= 0): no pre-activation copy is written or kept
-        ctx.save_for_backward(xs, weight, y if elu else None)
-        ctx.elu, ctx.has_bias, ctx.xshape = elu, bias is not None, x.shape
+        act = int(elu)
+        if act == 2:
+            need_pre = any(ctx.needs_input_grad[:3])
+            res = gemm_tn(xs, weight, bias, 2, passes=passes, want_pre=need_pre)
+            y, pre = res if need_pre else (res, None)
+            ctx.save_for_backward(xs, weight, pre)
+        else:
+            y = gemm_tn(xs, weight, bias, act, passes=passes)
+            # ELU backward from the OUTPUT (elu' = y + 1 for y <= 0): no pre-activation copy is written or kept
+            ctx.save_for_backward(xs, weight, y if act else None)
+        ctx.elu, ctx.has_bias, ctx.xshape = act, bias is not None, x.shape
         return y.view(*x.shape[:-1], Nn)
 
     @staticmethod
@@ -930,7 +944,9 @@ class LinearTC(Function):
         g = _f32c(dy.reshape(-1, Nn))
         dx = dw = db = None
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
-        if ctx.elu:
+        if ctx.elu == 2:
+            g, db = gelu_bwd_colsum(g, yout)                 # yout holds the PRE-activation in this mode
+        elif ctx.elu:
             g, db = elu_bwd_colsum(g, yout)                  # ELU' and the bias gradient in one pass over dy
         elif want_db:
             db = colsum(g)
@@ -941,6 +957,17 @@ class LinearTC(Function):
         if ctx.needs_input_grad[1]:
             dw = gemm_nt(g, xs, passes=ctx.passes) if _gemm_nt_ok(Nn, xs.shape[1], xs.shape[0]) else g.t() @ xs
         return dx, dw, db, None, None
+
+
+def linear_gelu_ok(x, weight, passes=None) -> bool:
+    """Can `gelu(linear(x))` run as one GEMM with the GELU in its epilogue?  (bf16 kernel: passes 2 / 4, K % 8 == 0.)"""
+    M = x.numel() // x.shape[-1]
+    return (x.is_cuda and x.dtype == torch.float32 and int(passes or GEMM_PASSES) in (2, 4) and weight.shape[1] % 8 == 0
+            and _gemm_ok(M, weight.shape[0], weight.shape[1]))
+
+
+def linear_gelu(x, weight, bias=None, passes=None):
+    return LinearTC.apply(x, weight, bias, 2, passes)
 
 
 def linear(x, weight, bias=None, elu=False, passes=None):

@@ -133,7 +133,11 @@ class PositionWiseFeedForward(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x):
-        return self.fc2(self.dropout(self.act(self.fc1(x))))
+        if K.linear_gelu_ok(x, self.fc1.weight):            # bias + exact GELU in fc1's GEMM epilogue; its backward fused with db
+            h = K.linear_gelu(x, self.fc1.weight, self.fc1.bias)
+        else:
+            h = self.act(self.fc1(x))
+        return self.fc2(self.dropout(h))
 
 
 class DecoderLayer(nn.Module):

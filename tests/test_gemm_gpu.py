@@ -222,3 +222,25 @@ def test_ensemble_hidden_to_scalar(K, Kh, M):
     for a, r, n in zip(got, ref, "x W2 b2 W3 b3".split()):
         assert a.shape == r.shape, n
         assert rel_err(a, r) < 1e-4, n
+
+
+@pytest.mark.parametrize("M,N,K_", [(1000, 2048, 512), (32608, 2048, 512), (77, 132, 40)])
+def test_linear_gelu_fused(K, M, N, K_):
+    """gelu(x W^T + b) with the exact (erf) GELU in the GEMM epilogue and its backward fused with the bias gradient
+    (rorl_gelu_bwd_colsum), against torch in float64: output, dx, dW, db."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, K_, device="cuda", generator=g, requires_grad=True)
+    W = (torch.randn(N, K_, device="cuda", generator=g) / K_ ** 0.5).requires_grad_()
+    b = torch.randn(N, device="cuda", generator=g, requires_grad=True)
+    assert K.linear_gelu_ok(x, W)
+    y = K.linear_gelu(x, W, b)
+    dy = torch.randn(M, N, device="cuda", generator=g)
+    got = torch.autograd.grad(y, (x, W, b), dy)
+    xd, Wd, bd = (t.detach().double().requires_grad_() for t in (x, W, b))
+    yr = torch.nn.functional.gelu(torch.nn.functional.linear(xd, Wd, bd))
+    ref = torch.autograd.grad(yr, (xd, Wd, bd), dy.double())
+    assert rel_err(y, yr) < 3e-5
+    for a, r, n in zip(got, ref, ("dx", "dW", "db")):
+        assert rel_err(a, r) < 1e-4, (n, rel_err(a, r))
+    with torch.no_grad():
+        assert rel_err(K.linear_gelu(x, W, b), yr) < 3e-5
