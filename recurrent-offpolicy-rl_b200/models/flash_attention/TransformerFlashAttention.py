@@ -153,9 +153,25 @@ class DecoderLayer(nn.Module):
         x = self.dropout(self.mha(self.mha_norm(x), tiles)) + x                  # ref :76-83
         return self.dropout(self.ffn(self.ffn_norm(x))) + x                      # ref :84 (pre_norm)
 
+    def forward_stream(self, branch, residual, tiles):
+        """The same layer on a (branch, residual stream) pair: every `branch + x` of the reference (ref :76-84) is the
+        residual add of the NEXT norm's fused add + norm kernel, so no separate add launches -- and, in the backward, no
+        gradient accumulation launches on the stream -- exist.  Returns (this layer's FFN branch, the stream before it is
+        added); the caller adds it in the following norm."""
+        h, residual = _norm_stream(self.mha_norm, branch, residual)            # residual = x_in
+        a = self.dropout(self.mha(h, tiles))
+        h, residual = _norm_stream(self.ffn_norm, a, residual)                 # residual = x_in + dropout(mha)
+        return self.dropout(self.ffn(h)), residual
+
     def decode_step(self, x, cache):
         x = self.dropout(self.mha.decode_step(self.mha_norm(x), cache)) + x
         return self.dropout(self.ffn(self.ffn_norm(x))) + x
+
+
+def _norm_stream(norm, branch, residual, prenorm=True):
+    """norm(branch + residual) on the fused add + norm kernel; with prenorm also the fp32 sum (the new residual stream)."""
+    return K.layer_norm_fn(branch, norm.weight, getattr(norm, 'bias', None), residual=residual, eps=norm.eps, prenorm=prenorm,
+                           is_rms_norm=isinstance(norm, RMSNorm))
 
 
 def sequences_of(seqlens_host: np.ndarray, L: int):
@@ -224,10 +240,10 @@ class TransformerDecoder(nn.Module):
                 self._tiles_cache.pop(next(iter(self._tiles_cache)))
             cached = self._tiles_cache[key] = (tiles, keep)
         tiles, keep = cached
-        h = x.reshape(B * L, C)
+        branch, residual = x.reshape(B * L, C), None
         for layer in self.decoder_layers:
-            h = layer(h, tiles)
-        h = self.output_fc(self.output_ln(h)).view(B, L, C)
+            branch, residual = layer.forward_stream(branch, residual, tiles)
+        h = self.output_fc(_norm_stream(self.output_ln, branch, residual, prenorm=False)).view(B, L, C)
         if keep is not None:
             h = h * keep
         return h
