@@ -244,3 +244,41 @@ def test_linear_gelu_fused(K, M, N, K_):
         assert rel_err(a, r) < 1e-4, (n, rel_err(a, r))
     with torch.no_grad():
         assert rel_err(K.linear_gelu(x, W, b), yr) < 3e-5
+
+
+def test_weight_split_cache_contract(K):
+    """kernels.WeightSplitCache: B operands that are views into a registered arena get a persistent bf16 hi | lo copy,
+    rebuilt by refresh() (one launch for the whole arena); GEMMs between two refreshes read that copy -- so a weight change
+    becomes visible at the next refresh, which is why the update engine refreshes after every optimizer step -- and
+    operands outside the arena are never cached."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    arena = torch.randn(512 * 256 + 8 * 256 * 384, device="cuda", generator=g)
+    W = arena[:512 * 256].view(512, 256)                       # nn.Linear layout [N, K]
+    We = arena[512 * 256:].view(8, 256, 384)                   # EnsembleLinear layout [E, in, out] -> transb
+    A = torch.randn(1000, 256, device="cuda", generator=g)
+    cache = K.WeightSplitCache(torch.device("cuda", 0))
+    owner = cache.add_owner(arena)
+    ref = lambda: (A.double() @ W.double().t(), torch.einsum('mk,ekn->emn', A.double(), We.double()))
+    with cache.active():
+        y0, e0 = K.gemm_tn(A, W[:256]), K.gemm_tn(A, We, transb=True)          # first sighting: own pre-split, entries recorded
+        assert len(cache.entries) == 2
+        cache.refresh(owner)
+        y1, e1 = K.gemm_tn(A, W[:256]), K.gemm_tn(A, We, transb=True)          # served from the cache
+        assert torch.equal(y0, y1) and torch.equal(e0, e1)
+        r = ref()
+        assert rel_err(y1, r[0][:, :256]) < 3e-5 and rel_err(e1, r[1]) < 3e-5
+        old = ref()
+        arena.mul_(-0.5)                                                        # the weights change ...
+        y2 = K.gemm_tn(A, W[:256])
+        assert rel_err(y2, old[0][:, :256]) < 3e-5                               # ... the kept copy does not, until
+        cache.refresh(owner)                                                    # the owner says so
+        r = ref()
+        assert rel_err(K.gemm_tn(A, W[:256]), r[0][:, :256]) < 3e-5
+        assert rel_err(K.gemm_tn(A, We, transb=True), r[1]) < 3e-5
+        cache.invalidate(owner)
+        arena.mul_(2.0)
+        assert rel_err(K.gemm_tn(A, W[:256]), ref()[0][:, :256]) < 3e-5         # invalidated: per-call pre-split again
+        other = torch.randn(128, 256, device="cuda", generator=g)
+        K.gemm_tn(A, other)
+        assert len(cache.entries) == 2                                          # not in a registered arena: never cached
+    assert K._ACTIVE_SPLIT_CACHE is None
