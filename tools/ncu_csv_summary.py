@@ -37,9 +37,15 @@ def main(path, out=None):
                 if name == "us":
                     v = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}.get(u, 1.0)
                 d[name] = round(v, 3)
-        stalls = [(float(r[i] or 0), h.split("issue_stalled_")[1].split("_per_warp_active")[0]) for i, h in enumerate(hdr)
-                  if "issue_stalled_" in h and h.endswith("_per_warp_active.pct") and "not_issued" not in h]
-        d["top_stalls_pct_of_warp_time"] = {n: round(v, 1) for v, n in sorted(stalls, reverse=True)[:5]}
+        stalls = []
+        for i, h in enumerate(hdr):                      # warp-state samples (pc sampling), issued and not issued together
+            if "pcsamp_warps_issue_stalled_" in h and "not_issued" not in h:
+                try:
+                    stalls.append((float(r[i].replace(",", "")), h.split("issue_stalled_")[1]))
+                except ValueError:
+                    pass
+        tot = sum(v for v, _ in stalls) or 1.0
+        d["warp_state_pct"] = {n: round(100 * v / tot, 1) for v, n in sorted(stalls, reverse=True)[:6]}
         res.append(d)
     if out:
         json.dump(res, open(out, "w"), indent=1)

@@ -46,3 +46,47 @@ for _ in range(reps):
     K.colsum(a)
 torch.cuda.synchronize()
 print("done")
+
+if os.environ.get("NCU_SET") == "2":
+    # second set: attention (cgpt shape), fused linear-recurrence scans, add + norm, Q-head kernels, narrow projections
+    import math
+    import rorl_b200._native as N
+    H, hd = 8, 64
+    lens, starts, pos = [], [], 0
+    for _ in range(32):
+        for n in (1, 1002):
+            starts.append(pos); lens.append(n); pos += n
+    qkv = rn(pos, 3, H, hd).requires_grad_()
+    dout = rn(pos, H * hd)
+    slopes = torch.tensor([2 ** (-(i + 1)) for i in range(H)], dtype=torch.float32, device=dev)
+    tiles, gmap = (t.to(dev) for t in K.attention_tiles(starts, lens))
+    for _ in range(reps):
+        torch.autograd.grad(K.attn_varlen_alibi(qkv, tiles, gmap, slopes, 1.0 / math.sqrt(hd)), qkv, dout)
+    Bq, Lq, Cq = 32, 1003, 256
+    u_re, u_im = rn(Bq, Lq, Cq).requires_grad_(), rn(Bq, Lq, Cq).requires_grad_()
+    lam_re, lam_im = (0.6 * torch.rand(Cq, device=dev)).requires_grad_(), (0.6 * torch.rand(Cq, device=dev)).requires_grad_()
+    gamma = (0.5 + torch.rand(Cq, device=dev)).requires_grad_()
+    st2 = torch.zeros(Bq, Lq, device=dev)
+    st2[:, 0] = 1
+    g1, g2 = rn(Bq, Lq, Cq), rn(Bq, Lq, Cq)
+    for _ in range(reps):
+        torch.autograd.grad(K.lru_fused_scan(u_re, u_im, lam_re, lam_im, gamma, st2), (u_re, u_im, lam_re, lam_im, gamma), (g1, g2))
+    uv, uf = rn(Bq, Lq, Cq).requires_grad_(), rn(Bq, Lq, Cq).requires_grad_()
+    for _ in range(reps):
+        torch.autograd.grad(K.gilr_fused_scan(uv, uf, st2), (uv, uf), g1)
+    xr, rr = rn(M, 256).requires_grad_(), rn(M, 256).requires_grad_()
+    wn, bn = rn(256).requires_grad_(), rn(256).requires_grad_()
+    for _ in range(reps):
+        yn, rs = K.layer_norm_fn(xr, wn, bn, rr, 1e-5, True)
+        torch.autograd.grad((yn, rs), (xr, rr, wn, bn), (rn(M, 256), rn(M, 256)))
+    x8 = rn(8, M, 256).requires_grad_()
+    W2, b2 = (0.05 * rn(8, 256, 256)).requires_grad_(), rn(8, 1, 256).requires_grad_()
+    W3, b3 = (0.05 * rn(8, 256, 1)).requires_grad_(), rn(8, 1, 1).requires_grad_()
+    for _ in range(reps):
+        q = K.EnsembleHiddenToScalar.apply(x8, W2, b2, W3, b3)
+        torch.autograd.grad(q, (x8, W2, b2, W3, b3), rn(8, M, 1))
+    xe, We, be = rn(M, 9), rn(128, 9), rn(128)
+    for _ in range(reps):
+        K.skinny_encoders([xe], [We], [be])
+    torch.cuda.synchronize()
+    print("done set 2")
